@@ -1,0 +1,108 @@
+"""Pin the oracle (oracle/pstl_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pstl_b200  # noqa: F401
+from pstl_b200 import synthetic
+from oracle import pstl_oracle as O
+from formulas import recipes, TupleNS
+from make_golden import kat_inputs, checksum
+
+RTOL = 1e-5
+
+
+def close(a, b, rtol=RTOL, atol=None):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    fin = np.isfinite(b)
+    assert (np.isfinite(a) == fin).all()
+    assert (a[~fin] == b[~fin]).all() or (np.isnan(a[~fin]) == np.isnan(b[~fin])).all()
+    if atol is None:
+        atol = rtol * max(1.0, float(np.abs(b[fin]).max()) if fin.any() else 1.0)
+    np.testing.assert_allclose(a[fin], b[fin], rtol=rtol, atol=atol)
+
+
+def test_stl_kats(golden_dir):
+    G = np.load(os.path.join(golden_dir, "stl_kats.npz"))
+    x0 = kat_inputs()
+    assert np.allclose([checksum(x0[k]) for k in "abc"], G["in_checksum"])
+    fs = recipes(TupleNS)
+    for name in G["names"]:
+        name = str(name)
+        for tau in (1.0, 100.0):
+            for hard in (False, True):
+                key = "%s|%g|%d" % (name, tau, int(hard))
+                x = {k: v.clone().requires_grad_() for k, v in x0.items()}
+                y = O.stl_eval(fs[name], x, tau, hard)
+                close(y.detach().numpy(), G[key])
+                if key + "|ga" in G.files:
+                    grs = torch.autograd.grad(y[:, 0].sum(), [x["a"], x["b"], x["c"]], allow_unused=True)
+                    for k, g in zip("abc", grs):
+                        g = torch.zeros_like(x0[k]) if g is None else g
+                        close(g.numpy(), G[key + "|g" + k], atol=1e-6)
+
+
+def test_seed_kats_from_survey(golden_dir):
+    G = np.load(os.path.join(golden_dir, "stl_kats.npz"))
+    # SURVEY.md §8(c) table values (captured independently from the reference)
+    np.testing.assert_allclose(G["seed|always_0_3"][0], [-0.2, -0.2, -0.4, -0.4, -0.4, 0.05, 0.05, 0.6], atol=2e-6)
+    ev = G["seed|eventually_1_4"][0]
+    np.testing.assert_allclose(ev[:7], [0.5, 0.5, 0.25, 0.25, 0.6, 0.6, 0.6], atol=2e-6)
+    assert ev[7] == -np.inf
+    np.testing.assert_allclose(G["seed|ev_alw_and|tau1"][0],
+                               [-1.0503844, -0.8605880, -0.5966869, -0.2603241, 0.4093887, 0.3100896, 0.1453476,
+                                -0.1709571], atol=2e-6)
+    assert str(G["str_symbol"]) == "♢[0:5] (◻[0:9] ((a) & (b)))"
+    assert str(G["str_word"]) == "EVENTUALLY[0:5] (ALWAYS[0:9] ((a) AND (b)))"
+
+
+@pytest.mark.parametrize("tag,n,nt,knei,seed", [("t20k8", 192, 20, 8, 1008), ("t50k16", 48, 50, 16, 1009)])
+def test_dense_scores(golden_dir, tag, n, nt, knei, seed):
+    G = np.load(os.path.join(golden_dir, "stl_dense.npz"))
+    x, idx, mask = synthetic.make_dense_stl_input(n, nt=nt, n_neighbors=knei, seed=seed)
+    assert np.allclose([checksum(x[k]) for k in sorted(x)], G[tag + "|in_checksum"])
+    x["ego_traj"] = x["ego_traj"].clone().requires_grad_()
+    sc = O.stl_scores(x, idx[:, 0], 100.0)
+    for k in ("x2curr_d", "x2curr_th", "x2left_d", "x2left_th", "x2right_d", "x2right_th", "min_nei_d"):
+        close(x[k].detach().numpy(), G[tag + "|" + k])
+    close(sc.detach().numpy(), G[tag + "|scores"])
+    loss = O.mask_mean(torch.relu(0.0005 - sc), mask)
+    (g,) = torch.autograd.grad(loss, [x["ego_traj"]])
+    close(g.numpy(), G[tag + "|grad_ego"], atol=1e-9)
+
+
+def _pipeline(tag, flags_guidance, K, n_rolls, seed):
+    bs, S, nt = 2, 16, 20
+    b = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=seed)
+    W = synthetic.make_weights(1007, nt=nt)
+    N = bs * S * 3
+    stream = synthetic.noise_stream(seed + 77, N, nt * 2, 99)
+    g = dict(before=10, lr=0.01, thres=0.0005, niters=1) if flags_guidance else None
+    return O.pipeline(W, b, stream[0], stream[1:], S=S, K=K, n_rolls=n_rolls, guidance=g, n_randoms=S), b, stream, W
+
+
+def test_pipeline_ours(golden_dir):
+    G = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    out, b, stream, W = _pipeline("ours", False, 5, 0, 2001)
+    want = G["ours|in_checksum"]
+    got = [checksum(b[k]) for k in sorted(b)] + [checksum(stream[0]), sum(checksum(v) for v in W.values())]
+    assert np.allclose(got, want)
+    close(out["feature"].numpy(), G["ours|feature"])
+    close(out["final_iterate"].numpy(), G["ours|final_iterate"])
+    close(out["cand_scores"].numpy(), G["ours|cand_scores"])
+    close(out["controls"].numpy(), G["ours|controls"])
+    close(out["scores"].numpy(), G["ours|scores"])
+
+
+def test_pipeline_guidance(golden_dir):
+    G = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    out, *_ = _pipeline("guide", True, 10, 3, 2002)
+    assert int(G["guide|n_guidance_calls"]) == 10
+    close(out["final_iterate"].numpy(), G["guide|final_iterate"])
+    close(out["cand_scores"].numpy(), G["guide|cand_scores"])
+    close(out["controls"].numpy(), G["guide|controls"])
+    close(out["scores"].numpy(), G["guide|scores"])
