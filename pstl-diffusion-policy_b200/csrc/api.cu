@@ -1,0 +1,25 @@
+// api.cu — error state, device facts
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pstl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* pstl_last_error(void) { return g_err; }
+
+extern "C" int pstl_version(void) { return 100; }
+
+extern "C" int pstl_device_info(int* sm_count, int* cc) {
+  int dev = 0;
+  PSTL_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  PSTL_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc) *cc = p.major * 10 + p.minor;
+  return PSTL_OK;
+}

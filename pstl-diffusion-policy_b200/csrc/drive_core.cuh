@@ -1,0 +1,141 @@
+// drive_core.cuh — per-pose driving predicates and the Euler unicycle, forward values and the
+// partial derivatives the fused backward needs.  Operation order mirrors the reference's fp32
+// PyTorch expressions (this translation unit is compiled with -fmad=false so products and sums
+// round separately, as they do upstream).
+#pragma once
+#include "stl_core.cuh"
+
+struct PstlPose {
+  float x, y, th, v;
+};
+
+// nusc_train.py:29-49: x += v cos(th) dt, y += v sin(th) dt, th += w dt, v += a dt (old th, v)
+PSTL_HD PstlPose pstl_unicycle_step(const PstlPose& s, float w, float a, float dt, float c, float sn) {
+  PstlPose n;
+  n.x = s.x + (s.v * c) * dt;
+  n.y = s.y + (s.v * sn) * dt;
+  n.th = s.th + w * dt;
+  n.v = s.v + a * dt;
+  return n;
+}
+
+// torch.linspace(0,1,n)[k] in fp32 (symmetric formula of ATen's linspace kernel)
+PSTL_HD float pstl_linspace01(int k, int n) {
+  if (n == 1) return 0.f;
+  const float step = 1.0f / (float)(n - 1);
+  return (k < n / 2) ? step * (float)k : 1.0f - step * (float)(n - k - 1);
+}
+
+#define PSTL_MAX_NL 8
+
+// utils.py:465-497 (num_W = 1): body-axis circle centres of a car and the common radius.
+struct PstlCircles {
+  float cx[PSTL_MAX_NL], cy[PSTL_MAX_NL];
+  float q[PSTL_MAX_NL];  // body-x offsets (needed for d centre / d heading)
+  float q_y;             // body-y offset (0 for car-shaped boxes)
+  float r;
+};
+
+PSTL_HD void pstl_car_circles(float x, float y, float c, float sn, float L, float W, int nL, PstlCircles& out) {
+  const float r_l = L / (float)nL / 2.f;
+  const float r_w = W / 1.f / 2.f;
+  const float r = fminf(fmaxf(r_l, r_w), W / 2.f);
+  const float x1 = L / 2.f, x2 = -L / 2.f;
+  const float y2 = W / 2.f, y3 = -(W / 2.f);
+  const float ys = (y3 + r) * (1.f - 0.f) + (y2 - r) * 0.f;  // linspace(0,1,1) = [0]
+  out.r = r;
+  out.q_y = ys;
+  for (int k = 0; k < nL; ++k) {
+    const float al = pstl_linspace01(k, nL);
+    const float xs = (x2 + r) * (1.f - al) + (x1 - r) * al;
+    out.q[k] = xs;
+    out.cx[k] = xs * c - ys * sn + x;
+    out.cy[k] = xs * sn + ys * c + y;
+  }
+}
+
+// utils.py:499-510 + nusc_train.py:142-148 for ONE neighbour: clipped clearance term and, when
+// grad != nullptr, d term / d (ego x, y, th).
+PSTL_HD float pstl_pair_clearance(const PstlCircles& e, float ec, float es, const float* ncx, const float* ncy,
+                                  float nr, float valid, int nL, float* grad /*3 or null*/) {
+  float best = INFINITY;
+  int bi = 0, bj = 0;
+  for (int i = 0; i < nL; ++i)
+    for (int j = 0; j < nL; ++j) {
+      const float dx = e.cx[i] - ncx[j], dy = e.cy[i] - ncy[j];
+      const float d2 = dx * dx + dy * dy;
+      if (d2 < best) { best = d2; bi = i; bj = j; }
+    }
+  const float mind = sqrtf(best);  // sqrt is monotone: min of norms == norm at the min square
+  const float car = mind - e.r - nr;
+  const float clipped = fminf(fmaxf(car, -5.f), 20.f);
+  const float term = clipped * valid + (1.f - valid) * 100.f;
+  if (grad) {
+    float gx = 0.f, gy = 0.f, gth = 0.f;
+    if (car >= -5.f && car <= 20.f) {
+      const float dx = e.cx[bi] - ncx[bj], dy = e.cy[bi] - ncy[bj];
+      const float ux = dx / mind, uy = dy / mind;  // NaN when coincident, as torch.norm's backward
+      gx = ux * valid;
+      gy = uy * valid;
+      // centre = (x + q c - qy s, y + q s + qy c): d/dth = (-q s - qy c, q c - qy s)
+      gth = (ux * (-e.q[bi] * es - e.q_y * ec) + uy * (e.q[bi] * ec - e.q_y * es)) * valid;
+    }
+    grad[0] = gx; grad[1] = gy; grad[2] = gth;
+  }
+  return term;
+}
+
+// nusc_api.py:693-735: signed lateral distance and heading error of pose p to polyline lane
+// (nseg points of [x,y,th], element stride ls floats between consecutive components' rows).
+// part (3 floats or null): d dist/d px, d dist/d py, d ang/d pth.
+template <class LaneAcc>
+PSTL_HD void pstl_lane_pred(float px, float py, float pth, const LaneAcc& lane, int nseg, int clip_dist,
+                            float& dist, float& ang, float* part) {
+  float prev = 0.f;
+  float bestv = INFINITY;
+  int bi = 0;
+  for (int j = 0; j < nseg; ++j) {
+    const float dx = px - lane(j, 0), dy = py - lane(j, 1);
+    const float d = sqrtf(dx * dx + dy * dy);
+    if (j > 0) {
+      const float sum = prev + d;
+      if (sum < bestv) { bestv = sum; bi = j - 1; }
+    }
+    prev = d;
+  }
+  const float x2 = lane(bi, 0), y2 = lane(bi, 1), x3 = lane(bi + 1, 0), y3 = lane(bi + 1, 1);
+  const float area = px * (y2 - y3) + x2 * (y3 - py) + x3 * (py - y2);
+  const float bx = x2 - x3, by = y2 - y3;
+  const float base = sqrtf(bx * bx + by * by);
+  const float ex = px - x2, ey = py - y2;
+  const float q = ex * ex + ey * ey;
+  const float l2 = sqrtf(fmaxf(q, 1e-3f));
+  const float ok = (base != 0.f) ? 1.f : 0.f;
+  const float den = fmaxf(base, 1e-7f);
+  float d0 = ok * area / den + (1.f - ok) * l2;
+  float gdx = ok * (y2 - y3) / den, gdy = ok * (x3 - x2) / den;
+  if (ok == 0.f && q >= 1e-3f) { gdx += ex / l2; gdy += ey / l2; }
+  if (clip_dist) {
+    if (d0 < -5.f || d0 > 5.f) { gdx = 0.f; gdy = 0.f; }
+    d0 = fminf(fmaxf(d0, -5.f), 5.f);
+  }
+  const float u = lane(bi, 2) - pth;
+  dist = d0;
+  ang = 1.f - cosf(u);
+  if (part) {
+    part[0] = gdx;
+    part[1] = gdy;
+    part[2] = -sinf(u);
+  }
+}
+
+// decode helpers for PSTL_OP_PRED
+PSTL_HD float pstl_pred_den(int den, const float* p) {
+  switch (den) {
+    case PSTL_DEN_THMAX: return p[5];
+    case PSTL_DEN_VFACTOR: return fmaxf(p[1] - p[0], 0.3f);
+    case PSTL_DEN_DFACTOR: return fmaxf((p[3] - p[2]) * 5.f, 0.3f);
+    case PSTL_DEN_SFACTOR: return fmaxf(p[4], 0.3f);
+    default: return 1.f;
+  }
+}

@@ -1,0 +1,506 @@
+// mlp_fp32.cu — fp32 SIMT path of the denoiser / sampler / RefineNet (the 1e-5 parity mode) and
+// the host-side orchestration of the reverse loop.
+//
+// Algebra: of policy_net's 303 input columns, 224 (scene feature) are constant
+// per scene and 32 (time embedding) constant per step, so
+//   W1 . [feat, x, temb, hl, stlp] + b1 = (W1f . feat + b1)[scene] + (W1t . temb)[step] + W1p . [x, hl, stlp]
+// and the per-step GEMM depth drops from 303 to 47.  The same split applies to rect_net (271 -> 47).
+#include <math.h>
+
+#include "mlp_common.cuh"
+
+enum { EPI_PLAIN = 0, EPI_DDPM = 1, EPI_REFINE = 2 };
+
+struct LinArgs {
+  const float* X; int ldx;
+  const float* W; int ldw;
+  const float* bias;
+  const float* rowbias; int rows_per_group; int ldrb;
+  const float* bias2;
+  const float* res; int ldres;
+  float* Y; int ldy;
+  int M, K, Nout, act;
+  // EPI_DDPM
+  float c1, c2, sqrt_beta;
+  const float* z;
+  unsigned long long seed, offset;
+  int step, noise_mode;  // 0: none, 1: injected, 2: philox
+  float* xio; int ldxio;
+  float* mu_out;
+  float* iter_out;
+  float w_max, a_max;
+  int clip;
+  // EPI_REFINE
+  const float* u0;
+  const float* scores;
+};
+
+#define BM 128
+#define BN 64
+#define BK 16
+
+template <int EPI>
+__global__ void __launch_bounds__(256) k_linear(LinArgs a) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ar = tid >> 1, ak = (tid & 1) * 8;  // A: row ar, k-offset ak..ak+7
+  const int br = tid >> 2, bk = (tid & 3) * 4;  // B: row br, k-offset bk..bk+3
+  const long long am = m0 + ar;
+  const int bn = n0 + br;
+  for (int k0 = 0; k0 < a.K; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + ak + j;
+      As[ak + j][ar] = (am < a.M && k < a.K) ? a.X[am * a.ldx + k] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + bk + j;
+      Bs[bk + j][br] = (bn < a.Nout && k < a.K) ? a.W[(long long)bn * a.ldw + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + ty * 8 + i;
+    if (m >= a.M) continue;
+    const float* rb = a.rowbias ? a.rowbias + (m / a.rows_per_group) * a.ldrb : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.Nout) continue;
+      float v = acc[i][j];
+      if (a.bias) v += a.bias[n];
+      if (rb) v += rb[n];
+      if (a.bias2) v += a.bias2[n];
+      if (EPI == EPI_PLAIN) {
+        if (a.res) v += a.res[m * a.ldres + n];
+        if (a.act) v = fmaxf(v, 0.f);
+        a.Y[m * a.ldy + n] = v;
+      } else if (EPI == EPI_DDPM) {
+        // nusc_model.py:162 eps = net + x ; nusc_train.py:587,628
+        const float x = a.xio[m * a.ldxio + n];
+        const float eps = v + x;
+        const float mu = a.c2 * (x - a.c1 * eps);
+        if (a.mu_out) {
+          a.mu_out[m * a.Nout + n] = mu;
+        } else {
+          float z = 0.f;
+          if (a.noise_mode == 1) z = a.z[m * a.Nout + n];
+          else if (a.noise_mode == 2) z = pstl_noise_at(a.seed, a.offset, a.step, m, n);
+          const float xn = mu + a.sqrt_beta * z;
+          a.xio[m * a.ldxio + n] = xn;
+          if (a.iter_out) {  // normalize_diff, nusc_train.py:647-655
+            const float sc = (n & 1) ? a.a_max : a.w_max;
+            float u = xn * sc;
+            if (a.clip) u = fminf(fmaxf(u, -sc), sc);
+            a.iter_out[m * a.Nout + n] = u;
+          }
+        }
+      } else {  // EPI_REFINE, nusc_model.py:212-233
+        const float r = tanhf(v);
+        const float init = a.u0[m * a.Nout + n];
+        const float lim = (n & 1) ? a.a_max : a.w_max;
+        const float mk = (r >= 0.f) ? 1.f : 0.f;
+        const float lo = r * (init - (-lim));
+        const float hi = r * (lim - init);
+        const float merged = lo * (1.f - mk) + hi * mk;
+        const float viol = (a.scores[m] < 0.f) ? 1.f : 0.f;
+        float o = init + merged * viol;
+        if (a.clip) o = fminf(fmaxf(o, -lim), lim);
+        a.Y[m * a.ldy + n] = o;
+      }
+    }
+  }
+}
+
+static void lin_defaults(LinArgs& a) { memset(&a, 0, sizeof(a)); a.rows_per_group = 1; }
+
+template <int EPI>
+static int launch_linear(const LinArgs& a, cudaStream_t st) {
+  if (a.M <= 0) return PSTL_OK;
+  dim3 grid(pstl_ceil_div(a.M, BM), pstl_ceil_div(a.Nout, BN));
+  k_linear<EPI><<<grid, 256, 0, st>>>(a);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
+extern "C" int pstl_linear(const float* x, const float* w, const float* b, int M, int K, int Nout, int act, float* y,
+                           pstl_stream_t stream) {
+  PSTL_CHECK_ARG(x && w && y && K > 0 && Nout > 0, "bad argument");
+  LinArgs a;
+  lin_defaults(a);
+  a.X = x; a.ldx = K; a.W = w; a.ldw = K; a.bias = b; a.Y = y; a.ldy = Nout; a.M = M; a.K = K; a.Nout = Nout; a.act = act;
+  return launch_linear<EPI_PLAIN>(a, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------------------
+// small helper kernels
+// --------------------------------------------------------------------------------------
+// xin[n] = [x (T2) | hl | stlp(6) | 0]
+__global__ void k_pack_xin(const float* __restrict__ x, int ldx_src, const float* __restrict__ hl,
+                           const float* __restrict__ stlp, float* __restrict__ xin, long long N, int T2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * PSTL_XIN_LD) return;
+  const long long n = i / PSTL_XIN_LD;
+  const int c = (int)(i - n * PSTL_XIN_LD);
+  float v = 0.f;
+  if (c < T2) v = x ? x[n * ldx_src + c] : 0.f;
+  else if (c == T2) v = hl[n];
+  else if (c < T2 + 7) v = stlp[n * 6 + (c - T2 - 1)];
+  xin[i] = v;
+}
+
+// RefineNet shard pooling (nusc_model.py:186-200): rows n=(b*R+r)*3+m; max over the `per` samples of a shard
+__global__ void k_group_fuse(const float* __restrict__ g, const float* __restrict__ u0, float* __restrict__ xin,
+                             long long N, int T2, int R, int per) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over (group, col)
+  const long long n_groups = N / per;                                    // (b, shard, m) triples
+  if (i >= n_groups * T2) return;
+  const long long gidx = i / T2;
+  const int c = (int)(i - gidx * T2);
+  const int m = (int)(gidx % 3);
+  const long long bs_sh = gidx / 3;            // b * n_shards + shard
+  const int n_shards = R / per;
+  const long long b = bs_sh / n_shards;
+  const int sh = (int)(bs_sh - b * n_shards);
+  float mx = -INFINITY;
+  for (int j = 0; j < per; ++j) {
+    const long long n = (b * R + sh * per + j) * 3 + m;
+    mx = fmaxf(mx, g[n * T2 + c]);
+  }
+  for (int j = 0; j < per; ++j) {
+    const long long n = (b * R + sh * per + j) * 3 + m;
+    xin[n * PSTL_XIN_LD + c] = u0[n * T2 + c] + mx;
+  }
+}
+
+__global__ void k_finish_step(const float* __restrict__ mu, float* __restrict__ xin, const float* __restrict__ z,
+                              long long N, int T2, float sqrt_beta, int noise_mode, unsigned long long seed,
+                              unsigned long long offset, int step, float* __restrict__ iter_out, float w_max,
+                              float a_max, int clip) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * T2) return;
+  const long long n = i / T2;
+  const int c = (int)(i - n * T2);
+  float zz = 0.f;
+  if (noise_mode == 1) zz = z[i];
+  else if (noise_mode == 2) zz = pstl_noise_at(seed, offset, step, n, c);
+  const float xn = mu[i] + sqrt_beta * zz;
+  xin[n * PSTL_XIN_LD + c] = xn;
+  if (iter_out) {
+    const float sc = (c & 1) ? a_max : w_max;
+    float u = xn * sc;
+    if (clip) u = fminf(fmaxf(u, -sc), sc);
+    iter_out[i] = u;
+  }
+}
+
+__global__ void k_extract_x(const float* __restrict__ xin, float* __restrict__ out, long long N, int T2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * T2) return;
+  const long long n = i / T2;
+  out[i] = xin[n * PSTL_XIN_LD + (int)(i - n * T2)];
+}
+
+// --------------------------------------------------------------------------------------
+// handle
+// --------------------------------------------------------------------------------------
+int pstl_tc_create(pstl_denoiser* d);   // denoiser_tc.cu
+void pstl_tc_destroy(pstl_denoiser* d);
+int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, const float* ct, float* xin, int N,
+                   const float* sched, int steps, const float* noise, unsigned long long seed,
+                   unsigned long long offset, float w_max, float a_max, int clip, int keep_last_k, float* iterates_out,
+                   int first_step, int last_step, cudaStream_t st);
+
+extern "C" int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_denoiser_t* out) {
+  PSTL_CHECK_ARG(w && out, "null argument");
+  PSTL_CHECK_ARG(w->p0_w && w->p0_b && w->p2_w && w->p2_b && w->p4_w && w->p4_b, "policy_net weights required");
+  PSTL_CHECK_ARG(w->T > 0 && w->hidden > 0 && w->feat_dim > 0 && w->time_dim > 0, "bad dims");
+  PSTL_CHECK_ARG(precision == PSTL_PRECISION_FP32 || precision == PSTL_PRECISION_BF16, "bad precision");
+  pstl_denoiser* d = new pstl_denoiser();
+  d->w = *w;
+  d->precision = precision;
+  d->T2 = 2 * w->T;
+  d->kin = d->T2 + 7;
+  d->w1p = d->r1p = nullptr;
+  d->tc = nullptr;
+  const int in1 = w->feat_dim + d->T2 + w->time_dim + 7;  // 303
+  const size_t f = sizeof(float);
+  cudaError_t e = cudaMalloc(&d->w1p, (size_t)w->hidden * d->kin * f);
+  // [x | hl | stlp] <- columns [feat : feat+T2], [feat+T2+time], [feat+T2+time+1 : +7]
+  if (e == cudaSuccess)
+    e = cudaMemcpy2D(d->w1p, d->kin * f, w->p0_w + w->feat_dim, in1 * f, d->T2 * f, w->hidden, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2D(d->w1p + d->T2, d->kin * f, w->p0_w + w->feat_dim + d->T2 + w->time_dim, in1 * f, 7 * f, w->hidden,
+                     cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess && w->r0_w) {
+    const int inr = w->feat_dim + 7 + d->T2;  // 271: [feat | hl | stlp | fused]
+    e = cudaMalloc(&d->r1p, (size_t)w->rect_hidden * d->kin * f);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2D(d->r1p, d->kin * f, w->r0_w + w->feat_dim + 7, inr * f, d->T2 * f, w->rect_hidden,
+                       cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2D(d->r1p + d->T2, d->kin * f, w->r0_w + w->feat_dim, inr * f, 7 * f, w->rect_hidden,
+                       cudaMemcpyDeviceToDevice);
+  }
+  if (e != cudaSuccess) {
+    pstl_set_error("pstl_denoiser_create: %s", cudaGetErrorString(e));
+    pstl_denoiser_destroy(d);
+    return PSTL_ERR_CUDA;
+  }
+  if (precision == PSTL_PRECISION_BF16) {
+    int rc = pstl_tc_create(d);
+    if (rc) {
+      pstl_denoiser_destroy(d);
+      return rc;
+    }
+  }
+  *out = d;
+  return PSTL_OK;
+}
+
+extern "C" int pstl_denoiser_destroy(pstl_denoiser_t d) {
+  if (!d) return PSTL_OK;
+  if (d->tc) pstl_tc_destroy(d);
+  cudaFree(d->w1p);
+  cudaFree(d->r1p);
+  delete d;
+  return PSTL_OK;
+}
+
+static size_t guidance_ws_floats(pstl_denoiser_t d, int N, const pstl_guidance_cfg* g) {
+  if (!g) return 0;
+  size_t tape = pstl_score_workspace_bytes(g->progs, N, d->w.T, 1) / sizeof(float);
+  return pstl_align_floats((size_t)N * d->T2) + pstl_align_floats(tape);
+}
+
+static void carve(pstl_denoiser_t d, int N, int n_scenes, int steps, const pstl_guidance_cfg* g, void* ws,
+                  DenoiserWs* o, size_t* total) {
+  const int H = d->w.hidden > d->w.rect_hidden ? d->w.hidden : d->w.rect_hidden;
+  float* p = (float*)ws;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* r = p ? p + off : nullptr; off += pstl_align_floats(n); return r; };
+  o->xin = take((size_t)N * PSTL_XIN_LD);
+  o->h1 = take((size_t)N * H);
+  o->h2 = take((size_t)N * H);
+  o->g = take((size_t)N * d->T2);
+  o->cscene = take((size_t)n_scenes * H);
+  o->ct = take((size_t)(steps > 1 ? steps : 1) * H);
+  o->adam = g ? take((size_t)3 * N * d->T2) : nullptr;
+  o->gws = g ? take(guidance_ws_floats(d, N, g)) : nullptr;
+  *total = off * sizeof(float);
+}
+
+extern "C" size_t pstl_denoiser_workspace_bytes(pstl_denoiser_t d, int N, int n_scenes, const pstl_guidance_cfg* g) {
+  if (!d) return 0;
+  DenoiserWs w;
+  size_t total;
+  carve(d, N, n_scenes, 1024, g, nullptr, &w, &total);
+  return total;
+}
+
+// hoisted first-layer terms: cscene = feat . W[:, :feat]^T + b ; ct = temb . W[:, tcol:tcol+time]^T
+static int hoist(const float* W, int ldw, const float* b, int H, const float* feat, int n_scenes, int feat_dim,
+                 float* cscene, const float* temb, int steps, int tcol, int time_dim, float* ct, cudaStream_t st) {
+  LinArgs a;
+  lin_defaults(a);
+  a.X = feat; a.ldx = feat_dim; a.W = W; a.ldw = ldw; a.bias = b; a.Y = cscene; a.ldy = H;
+  a.M = n_scenes; a.K = feat_dim; a.Nout = H;
+  int rc = launch_linear<EPI_PLAIN>(a, st);
+  if (rc || !temb) return rc;
+  lin_defaults(a);
+  a.X = temb; a.ldx = time_dim; a.W = W + tcol; a.ldw = ldw; a.Y = ct; a.ldy = H; a.M = steps; a.K = time_dim; a.Nout = H;
+  return launch_linear<EPI_PLAIN>(a, st);
+}
+
+static int mlp_hidden(pstl_denoiser_t d, const DenoiserWs& w, int N, int rows_per_scene, const float* W1p, int H,
+                      const float* ct_row, const float* W2, const float* b2, cudaStream_t st) {
+  LinArgs a;
+  lin_defaults(a);
+  a.X = w.xin; a.ldx = PSTL_XIN_LD; a.W = W1p; a.ldw = d->kin; a.rowbias = w.cscene; a.rows_per_group = rows_per_scene;
+  a.ldrb = H; a.bias2 = ct_row; a.Y = w.h1; a.ldy = H; a.M = N; a.K = d->kin; a.Nout = H; a.act = 1;
+  int rc = launch_linear<EPI_PLAIN>(a, st);
+  if (rc) return rc;
+  lin_defaults(a);
+  a.X = w.h1; a.ldx = H; a.W = W2; a.ldw = H; a.bias = b2; a.Y = w.h2; a.ldy = H; a.M = N; a.K = H; a.Nout = H; a.act = 1;
+  return launch_linear<EPI_PLAIN>(a, st);
+}
+
+extern "C" int pstl_denoiser_eps(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                                 const float* hl, const float* stlp, const float* x, int N, const float* temb_row,
+                                 float* eps_out, void* workspace, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && x && temb_row && eps_out && workspace, "null argument");
+  PSTL_CHECK_ARG(rows_per_scene >= 1 && (long long)n_scenes * rows_per_scene >= N, "bad scene mapping");
+  cudaStream_t st = (cudaStream_t)stream;
+  DenoiserWs w;
+  size_t total;
+  carve(d, N, n_scenes, 1, nullptr, workspace, &w, &total);
+  const int H = d->w.hidden, T2 = d->T2;
+  const int in1 = d->w.feat_dim + T2 + d->w.time_dim + 7;
+  int rc = hoist(d->w.p0_w, in1, d->w.p0_b, H, scene_feat, n_scenes, d->w.feat_dim, w.cscene, temb_row, 1,
+                 d->w.feat_dim + T2, d->w.time_dim, w.ct, st);
+  if (rc) return rc;
+  const long long tot = (long long)N * PSTL_XIN_LD;
+  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x, T2, hl, stlp, w.xin, N, T2);
+  PSTL_LAUNCH_CHECK();
+  rc = mlp_hidden(d, w, N, rows_per_scene, d->w1p, H, w.ct, d->w.p2_w, d->w.p2_b, st);
+  if (rc) return rc;
+  LinArgs a;
+  lin_defaults(a);
+  a.X = w.h2; a.ldx = H; a.W = d->w.p4_w; a.ldw = H; a.bias = d->w.p4_b; a.res = x; a.ldres = T2;
+  a.Y = eps_out; a.ldy = T2; a.M = N; a.K = H; a.Nout = T2;
+  return launch_linear<EPI_PLAIN>(a, st);
+}
+
+extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                                    const float* hl, const float* stlp, int N, const float* sched, const float* temb,
+                                    int steps, const float* x_init, const float* noise, uint64_t seed, uint64_t offset,
+                                    float w_max, float a_max, int clip, int keep_last_k,
+                                    const pstl_guidance_cfg* guidance, float* iterates_out, float* x_final,
+                                    void* workspace, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && sched && temb && x_init && workspace, "null argument");
+  PSTL_CHECK_ARG(steps >= 2 && keep_last_k >= 0 && keep_last_k <= steps - 1, "bad steps / keep_last_k");
+  PSTL_CHECK_ARG(rows_per_scene >= 1 && (long long)n_scenes * rows_per_scene >= N, "bad scene mapping");
+  PSTL_CHECK_ARG(!keep_last_k || iterates_out, "iterates_out required");
+  if (N <= 0) return PSTL_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DenoiserWs w;
+  size_t total;
+  carve(d, N, n_scenes, steps, guidance, workspace, &w, &total);
+  const int H = d->w.hidden, T2 = d->T2;
+  const int in1 = d->w.feat_dim + T2 + d->w.time_dim + 7;
+  int rc = hoist(d->w.p0_w, in1, d->w.p0_b, H, scene_feat, n_scenes, d->w.feat_dim, w.cscene, temb, steps,
+                 d->w.feat_dim + T2, d->w.time_dim, w.ct, st);
+  if (rc) return rc;
+  const long long tot = (long long)N * PSTL_XIN_LD;
+  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x_init, T2, hl, stlp, w.xin, N, T2);
+  PSTL_LAUNCH_CHECK();
+  const float* hs = sched;  // host pointer by contract
+  const float *beta = hs, *alpha = hs + steps, *abar = hs + 2 * steps;
+  const size_t NT2 = (size_t)N * T2;
+
+  int tc_from = steps;  // reverse steps [tc_lo, steps-1] run on the tcgen05 engine when available
+  if (d->precision == PSTL_PRECISION_BF16) {
+    // guided steps (i <= before) need mu materialised: they run on the fp32 path below
+    const int lo = guidance ? (guidance->before + 1 > 1 ? guidance->before + 1 : 1) : 1;
+    if (lo <= steps - 1) {
+      rc = pstl_tc_sample(d, w.cscene, rows_per_scene, w.ct, w.xin, N, sched, steps, noise, seed, offset, w_max, a_max,
+                          clip, keep_last_k, iterates_out, steps - 1, lo, st);
+      if (rc) return rc;
+      tc_from = lo;
+    }
+  }
+
+  for (int i = tc_from - 1; i >= 1; --i) {
+    rc = mlp_hidden(d, w, N, rows_per_scene, d->w1p, H, w.ct + (size_t)i * H, d->w.p2_w, d->w.p2_b, st);
+    if (rc) break;
+    const bool guided = guidance && i <= guidance->before;
+    const int zi = steps - 1 - i;  // index into the injected z stream (i = steps-1 first)
+    const int noise_mode = (i > 1) ? (noise ? 1 : 2) : 0;
+    const int kidx = keep_last_k - i;  // iterate after step i is the (i)-th from the end
+    float* it_out = (kidx >= 0 && keep_last_k > 0) ? iterates_out + (size_t)kidx * NT2 : nullptr;
+    LinArgs a;
+    lin_defaults(a);
+    a.X = w.h2; a.ldx = H; a.W = d->w.p4_w; a.ldw = H; a.bias = d->w.p4_b; a.M = N; a.K = H; a.Nout = T2;
+    a.c1 = (1.0f - alpha[i]) / sqrtf(1.0f - abar[i]);
+    a.c2 = 1.0f / sqrtf(alpha[i]);
+    a.sqrt_beta = sqrtf(beta[i]);
+    a.z = (noise && i > 1) ? noise + (size_t)zi * NT2 : nullptr;
+    a.seed = seed; a.offset = offset; a.step = i; a.noise_mode = noise_mode;
+    a.xio = w.xin; a.ldxio = PSTL_XIN_LD;
+    a.mu_out = guided ? w.g : nullptr;
+    a.iter_out = guided ? nullptr : it_out;
+    a.w_max = w_max; a.a_max = a_max; a.clip = clip;
+    rc = launch_linear<EPI_DDPM>(a, st);
+    if (rc) break;
+    if (guided) {
+      float* m = w.adam;
+      float* v = w.adam + NT2;
+      float* anchor = w.adam + 2 * NT2;
+      cudaError_t e = cudaMemsetAsync(m, 0, sizeof(float) * 2 * NT2, st);
+      if (e != cudaSuccess) { rc = PSTL_ERR_CUDA; pstl_set_error("memset: %s", cudaGetErrorString(e)); break; }
+      for (int j = 0; j < guidance->niters && !rc; ++j)
+        rc = pstl_guidance_step(guidance->progs, guidance->scenes, guidance->sp, hl, guidance->state0, stlp,
+                                guidance->valid, N, guidance->thres, guidance->inv_norm, guidance->lr, beta[i], j, w.g,
+                                m, v, anchor, w.gws, stream);
+      if (rc) break;
+      k_finish_step<<<pstl_ceil_div((long long)NT2, 256), 256, 0, st>>>(w.g, w.xin, a.z, N, T2, a.sqrt_beta, noise_mode,
+                                                                       seed, offset, i, it_out, w_max, a_max, clip);
+      cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) { rc = PSTL_ERR_CUDA; pstl_set_error("k_finish_step: %s", cudaGetErrorString(le)); break; }
+    }
+  }
+  if (rc) return rc;
+  if (x_final) {
+    k_extract_x<<<pstl_ceil_div((long long)NT2, 256), 256, 0, st>>>(w.xin, x_final, N, T2);
+    PSTL_LAUNCH_CHECK();
+  }
+  return PSTL_OK;
+}
+
+extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                           const float* hl, const float* stlp, const float* u0, const float* scores, int N,
+                           int n_randoms, int n_shards, float w_max, float a_max, int clip_rect, float* out,
+                           void* workspace, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && u0 && scores && out && workspace, "null argument");
+  PSTL_CHECK_ARG(d->w.r0_w && d->w.m0_w && d->r1p, "handle was created without rect_net / merge_net weights");
+  PSTL_CHECK_ARG(n_shards > 0 && n_randoms % n_shards == 0 && N % (3 * n_randoms) == 0,
+                 "rows must be (scene, n_randoms, 3 modes) with n_shards | n_randoms");
+  if (N <= 0) return PSTL_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DenoiserWs w;
+  size_t total;
+  carve(d, N, n_scenes, 1, nullptr, workspace, &w, &total);
+  const int H = d->w.rect_hidden, T2 = d->T2, MH = d->w.merge_hidden;
+  const int inr = d->w.feat_dim + 7 + T2;
+  int rc = hoist(d->w.r0_w, inr, d->w.r0_b, H, scene_feat, n_scenes, d->w.feat_dim, w.cscene, nullptr, 0, 0, 0, nullptr, st);
+  if (rc) return rc;
+  // merge_net on every chain (nusc_model.py:186)
+  LinArgs a;
+  lin_defaults(a);
+  a.X = u0; a.ldx = T2; a.W = d->w.m0_w; a.ldw = T2; a.bias = d->w.m0_b; a.Y = w.h1; a.ldy = MH; a.M = N; a.K = T2; a.Nout = MH; a.act = 1;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  lin_defaults(a);
+  a.X = w.h1; a.ldx = MH; a.W = d->w.m2_w; a.ldw = MH; a.bias = d->w.m2_b; a.Y = w.h2; a.ldy = MH; a.M = N; a.K = MH; a.Nout = MH; a.act = 1;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  lin_defaults(a);
+  a.X = w.h2; a.ldx = MH; a.W = d->w.m4_w; a.ldw = MH; a.bias = d->w.m4_b; a.Y = w.g; a.ldy = T2; a.M = N; a.K = MH; a.Nout = T2;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  const long long tot = (long long)N * PSTL_XIN_LD;
+  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(nullptr, 0, hl, stlp, w.xin, N, T2);
+  PSTL_LAUNCH_CHECK();
+  const int per = n_randoms / n_shards;
+  const long long gtot = (long long)(N / per) * T2;
+  k_group_fuse<<<pstl_ceil_div(gtot, 256), 256, 0, st>>>(w.g, u0, w.xin, N, T2, n_randoms, per);
+  PSTL_LAUNCH_CHECK();
+  rc = mlp_hidden(d, w, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st);
+  if (rc) return rc;
+  lin_defaults(a);
+  a.X = w.h2; a.ldx = H; a.W = d->w.r4_w; a.ldw = H; a.bias = d->w.r4_b; a.Y = out; a.ldy = T2; a.M = N; a.K = H; a.Nout = T2;
+  a.u0 = u0; a.scores = scores; a.w_max = w_max; a.a_max = a_max; a.clip = clip_rect;
+  return launch_linear<EPI_REFINE>(a, st);
+}

@@ -1,0 +1,549 @@
+// stl_kernels.cu — STL program interpreter kernels and the fused rollout+predicate+STL scoring
+// kernels (forward, reverse, guidance).  Compiled with -fmad=false (see drive_core.cuh).
+//
+// Thread mapping: one thread per trajectory row.  The per-row traces ("tape") live in shared
+// memory with stride blockDim+1 (bank-conflict free) or, when they do not fit, in a caller
+// workspace with stride N (coalesced).  In the scene-indexed layout all rows of a block belong
+// to one scene, whose lanes and pre-computed neighbour circles are staged once in shared memory
+// and read as broadcasts.
+#include <new>
+
+#include "common.cuh"
+#include "drive_eval.cuh"
+
+struct pstl_program {
+  PstlProgView h;        // host copy
+  PstlProgView* d;       // device copy
+};
+
+static const int kSmemBudget = 200 * 1024;
+
+// --------------------------------------------------------------------------------------
+// program handles
+// --------------------------------------------------------------------------------------
+extern "C" int pstl_program_create(const pstl_op* postfix, int n_ops, int n_signals, int T, int need_t,
+                                   pstl_program_t* out) {
+  PSTL_CHECK_ARG(postfix && out, "null argument");
+  pstl_program* p = new (std::nothrow) pstl_program();
+  PSTL_CHECK_ARG(p, "out of host memory");
+  char err[256];
+  if (pstl_resolve_program(postfix, n_ops, n_signals, T, need_t, &p->h, err, sizeof(err)) != 0) {
+    delete p;
+    pstl_set_error("pstl_program_create: %s", err);
+    return PSTL_ERR_ARG;
+  }
+  p->d = nullptr;
+  cudaError_t e = cudaMalloc(&p->d, sizeof(PstlProgView));
+  if (e == cudaSuccess) e = cudaMemcpy(p->d, &p->h, sizeof(PstlProgView), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->d) cudaFree(p->d);
+    delete p;
+    pstl_set_error("pstl_program_create: %s", cudaGetErrorString(e));
+    return PSTL_ERR_CUDA;
+  }
+  *out = p;
+  return PSTL_OK;
+}
+
+extern "C" int pstl_program_destroy(pstl_program_t prog) {
+  if (!prog) return PSTL_OK;
+  cudaFree(prog->d);
+  delete prog;
+  return PSTL_OK;
+}
+
+extern "C" int pstl_program_tape_floats(pstl_program_t prog, int with_grad) {
+  if (!prog) return PSTL_ERR_ARG;
+  return with_grad ? prog->h.grad_floats : prog->h.val_floats;
+}
+
+// pick block size / tape placement for F floats per row (+ extra shared bytes)
+struct TapePlan {
+  int block;
+  int smem_tape;  // 1: shared, 0: workspace
+  size_t smem_bytes;
+};
+
+static TapePlan plan_tape(int F, size_t extra, int prefer_block) {
+  TapePlan p;
+  for (int b = prefer_block; b >= 32; b >>= 1) {
+    size_t bytes = extra + (size_t)F * (b + 1) * sizeof(float);
+    if (bytes <= (size_t)kSmemBudget) {
+      p.block = b;
+      p.smem_tape = 1;
+      p.smem_bytes = bytes;
+      return p;
+    }
+  }
+  p.block = prefer_block;
+  p.smem_tape = 0;
+  p.smem_bytes = extra;
+  return p;
+}
+
+// --------------------------------------------------------------------------------------
+// generic signal programs:  node(x, tau, d) of stl_d_lib.py on pre-evaluated AP signals
+// --------------------------------------------------------------------------------------
+struct LeafNone {
+  __device__ float signal(int, int) const { return 0.f; }
+  __device__ float pred(int, int, int) const { return 0.f; }
+  __device__ void signal(int, int, float) const {}
+  __device__ void pred(int, int, int, float) const {}
+};
+
+template <bool BWD>
+__global__ void k_stl_signals(const PstlProgView* __restrict__ dprog, const float* __restrict__ sig,
+                              const float* __restrict__ grad_trace, int N, int P, int T, float tau, int hard,
+                              float* __restrict__ out_trace, float* __restrict__ out_t0, float* __restrict__ grad_sig,
+                              float* __restrict__ ws, int smem_tape) {
+  extern __shared__ float sm[];
+  __shared__ PstlProgView prog;
+  {
+    const int* src = reinterpret_cast<const int*>(dprog);
+    int* dst = reinterpret_cast<int*>(&prog);
+    for (int i = threadIdx.x; i < (int)(sizeof(PstlProgView) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int B = blockDim.x;
+  const int n0 = blockIdx.x * B;
+  const int cnt = min(B, N - n0);
+  const int n = n0 + threadIdx.x;
+  const int F = prog.val_floats;
+  float *vt, *gt = nullptr;
+  int stride;
+  if (smem_tape) {
+    stride = B + 1;
+    vt = sm + threadIdx.x;
+    if (BWD) gt = sm + (size_t)F * stride + threadIdx.x;
+  } else {
+    stride = N;
+    vt = ws + min(n, N - 1);
+    if (BWD) gt = ws + (size_t)F * N + min(n, N - 1);
+  }
+  // stage the (cnt,P,T) signal chunk transposed into the tape: coalesced global reads
+  const int PT_ = P * T;
+  const float* chunk = sig + (size_t)n0 * PT_;
+  for (int e = threadIdx.x; e < cnt * PT_; e += B) {
+    const int r = e / PT_, q = e - r * PT_;
+    const float v = chunk[e];
+    if (smem_tape) sm[(size_t)q * stride + r] = v; else ws[(size_t)q * N + n0 + r] = v;
+  }
+  __syncthreads();
+  LeafNone leaf;
+  const PstlROp top = prog.ops[prog.n_ops - 1];
+  if (n < N) {
+    pstl_interp_fwd(prog, vt, stride, tau, hard, leaf);
+    if (!BWD) {
+      if (out_trace)
+        for (int t = 0; t < prog.need_t; ++t) out_trace[(size_t)n * prog.need_t + t] = vt[(size_t)(top.out_off + t) * stride];
+      if (out_t0) out_t0[n] = vt[(size_t)top.out_off * stride];
+    } else {
+      for (int i = 0; i < F; ++i) gt[(size_t)i * stride] = 0.f;
+      for (int t = 0; t < prog.need_t; ++t) gt[(size_t)(top.out_off + t) * stride] += grad_trace[(size_t)n * prog.need_t + t];
+      pstl_interp_bwd(prog, vt, gt, stride, tau, hard, leaf);
+    }
+  }
+  if (BWD) {
+    __syncthreads();
+    float* gchunk = grad_sig + (size_t)n0 * PT_;
+    for (int e = threadIdx.x; e < cnt * PT_; e += B) {
+      const int r = e / PT_, q = e - r * PT_;
+      gchunk[e] = smem_tape ? sm[(size_t)F * stride + (size_t)q * stride + r] : ws[(size_t)F * N + (size_t)q * N + n0 + r];
+    }
+  }
+}
+
+extern "C" size_t pstl_stl_workspace_bytes(pstl_program_t prog, int N, int with_grad) {
+  if (!prog) return 0;
+  const int F = prog->h.val_floats * (with_grad ? 2 : 1);
+  TapePlan p = plan_tape(F, 0, 128);
+  return p.smem_tape ? 0 : (size_t)F * N * sizeof(float);
+}
+
+static int launch_signals(bool bwd, pstl_program_t prog, const float* sig, const float* grad_trace, int N, int P,
+                          int T, float tau, int hard, float* out_trace, float* out_t0, float* grad_sig, void* ws,
+                          pstl_stream_t stream) {
+  PSTL_CHECK_ARG(prog && sig, "null argument");
+  PSTL_CHECK_ARG(P == prog->h.n_signals && T == prog->h.T, "signal shape does not match the program");
+  if (N <= 0) return PSTL_OK;
+  const int F = prog->h.val_floats * (bwd ? 2 : 1);
+  TapePlan p = plan_tape(F, 0, 128);
+  PSTL_CHECK_ARG(p.smem_tape || ws, "workspace required (see pstl_stl_workspace_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = pstl_ceil_div(N, p.block);
+  if (bwd) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_stl_signals<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    k_stl_signals<true><<<grid, p.block, p.smem_bytes, st>>>(prog->d, sig, grad_trace, N, P, T, tau, hard, nullptr,
+                                                             nullptr, grad_sig, (float*)ws, p.smem_tape);
+  } else {
+    PSTL_CUDA(cudaFuncSetAttribute(k_stl_signals<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    k_stl_signals<false><<<grid, p.block, p.smem_bytes, st>>>(prog->d, sig, nullptr, N, P, T, tau, hard, out_trace,
+                                                              out_t0, nullptr, (float*)ws, p.smem_tape);
+  }
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
+extern "C" int pstl_stl_eval_signals(pstl_program_t prog, const float* sig, int N, int P, int T, float tau, int hard,
+                                     float* out_trace, float* out_t0, void* workspace, pstl_stream_t stream) {
+  return launch_signals(false, prog, sig, nullptr, N, P, T, tau, hard, out_trace, out_t0, nullptr, workspace, stream);
+}
+
+extern "C" int pstl_stl_eval_signals_bwd(pstl_program_t prog, const float* sig, const float* grad_trace, int N, int P,
+                                         int T, float tau, int hard, float* grad_sig, void* workspace,
+                                         pstl_stream_t stream) {
+  PSTL_CHECK_ARG(grad_trace && grad_sig, "null gradient buffers");
+  return launch_signals(true, prog, sig, grad_trace, N, P, T, tau, hard, nullptr, nullptr, grad_sig, workspace, stream);
+}
+
+// --------------------------------------------------------------------------------------
+// fused scoring
+// --------------------------------------------------------------------------------------
+struct SceneSmem {
+  const float* circ;  // (K,T,2nL+2): cx[nL], cy[nL], r, valid
+  const float* ln;    // (3,nseg,3)
+  int K, T, nL, nseg;
+  __device__ float lane(int l, int j, int f) const { return ln[(l * nseg + j) * 3 + f]; }
+  __device__ void nei_circles(int k, int t, float* cx, float* cy, float& r, float& valid) const {
+    const float* p = circ + ((size_t)k * T + t) * (2 * nL + 2);
+    for (int i = 0; i < nL; ++i) { cx[i] = p[i]; cy[i] = p[nL + i]; }
+    r = p[2 * nL];
+    valid = p[2 * nL + 1];
+  }
+};
+
+struct ScoreArgs {
+  const PstlProgView* progs[3];
+  const float* neighbors;
+  const float* lanes[3];
+  int n_scenes, rows_per_scene;
+  PstlEvalCfg cfg;
+  const float *mode, *state0, *controls, *ego, *stlp;
+  int ego_stride, N, C;
+  float *scores_all, *best_score, *best_controls, *traj_out;
+  int32_t* best_idx;
+  // reverse mode
+  const float *grad_score, *valid;
+  float thres, inv_norm;
+  float *scores, *grad_controls, *grad_ego;
+  float* ws;
+  int smem_tape, F;
+};
+
+__device__ __forceinline__ size_t scene_tile_floats(const PstlEvalCfg& c) {
+  return (size_t)c.K * c.T * (2 * c.nL + 2) + (size_t)3 * c.nseg * 3;
+}
+
+// block-cooperative staging of one scene into shared memory
+__device__ void stage_scene(const ScoreArgs& a, int scene, float* tile) {
+  const PstlEvalCfg& c = a.cfg;
+  const int W = 2 * c.nL + 2;
+  float* circ = tile;
+  float* ln = tile + (size_t)c.K * c.T * W;
+  const float* nb = a.neighbors + (size_t)scene * c.K * c.T * 7;
+  for (int e = threadIdx.x; e < c.K * c.T; e += blockDim.x) {
+    const float* p = nb + (size_t)e * 7;
+    PstlCircles cc;
+    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], c.nL, cc);
+    float* o = circ + (size_t)e * W;
+    for (int i = 0; i < c.nL; ++i) { o[i] = cc.cx[i]; o[c.nL + i] = cc.cy[i]; }
+    o[2 * c.nL] = cc.r;
+    o[2 * c.nL + 1] = p[0];
+  }
+  for (int l = 0; l < 3; ++l) {
+    const float* src = a.lanes[l] + (size_t)scene * c.nseg * 3;
+    for (int e = threadIdx.x; e < c.nseg * 3; e += blockDim.x) ln[l * c.nseg * 3 + e] = src[e];
+  }
+}
+
+template <bool SMEM_SCENE, bool BWD>
+__global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
+  extern __shared__ float sm[];
+  __shared__ PstlProgView progs[3];
+  for (int k = 0; k < 3; ++k) {
+    const int* src = reinterpret_cast<const int*>(a.progs[k]);
+    int* dst = reinterpret_cast<int*>(&progs[k]);
+    for (int i = threadIdx.x; i < (int)(sizeof(PstlProgView) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  const PstlEvalCfg c = a.cfg;
+  const int B = blockDim.x;
+  const int n0 = blockIdx.x * B;
+  const int n = n0 + threadIdx.x;
+  float* tile = sm;
+  float* tape0 = sm;
+  if (SMEM_SCENE) {
+    stage_scene(a, n0 / a.rows_per_scene, tile);
+    tape0 = sm + ((scene_tile_floats(c) + 3) & ~(size_t)3);
+  }
+  __syncthreads();
+  if (n >= a.N) return;
+  const int T = c.T;
+  float *vt, *gt = nullptr, *pt = nullptr;
+  int stride;
+  if (a.smem_tape) {
+    stride = B + 1;
+    vt = tape0 + threadIdx.x;
+  } else {
+    stride = a.N;
+    vt = a.ws + n;
+  }
+  const float md = a.mode[n];
+  const int m = (md == 0.f) ? 0 : (md == 1.f) ? 1 : (md == 2.f) ? 2 : (md == 3.f) ? 3 : 4;
+  const PstlProgView& P = progs[m < 3 ? m : 0];
+  if (BWD) {
+    gt = vt + (size_t)P.val_floats * stride;
+    pt = vt + (size_t)P.part_off * stride;
+  }
+  PstlPose s0{0.f, 0.f, 0.f, 0.f};
+  if (a.state0) { s0.x = a.state0[n * 4 + 0]; s0.y = a.state0[n * 4 + 1]; s0.th = a.state0[n * 4 + 2]; s0.v = a.state0[n * 4 + 3]; }
+  const float* stlp = a.stlp + (size_t)n * 6;
+  const float* ego = a.ego ? a.ego + (size_t)n * T * a.ego_stride : nullptr;
+  const int scene = n / a.rows_per_scene;
+
+  SceneSmem ss{tile, tile + (size_t)c.K * c.T * (2 * c.nL + 2), c.K, c.T, c.nL, c.nseg};
+  PstlSceneGlobal sg;
+  sg.nei = a.neighbors + (size_t)scene * c.K * c.T * 7;
+  for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
+  sg.K = c.K; sg.T = c.T; sg.nL = c.nL;
+
+  if (!BWD) {
+    float best = -INFINITY;
+    int bi = 0;
+    for (int cand = 0; cand < a.C; ++cand) {
+      const float* u = a.controls ? a.controls + ((size_t)cand * a.N + n) * T * 2 : nullptr;
+      float sc;
+      if (m < 3) {
+        sc = SMEM_SCENE ? pstl_eval_traj<SceneSmem, false>(P, ss, c, s0, u, ego, a.ego_stride, stlp, vt, nullptr, stride)
+                        : pstl_eval_traj<PstlSceneGlobal, false>(P, sg, c, s0, u, ego, a.ego_stride, stlp, vt, nullptr, stride);
+      } else {
+        sc = (m == 3) ? 1.0f : 0.0f;  // nusc_train.py:322 outlier score; unknown mode selects nothing (:150-151)
+      }
+      if (a.scores_all) a.scores_all[(size_t)cand * a.N + n] = sc;
+      if (cand == 0 || sc > best) { best = sc; bi = cand; }  // torch.max(dim=0): first maximum
+    }
+    if (a.best_score) a.best_score[n] = best;
+    if (a.best_idx) a.best_idx[n] = bi;
+    if ((a.best_controls || a.traj_out) && a.controls) {
+      const float* u = a.controls + ((size_t)bi * a.N + n) * T * 2;
+      PstlPose s = s0;
+      for (int t = 0; t < T; ++t) {
+        float w, ac;
+        pstl_scaled_control(u, t, c, w, ac);
+        if (a.best_controls) { a.best_controls[((size_t)n * T + t) * 2] = w; a.best_controls[((size_t)n * T + t) * 2 + 1] = ac; }
+        if (a.traj_out) {
+          float* o = a.traj_out + ((size_t)n * (T + 1) + t) * 4;
+          o[0] = s.x; o[1] = s.y; o[2] = s.th; o[3] = s.v;
+          s = pstl_unicycle_step(s, w, ac, c.dt, cosf(s.th), sinf(s.th));
+        }
+      }
+      if (a.traj_out) {
+        float* o = a.traj_out + ((size_t)n * (T + 1) + T) * 4;
+        o[0] = s.x; o[1] = s.y; o[2] = s.th; o[3] = s.v;
+      }
+    }
+  } else {
+    const float* u = a.controls ? a.controls + (size_t)n * T * 2 : nullptr;
+    float* gu = a.grad_controls ? a.grad_controls + (size_t)n * T * 2 : nullptr;
+    float* ge = a.grad_ego ? a.grad_ego + (size_t)n * T * 4 : nullptr;
+    if (m >= 3) {
+      if (a.scores) a.scores[n] = (m == 3) ? 1.0f : 0.0f;
+      if (gu) for (int i = 0; i < T * 2; ++i) gu[i] = 0.f;
+      if (ge) for (int i = 0; i < T * 4; ++i) ge[i] = 0.f;
+      return;
+    }
+    const float sc = SMEM_SCENE ? pstl_eval_traj<SceneSmem, true>(P, ss, c, s0, u, ego, a.ego_stride, stlp, vt, pt, stride)
+                                : pstl_eval_traj<PstlSceneGlobal, true>(P, sg, c, s0, u, ego, a.ego_stride, stlp, vt, pt, stride);
+    if (a.scores) a.scores[n] = sc;
+    float g;
+    if (a.grad_score) {
+      g = a.grad_score[n];
+    } else {  // guidance loss (nusc_train.py:616-619): mean(relu(thres-score)*valid)/clip(mean(valid),1e-2)
+      g = (a.thres - sc > 0.f) ? -a.valid[n] * a.inv_norm : 0.f;
+    }
+    pstl_eval_traj_bwd(P, c, u, stlp, g, vt, gt, pt, stride, gu, ge);
+  }
+}
+
+static int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+
+static int fill_cfg(const pstl_scene_view* sv, const pstl_spec_params* sp, PstlEvalCfg* c) {
+  c->dt = sp->dt; c->tau = sp->tau; c->ego_L = sp->ego_L; c->ego_W = sp->ego_W;
+  c->w_scale = sp->w_scale; c->a_scale = sp->a_scale;
+  c->clip_controls = sp->clip_controls; c->clip_dist = sp->clip_dist; c->hard = sp->hard;
+  c->nL = 4; c->nseg = sv->nseg; c->K = sv->Knei; c->T = sv->T;
+  return 0;
+}
+
+struct ScorePlan {
+  TapePlan tp;
+  int smem_scene;
+  int F;
+};
+
+static ScorePlan plan_score(pstl_program_t const* progs, const pstl_scene_view* sv, int N, int with_grad) {
+  ScorePlan sp;
+  sp.F = with_grad ? max3(progs[0]->h.grad_floats, progs[1]->h.grad_floats, progs[2]->h.grad_floats)
+                   : max3(progs[0]->h.val_floats, progs[1]->h.val_floats, progs[2]->h.val_floats);
+  const size_t tile = (((size_t)sv->Knei * sv->T * 10 + (size_t)9 * sv->nseg + 3) & ~(size_t)3) * sizeof(float);
+  // one scene per block needs rows_per_scene to be a multiple of the block size
+  sp.smem_scene = 0;
+  const int prefer = with_grad ? 64 : 128;
+  if (sv->rows_per_scene >= 32 && tile <= 96 * 1024) {
+    for (int b = prefer; b >= 32; b >>= 1)
+      if (sv->rows_per_scene % b == 0) {
+        sp.tp = plan_tape(sp.F, tile, b);  // a smaller power-of-two block still divides rows_per_scene
+        sp.smem_scene = 1;
+        return sp;
+      }
+  }
+  sp.tp = plan_tape(sp.F, 0, prefer);
+  return sp;
+}
+
+extern "C" size_t pstl_score_workspace_bytes(pstl_program_t const* progs, int N, int T, int with_grad) {
+  if (!progs || !progs[0] || !progs[1] || !progs[2]) return 0;
+  // conservative: size for the workspace tape; the launch uses shared memory when it fits
+  const int F = with_grad ? max3(progs[0]->h.grad_floats, progs[1]->h.grad_floats, progs[2]->h.grad_floats)
+                          : max3(progs[0]->h.val_floats, progs[1]->h.val_floats, progs[2]->h.val_floats);
+  TapePlan t = plan_tape(F, 96 * 1024, 32);
+  (void)T;
+  return t.smem_tape ? 0 : (size_t)F * N * sizeof(float);
+}
+
+template <bool BWD>
+static int launch_score(ScoreArgs& a, const ScorePlan& sp, cudaStream_t st) {
+  const int grid = pstl_ceil_div(a.N, sp.tp.block);
+  a.smem_tape = sp.tp.smem_tape;
+  a.F = sp.F;
+  if (sp.smem_scene) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score<true, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    k_score<true, BWD><<<grid, sp.tp.block, sp.tp.smem_bytes, st>>>(a);
+  } else {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score<false, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    k_score<false, BWD><<<grid, sp.tp.block, sp.tp.smem_bytes, st>>>(a);
+  }
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
+static int check_score_args(pstl_program_t const* progs, const pstl_scene_view* sv, const pstl_spec_params* sp,
+                            const float* mode, const float* stlp, int N) {
+  PSTL_CHECK_ARG(progs && progs[0] && progs[1] && progs[2], "three programs required");
+  PSTL_CHECK_ARG(sv && sp && mode && stlp, "null argument");
+  PSTL_CHECK_ARG(sv->rows_per_scene >= 1 && sv->Knei >= 0 && sv->nseg >= 2, "bad scene view");
+  for (int k = 0; k < 3; ++k) PSTL_CHECK_ARG(progs[k]->h.T == sv->T && progs[k]->h.n_signals == 0, "program/scene horizon mismatch");
+  PSTL_CHECK_ARG((long long)sv->n_scenes * sv->rows_per_scene >= N, "fewer scene rows than trajectories");
+  return PSTL_OK;
+}
+
+static void base_args(ScoreArgs& a, pstl_program_t const* progs, const pstl_scene_view* sv,
+                      const pstl_spec_params* sp) {
+  memset(&a, 0, sizeof(a));
+  for (int k = 0; k < 3; ++k) { a.progs[k] = progs[k]->d; a.lanes[k] = sv->lanes[k]; }
+  a.neighbors = sv->neighbors;
+  a.n_scenes = sv->n_scenes;
+  a.rows_per_scene = sv->rows_per_scene;
+  fill_cfg(sv, sp, &a.cfg);
+}
+
+extern "C" int pstl_score_fused(pstl_program_t const* progs, const pstl_scene_view* scenes, const pstl_spec_params* sp,
+                                const float* mode, const float* state0, const float* controls, int C,
+                                const float* ego_traj, int ego_stride, const float* stlp, int N, float* scores_all,
+                                float* best_score, int32_t* best_idx, float* best_controls, float* traj_out,
+                                void* workspace, pstl_stream_t stream) {
+  int rc = check_score_args(progs, scenes, sp, mode, stlp, N);
+  if (rc) return rc;
+  PSTL_CHECK_ARG((controls && state0 && C >= 1) || (ego_traj && ego_stride >= 4), "need controls+state0 or ego_traj");
+  if (N <= 0) return PSTL_OK;
+  ScoreArgs a;
+  base_args(a, progs, scenes, sp);
+  a.mode = mode; a.state0 = state0; a.controls = ego_traj ? nullptr : controls; a.ego = ego_traj;
+  a.ego_stride = ego_stride; a.stlp = stlp; a.N = N; a.C = ego_traj ? 1 : C;
+  a.scores_all = scores_all; a.best_score = best_score; a.best_idx = best_idx;
+  a.best_controls = best_controls; a.traj_out = traj_out; a.ws = (float*)workspace;
+  ScorePlan plan = plan_score(progs, scenes, N, 0);
+  PSTL_CHECK_ARG(plan.tp.smem_tape || workspace, "workspace required (see pstl_score_workspace_bytes)");
+  return launch_score<false>(a, plan, (cudaStream_t)stream);
+}
+
+extern "C" int pstl_score_fused_bwd(pstl_program_t const* progs, const pstl_scene_view* scenes,
+                                    const pstl_spec_params* sp, const float* mode, const float* state0,
+                                    const float* controls, const float* ego_traj, int ego_stride, const float* stlp,
+                                    int N, const float* grad_score, float* scores, float* grad_controls,
+                                    float* grad_ego, void* workspace, pstl_stream_t stream) {
+  int rc = check_score_args(progs, scenes, sp, mode, stlp, N);
+  if (rc) return rc;
+  PSTL_CHECK_ARG(grad_score, "grad_score required");
+  PSTL_CHECK_ARG((controls && state0 && grad_controls && !ego_traj) || (ego_traj && ego_stride >= 4 && grad_ego),
+                 "need (controls,state0,grad_controls) or (ego_traj,grad_ego)");
+  if (N <= 0) return PSTL_OK;
+  ScoreArgs a;
+  base_args(a, progs, scenes, sp);
+  a.mode = mode; a.state0 = state0; a.controls = ego_traj ? nullptr : controls; a.ego = ego_traj;
+  a.ego_stride = ego_stride; a.stlp = stlp; a.N = N; a.C = 1;
+  a.grad_score = grad_score; a.scores = scores;
+  a.grad_controls = ego_traj ? nullptr : grad_controls; a.grad_ego = ego_traj ? grad_ego : nullptr;
+  a.ws = (float*)workspace;
+  ScorePlan plan = plan_score(progs, scenes, N, 1);
+  PSTL_CHECK_ARG(plan.tp.smem_tape || workspace, "workspace required (see pstl_score_workspace_bytes)");
+  return launch_score<true>(a, plan, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------------------
+// guidance: gradient (fused above) + Adam / clip epilogue (nusc_train.py:606-626)
+// --------------------------------------------------------------------------------------
+__global__ void k_guidance_apply(const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ m,
+                                 float* __restrict__ v, float* __restrict__ anchor, size_t n, float step_size,
+                                 float bc2_sqrt, float beta_t, int iter) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // torch.optim.Adam defaults: betas (0.9, 0.999), eps 1e-8, single-tensor path
+  const float b2 = 0.999f, eps = 1e-8f;
+  const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
+  const float gi = g[i];
+  const float mi = m[i] + w1 * (gi - m[i]);                   // exp_avg.lerp_(grad, 1-beta1), weight < 0.5 branch
+  const float vi = v[i] * b2 + (w2 * gi) * gi;                // exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2)
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;             // (exp_avg_sq.sqrt()/bias_correction2_sqrt).add_(eps)
+  float p = mu[i] + ((-step_size) * mi) / denom;              // param.addcdiv_(exp_avg, denom, value=-step_size)
+  if (iter == 0) {
+    // upstream aliases mu_init with the parameter: the first "clip" sees delta == 0 and the
+    // once-stepped value becomes the anchor of every later clip
+    anchor[i] = p;
+  } else {
+    const float a0 = anchor[i];
+    const float d = fminf(fmaxf(fabsf(p - a0), -beta_t), beta_t);
+    p = a0 + d;
+  }
+  mu[i] = p;
+}
+
+extern "C" int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_view* scenes,
+                                  const pstl_spec_params* sp, const float* mode, const float* state0,
+                                  const float* stlp, const float* valid, int N, float thres, float inv_norm, float lr,
+                                  float beta_t, int iter, float* mu, float* adam_m, float* adam_v, float* mu_anchor,
+                                  void* workspace, pstl_stream_t stream) {
+  int rc = check_score_args(progs, scenes, sp, mode, stlp, N);
+  if (rc) return rc;
+  PSTL_CHECK_ARG(state0 && valid && mu && adam_m && adam_v && mu_anchor && workspace, "null argument");
+  if (N <= 0) return PSTL_OK;
+  const int T = scenes->T;
+  // workspace layout: [grad (N,T,2)] [tape]
+  float* grad = (float*)workspace;
+  float* tape = grad + (size_t)N * T * 2;
+  ScoreArgs a;
+  base_args(a, progs, scenes, sp);
+  a.mode = mode; a.state0 = state0; a.controls = mu; a.stlp = stlp; a.N = N; a.C = 1;
+  a.valid = valid; a.thres = thres; a.inv_norm = inv_norm; a.grad_controls = grad; a.ws = tape;
+  ScorePlan plan = plan_score(progs, scenes, N, 1);
+  rc = launch_score<true>(a, plan, (cudaStream_t)stream);
+  if (rc) return rc;
+  const size_t n = (size_t)N * T * 2;
+  // torch computes the bias corrections in Python doubles, then applies them to fp32 tensors
+  const double bc1 = 1.0 - pow(0.9, (double)(iter + 1)), bc2 = 1.0 - pow(0.999, (double)(iter + 1));
+  k_guidance_apply<<<pstl_ceil_div((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(
+      grad, mu, adam_m, adam_v, mu_anchor, n, (float)((double)lr / bc1), (float)sqrt(bc2), beta_t, iter);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}

@@ -1,0 +1,207 @@
+"""Drop-in for the reference's ``nusc_model.Net`` on the diffusion + RefineNet path
+(reference nusc_model.py:8-235): same constructor, sub-module names (so reference checkpoints
+load with ``load_state_dict``), ``forward`` / ``rect_forward`` signatures.
+
+The eps-MLP and RefineNet run in libpstl_b200.so; the per-scene encoders (O(bs) work, SURVEY.md
+§8(f) "next") stay PyTorch.  VAE / BC / init-hint variants are out of scope and raise.
+"""
+import torch
+import torch.nn as nn
+
+from . import native as _nv
+
+
+def build_relu_nn(input_dim, output_dim, hiddens, activation_fn=nn.ReLU, last_fn=None):
+    """Linear/ReLU stack with the reference's state_dict key layout ``*.0/2/4`` (reference utils.py:91-101)."""
+    dims = [input_dim] + list(hiddens) + [output_dim]
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        layers.append(activation_fn())
+    if last_fn is not None:
+        layers[-1] = last_fn()
+    else:
+        del layers[-1]
+    return nn.Sequential(*layers)
+
+
+def normalize_xyth(state, base, valid=None, no_theta=False):
+    """ego-frame transform (reference nusc_model.py:238-263)."""
+    assert len(state.shape) == len(base.shape) and state.shape[0] == base.shape[0]
+    x, y = state[..., 0], state[..., 1]
+    bx, by, bth = base[..., 0], base[..., 1], base[..., 2]
+    if valid is not None:
+        xt, yt = x - bx * valid, y - by * valid
+    else:
+        xt, yt = x - bx, y - by
+    xr = xt * torch.cos(bth) + yt * torch.sin(bth)
+    yr = -xt * torch.sin(bth) + yt * torch.cos(bth)
+    if no_theta:
+        return torch.stack([xr, yr], dim=-1)
+    th = state[..., 2]
+    tr = th - bth * valid if valid is not None else th - bth
+    return torch.stack([xr, yr, tr], dim=-1)
+
+
+class Net(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        if not args.diffusion or getattr(args, "vae", False) or getattr(args, "bc", False) or \
+                getattr(args, "use_init_hint", False):
+            raise NotImplementedError("pstl_b200.Net builds the --diffusion model only")
+        self.output_dim = args.nt * 2
+        self.feat_dim = feat_dim = 32
+        self.stlp_dim = stlp_dim = 6
+        self.lane_dim = 3
+        self.n_segs = args.n_segs
+        self.time_dim = 32
+        self.ego_encoder = build_relu_nn(6, feat_dim, args.hiddens)
+        self.neighbor_encoder = build_relu_nn(7, feat_dim, args.hiddens)
+        self.lane_encoder = build_relu_nn(self.n_segs * self.lane_dim, feat_dim, args.hiddens)
+        latent_dim = args.nt * 2 + self.time_dim + 1 + stlp_dim
+        self.policy_net = build_relu_nn(latent_dim + feat_dim * 7, args.nt * 2, args.hiddens)
+        if args.rect_head:
+            if args.diverse_loss and not args.no_arch and args.diverse_fuse_type != "add":
+                raise NotImplementedError("only --diverse_fuse_type add is built")
+            if args.diverse_loss:
+                self.merge_net = build_relu_nn(args.nt * 2, args.nt * 2, [32, 32])
+            self.rect_net = build_relu_nn(latent_dim - self.time_dim + feat_dim * 7, args.nt * 2, args.rect_hiddens)
+        self._handles = {}
+
+    # --- native handle -------------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def native_handle(self, precision="fp32"):
+        """pstl_denoiser_t over this module's parameters (rebuilt if they were modified)."""
+        prec = {"fp32": _nv.PRECISION_FP32, "bf16": _nv.PRECISION_BF16}[precision]
+        key = (prec, self._weights_key())
+        cached = self._handles.get(prec)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        if len(self.args.hiddens) != 2 or len(getattr(self.args, "rect_hiddens", [0, 0])) != 2 or \
+                self.args.hiddens[0] != self.args.hiddens[1]:
+            raise NotImplementedError("native denoiser needs two equal hidden layers")
+        w = _nv.Weights()
+        keep = []
+
+        def put(prefix, seq):
+            for li in (0, 2, 4):
+                for kind in ("weight", "bias"):
+                    t = getattr(seq[li], kind).detach()
+                    _nv.require_cuda(t, "model parameters")
+                    t = t.to(torch.float32).contiguous()
+                    keep.append(t)
+                    setattr(w, "%s%d_%s" % (prefix, li, kind[0]), t.data_ptr())
+
+        put("p", self.policy_net)
+        w.merge_hidden = 32
+        if hasattr(self, "rect_net"):
+            put("r", self.rect_net)
+            if hasattr(self, "merge_net"):
+                put("m", self.merge_net)
+        w.hidden = self.args.hiddens[0]
+        w.rect_hidden = self.args.rect_hiddens[0] if hasattr(self, "rect_net") else self.args.hiddens[0]
+        w.feat_dim, w.time_dim, w.T = self.feat_dim * 7, self.time_dim, self.args.nt
+        h = _nv.C.c_void_p()
+        _nv.check(_nv.lib().pstl_denoiser_create(_nv.C.byref(w), prec, _nv.C.byref(h)), "pstl_denoiser_create")
+        if cached is not None:
+            _nv.lib().pstl_denoiser_destroy(cached[1])
+        self._handles[prec] = (key, h, keep)
+        return h
+
+    def pos_encoding(self, t, channels):
+        """sinusoidal embedding (reference nusc_model.py:48-53)."""
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, channels, 2, device=t.device).float() / channels))
+        a = torch.sin(t.repeat(1, channels // 2) * inv_freq)
+        b = torch.cos(t.repeat(1, channels // 2) * inv_freq)
+        return torch.cat([a, b], dim=-1)
+
+    def time_table(self, steps, device):
+        """(steps, time_dim) table of pos_encoding(t), t = 0..steps-1, built on the host exactly as the
+        reference builds each row, then uploaded once."""
+        t = torch.arange(steps, dtype=torch.long).reshape(steps, 1)
+        return self.pos_encoding(t, self.time_dim).to(device=device, dtype=torch.float32).contiguous()
+
+    # --- encoders (reference nusc_model.py:55-95) ----------------------------------------
+    def encode_feat(self, nn_input, ext=None):
+        bs = nn_input["ego_traj"].shape[0]
+        ego = nn_input["ego_traj"][:, 0]
+        ego_un = ego.unsqueeze(1)
+        neis_ = nn_input["neighbors"]
+        neis_xyth = normalize_xyth(neis_[..., 1:4], ego_un, neis_[..., 0])
+        neis_input = torch.cat([neis_[..., 0:1], neis_xyth, neis_[..., 4:7]], dim=-1)
+        lanes = torch.stack([normalize_xyth(nn_input["%slane_wpts" % k], ego_un, nn_input["%s_id" % k])
+                             for k in ("curr", "left", "right")], dim=1)
+        lanes_input = torch.cat([lanes[..., 0:1, :], lanes[..., 1:, :] - lanes[..., :-1, :]], dim=-2)
+        lanes_input = lanes_input.reshape(bs, 3, lanes.shape[-2] * self.lane_dim)
+        ego_input = torch.cat([normalize_xyth(ego[..., :3], ego[..., :3]), ego[..., 3:]], dim=-1)
+        ego_feat = self.ego_encoder(ego_input)
+        nei_feat = self.neighbor_encoder(neis_input)
+        nei_feat = torch.cat([torch.min(nei_feat, dim=1)[0], torch.mean(nei_feat, dim=1), torch.max(nei_feat, dim=1)[0]],
+                             dim=-1)
+        lanes_feat = self.lane_encoder(lanes_input).reshape(bs, -1)
+        return torch.cat([ego_feat, nei_feat, lanes_feat], dim=-1)
+
+    # --- eps model (reference nusc_model.py:97-180, diffusion + multi_check branch) -------
+    def forward(self, nn_input, ext=None, get_feature=False, prev_feature=None, sample=False, n_randoms=None):
+        if getattr(self.args, "gt_data_training", False):
+            raise NotImplementedError("--gt_data_training is out of scope")
+        bs = nn_input["ego_traj"].shape[0]
+        if n_randoms is None:
+            n_randoms = self.args.n_randoms
+        n_rep = n_randoms * 3
+        scene_feat = getattr(prev_feature, "_pstl_scene_feat", None) if prev_feature is not None else None
+        if scene_feat is None:
+            if prev_feature is not None:
+                scene_feat = prev_feature.reshape(bs, -1, prev_feature.shape[-1])[:, 0].contiguous()
+            else:
+                scene_feat = self.encode_feat(nn_input)
+        x = _nv.f32(ext["noise"])
+        _nv.require_cuda(x, "ext['noise']")
+        n = x.shape[0]
+        t = ext["timestep"]
+        hl = _nv.f32(ext["highlevel"].reshape(n))
+        stlp = _nv.f32(nn_input["stlp_dense"][:, 0])
+        t0 = int(t.reshape(-1)[0].item())
+        if not bool((t == t0).all()):
+            raise NotImplementedError("native eps needs one timestep per call (the sampler's case)")
+        temb_row = self.pos_encoding(torch.tensor([[t0]], dtype=torch.long), self.time_dim).to(x.device).contiguous()
+        handle = self.native_handle("fp32")
+        eps = torch.empty_like(x)
+        L = _nv.lib()
+        ws = _nv.workspace(L.pstl_denoiser_workspace_bytes(handle, n, bs, None), x.device, "denoiser")
+        _nv.check(L.pstl_denoiser_eps(handle, _nv.fptr(_nv.f32(scene_feat)), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp),
+                                      _nv.fptr(x), n, _nv.fptr(temb_row), _nv.fptr(eps), _nv.ptr(ws), _nv.stream()),
+                  "pstl_denoiser_eps")
+        controls = eps.reshape(-1, self.args.nt, 2)
+        if get_feature:
+            k = scene_feat.shape[-1]
+            feature = scene_feat.reshape(bs, 1, k).expand(bs, n_rep, k).reshape(-1, k)
+            feature._pstl_scene_feat = scene_feat
+            return controls, feature
+        return controls
+
+    # --- RefineNet (reference nusc_model.py:182-235) --------------------------------------
+    def rect_forward(self, feature, highlevel, stlp_dense_feat, init_controls, scores, extras=None):
+        a = self.args
+        if not (a.diverse_loss and not a.no_arch and a.interval):
+            raise NotImplementedError("native RefineNet is built for --diverse_loss --interval (implied by --rect_head)")
+        n = init_controls.shape[0]
+        bs = int(n / 3 / a.n_randoms)
+        scene_feat = getattr(feature, "_pstl_scene_feat", None)
+        if scene_feat is None:
+            scene_feat = feature.reshape(bs, -1, feature.shape[-1])[:, 0].contiguous()
+        u0 = _nv.f32(init_controls.reshape(n, a.nt * 2))
+        _nv.require_cuda(u0, "init_controls")
+        out = torch.empty((n, a.nt, 2), dtype=torch.float32, device=u0.device)
+        handle = self.native_handle("fp32")
+        L = _nv.lib()
+        ws = _nv.workspace(L.pstl_denoiser_workspace_bytes(handle, n, bs, None), u0.device, "denoiser")
+        _nv.check(L.pstl_refine(handle, _nv.fptr(_nv.f32(scene_feat)), bs, n // bs, _nv.fptr(_nv.f32(highlevel.reshape(n))),
+                                _nv.fptr(_nv.f32(stlp_dense_feat.reshape(n, 6))), _nv.fptr(u0),
+                                _nv.fptr(_nv.f32(scores.reshape(n))), n, a.n_randoms, a.n_shards,
+                                _nv.C.c_float(a.mul_w_max), _nv.C.c_float(a.mul_a_max), int(bool(a.clip_rect)),
+                                _nv.fptr(out), _nv.ptr(ws), _nv.stream()), "pstl_refine")
+        return out

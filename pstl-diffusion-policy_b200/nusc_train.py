@@ -1,0 +1,930 @@
+"""Hot-path functions of the reference's ``nusc_train.py`` with the same names and signatures,
+running on the CUDA kernels of libpstl_b200.so (reference nusc_train.py line ranges in each docstring).
+
+Two calling styles are served by the same functions:
+  * reference style — dense per-row dicts exactly as upstream builds them (``rows_per_scene = 1``);
+  * scene-indexed — ``augment_batch_data`` / ``pre_prepare_stl_cache`` return lazy dicts that carry a
+    ``ScenePack`` (compact scene tensors + per-row state/pSTL/mode), so the kernels index scenes
+    instead of reading K-times-replicated copies; the dense tensors are only materialised if a
+    caller actually reads them.
+Out of scope: training loop, losses, traj-opt, dataset, visualisation.
+"""
+import argparse
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import native as _nv
+from .stl_d_lib import *  # noqa: F401,F403  (the reference does the same star import)
+from .stl_d_lib import AP, Always, And, Eventually, ListAnd, compile_formula, get_program
+
+I_VAL = 0
+I_X, I_Y, I_TH, I_V = 0, 1, 2, 3
+I_VMIN, I_VMAX, I_DMIN, I_DMAX, I_DSAFE, I_THMAX = 0, 1, 2, 3, 4, 5
+
+
+def dup(x, m):
+    """(N,d) -> (N*m,d) (reference :20-21)."""
+    return x.unsqueeze(1).repeat((1, m) + tuple(1 for _ in x.shape[1:])).reshape((-1,) + x.shape[1:])
+
+
+def mul_n(x, n):
+    """reference :253-256."""
+    return x[:, None].repeat(1, n, *[1] * (x.dim() - 1)).reshape(x.shape[0] * n, *x.shape[1:])
+
+
+def mask_mean(loss, mask, dim=None):
+    """reference :23-27."""
+    if dim is not None:
+        return torch.mean(loss * mask, dim=dim) / torch.clip(torch.mean(mask, dim=dim), 1e-2)
+    return torch.mean(loss * mask) / torch.clip(torch.mean(mask), 1e-2)
+
+
+def dynamics(s, u):
+    """reference :29-37 (one Euler derivative; elementwise, stays in PyTorch)."""
+    th, v = s[..., 2], s[..., 3]
+    return torch.stack([v * torch.cos(th), v * torch.sin(th), u[..., 0], u[..., 1]], dim=-1)
+
+
+class _Rollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, us, dt):
+        N, T = us.shape[0], us.shape[1]
+        traj = torch.empty((N, T + 1, 4), dtype=torch.float32, device=us.device)
+        _nv.check(_nv.lib().pstl_rollout(_nv.fptr(s), _nv.fptr(us), N, T, _nv.C.c_float(dt), _nv.fptr(traj),
+                                         _nv.stream()), "pstl_rollout")
+        ctx.save_for_backward(traj)
+        ctx.dt = dt
+        return traj
+
+    @staticmethod
+    def backward(ctx, g):
+        (traj,) = ctx.saved_tensors
+        N, T = traj.shape[0], traj.shape[1] - 1
+        gs = torch.empty((N, 4), dtype=torch.float32, device=traj.device)
+        gu = torch.empty((N, T, 2), dtype=torch.float32, device=traj.device)
+        _nv.check(_nv.lib().pstl_rollout_bwd(_nv.fptr(traj), _nv.fptr(_nv.f32(g)), N, T, _nv.C.c_float(ctx.dt),
+                                             _nv.fptr(gs), _nv.fptr(gu), _nv.stream()), "pstl_rollout_bwd")
+        return gs, gu, None
+
+
+def generate_trajs(s, us, dt):
+    """(...,4) x (...,T,2) -> (...,T+1,4) Euler unicycle rollout (reference :39-49)."""
+    assert s.shape[-1] == 4
+    assert us.shape[-1] == 2
+    assert us.shape[:-2] == s.shape[:-1]
+    _nv.require_cuda(us, "controls")
+    lead = us.shape[:-2]
+    T = us.shape[-2]
+    s2 = s.reshape(-1, 4).to(torch.float32).contiguous()
+    u2 = us.reshape(-1, T, 2).to(torch.float32).contiguous()
+    return _Rollout.apply(s2, u2, float(dt)).reshape(*lead, T + 1, 4)
+
+
+def get_neighbor_trajs(neighbors, nt, dt, full=False):
+    """constant-velocity neighbour prediction (reference :51-60)."""
+    no_cmd = torch.zeros_like(neighbors[..., :2]).unsqueeze(-2).repeat(1, 1, nt - 1, 1)
+    trajs = generate_trajs(neighbors[..., 1:5], no_cmd, dt)
+    valids = neighbors[..., 0:1].unsqueeze(-2).repeat(1, 1, nt, 1)
+    if full:
+        lws = neighbors[..., 5:7].unsqueeze(-2).repeat(1, 1, nt, 1)
+        return torch.cat([valids, trajs, lws], dim=-1)
+    return torch.cat([valids, trajs], dim=-1)
+
+
+# ---------------------------------------------------------------------------------------
+# scene-indexed containers
+# ---------------------------------------------------------------------------------------
+
+class ScenePack:
+    """Compact inputs of the scoring / guidance kernels for N = bs*S*3 chains
+    (flat index n = (scene*S + sample)*3 + mode)."""
+
+    def __init__(self, neighbors, lanes, state0, stlp, mode, valid, rows_per_scene):
+        self.neighbors = _nv.f32(neighbors)
+        self.lanes = [_nv.f32(l) for l in lanes]
+        self.state0 = _nv.f32(state0)
+        self.stlp = _nv.f32(stlp)
+        self.mode = _nv.f32(mode)
+        self.valid = _nv.f32(valid)
+        self.rows_per_scene = int(rows_per_scene)
+        self.N = self.state0.shape[0]
+
+    @property
+    def T(self):
+        return self.neighbors.shape[2]
+
+    def view(self):
+        return _nv.make_scene_view(self.neighbors, self.lanes, self.rows_per_scene)
+
+    @staticmethod
+    def from_batch(batch, stlp_dense, S):
+        bs = batch["currlane_wpts"].shape[0]
+        m = S * 3
+        nei = batch["neighbor_trajs_aug"] if "neighbor_trajs_aug" in batch else batch["neighbors_traj"][..., :7]
+        state0 = dup(batch["ego_traj"][:, 0, :4], m)
+        valids = torch.cat([batch["curr_id"], batch["left_id"], batch["right_id"]], dim=-1)
+        valid = dup(valids, S).reshape(-1)
+        mode = torch.tensor([0.0, 1.0, 2.0], device=nei.device).repeat(bs * S)
+        return ScenePack(nei, [batch["currlane_wpts"], batch["leftlane_wpts"], batch["rightlane_wpts"]], state0,
+                         stlp_dense.reshape(bs * m, 6), mode, valid, m)
+
+
+class LazyBatch(dict):
+    """dict whose dense (row-replicated) tensors are built only when somebody reads them."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def set_lazy(self, key, fn):
+        self._lazy[key] = fn
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            v = self._lazy.pop(key)()
+            self[key] = v
+            return v
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def keys_all(self):
+        return list(dict.keys(self)) + list(self._lazy)
+
+
+# ---------------------------------------------------------------------------------------
+# STL spec (reference :95-140) with typed predicate leaves
+# ---------------------------------------------------------------------------------------
+
+def build_stl_cache(args):
+    """[stl_curr, stl_left, stl_right] (reference :95-140).  Leaves are ``AP.predicate`` objects:
+    the lambdas are the reference's expressions (generic path), the typed part feeds the fused kernel."""
+    nt = args.nt
+    norm = bool(getattr(args, "norm_stl", False))
+    dv = _nv.DEN_VFACTOR if norm else _nv.DEN_ONE
+    dd = _nv.DEN_DFACTOR if norm else _nv.DEN_ONE
+    ds = _nv.DEN_SFACTOR if norm else _nv.DEN_ONE
+    P = AP.predicate
+    f = (lambda k: (lambda x: x[k])) if norm else (lambda k: (lambda x: 1.0))
+    vf, df, sf = f("v_factor"), f("d_factor"), f("safe_factor")
+    G = lambda ap: Always(0, nt, ap)
+    keep_v_min = G(P(lambda x: (x["ego_traj"][..., I_V] - x["stlp"][..., I_VMIN]) / vf(x), _nv.SIG_V, 0, I_VMIN, 1, dv))
+    keep_v_max = G(P(lambda x: (-x["ego_traj"][..., I_V] + x["stlp"][..., I_VMAX]) / vf(x), _nv.SIG_V, 1, I_VMAX, 0, dv))
+    keep_d_min = G(P(lambda x: (x["x2curr_d"] - x["stlp"][..., I_DMIN]) / df(x), _nv.SIG_D_CURR, 0, I_DMIN, 1, dd))
+    keep_d_max = G(P(lambda x: (-x["x2curr_d"] + x["stlp"][..., I_DMAX]) / df(x), _nv.SIG_D_CURR, 1, I_DMAX, 0, dd))
+
+    def reach(side, sd, sa):
+        band = And(P(lambda x: (x["x2%s_d" % side] - x["stlp"][..., I_DMIN]) / df(x), sd, 0, I_DMIN, 1, dd),
+                   P(lambda x: (-x["x2%s_d" % side] + x["stlp"][..., I_DMAX]) / df(x), sd, 1, I_DMAX, 0, dd))
+        rd = Eventually(0, nt // 2, G(band))
+        rt = Eventually(0, nt // 2, G(P(lambda x: (x["stlp"][..., I_THMAX] - x["x2%s_th" % side]) / x["stlp"][..., I_THMAX],
+                                        sa, 1, I_THMAX, 0, _nv.DEN_THMAX)))
+        return rd, rt
+
+    reach_left_d, reach_left_th = reach("left", _nv.SIG_D_LEFT, _nv.SIG_TH_LEFT)
+    reach_right_d, reach_right_th = reach("right", _nv.SIG_D_RIGHT, _nv.SIG_TH_RIGHT)
+    safe_list = [G(P(lambda x: (x["min_nei_d"] - x["stlp"][..., I_DSAFE]) / sf(x), _nv.SIG_NEI, 0, I_DSAFE, 1, ds))]
+    keep_th_max = G(P(lambda x: (x["stlp"][..., I_THMAX] - x["x2curr_th"]) / x["stlp"][..., I_THMAX],
+                      _nv.SIG_TH_CURR, 1, I_THMAX, 0, _nv.DEN_THMAX))
+    stl_curr = ListAnd([keep_v_min, keep_v_max, keep_d_min, keep_d_max, keep_th_max] + safe_list)
+    stl_left = ListAnd([keep_v_min, keep_v_max, reach_left_d, reach_left_th] + safe_list)
+    stl_right = ListAnd([keep_v_min, keep_v_max, reach_right_d, reach_right_th] + safe_list)
+    return [stl_curr, stl_left, stl_right]
+
+
+def _fused_programs(stls_cac, T):
+    """Compile the three formulas for the fused kernel; None if a leaf is an untyped lambda."""
+    key = "_pstl_fused_%d_%d" % (T, torch.cuda.current_device())
+    cache = getattr(stls_cac[0], "__dict__", {})
+    if key in cache:
+        return cache[key]
+    try:
+        progs = [get_program(compile_formula(f, fused=True)[0], 0, T, 1) for f in stls_cac]
+    except ValueError:
+        progs = None
+    cache[key] = progs
+    return progs
+
+
+def _spec(args, w_scale=1.0, a_scale=1.0, clip_controls=0):
+    return _nv.make_spec(args.dt, args.smoothing_factor, args.ego_L, args.ego_W, w_scale, a_scale, clip_controls,
+                         int(bool(args.clip_dist)), 0)
+
+
+def _check_supported(args):
+    if getattr(args, "inline", False):
+        raise NotImplementedError("--inline lane end-caps are not implemented in the fused kernels")
+    if getattr(args, "collision_loss", None) is not None:
+        raise NotImplementedError("--collision_loss (TrafficSim baseline) is out of scope")
+    if int(getattr(args, "refined_nL", 4)) != 4 or int(getattr(args, "refined_nW", 1)) != 1:
+        raise NotImplementedError("only refined_nL=4, refined_nW=1 are built")
+
+
+class _Predicates(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ego, sv_holder, args):
+        nei, lanes, rps = sv_holder
+        N, T = ego.shape[0], ego.shape[1]
+        e = _nv.f32(ego)
+        sig = torch.empty((N, 7, T), dtype=torch.float32, device=ego.device)
+        part = torch.empty((N, 12, T), dtype=torch.float32, device=ego.device)
+        sv = _nv.make_scene_view(nei, lanes, rps)
+        _nv.check(_nv.lib().pstl_predicates(_nv.C.byref(sv), _nv.C.c_float(args.ego_L), _nv.C.c_float(args.ego_W),
+                                            int(bool(args.clip_dist)), _nv.fptr(e), e.shape[2], N, _nv.fptr(sig),
+                                            _nv.fptr(part), _nv.stream()), "pstl_predicates")
+        ctx.save_for_backward(part)
+        ctx.width = ego.shape[2]
+        return sig
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        N, _, T = p.shape
+        ge = torch.zeros((N, T, ctx.width), dtype=torch.float32, device=p.device)
+        for l in range(3):
+            ge[..., 0] += g[:, 2 * l] * p[:, 3 * l]
+            ge[..., 1] += g[:, 2 * l] * p[:, 3 * l + 1]
+            ge[..., 2] += g[:, 2 * l + 1] * p[:, 3 * l + 2]
+        ge[..., 0] += g[:, 6] * p[:, 9]
+        ge[..., 1] += g[:, 6] * p[:, 10]
+        ge[..., 2] += g[:, 6] * p[:, 11]
+        return ge, None, None
+
+
+def prep_stl_cache(x, args):
+    """adds x2{curr,left,right}_{d,th} and min_nei_d to the dense dict (reference :74-93)."""
+    _check_supported(args)
+    ego = x["ego_traj"]
+    _nv.require_cuda(ego, "ego_traj")
+    pack = x.get("_pstl_pack") if isinstance(x, dict) else None
+    if pack is not None:
+        rep = x.get("_pstl_repeat", 1)
+        if rep != 1:
+            raise NotImplementedError("prep_stl_cache on candidate-stacked lazy inputs: use compute_stl_dense")
+        holder = (pack.neighbors, pack.lanes, pack.rows_per_scene)
+    else:
+        holder = (_nv.f32(x["neighbors"]), [_nv.f32(x["%slane_wpts" % k]) for k in ("curr", "left", "right")], 1)
+    sig = _Predicates.apply(ego, holder, args)
+    for l, k in enumerate(("curr", "left", "right")):
+        x["x2%s_d" % k], x["x2%s_th" % k] = sig[:, 2 * l], sig[:, 2 * l + 1]
+    x["min_nei_d"] = sig[:, 6]
+    if getattr(args, "norm_stl", False):
+        x["v_factor"] = torch.clip((x["stlp"][..., I_VMAX] - x["stlp"][..., I_VMIN]), 0.3)
+        x["d_factor"] = torch.clip((x["stlp"][..., I_DMAX] - x["stlp"][..., I_DMIN]) * 5, 0.3)
+        x["safe_factor"] = torch.clip(x["stlp"][..., I_DSAFE], 0.3)
+    return x
+
+
+def get_stl_scores(scores_list, stl_i):
+    """reference :150-151."""
+    return sum(scores_list[k] * (stl_i == k).float() for k in range(4))
+
+
+def pre_prepare_stl_cache(batch_cuda, dense_trajs=None, detach=False, repeat_n=None, mono=False, mono_n=None,
+                          gt_stlp=None):
+    """reference :258-285.  On a batch produced by this module's ``augment_batch_data`` the result
+    stays scene-indexed (lazy); on a plain dict it replicates exactly like upstream."""
+    pack = batch_cuda.get("_pstl_pack") if not mono else None
+    if pack is not None:
+        out = LazyBatch()
+        out["_pstl_pack"] = pack
+        out["_pstl_repeat"] = 1 if repeat_n is None else int(repeat_n)
+        rep = (lambda v: v) if repeat_n is None else (lambda v: v.repeat(repeat_n, *[1] * (v.dim() - 1)))
+        for k_out, k_in in (("neighbors", "neighbors_dense"), ("currlane_wpts", "currlane_wpts_dense"),
+                            ("leftlane_wpts", "leftlane_wpts_dense"), ("rightlane_wpts", "rightlane_wpts_dense")):
+            out.set_lazy(k_out, (lambda ki: (lambda: rep(batch_cuda[ki])))(k_in))
+        out["stlp"] = rep(batch_cuda["stlp_dense"])
+        out["dense_valids"] = rep(batch_cuda["valids_dense"])
+        out["gt_high_level"] = rep(batch_cuda["gt_high_level"])
+        if dense_trajs is not None:
+            out["ego_traj"] = dense_trajs
+        return out
+    if mono:
+        stl_input = {
+            "neighbors": mul_n(batch_cuda["neighbors_traj"], mono_n),
+            "currlane_wpts": mul_n(batch_cuda["currlane_wpts"], mono_n),
+            "leftlane_wpts": mul_n(batch_cuda["leftlane_wpts"], mono_n),
+            "rightlane_wpts": mul_n(batch_cuda["rightlane_wpts"], mono_n),
+            "stlp": mul_n(gt_stlp, mono_n)[:, None, :],
+            "dense_valids": mul_n(torch.ones_like(batch_cuda["gt_high_level"]), mono_n),
+            "gt_high_level": mul_n(batch_cuda["gt_high_level"], mono_n),
+        }
+    else:
+        stl_input = {
+            "neighbors": batch_cuda["neighbors_dense"],
+            "currlane_wpts": batch_cuda["currlane_wpts_dense"],
+            "leftlane_wpts": batch_cuda["leftlane_wpts_dense"],
+            "rightlane_wpts": batch_cuda["rightlane_wpts_dense"],
+            "stlp": batch_cuda["stlp_dense"],
+            "dense_valids": batch_cuda["valids_dense"],
+            "gt_high_level": batch_cuda["gt_high_level"],
+        }
+    if detach:
+        stl_input = {k: v.detach() for k, v in stl_input.items()}
+    if repeat_n is not None:
+        stl_input = {k: v.repeat(repeat_n, *[1] * (v.dim() - 1)) for k, v in stl_input.items()}
+    if dense_trajs is not None:
+        stl_input["ego_traj"] = dense_trajs
+    return stl_input
+
+
+def augment_batch_data(batch, the_stlp, args, n_randoms=None, stlp_dense=None):
+    """densify a scene batch to one row per chain (reference :724-754).  The replicated scene
+    tensors are lazy; the kernels read the compact ``_pstl_pack`` instead."""
+    if n_randoms is None:
+        new_sample = False
+        n_randoms = args.n_randoms
+    else:
+        new_sample = True
+    m = n_randoms * 3
+    bs = batch["currlane_wpts"].shape[0]
+    if not isinstance(batch, LazyBatch):
+        lb = LazyBatch(batch)
+        batch = lb
+    batch.set_lazy("neighbors_dense", lambda: dup(batch["neighbor_trajs_aug"], m))
+    for k in ("curr", "left", "right"):
+        batch.set_lazy("%slane_wpts_dense" % k, (lambda kk: (lambda: dup(batch["%slane_wpts" % kk], m)))(k))
+    batch["stlp"] = the_stlp.unsqueeze(-2) if the_stlp is not None else None
+    if stlp_dense is not None:
+        batch["stlp_dense"] = stlp_dense
+    elif args.load_stlp:
+        if new_sample:
+            batch["stlp_dense"] = batch["pre_stlp"].reshape(bs, args.n_randoms, 3, 6)[:, 0:1].repeat(
+                1, args.sampling_size, 1, 1).reshape(bs * m, 1, 6)
+        else:
+            batch["stlp_dense"] = batch["pre_stlp"].reshape(bs * m, 1, 6)
+    else:
+        raise NotImplementedError("get_dense_stlp (pSTL calibration, reference :657-722) is out of scope: "
+                                  "pass stlp_dense or use --load_stlp")
+    valids = torch.cat([batch["curr_id"], batch["left_id"], batch["right_id"]], dim=-1)
+    batch["valids_dense"] = dup(valids, n_randoms).reshape(bs * n_randoms, 3)
+    batch["highlevel_dense"] = torch.tensor([0, 1.0, 2.0], device=valids.device).reshape(1, 3, 1).repeat(
+        bs * n_randoms, 1, 1).reshape(bs * m, 1).float()
+    if "neighbor_trajs_aug" not in batch and "neighbors_traj" in batch:
+        batch["neighbor_trajs_aug"] = batch["neighbors_traj"][..., :7]
+    batch["_pstl_pack"] = ScenePack.from_batch(batch, batch["stlp_dense"], n_randoms)
+    return batch
+
+
+# ---------------------------------------------------------------------------------------
+# scoring (reference :318-345) and best-of-K (:992-1013)
+# ---------------------------------------------------------------------------------------
+
+class _FusedScoreEgo(torch.autograd.Function):
+    """scores of pre-rolled trajectories; differentiable w.r.t. ego_traj."""
+
+    @staticmethod
+    def forward(ctx, ego, progs, sv_parts, spec, mode, stlp):
+        nei, lanes, rps = sv_parts
+        N, T, W = ego.shape
+        e = _nv.f32(ego)
+        sv = _nv.make_scene_view(nei, lanes, rps)
+        scores = torch.empty((N,), dtype=torch.float32, device=ego.device)
+        L = _nv.lib()
+        pa = _nv.prog_array(progs)
+        ws = _nv.workspace(L.pstl_score_workspace_bytes(pa, N, T, 0), ego.device, "score")
+        _nv.check(L.pstl_score_fused(pa, _nv.C.byref(sv), _nv.C.byref(spec), _nv.fptr(mode), None, None, 1,
+                                     _nv.fptr(e), W, _nv.fptr(stlp), N, None, _nv.fptr(scores), None, None, None,
+                                     _nv.ptr(ws), _nv.stream()), "pstl_score_fused")
+        ctx.save_for_backward(e, mode, stlp)
+        ctx.misc = (progs, sv_parts, spec, W)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        e, mode, stlp = ctx.saved_tensors
+        progs, (nei, lanes, rps), spec, W = ctx.misc
+        N, T, _ = e.shape
+        sv = _nv.make_scene_view(nei, lanes, rps)
+        ge4 = torch.empty((N, T, 4), dtype=torch.float32, device=e.device)
+        L = _nv.lib()
+        pa = _nv.prog_array(progs)
+        ws = _nv.workspace(L.pstl_score_workspace_bytes(pa, N, T, 1), e.device, "score")
+        _nv.check(L.pstl_score_fused_bwd(pa, _nv.C.byref(sv), _nv.C.byref(spec), _nv.fptr(mode), None, None,
+                                         _nv.fptr(e), W, _nv.fptr(stlp), N, _nv.fptr(_nv.f32(g)), None, None,
+                                         _nv.fptr(ge4), _nv.ptr(ws), _nv.stream()), "pstl_score_fused_bwd")
+        if W == 4:
+            ge = ge4
+        else:
+            ge = torch.zeros((N, T, W), dtype=torch.float32, device=e.device)
+            ge[..., :4] = ge4
+        return ge, None, None, None, None, None
+
+
+class _LazyScores(list):
+    """scores_list of compute_stl_dense: the per-formula scores are evaluated on first access."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self._fn = fn
+
+    def _fill(self):
+        if self._fn is not None:
+            super().extend(self._fn())
+            self._fn = None
+
+    def __getitem__(self, i):
+        self._fill()
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+
+def score_pack(pack, controls, args, progs, scaled=True, want=("best_score",)):
+    """Fused rollout+predicates+STL(+best-of-K) on a ScenePack.
+    controls: (C,N,T,2) or (N,T,2) physical controls (``scaled``) or raw mu/x (then scaled+clipped
+    per normalize_diff).  Returns dict with the requested outputs among
+    scores_all (C,N), best_score (N), best_idx (N), best_controls (N,T,2), traj (N,T+1,4)."""
+    c = controls if controls.dim() == 4 else controls.unsqueeze(0)
+    c = _nv.f32(c)
+    C_, N, T, _ = c.shape
+    assert N == pack.N and T == pack.T
+    dev = c.device
+    out = {}
+    if "scores_all" in want:
+        out["scores_all"] = torch.empty((C_, N), dtype=torch.float32, device=dev)
+    if "best_score" in want:
+        out["best_score"] = torch.empty((N,), dtype=torch.float32, device=dev)
+    if "best_idx" in want:
+        out["best_idx"] = torch.empty((N,), dtype=torch.int32, device=dev)
+    if "best_controls" in want:
+        out["best_controls"] = torch.empty((N, T, 2), dtype=torch.float32, device=dev)
+    if "traj" in want:
+        out["traj"] = torch.empty((N, T + 1, 4), dtype=torch.float32, device=dev)
+    spec = _spec(args) if scaled else _spec(args, args.mul_w_max, args.mul_a_max, int(bool(args.diffusion_clip)))
+    sv = pack.view()
+    L = _nv.lib()
+    pa = _nv.prog_array(progs)
+    ws = _nv.workspace(L.pstl_score_workspace_bytes(pa, N, T, 0), dev, "score")
+    _nv.check(L.pstl_score_fused(pa, _nv.C.byref(sv), _nv.C.byref(spec), _nv.fptr(pack.mode), _nv.fptr(pack.state0),
+                                 _nv.fptr(c), C_, None, 0, _nv.fptr(pack.stlp), N, _nv.fptr(out.get("scores_all")),
+                                 _nv.fptr(out.get("best_score")), _nv.ptr(out.get("best_idx")),
+                                 _nv.fptr(out.get("best_controls")), _nv.fptr(out.get("traj")), _nv.ptr(ws),
+                                 _nv.stream()), "pstl_score_fused")
+    return out
+
+
+def compute_stl_dense(stl_input, stls_cac, stl_idx, mask, args, debug=False, tj_scores=None, scene=False):
+    """evaluate the three formulas at t=0 and select by mode (reference :318-345).
+
+    Returns (scores_list, scores, acc[, scene_acc | stl_input]) like upstream.  With the typed
+    spec of ``build_stl_cache`` this is ONE fused kernel (predicates + formula, only the row's own
+    formula — the reference evaluates all three and multiplies by one-hot masks, equal whenever the
+    unused formulas are finite); custom AP lambdas fall back to predicates + generic interpreter."""
+    _check_supported(args)
+    ego = stl_input["ego_traj"]
+    _nv.require_cuda(ego, "ego_traj")
+    N, T = ego.shape[0], ego.shape[1]
+    mode = _nv.f32(stl_idx[:, 0])
+    progs = _fused_programs(stls_cac, T)
+    pack = stl_input.get("_pstl_pack") if isinstance(stl_input, dict) else None
+    if progs is not None:
+        if pack is not None:
+            rep = stl_input.get("_pstl_repeat", 1)
+            if rep == 1:
+                parts, stlp = (pack.neighbors, pack.lanes, pack.rows_per_scene), pack.stlp
+            else:  # candidate-major stacking: row r of candidate c -> scene of row r
+                assert N == rep * pack.N
+                parts, stlp = None, pack.stlp
+        else:
+            parts = (_nv.f32(stl_input["neighbors"]),
+                     [_nv.f32(stl_input["%slane_wpts" % k]) for k in ("curr", "left", "right")], 1)
+            stlp = _nv.f32(stl_input["stlp"].reshape(N, 6))
+        if parts is None:
+            chunks = [_FusedScoreEgo.apply(ego[c * pack.N:(c + 1) * pack.N], progs,
+                                           (pack.neighbors, pack.lanes, pack.rows_per_scene), _spec(args),
+                                           mode[c * pack.N:(c + 1) * pack.N].contiguous(), stlp) for c in range(rep)]
+            scores = torch.cat(chunks, 0)
+        else:
+            scores = _FusedScoreEgo.apply(ego, progs, parts, _spec(args), mode, stlp)
+
+        def all_formulas():
+            outs = []
+            for k in range(3):
+                mk = torch.full_like(mode, float(k))
+                if parts is None:
+                    outs.append(torch.cat([_FusedScoreEgo.apply(ego[c * pack.N:(c + 1) * pack.N], progs,
+                                                                (pack.neighbors, pack.lanes, pack.rows_per_scene),
+                                                                _spec(args), mk[:pack.N].contiguous(), stlp)
+                                           for c in range(rep)], 0))
+                else:
+                    outs.append(_FusedScoreEgo.apply(ego, progs, parts, _spec(args), mk, stlp))
+            outs.append(outs[-1].detach() * 0.0 + 1.0)
+            return outs
+
+        scores_list = _LazyScores(all_formulas)
+    else:
+        stl_input = prep_stl_cache(stl_input, args)
+        res = [f(stl_input, args.smoothing_factor) for f in stls_cac]
+        scores_list = [r[:, 0] for r in res]
+        scores_list.append(scores_list[-1].detach() * 0.0 + 1.0)
+        scores = get_stl_scores(scores_list, stl_idx[:, 0])
+    mask_flat = mask.reshape(-1)
+    if getattr(args, "oracle_filter", False) and tj_scores is not None:
+        cube = torch.max(tj_scores.reshape(-1, args.n_randoms, 3), dim=1, keepdim=True)[0]
+        tj_val = ((cube > 0).float()).repeat(1, args.n_randoms, 1).reshape(-1)
+        acc = mask_mean((scores > 0).float(), mask_flat * tj_val)
+    else:
+        acc = mask_mean((scores > 0).float(), mask_flat)
+    if debug:
+        if progs is not None and "x2curr_d" not in stl_input:
+            stl_input = prep_stl_cache(stl_input, args)
+        return scores_list, scores, acc, stl_input
+    if scene:
+        scores_cube = scores.reshape(-1, args.n_randoms, 3)
+        mask_cube = mask.reshape(-1, args.n_randoms, 3)
+        scene_acc = mask_mean((torch.max(scores_cube, dim=1)[0] > 0).float(), mask_cube[:, 0, :])
+        return scores_list, scores, acc, scene_acc
+    return scores_list, scores, acc
+
+
+# ---------------------------------------------------------------------------------------
+# sampler (reference :528-655)
+# ---------------------------------------------------------------------------------------
+
+def get_diffusion_coeffs(args):
+    """cosine / linear schedule (reference :528-537): (beta, alpha, alpha_hat) on the GPU."""
+    if args.cos:
+        t = torch.linspace(0, 1, args.diffusion_steps + 1)
+        alpha_bar = torch.cos((t + 0.008) / 1.008 * np.pi / 2) ** 2
+        beta = torch.clip(1 - alpha_bar[1:] / alpha_bar[:-1], 0, 0.999) * 0.2
+    else:
+        beta = torch.linspace(args.beta_start, args.beta_end, args.diffusion_steps)
+    alpha = 1.0 - beta
+    alpha_hat = torch.cumprod(alpha, dim=0)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    return (beta.to(dev), alpha.to(dev), alpha_hat.to(dev))
+
+
+def normalize_diff(x, n, nt, w_max, a_max, clip):
+    """reference :647-655 (elementwise; the sampler fuses it, this is the standalone form)."""
+    x = x.reshape(n, nt, 2)
+    w, a = x[..., 0] * w_max, x[..., 1] * a_max
+    if clip:
+        w, a = torch.clip(w, -w_max, w_max), torch.clip(a, -a_max, a_max)
+    return torch.stack([w, a], dim=-1)
+
+
+class IterateList:
+    """final_list of diffusion_rollout (reference :633-634): ``steps`` entries x_T..x_0, of which only
+    the last ``K`` are stored (the reference keeps all 100 = 3.1 GB at 196,608 chains)."""
+
+    def __init__(self, steps, kept):
+        self.steps, self.kept = steps, kept  # kept (K,N,T,2), chronological
+
+    def __len__(self):
+        return self.steps
+
+    def _one(self, i):
+        if i < 0:
+            i += self.steps
+        j = i - (self.steps - self.kept.shape[0])
+        if j < 0 or i >= self.steps:
+            raise IndexError("iterate %d was not kept (only the last %d are; pass keep_all_iterates)"
+                             % (i, self.kept.shape[0]))
+        return self.kept[j]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(j) for j in range(*i.indices(self.steps))]
+        return self._one(i)
+
+    def stacked_last(self, k):
+        return self.kept[self.kept.shape[0] - k:]
+
+
+_call_counter = [0]
+
+
+def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, coeffs=None, fastforward=False,
+                      n_randoms=None, return_feature=False, mono=False, tmp_stlp=None, guidance_extras=None,
+                      maximize=False):
+    """DDPM reverse loop i = steps-1..1 with t == i (reference :557-645): ONE native call that runs all
+    steps (eps-MLP, posterior update, noise, optional STL guidance) instead of ~100 launches per step.
+
+    ``noise`` gives only shape/device, as upstream (:563).  Deterministic mode: ``args.inject_noise`` =
+    [x_T, z_1, ...] tensors (N,2nt) consumed in upstream's randn_like order; otherwise x_T is drawn with
+    torch and z by the kernel's Philox stream (``args.seed``)."""
+    if mono or fastforward:
+        raise NotImplementedError("mono / fastforward sampling is not on the hot path")
+    _nv.require_cuda(noise, "noise")
+    n = noise.shape[0]
+    nt, T2, steps = args.nt, args.nt * 2, args.diffusion_steps
+    beta, alpha, alpha_hat = coeffs
+    net.eval()
+    bs = batch_cuda["ego_traj"].shape[0]
+    if n_randoms is None:
+        n_randoms = args.n_randoms
+    scene_feat = getattr(feature, "_pstl_scene_feat", None) if feature is not None else None
+    if scene_feat is None:
+        if feature is not None:
+            scene_feat = feature.reshape(bs, -1, feature.shape[-1])[:, 0].contiguous()
+        else:
+            with torch.no_grad():
+                scene_feat = net.encode_feat(batch_cuda)
+    rows_per_scene = n // bs
+    hl = _nv.f32(highlevel_dense.reshape(n))
+    stlp = _nv.f32(batch_cuda["stlp_dense"].reshape(n, 6))
+    inj = getattr(args, "inject_noise", None)
+    if inj is not None:
+        x_T = _nv.f32(inj[0])
+        z = torch.stack([_nv.f32(t) for t in inj[1:steps - 1]], 0).contiguous() if steps > 2 else None
+    else:
+        x_T = torch.randn((n, T2), dtype=torch.float32, device=noise.device)
+        z = None
+    keep_all = bool(getattr(args, "refinement", False) or getattr(args, "keep_all_iterates", False))
+    K = steps - 1 if keep_all else max(1, int(args.multi_cands or 1))
+    K = min(K, steps - 1)
+    iterates = torch.empty((K, n, nt, 2), dtype=torch.float32, device=noise.device)
+    handle = net.native_handle(getattr(args, "precision", "fp32"))
+    L = _nv.lib()
+    gcfg = None
+    keepalive = []
+    if args.guidance:
+        if args.guidance_sets is not None or args.guidance_freq is not None or args.guidance_reverse:
+            raise NotImplementedError("only the `i <= guidance_before` trigger (README flags) is built")
+        new_batch, states_flat_new, stls_cac = guidance_extras
+        pack = new_batch.get("_pstl_pack")
+        if pack is None:
+            pack = ScenePack.from_batch(new_batch, batch_cuda["stlp_dense"], n_randoms)
+        progs = _fused_programs(stls_cac, nt)
+        if progs is None:
+            raise NotImplementedError("guidance needs the typed spec of build_stl_cache")
+        valid = pack.valid
+        sv = pack.view()
+        sp = _spec(args, args.mul_w_max, args.mul_a_max, 0)
+        pa = _nv.prog_array(progs)
+        n_total = float(getattr(args, "guidance_n_total", n))
+        mean_valid = float(getattr(args, "guidance_mean_valid", valid.mean().item()))
+        gcfg = _nv.GuidanceCfg()
+        s0 = _nv.f32(states_flat_new)
+        keepalive.append(s0)
+        gcfg.valid, gcfg.state0 = valid.data_ptr(), s0.data_ptr()
+        gcfg.progs = _nv.C.cast(pa, _nv.C.POINTER(_nv.C.c_void_p))
+        gcfg.scenes, gcfg.sp = _nv.C.pointer(sv), _nv.C.pointer(sp)
+        gcfg.before, gcfg.niters = int(min(args.guidance_before, steps - 1)), int(args.guidance_niters)
+        gcfg.lr = args.guidance_lr
+        gcfg.thres = 100.0 if maximize else args.stl_nn_thres
+        gcfg.inv_norm = 1.0 / (n_total * max(mean_valid, 1e-2))
+        keepalive += [pack, sv, sp, pa, progs, states_flat_new]
+    ws_bytes = L.pstl_denoiser_workspace_bytes(handle, n, bs, _nv.C.byref(gcfg) if gcfg is not None else None)
+    ws = _nv.workspace(ws_bytes, noise.device, "denoiser")
+    sched = torch.stack([beta, alpha, alpha_hat], 0).to("cpu", torch.float32).contiguous()
+    temb = net.time_table(steps, noise.device)
+    _call_counter[0] += 1
+    _nv.check(L.pstl_denoiser_sample(
+        handle, _nv.fptr(_nv.f32(scene_feat)), bs, rows_per_scene, _nv.fptr(hl), _nv.fptr(stlp), n,
+        _nv.C.c_void_p(sched.data_ptr()), _nv.fptr(temb), steps, _nv.fptr(x_T), _nv.fptr(z),
+        _nv.C.c_uint64(int(getattr(args, "seed", 0)) & (2 ** 64 - 1)), _nv.C.c_uint64(_call_counter[0] * 1000),
+        _nv.C.c_float(args.mul_w_max), _nv.C.c_float(args.mul_a_max), int(bool(args.diffusion_clip)), K,
+        _nv.C.byref(gcfg) if gcfg is not None else None, _nv.fptr(iterates), None, _nv.ptr(ws), _nv.stream()),
+        "pstl_denoiser_sample")
+    diffused_result = iterates[-1]
+    dense_feature = None
+    if return_feature:
+        k = scene_feat.shape[-1]
+        dense_feature = scene_feat.reshape(bs, 1, k).expand(bs, rows_per_scene, k).reshape(-1, k)
+        dense_feature._pstl_scene_feat = scene_feat
+    if args.diff_full:
+        final_list = IterateList(steps, iterates)
+        return (diffused_result, dense_feature, final_list) if return_feature else (diffused_result, final_list)
+    return (diffused_result, dense_feature) if return_feature else diffused_result
+
+
+# ---------------------------------------------------------------------------------------
+# open-loop sampling test (reference :890-1183; the timed region :957-1105)
+# ---------------------------------------------------------------------------------------
+
+def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
+    """The timed region of run_sampling_test for the diffusion + RefineNet path:
+    augment -> sampler -> best-of-K -> RefineNet (+n_rolls) -> final rollout + scores."""
+    S = args.sampling_size
+    bs = batch_cuda["ego_traj"].shape[0]
+    N = bs * S * 3
+    new_batch = LazyBatch({k: batch_cuda[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts",
+                                                       "rightlane_wpts", "curr_id", "left_id", "right_id",
+                                                       "gt_high_level", "pre_stlp") if k in batch_cuda})
+    new_batch["neighbor_trajs_aug"] = batch_cuda["neighbors_traj"][..., :7]
+    new_batch = augment_batch_data(new_batch, None, args, n_randoms=S)
+    pack = new_batch["_pstl_pack"]
+    highlevel_new = new_batch["highlevel_dense"]
+    noise = torch.empty((N, args.nt * 2), device=highlevel_new.device)
+    guidance_extras = (new_batch, pack.state0, stls_cac) if args.guidance else None
+    progs = _fused_programs(stls_cac, args.nt)
+    res = diffusion_rollout(noise, net, new_batch, highlevel_new, None, args, coeffs, n_randoms=S,
+                            return_feature=True, guidance_extras=guidance_extras)
+    if args.diff_full:
+        nn_controls, feature, nn_list = res
+    else:
+        nn_controls, feature = res
+        nn_list = None
+    out = {"final_iterate": nn_controls}
+    if args.rect_head and not args.not_use_rect:
+        if args.multi_cands is not None:
+            cand = nn_list.stacked_last(args.multi_cands)  # (K,N,T,2) physical controls
+            r = score_pack(pack, cand, args, progs, want=("scores_all", "best_score", "best_idx", "best_controls"))
+            nn_controls, prev_scores = r["best_controls"], r["best_score"]
+            out.update(cand_scores=r["scores_all"], best_idx=r["best_idx"], best_controls=nn_controls)
+        else:
+            prev_scores = score_pack(pack, nn_controls, args, progs)["best_score"]
+        if not (args.multi_cands is not None and args.no_refinenet):
+            nn_controls = net.rect_forward(feature, highlevel_new, new_batch["stlp_dense"][:, 0], nn_controls, prev_scores)
+        if args.n_rolls is not None:
+            for _ in range(args.n_rolls):
+                sc = score_pack(pack, nn_controls, args, progs)["best_score"]
+                nn_controls = net.rect_forward(feature, highlevel_new, new_batch["stlp_dense"][:, 0], nn_controls, sc)
+    r = score_pack(pack, nn_controls, args, progs, want=("best_score", "traj"))
+    scores, nn_trajs = r["best_score"], r["traj"]
+    acc = mask_mean((scores > 0).float(), pack.valid)
+    sc_cube, m_cube = scores.reshape(-1, S, 3), pack.valid.reshape(-1, S, 3)
+    scene_acc = mask_mean((torch.max(sc_cube, dim=1)[0] > 0).float(), m_cube[:, 0, :])
+    out.update(controls=nn_controls, scores=scores, trajs=nn_trajs, acc=acc, scene_acc=scene_acc, pack=pack)
+    return out
+
+
+def run_sampling_test(stls_cac, data_loader, net, coeffs, args, result_queue=None, thread_nusc=None):
+    """open-loop sampling test over ``data_loader`` (any iterable of batch dicts).  Metrics that need the
+    NuScenes map / scipy hulls are out of scope; acc, scene_acc and the timed region are reported."""
+    meters = {}
+    results = []
+    for bi, batch in enumerate(data_loader):
+        if bi > args.n_trials:
+            continue
+        batch_cuda = {k: (v.cuda() if hasattr(v, "cuda") else v) for k, v in batch.items()}
+        torch.cuda.synchronize()
+        t1 = time.time()
+        out = sample_and_score(net, batch_cuda, stls_cac, coeffs, args)
+        torch.cuda.synchronize()
+        t2 = time.time()
+        for k, v in (("acc", out["acc"].item()), ("scene_acc", out["scene_acc"].item()), ("time", t2 - t1)):
+            meters.setdefault(k, []).append(v)
+        print("###[%02d] NN acc:%.3f scene_acc:%.3f ||| T:%.3f" % (bi, np.mean(meters["acc"]),
+                                                                   np.mean(meters["scene_acc"]), np.mean(meters["time"])))
+        results.append(out)
+    return meters, results
+
+
+# ---------------------------------------------------------------------------------------
+# flags (reference :1635-1814)
+# ---------------------------------------------------------------------------------------
+
+def generate_parser(argv=None):
+    """Same flags and post-parse overrides as the reference parser, plus --synthetic / --precision."""
+    parser = argparse.ArgumentParser("")
+    add = parser.add_argument
+    add("--seed", type=int, default=1007)
+    add("--exp_name", "-e", type=str, default=None)
+    add("--gpus", type=str, default="0")
+    add("--epochs", type=int, default=500)
+    add("--test", action="store_true", default=False)
+    add("--net_pretrained_path", "-P", type=str, default=None)
+    add("--num_workers", type=int, default=8)
+    add("--batch_size", "-b", type=int, default=128)
+    add("--lr", type=float, default=3e-4)
+    add("--hiddens", type=int, nargs="+", default=[256, 256])
+    for name, dflt in (("print_freq", 10), ("save_freq", 100), ("viz_freq", 50), ("num_viz", 10)):
+        add("--" + name, type=int, default=dflt)
+    for name in ("no_viz", "mini", "collect_data", "offline", "refined_safety", "debug", "use_gt_stlp", "skip_nusc_load",
+                 "clip_dist", "gt_nei", "stl_bc_mask", "trajopt_only", "inline", "use_init_hint",
+                 "generate_split_on_the_fly", "check_stl_params", "norm_stl", "flex", "load_stlp", "load_tj", "bc", "vae",
+                 "diffusion", "cos", "grad_rollout", "rect_head", "joint", "not_use_rect", "measure_diversity",
+                 "extra_diversity", "viz_correct", "run_sampling_test", "replace_hint", "diff_full", "refinement",
+                 "raw_refinement", "diverse_loss", "no_arch", "diverse_detach", "test_t1", "test_scenes",
+                 "test_aggressive", "viz_last", "lite_refine", "interval", "diffusion_clip", "gt_data_training",
+                 "guidance", "guidance_reverse", "oracle_filter", "clip_rect", "ego", "other", "backup", "no_refinenet",
+                 "time_profile"):
+        add("--" + name, action="store_true", default=False)
+    add("--train_ratio", type=float, default=0.7)
+    add("--n_neighbors", "-N", type=int, default=8)
+    add("--n_randoms", type=int, default=64)
+    add("--n_segs", type=int, default=15)
+    add("--n_expands", type=int, default=4)
+    add("--cache_path", type=str, default="e0_nusc_cache")
+    add("--ego_L", type=float, default=4.084)
+    add("--ego_W", type=float, default=1.730)
+    add("--refined_nL", type=int, default=4)
+    add("--refined_nW", type=int, default=1)
+    add("--nt", type=int, default=20)
+    add("--dt", type=float, default=0.5)
+    add("--mul_w_max", type=float, default=0.5)
+    add("--mul_a_max", type=float, default=5.0)
+    add("--smoothing_factor", type=float, default=100.0)
+    add("--anno_path", type=str, default="annotated_data_trainval")
+    add("--stl_nn_thres", type=float, default=0.0005)
+    add("--stl_trajopt_thres", type=float, default=0.01)
+    add("--traj_opt_iters", type=int, default=2000)
+    add("--trajopt_lr", type=float, default=0.005)
+    add("--opt_epochs", type=int, default=0)
+    add("--trajopt_save_freq", type=int, default=1000)
+    add("--params_load_path", "-P2", type=str, default="e1_nusc_trajopt")
+    add("--filter_traj", type=int, nargs="+", default=None)
+    add("--stl_weight", type=float, default=1.0)
+    add("--bc_weight", type=float, default=0.0)
+    add("--vae_dim", type=int, default=64)
+    add("--weight_vae_bc", type=float, default=1.0)
+    add("--weight_vae_kl", type=float, default=1.0)
+    add("--diffusion_steps", type=int, default=100)
+    add("--diffusion_weight", type=float, default=1.0)
+    add("--beta_start", type=float, default=1e-4)
+    add("--beta_end", type=float, default=0.02)
+    add("--reg_loss", type=float, default=10.0)
+    add("--rect_hiddens", type=int, nargs="+", default=[256, 256])
+    add("--rect_reg_loss", type=float, default=0.000)
+    add("--extra_rect_reg", type=float, default=0.0)
+    add("--epi_print_freq", type=int, default=1)
+    add("--sampling_size", type=int, default=64)
+    add("--n_trials", type=int, default=100)
+    add("--diversity_weight", type=float, default=1.0)
+    add("--diversity_scale", type=float, default=1.0)
+    add("--n_shards", type=int, default=4)
+    add("--diverse_fuse_type", type=str, default="add")
+    add("--multi_cands", type=int, default=None)
+    add("--collision_loss", type=float, default=None)
+    add("--guidance_niters", type=int, default=3)
+    add("--guidance_before", type=int, default=1000)
+    add("--guidance_lr", type=float, default=0.01)
+    add("--guidance_sets", nargs="+", type=int, default=None)
+    add("--guidance_freq", type=int, default=None)
+    add("--n_rolls", type=int, default=None)
+    add("--suffix", type=str, default=None)
+    # additive flags (not in the reference)
+    add("--synthetic", type=int, default=None, help="run on this many synthetic scenes per batch")
+    add("--precision", type=str, default="fp32", choices=["fp32", "bf16"], help="denoiser arithmetic")
+    args = parser.parse_args(argv)
+    # post-parse overrides, reference :1780-1812
+    args.gt_nei = True
+    args.stl_bc_mask = True
+    args.cos = True
+    if not args.collect_data and not args.trajopt_only:
+        args.measure_diversity = True
+    if args.run_sampling_test:
+        args.test = True
+        args.extra_diversity = True
+    if args.collect_data:
+        args.epochs, args.batch_size, args.viz_freq, args.print_freq, args.uturn = 1, 1024, 10, 1, True
+    if args.trajopt_only:
+        args.opt_epochs, args.epochs, args.batch_size, args.viz_freq = 1, 1, 1024, 10
+        args.diffusion, args.num_viz, args.flex = True, 256, True
+    if args.opt_epochs > 0:
+        args.epochs = args.opt_epochs
+    if args.load_stlp:
+        args.load_tj = True
+    if args.rect_head:
+        args.interval = True
+        args.diffusion_clip = True
+        args.diff_full = True
+    args.offline = not args.collect_data
+    if args.test:
+        args.epochs = 1
+    return args
+
+
+OURS_FLAGS = ["-e", "e7_ours", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--rect_head", "--flex",
+              "--diverse_loss", "--multi_cands", "5", "--test", "--run_sampling_test", "--skip_nusc_load",
+              "--viz_correct"]
+GUIDANCE_FLAGS = ["-e", "e7_ours", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--rect_head", "--flex",
+                  "--diverse_loss", "--multi_cands", "10", "--test", "--run_sampling_test", "--viz_correct",
+                  "--guidance", "--guidance_before", "10", "--guidance_niters", "1", "--guidance_lr", "0.01",
+                  "--n_rolls", "3", "--other", "--skip_nusc_load"]
+
+
+def default_args(flags=None, **over):
+    """parsed defaults (README "Ours" flags unless given) with attribute overrides — for tests/bench."""
+    args = generate_parser(list(OURS_FLAGS if flags is None else flags))
+    for k, v in over.items():
+        setattr(args, k, v)
+    return args
+
+
+def main(argv=None):
+    """``python -m pstl_b200.nusc_train ... --run_sampling_test --synthetic 32``"""
+    from . import synthetic
+    from .nusc_model import Net
+    args = generate_parser(argv)
+    if not args.run_sampling_test:
+        raise SystemExit("only --run_sampling_test is built (training / traj-opt are out of scope)")
+    torch.manual_seed(args.seed)
+    stls_cac = build_stl_cache(args)
+    net = Net(args).cuda()
+    if args.net_pretrained_path is not None:
+        net.load_state_dict(torch.load(args.net_pretrained_path), strict=(not args.rect_head))
+    coeffs = get_diffusion_coeffs(args)
+    bs = args.synthetic or args.batch_size
+    loader = [synthetic.make_scene_batch(bs, nt=args.nt, dt=args.dt, n_neighbors=args.n_neighbors,
+                                         n_segs=args.n_segs, n_randoms=args.n_randoms, seed=args.seed + i)
+              for i in range(min(args.n_trials + 1, 3))]
+    return run_sampling_test(stls_cac, loader, net, coeffs, args)
+
+
+if __name__ == "__main__":
+    main()

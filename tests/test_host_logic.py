@@ -1,0 +1,181 @@
+"""CPU tier: host-side logic of the drop-in (formula compiler, parser, containers, sharding) and the
+C-ABI library's load/exports.  No compute calls without a GPU."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import pstl_b200  # noqa: F401
+from pstl_b200 import native, sharding, stl_d_lib as S, synthetic
+from pstl_b200 import nusc_train as NT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = native.lib()
+    hdr = open(os.path.join(ROOT, "include", "pstl.h")).read()
+    declared = set(re.findall(r"\b(pstl_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for sym in sorted(declared):
+        assert hasattr(L, sym), "libpstl_b200.so does not export %s" % sym
+    assert set(native.EXPORTS) <= declared
+    assert L.pstl_version() >= 100
+
+
+def test_ops_fail_loudly_without_cuda():
+    x = {"a": torch.zeros(2, 5)}
+    with pytest.raises(native.PstlNativeError):
+        S.Always(0, 3, S.AP(lambda q: q["a"]))(x, 100.0)
+    with pytest.raises(native.PstlNativeError):
+        NT.generate_trajs(torch.zeros(2, 4), torch.zeros(2, 5, 2), 0.5)
+
+
+def test_compile_formula_postfix():
+    a, b = S.AP(lambda x: x["a"], "a"), S.AP(lambda x: x["b"], "b")
+    ops, leaves = S.compile_formula(S.Eventually(0, 4, S.Always(0, 8, S.And(a, b))))
+    assert leaves == [a, b]
+    assert ops == [(native.OP_SIGNAL, 0, 0), (native.OP_SIGNAL, 1, 0), (native.OP_SMIN2, 0, 0),
+                   (native.OP_WIN_SMIN, 0, 8), (native.OP_WIN_SMAX, 0, 4)]
+    ops, _ = S.compile_formula(S.Imply(a, b))
+    assert [o[0] for o in ops] == [native.OP_SIGNAL, native.OP_NEG, native.OP_SIGNAL, native.OP_SMAX2]
+    ops, leaves = S.compile_formula(S.Until(2, 5, a, b))
+    assert [o[0] for o in ops] == [native.OP_SIGNAL, native.OP_WIN_SMAX, native.OP_SIGNAL, native.OP_SIGNAL,
+                                   native.OP_PREFIX_SMIN, native.OP_SMIN2, native.OP_SUFFIX_SMAX, native.OP_WIN_SMIN,
+                                   native.OP_SMIN2]
+    assert len(leaves) == 2  # shared leaves are pushed by id, not duplicated
+
+
+def test_driving_spec_compiles_to_typed_programs():
+    args = NT.default_args()
+    stls = NT.build_stl_cache(args)
+    sizes = []
+    for f in stls:
+        ops, leaves = S.compile_formula(f, fused=True)
+        assert not leaves and all(o[0] != native.OP_SIGNAL for o in ops)
+        sizes.append(len(ops))
+    assert sizes == [13, 15, 15]  # SURVEY §8(a) a12 node counts
+    with pytest.raises(ValueError):
+        S.compile_formula(S.Always(0, 3, S.AP(lambda x: x)), fused=True)
+
+
+def test_str_matches_reference_format():
+    a, b = S.AP(None, "a"), S.AP(None, "b")
+    f = S.Eventually(0, 4, S.Always(0, 8, S.And(a, b)))
+    assert str(f) == "♢[0:5] (◻[0:9] ((a) & (b)))"
+    f.update_format("word")
+    assert str(f) == "EVENTUALLY[0:5] (ALWAYS[0:9] ((a) AND (b)))"
+    n0 = S.AP.n_aps
+    assert str(S.AP(None)) == "AP%d" % n0 and S.AP.n_aps == n0 + 1
+
+
+@pytest.mark.ref
+def test_parser_matches_reference_defaults_and_overrides():
+    import ref_shim
+    for flags in (ref_shim.OURS_FLAGS, ref_shim.GUIDE_FLAGS):
+        _, rargs = ref_shim.load(flags)
+        ours = NT.generate_parser(list(flags))
+        r, o = vars(rargs), vars(ours)
+        for k, v in r.items():
+            assert k in o, "flag %s missing" % k
+            assert o[k] == v, "flag %s: %r != %r" % (k, o[k], v)
+        assert set(o) - set(r) <= {"synthetic", "precision"}
+
+
+def test_schedule_matches_oracle():
+    from oracle import pstl_oracle as O
+    args = NT.default_args()
+    beta, alpha, ah = [t.cpu() for t in NT.get_diffusion_coeffs(args)]
+    b2, a2, h2 = O.ddpm_schedule(100)
+    assert torch.equal(beta, b2) and torch.equal(alpha, a2) and torch.equal(ah, h2)
+    assert abs(beta[10].item() - 1.1061e-3) < 1e-6 and abs(ah[99].item() - 0.1946) < 1e-4
+
+
+def test_iterate_list_semantics():
+    kept = torch.arange(5 * 2 * 3 * 2).reshape(5, 2, 3, 2).float()
+    il = NT.IterateList(100, kept)
+    assert len(il) == 100
+    assert torch.equal(il[-1], kept[-1]) and torch.equal(il[99], kept[4]) and torch.equal(il[95], kept[0])
+    assert [t.sum().item() for t in il[-5:]] == [kept[i].sum().item() for i in range(5)]
+    with pytest.raises(IndexError):
+        il[50]
+
+
+def test_lazy_batch_materialises_on_read_only():
+    calls = []
+    lb = NT.LazyBatch({"a": 1})
+    lb.set_lazy("big", lambda: calls.append(1) or 42)
+    assert "big" in lb and not calls
+    assert lb["big"] == 42 and lb["big"] == 42 and calls == [1]
+
+
+def test_augment_batch_index_conventions():
+    """flat chain index n=(scene*S+sample)*3+mode on CPU tensors"""
+    args = NT.default_args(n_randoms=4, sampling_size=4)
+    b = synthetic.make_scene_batch(3, n_randoms=4, seed=1)
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    nb = NT.augment_batch_data(NT.LazyBatch(b), None, args, n_randoms=4)
+    pack = nb["_pstl_pack"]
+    assert pack.N == 36 and pack.rows_per_scene == 12
+    assert pack.mode.tolist() == [0.0, 1.0, 2.0] * 12
+    assert torch.equal(pack.state0[12:24], b["ego_traj"][1, 0, :4].expand(12, 4))
+    assert torch.equal(pack.stlp.reshape(3, 4, 3, 6)[:, 2], b["pre_stlp"].reshape(3, 4, 3, 6)[:, 0])
+    v = torch.cat([b["curr_id"], b["left_id"], b["right_id"]], -1)
+    assert torch.equal(pack.valid.reshape(3, 4, 3)[:, 1], v)
+    assert torch.equal(nb["neighbors_dense"], NT.dup(b["neighbor_trajs_aug"], 12))
+
+
+def test_shard_bounds_cover_and_are_disjoint():
+    for n, w in ((1024, 8), (10, 4), (3, 8), (65536, 8)):
+        spans = [sharding.shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = synthetic.make_scene_batch(5, n_randoms=4, seed=9)
+    mine = sharding.shard_batch(b, rank, world)
+    lo, hi = sharding.shard_bounds(5, rank, world)
+    ok = torch.equal(mine["ego_traj"], b["ego_traj"][lo:hi])
+    scores = torch.arange(lo * 12, hi * 12).float()  # 12 chains per scene
+    idx = torch.arange(lo * 12, hi * 12).int()
+    all_s, all_i = sharding.gather_scores(scores, idx)
+    ok = ok and torch.equal(all_s, torch.arange(60).float()) and torch.equal(all_i, torch.arange(60).int())
+    valid = (torch.arange(lo * 12, hi * 12) % 3 != 1).float()
+    n_tot, mean_v = sharding.guidance_normaliser(valid)
+    ok = ok and n_tot == 60 and abs(mean_v - 2.0 / 3.0) < 1e-6
+    red = sharding.reduce_metrics({"num": torch.tensor(float(rank + 1)), "den": torch.tensor(2.0)})
+    ok = ok and red == {"den": 2.0 * world, "num": world * (world + 1) / 2}
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharding_and_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

@@ -1,0 +1,108 @@
+"""CPU tier: the per-trajectory math the CUDA kernels run (csrc/*.cuh, compiled for the host by
+tests/hostsim) against the golden fixtures produced from the unmodified reference."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pstl_b200  # noqa: F401
+from pstl_b200 import stl_d_lib as S, synthetic, native
+from pstl_b200.nusc_train import build_stl_cache, default_args
+from formulas import recipes
+from make_golden import kat_inputs
+from hostsim.loader import load
+
+
+def fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ops_array(ops):
+    return (native.Op * len(ops))(*[native.Op(*o) for o in ops])
+
+
+def close(a, b, rtol=1e-5, atol=None):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    fin = np.isfinite(b)
+    assert (np.isfinite(a) == fin).all()
+    assert (a[~fin] == b[~fin]).all()
+    if atol is None:
+        atol = rtol * max(1.0, float(np.abs(b[fin]).max()) if fin.any() else 1.0)
+    np.testing.assert_allclose(a[fin], b[fin], rtol=rtol, atol=atol)
+
+
+def test_interpreter_kats(golden_dir):
+    hs = load()
+    G = np.load(os.path.join(golden_dir, "stl_kats.npz"))
+    x0 = kat_inputs()
+    N, T = x0["a"].shape
+    fs = recipes(S)
+    for name in [str(n) for n in G["names"]]:
+        ops, leaves = S.compile_formula(fs[name])
+        sig = np.ascontiguousarray(torch.stack([l.expression(x0) for l in leaves], 1).numpy(), np.float32)
+        P = len(leaves)
+        for tau in (1.0, 100.0):
+            for hard in (0, 1):
+                key = "%s|%g|%d" % (name, tau, hard)
+                out = np.zeros((N, T), np.float32)
+                gtr = np.zeros((N, T), np.float32)
+                gtr[:, 0] = 1.0
+                gsig = np.zeros_like(sig)
+                want_g = (key + "|ga") in G.files
+                rc = hs.hs_stl_signals(ops_array(ops), len(ops), P, T, T, fp(sig), N, C.c_float(tau), hard, fp(out),
+                                       fp(gtr) if want_g else None, fp(gsig) if want_g else None)
+                assert rc == 0
+                close(out, G[key])
+                if want_g:
+                    got = {k: np.zeros((N, T), np.float32) for k in "abc"}
+                    for i, l in enumerate(leaves):
+                        got[l.comment] += gsig[:, i]
+                    for k in "abc":
+                        close(got[k], G[key + "|g" + k], atol=2e-6)
+
+
+def test_need_t_one_matches_full(golden_dir):
+    """demand-driven evaluation (need_t=1) gives the same t=0 robustness as the full trace"""
+    hs = load()
+    x0 = kat_inputs()
+    N, T = x0["a"].shape
+    fs = recipes(S)
+    for name in ("nested_mix", "ev_alw_and", "until_2_5", "alw_ev"):
+        ops, leaves = S.compile_formula(fs[name])
+        sig = np.ascontiguousarray(torch.stack([l.expression(x0) for l in leaves], 1).numpy(), np.float32)
+        full = np.zeros((N, T), np.float32)
+        one = np.zeros((N, 1), np.float32)
+        assert hs.hs_stl_signals(ops_array(ops), len(ops), len(leaves), T, T, fp(sig), N, C.c_float(100.0), 0, fp(full), None, None) == 0
+        assert hs.hs_stl_signals(ops_array(ops), len(ops), len(leaves), T, 1, fp(sig), N, C.c_float(100.0), 0, fp(one), None, None) == 0
+        np.testing.assert_array_equal(full[:, 0], one[:, 0])
+
+
+@pytest.mark.parametrize("tag,n,nt,knei,seed", [("t20k8", 192, 20, 8, 1008), ("t50k16", 48, 50, 16, 1009)])
+def test_fused_dense_scores_and_grads(golden_dir, tag, n, nt, knei, seed):
+    hs = load()
+    G = np.load(os.path.join(golden_dir, "stl_dense.npz"))
+    x, idx, mask = synthetic.make_dense_stl_input(n, nt=nt, n_neighbors=knei, seed=seed)
+    args = default_args(nt=nt)
+    stls = build_stl_cache(args)
+    progs = [S.compile_formula(f, fused=True)[0] for f in stls]
+    arrs = [ops_array(p) for p in progs]
+    ops3 = (C.c_void_p * 3)(*[C.cast(a, C.c_void_p) for a in arrs])
+    nops = (C.c_int * 3)(*[len(p) for p in progs])
+    f = lambda t: np.ascontiguousarray(t.numpy(), np.float32)
+    nei, l0, l1, l2 = f(x["neighbors"]), f(x["currlane_wpts"]), f(x["leftlane_wpts"]), f(x["rightlane_wpts"])
+    ego, stlp, mode = f(x["ego_traj"]), f(x["stlp"][:, 0]), f(idx[:, 0])
+    scores = np.zeros(n, np.float32)
+    # guidance-style loss gradient: d loss/d score = -[thres-score>0]*mask/(n*clip(mean(mask),1e-2))
+    sc_ref = G[tag + "|scores"]
+    m = mask.numpy()
+    gs = np.where(0.0005 - sc_ref > 0, -m / (n * max(m.mean(), 1e-2)), 0.0).astype(np.float32)
+    gego = np.zeros((n, nt, 4), np.float32)
+    rc = hs.hs_score(ops3, nops, nt, knei, 15, fp(nei), fp(l0), fp(l1), fp(l2), 1, fp(mode), None, None, fp(ego), 4,
+                     fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(1.0), C.c_float(1.0), 0, 0, fp(gs),
+                     fp(scores), None, fp(gego))
+    assert rc == 0
+    close(scores, sc_ref)
+    gref = G[tag + "|grad_ego"]
+    np.testing.assert_allclose(gego, gref, rtol=2e-4, atol=2e-4 * np.abs(gref).max())
