@@ -1,15 +1,501 @@
-// denoiser_tc.cu — tcgen05/TMEM bf16 engine of the denoiser (placeholder until the engine lands:
-// creation reports "unsupported" so callers fall back to asking for PSTL_PRECISION_FP32 explicitly).
+// denoiser_tc.cu — persistent tcgen05 / TMEM engine of the DDPM reverse loop (bf16 operands, fp32
+// accumulate and fp32 chain state).  Replaces, for reverse steps without guidance, the per-step
+// cat + 3 addmm + ReLU + residual of Net.forward (reference nusc_model.py:118-162) and the posterior
+// update + randn_like of diffusion_rollout (reference nusc_train.py:580-629) with ONE launch.
+//
+// One CTA per SM; each CTA owns 128 chains at a time and runs ALL reverse steps on them:
+//   * weights (hoisted W1' 256x48, W2 256x256, W3 40x256; bf16, K-major, 128B-swizzled image built
+//     at handle creation) are pulled into shared memory once per CTA with cp.async.bulk (TMA 1D);
+//   * layer 1:  D[128x256] (TMEM, fp32)  = X[128x48] (smem, bf16) . W1'^T          tcgen05.mma SS
+//     epilogue: + c_scene[scene] + c_t[step], ReLU, pack bf16 -> H (TMEM)           tcgen05.ld / .st
+//   * layer 2:  D[128x256]               = H[128x256] (TMEM) . W2^T                 tcgen05.mma TS
+//     epilogue: + b2, ReLU, pack bf16 -> H (TMEM)
+//   * layer 3:  D3[128x48]               = H . W3^T                                 tcgen05.mma TS
+//     epilogue: eps = D3 + b3 + x ; mu ; x <- mu + sqrt(beta) z (Philox or injected) ; the fp32 state
+//               never leaves registers; its bf16 image goes back to the X tile for the next step and,
+//               in the last K steps, the normalised controls go to HBM.
+// TMEM columns: D [0,256)  H [256,384)  D3 [384,432).   Warps 0-7: epilogue (lane quarter = warp%4,
+// column half = warp/4); warp 8: barrier init, TMEM alloc, weight load and the single MMA-issuing lane.
+#include <cuda_bf16.h>
+
 #include "mlp_common.cuh"
 
-int pstl_tc_create(pstl_denoiser* d) {
-  (void)d;
-  pstl_set_error("PSTL_PRECISION_BF16: tcgen05 engine not built in this revision");
-  return PSTL_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kH = 256;        // hidden width (checked at create)
+constexpr int kK1 = 48;        // layer-1 depth: 40 + 7, padded to 3 UMMA K-steps
+constexpr int kN3 = 48;        // layer-3 width padded to a multiple of 16
+constexpr int kMaxClasses = 8; // distinct scenes a 128-row tile may span
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 1) * 32;
+
+// shared-memory image offsets (bytes)
+constexpr int kOffW1 = 0;                         // [256 x 64] bf16 SW128 (cols >= 48 unused)
+constexpr int kOffW2 = kOffW1 + 256 * 128;        // 4 K-blocks of [256 x 64]
+constexpr int kOffW3 = kOffW2 + 4 * 256 * 128;    // 4 K-blocks of [48 x 64]
+constexpr int kWeightBytes = kOffW3 + 4 * kN3 * 128;
+constexpr int kOffX = kWeightBytes;               // [128 x 64] bf16 SW128
+constexpr int kOffCs = kOffX + kTileM * 128;      // [kMaxClasses][256] fp32
+constexpr int kOffB2 = kOffCs + kMaxClasses * kH * 4;
+constexpr int kOffB3 = kOffB2 + kH * 4;
+constexpr int kOffBar = kOffB3 + 64 * 4;
+constexpr int kSmemBytes = kOffBar + 128;
+static_assert(kWeightBytes == 188416, "weight image size");
+static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
+
+constexpr uint32_t kColD = 0, kColH = 256, kColD3 = 384;
+
+struct TcState {
+  uint8_t* image;  // device: swizzled bf16 weight image (kWeightBytes)
+  int sm_count;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-void pstl_tc_destroy(pstl_denoiser* d) { (void)d; }
-int pstl_tc_sample(pstl_denoiser*, const float*, int, const float*, float*, int, const float*, int, const float*,
-                   unsigned long long, unsigned long long, float, float, int, int, float*, int, int, cudaStream_t) {
-  pstl_set_error("tcgen05 engine not built");
-  return PSTL_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  unsigned spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();  // a protocol bug must fail the launch, not hang the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+#define TMEM_LD_X32(taddr, r)                                                                                        \
+  asm volatile(                                                                                                      \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                      \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28," \
+      "%29,%30,%31}, [%32];"                                                                                         \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+      : "r"(taddr))
+
+#define TMEM_LD_X16(taddr, r)                                                                                   \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+               : "r"(taddr))
+
+#define TMEM_LD_X4(taddr, r) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr))
+
+#define TMEM_ST_X16(taddr, r)                                                                                    \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+               "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])        \
+               : "memory")
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// relu + round-to-nearest bf16 of (lo, hi) packed as {hi:16 | lo:16}
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// byte offset of element (row, k) inside a [rows x 64] bf16 K-major SW128 block
+__host__ __device__ __forceinline__ int sw128_off(int row, int k) {
+  return (row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) & 7) ^ (row & 7)) << 4) + (k & 7) * 2;
+}
+
+// ---------------------------------------------------------------------------------------
+// weight image (run once per handle)
+// ---------------------------------------------------------------------------------------
+__global__ void k_build_image(const float* __restrict__ w1p, int kin, const float* __restrict__ w2,
+                              const float* __restrict__ w3, int n3, uint8_t* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  auto put = [&](int off, float v) { *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v); };
+  if (i < 256 * 64) {  // W1'
+    const int n = i / 64, k = i % 64;
+    put(kOffW1 + sw128_off(n, k), k < kin ? w1p[n * kin + k] : 0.f);
+  }
+  if (i < 256 * 256) {  // W2: K-block kb = k/64
+    const int n = i / 256, k = i % 256;
+    put(kOffW2 + (k / 64) * (256 * 128) + sw128_off(n, k % 64), w2[n * 256 + k]);
+  }
+  if (i < kN3 * 256) {  // W3 rows >= n3 are zero
+    const int n = i / 256, k = i % 256;
+    put(kOffW3 + (k / 64) * (kN3 * 128) + sw128_off(n, k % 64), n < n3 ? w3[n * 256 + k] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// the persistent kernel
+// ---------------------------------------------------------------------------------------
+struct TcArgs {
+  const uint8_t* image;
+  const float* cscene;  // (n_scenes, 256)  W1f.feat + b1
+  const float* ct;      // (steps, 256)     W1t.temb(t)
+  const float* b2;
+  const float* b3;
+  float* xin;           // (N, 48): [x(40) | hl | stlp(6) | 0], x updated in place at the end
+  const float* noise;   // injected z (steps-2, N, 40) or null
+  float* iterates;      // (keep, N, 40) or null
+  float c1[128], c2[128], sb[128];  // per reverse step i: (1-a)/sqrt(1-abar), 1/sqrt(a), sqrt(beta)
+  int N, rows_per_scene, steps, first_step, last_step, keep, clip;
+  float w_max, a_max;
+  unsigned long long seed, offset;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  const uint32_t bar_w = smem_u32(&bars[0]), bar_x = smem_u32(&bars[1]), bar_d1 = smem_u32(&bars[2]),
+                 bar_h1 = smem_u32(&bars[3]), bar_d2 = smem_u32(&bars[4]), bar_h2 = smem_u32(&bars[5]),
+                 bar_d3 = smem_u32(&bars[6]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[8]);
+  float* cs = reinterpret_cast<float*>(smem + kOffCs);
+  float* b2s = reinterpret_cast<float*>(smem + kOffB2);
+  float* b3s = reinterpret_cast<float*>(smem + kOffB3);
+
+  if (warp == kEpiWarps) {
+    if (lane == 0) {
+      mbar_init(bar_w, 1);
+      mbar_init(bar_x, kEpiWarps);
+      mbar_init(bar_d1, 1);
+      mbar_init(bar_h1, kEpiWarps);
+      mbar_init(bar_d2, 1);
+      mbar_init(bar_h2, kEpiWarps);
+      mbar_init(bar_d3, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < kH; i += kThreads) b2s[i] = a.b2[i];
+  for (int i = threadIdx.x; i < 64; i += kThreads) b3s[i] = i < 40 ? a.b3[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kEpiWarps && lane == 0) {
+    // weights: one TMA bulk stream into the resident image
+    mbar_expect_tx(bar_w, kWeightBytes);
+    constexpr int kChunk = 32768;
+    for (int off = 0; off < kWeightBytes; off += kChunk) {
+      const int n = (kWeightBytes - off) < kChunk ? (kWeightBytes - off) : kChunk;
+      bulk_g2s(sbase + kOffW1 + off, a.image + off, n, bar_w);
+    }
+  }
+
+  const int n_tiles = (a.N + kTileM - 1) / kTileM;
+  const int n_steps = a.first_step - a.last_step + 1;
+  uint32_t it = 0;  // tile-steps done by this CTA: every barrier completes once per tile-step
+
+  if (warp == kEpiWarps) {
+    // ================= MMA issuer: the whole warp walks the protocol, lane 0 issues =================
+    mbar_wait(bar_w, 0);
+    const uint32_t id12 = make_idesc(kTileM, kH), id3 = make_idesc(kTileM, kN3);
+    const uint64_t dX = make_desc(sbase + kOffX), dW1 = make_desc(sbase + kOffW1);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = 0; s < n_steps; ++s, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(bar_x, ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < kK1 / 16; ++k)  // advancing 32 B inside the 128 B swizzle atom
+            mma_ss(tmem + kColD, dX + (uint64_t)(k * 2), dW1 + (uint64_t)(k * 2), id12, k > 0);
+          tc_commit(bar_d1);
+        }
+        __syncwarp();
+        mbar_wait(bar_h1, ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < kH / 16; ++k) {
+            const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)((k & 3) * 2);
+            mma_ts(tmem + kColD, tmem + kColH + k * 8, dB, id12, k > 0);
+          }
+          tc_commit(bar_d2);
+        }
+        __syncwarp();
+        mbar_wait(bar_h2, ph);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < kH / 16; ++k) {
+            const uint64_t dB = make_desc(sbase + kOffW3 + (k >> 2) * (kN3 * 128)) + (uint64_t)((k & 3) * 2);
+            mma_ts(tmem + kColD3, tmem + kColH + k * 8, dB, id3, k > 0);
+          }
+          tc_commit(bar_d3);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3, half = warp >> 2;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    const int c0 = half * 20;  // this thread's 20 state columns
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * kTileM + row_in_tile;
+      const bool live = row < a.N;
+      const long long rrow = live ? row : (long long)a.N - 1;
+      const int scene0 = (int)(((long long)tile * kTileM) / a.rows_per_scene);
+      const int cls = (int)(rrow / a.rows_per_scene) - scene0;
+      // per-tile scene bias rows -> smem (the previous tile's readers are past their last use: they
+      // have all arrived on bar_x of the final step, which the loop below waits for implicitly)
+      {
+        const int t = warp * 32 + lane;  // 256 epilogue threads
+        const long long last_row = ((long long)tile * kTileM + kTileM - 1 < a.N ? (long long)tile * kTileM + kTileM - 1 : (long long)a.N - 1);
+        const int n_cls = (int)(last_row / a.rows_per_scene) - scene0 + 1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = 0; c < n_cls && c < kMaxClasses; ++c) cs[c * kH + t] = a.cscene[(size_t)(scene0 + c) * kH + t];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      // chain state: fp32 in registers for the whole reverse loop
+      float x[20];
+      const float* xr = a.xin + rrow * PSTL_XIN_LD;
+#pragma unroll
+      for (int j = 0; j < 20; ++j) x[j] = xr[c0 + j];
+      uint8_t* xt = smem + kOffX;
+      auto store_x_tile = [&]() {
+#pragma unroll
+        for (int j = 0; j < 20; j += 2) {
+          const __nv_bfloat162 v = __floats2bfloat162_rn(x[j], x[j + 1]);
+          *reinterpret_cast<__nv_bfloat162*>(xt + sw128_off(row_in_tile, c0 + j)) = v;
+        }
+      };
+      store_x_tile();
+      if (half == 1) {  // constant columns 40..47: hl, stlp(6), 0
+#pragma unroll
+        for (int j = 0; j < 8; j += 2)
+          *reinterpret_cast<__nv_bfloat162*>(xt + sw128_off(row_in_tile, 40 + j)) = __floats2bfloat162_rn(xr[40 + j], xr[41 + j]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_x);
+
+      for (int s = 0; s < n_steps; ++s, ++it) {
+        const uint32_t ph = it & 1;
+        const int i = a.first_step - s;  // reverse step index (t == i)
+        const float* ctr = a.ct + (size_t)i * kH;
+        // ---- layers 1 and 2: D -> (+bias, relu, bf16) -> H ----
+#pragma unroll 1
+        for (int layer = 0; layer < 2; ++layer) {
+          mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
+          tc_fence_after();
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            const int col = half * 128 + ch * 32;
+            uint32_t r[32];
+            TMEM_LD_X32(tmem + lane_addr + kColD + col, r);
+            tmem_wait_ld();
+            uint32_t p[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b;
+              if (layer == 0) {
+                const float4 b0 = *reinterpret_cast<const float4*>(cs + cls * kH + col + j);
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ctr + col + j));
+                b = make_float4(b0.x + b1.x, b0.y + b1.y, b0.z + b1.z, b0.w + b1.w);
+              } else {
+                b = *reinterpret_cast<const float4*>(b2s + col + j);
+              }
+              p[j / 2] = pack_relu_bf16(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y);
+              p[j / 2 + 1] = pack_relu_bf16(__uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
+            }
+            TMEM_ST_X16(tmem + lane_addr + kColH + col / 2, p);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(layer == 0 ? bar_h1 : bar_h2);
+        }
+        // ---- layer 3: eps, posterior mean, noise, next x ----
+        mbar_wait(bar_d3, ph);
+        tc_fence_after();
+        uint32_t r[20];
+        TMEM_LD_X16(tmem + lane_addr + kColD3 + c0, r);
+        TMEM_LD_X4(tmem + lane_addr + kColD3 + c0 + 16, (r + 16));
+        tmem_wait_ld();
+        const float c1 = a.c1[i], c2 = a.c2[i], sb = a.sb[i];
+        const int zi = a.steps - 1 - i;
+        const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 20; j += 4) {
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (i > 1) {
+            if (zr) {
+              const float4 zz = *reinterpret_cast<const float4*>(zr + j);
+              z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+            } else {
+              uint4 ctr4 = make_uint4((unsigned)(rrow & 0xffffffff), (unsigned)(rrow >> 32), (unsigned)((c0 + j) >> 2),
+                                      (unsigned)i + (unsigned)a.offset);
+              const uint4 rn = pstl_philox(ctr4, make_uint2((unsigned)(a.seed & 0xffffffff), (unsigned)(a.seed >> 32)));
+              pstl_box_muller(rn.x, rn.y, z[0], z[1]);
+              pstl_box_muller(rn.z, rn.w, z[2], z[3]);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float eps = __uint_as_float(r[j + e]) + b3s[c0 + j + e] + x[j + e];
+            const float mu = c2 * (x[j + e] - c1 * eps);
+            x[j + e] = mu + sb * z[e];
+          }
+        }
+        const int kidx = a.keep - i;
+        if (a.iterates && kidx >= 0 && live) {
+          float* o = a.iterates + ((size_t)kidx * a.N + row) * 40 + c0;
+#pragma unroll
+          for (int j = 0; j < 20; j += 2) {
+            float w = x[j] * a.w_max, ac = x[j + 1] * a.a_max;
+            if (a.clip) {
+              w = fminf(fmaxf(w, -a.w_max), a.w_max);
+              ac = fminf(fmaxf(ac, -a.a_max), a.a_max);
+            }
+            *reinterpret_cast<float2*>(o + j) = make_float2(w, ac);
+          }
+        }
+        if (s + 1 < n_steps) {
+          store_x_tile();
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x);
+        }
+      }
+      if (live) {
+        float* xw = a.xin + row * PSTL_XIN_LD;
+#pragma unroll
+        for (int j = 0; j < 20; ++j) xw[c0 + j] = x[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+}  // namespace
+
+int pstl_tc_create(pstl_denoiser* d) {
+  if (d->w.hidden != kH || d->T2 != 40 || d->kin != 47) {
+    pstl_set_error("PSTL_PRECISION_BF16 engine is built for hidden=256, nt=20 (got hidden=%d, nt=%d)", d->w.hidden, d->w.T);
+    return PSTL_ERR_UNSUPPORTED;
+  }
+  int dev = 0, cc_major = 0, sms = 0;
+  PSTL_CUDA(cudaGetDevice(&dev));
+  PSTL_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  PSTL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major != 10) {
+    pstl_set_error("PSTL_PRECISION_BF16 needs an sm_100 device (tcgen05)");
+    return PSTL_ERR_UNSUPPORTED;
+  }
+  TcState* s = new TcState();
+  s->sm_count = sms;
+  s->image = nullptr;
+  PSTL_CUDA(cudaMalloc(&s->image, kWeightBytes));
+  PSTL_CUDA(cudaMemset(s->image, 0, kWeightBytes));
+  k_build_image<<<(256 * 256 + 255) / 256, 256>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image);
+  PSTL_LAUNCH_CHECK();
+  PSTL_CUDA(cudaDeviceSynchronize());
+  PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+  d->tc = s;
+  return PSTL_OK;
+}
+
+void pstl_tc_destroy(pstl_denoiser* d) {
+  TcState* s = (TcState*)d->tc;
+  if (!s) return;
+  cudaFree(s->image);
+  delete s;
+  d->tc = nullptr;
+}
+
+// runs reverse steps first_step .. last_step (inclusive, descending) on xin in place
+int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, const float* ct, float* xin, int N,
+                   const float* sched, int steps, const float* noise, unsigned long long seed,
+                   unsigned long long offset, float w_max, float a_max, int clip, int keep_last_k, float* iterates_out,
+                   int first_step, int last_step, cudaStream_t st) {
+  TcState* s = (TcState*)d->tc;
+  PSTL_CHECK_ARG(s, "engine not created");
+  PSTL_CHECK_ARG(steps <= 128, "at most 128 diffusion steps");
+  PSTL_CHECK_ARG((kTileM + rows_per_scene - 1) / rows_per_scene + 1 <= kMaxClasses, "rows_per_scene too small for the tcgen05 tile");
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.image = s->image; a.cscene = cscene; a.ct = ct; a.b2 = d->w.p2_b; a.b3 = d->w.p4_b; a.xin = xin;
+  a.noise = noise; a.iterates = keep_last_k > 0 ? iterates_out : nullptr;
+  const float *beta = sched, *alpha = sched + steps, *abar = sched + 2 * steps;
+  for (int i = 1; i < steps; ++i) {
+    a.c1[i] = (1.0f - alpha[i]) / sqrtf(1.0f - abar[i]);
+    a.c2[i] = 1.0f / sqrtf(alpha[i]);
+    a.sb[i] = sqrtf(beta[i]);
+  }
+  a.N = N; a.rows_per_scene = rows_per_scene; a.steps = steps; a.first_step = first_step; a.last_step = last_step;
+  a.keep = keep_last_k; a.clip = clip; a.w_max = w_max; a.a_max = a_max; a.seed = seed; a.offset = offset;
+  const int n_tiles = (N + kTileM - 1) / kTileM;
+  const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
+  k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
 }

@@ -137,12 +137,29 @@ class Net(nn.Module):
         lanes_input = torch.cat([lanes[..., 0:1, :], lanes[..., 1:, :] - lanes[..., :-1, :]], dim=-2)
         lanes_input = lanes_input.reshape(bs, 3, lanes.shape[-2] * self.lane_dim)
         ego_input = torch.cat([normalize_xyth(ego[..., :3], ego[..., :3]), ego[..., 3:]], dim=-1)
-        ego_feat = self.ego_encoder(ego_input)
-        nei_feat = self.neighbor_encoder(neis_input)
+        ego_feat = self._mlp(self.ego_encoder, ego_input)
+        nei_feat = self._mlp(self.neighbor_encoder, neis_input)
         nei_feat = torch.cat([torch.min(nei_feat, dim=1)[0], torch.mean(nei_feat, dim=1), torch.max(nei_feat, dim=1)[0]],
                              dim=-1)
-        lanes_feat = self.lane_encoder(lanes_input).reshape(bs, -1)
+        lanes_feat = self._mlp(self.lane_encoder, lanes_input).reshape(bs, -1)
         return torch.cat([ego_feat, nei_feat, lanes_feat], dim=-1)
+
+    def _mlp(self, seq, x):
+        """encoder MLP.  Inference on the GPU goes through pstl_linear (row-independent summation order,
+        so a scene's feature does not depend on which other scenes share its batch / shard); with autograd
+        on (training, out of scope) it is the plain nn.Sequential."""
+        if torch.is_grad_enabled() or not x.is_cuda:
+            return seq(x)
+        lead = x.shape[:-1]
+        h = _nv.f32(x.reshape(-1, x.shape[-1]))
+        L = _nv.lib()
+        for li in (0, 2, 4):
+            w, b = _nv.f32(seq[li].weight), _nv.f32(seq[li].bias)
+            y = torch.empty((h.shape[0], w.shape[0]), dtype=torch.float32, device=h.device)
+            _nv.check(L.pstl_linear(_nv.fptr(h), _nv.fptr(w), _nv.fptr(b), h.shape[0], h.shape[1], w.shape[0],
+                                    int(li != 4), _nv.fptr(y), _nv.stream()), "pstl_linear")
+            h = y
+        return h.reshape(*lead, -1)
 
     # --- eps model (reference nusc_model.py:97-180, diffusion + multi_check branch) -------
     def forward(self, nn_input, ext=None, get_feature=False, prev_feature=None, sample=False, n_randoms=None):

@@ -343,3 +343,39 @@ def test_ops_fail_loudly_on_cpu_tensors():
     x0 = kat_inputs()
     with pytest.raises(native.PstlNativeError):
         S.Always(0, 3, S.AP(lambda x: x["a"]))(x0, 100.0)
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 bf16 engine vs the fp32 path (north_star tolerance for the bf16 denoiser: 2e-2)
+# ------------------------------------------------------------------------------------------
+def _sampler_pair(bs, S_, steps, seed):
+    nt = 20
+    out = {}
+    W = synthetic.make_weights(1007, nt=nt)
+    batch = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=seed))
+    N = bs * S_ * 3
+    stream = [t.cuda() for t in synthetic.noise_stream(seed + 1, N, nt * 2, steps - 1)]
+    for prec in ("fp32", "bf16"):
+        args = NT.default_args(n_randoms=S_, sampling_size=S_, diffusion_steps=steps, precision=prec, multi_cands=1)
+        net = Net(args)
+        net.load_state_dict(W)
+        net = net.cuda()
+        args.inject_noise = stream
+        b = NT.LazyBatch(dict(batch))
+        b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+        b = NT.augment_batch_data(b, None, args, n_randoms=S_)
+        noise = torch.empty((N, nt * 2), device="cuda")
+        res = NT.diffusion_rollout(noise, net, b, b["highlevel_dense"], None, args, NT.get_diffusion_coeffs(args), n_randoms=S_)
+        out[prec] = res[0]
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("bs,S_,steps", [(2, 16, 2), (2, 16, 100), (24, 64, 100)])
+def test_bf16_tcgen05_sampler_vs_fp32(bs, S_, steps):
+    o = _sampler_pair(bs, S_, steps, 4242)
+    a, b = o["bf16"], o["fp32"]
+    assert torch.isfinite(a).all()
+    scale = torch.tensor([0.5, 5.0], device="cuda")  # compare in normalised units
+    err = ((a - b) / scale).abs()
+    assert err.max().item() < 2e-2, err.max().item()
