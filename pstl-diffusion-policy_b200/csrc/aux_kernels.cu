@@ -78,15 +78,16 @@ __global__ void k_predicates(const float* __restrict__ nei, const float* __restr
   }
   const float cs = cosf(pth), sn = sinf(pth);
   PstlCircles ec;
-  pstl_car_circles(px, py, cs, sn, ego_L, ego_W, 4, ec);
+  pstl_car_circles(px, py, cs, sn, ego_L, ego_W, ec);
   PstlSceneGlobal sg;
-  sg.nei = nei + (size_t)scene * K * T * 7;
-  sg.K = K; sg.T = T; sg.nL = 4;
+  sg.neib = nei + (size_t)scene * K * T * 7;
+  sg.K = K; sg.T = T;
   float best = INFINITY, bg[3] = {0.f, 0.f, 0.f};
   for (int k = 0; k < K; ++k) {
-    float ncx[PSTL_MAX_NL], ncy[PSTL_MAX_NL], nr, valid, g[3];
-    sg.nei_circles(k, t, ncx, ncy, nr, valid);
-    const float term = pstl_pair_clearance(ec, cs, sn, ncx, ncy, nr, valid, 4, g);
+    PstlNei nb;
+    float g[3];
+    sg.nei(k, t, nb);
+    const float term = pstl_pair_clearance(ec, cs, sn, nb, g);
     if (term < best) { best = term; bg[0] = g[0]; bg[1] = g[1]; bg[2] = g[2]; }
   }
   sig[((size_t)n * 7 + 6) * T + t] = best;

@@ -36,8 +36,8 @@ constexpr int kOffW2 = kOffW1 + 256 * 128;        // 4 K-blocks of [256 x 64]
 constexpr int kOffW3 = kOffW2 + 4 * 256 * 128;    // 4 K-blocks of [48 x 64]
 constexpr int kWeightBytes = kOffW3 + 4 * kN3 * 128;
 constexpr int kOffX = kWeightBytes;               // [128 x 64] bf16 SW128
-constexpr int kOffCs = kOffX + kTileM * 128;      // [kMaxClasses][256] fp32
-constexpr int kOffB2 = kOffCs + kMaxClasses * kH * 4;
+constexpr int kOffCs = kOffX + kTileM * 128;      // comb[2][kMaxClasses][256] fp32: c_scene[scene] + c_t[step]
+constexpr int kOffB2 = kOffCs + 2 * kMaxClasses * kH * 4;
 constexpr int kOffB3 = kOffB2 + kH * 4;
 constexpr int kOffBar = kOffB3 + 64 * 4;
 constexpr int kSmemBytes = kOffBar + 128;
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
   const uint32_t bar_w = smem_u32(&bars[0]), bar_x = smem_u32(&bars[1]), bar_d1 = smem_u32(&bars[2]),
                  bar_h1 = smem_u32(&bars[3]), bar_d2 = smem_u32(&bars[4]), bar_h2 = smem_u32(&bars[5]),
                  bar_d3 = smem_u32(&bars[6]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[8]);
+  const uint32_t bar_c0 = smem_u32(&bars[7]);  // two bias barriers, 8 bytes apart
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[10]);
   float* cs = reinterpret_cast<float*>(smem + kOffCs);
   float* b2s = reinterpret_cast<float*>(smem + kOffB2);
   float* b3s = reinterpret_cast<float*>(smem + kOffB3);
@@ -219,6 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       mbar_init(bar_d2, 1);
       mbar_init(bar_h2, kEpiWarps);
       mbar_init(bar_d3, 1);
+      mbar_init(bar_c0, 1);
+      mbar_init(bar_c0 + 8, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -252,9 +255,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
     mbar_wait(bar_w, 0);
     const uint32_t id12 = make_idesc(kTileM, kH), id3 = make_idesc(kTileM, kN3);
     const uint64_t dX = make_desc(sbase + kOffX), dW1 = make_desc(sbase + kOffW1);
+    // layer-1 bias rows of a tile-step, comb[buf][class][col] = c_scene[scene0+class][col] + c_t[i][col],
+    // are prepared one step ahead by this otherwise idle warp
+    auto write_comb = [&](uint32_t buf, int tile, int i) {
+      const long long r0 = (long long)tile * kTileM;
+      const long long r1 = (r0 + kTileM - 1 < a.N) ? r0 + kTileM - 1 : (long long)a.N - 1;
+      const int scene0 = (int)(r0 / a.rows_per_scene);
+      const int n_cls = (int)(r1 / a.rows_per_scene) - scene0 + 1;
+      float* dst = cs + buf * (kMaxClasses * kH);
+      const float* ctr = a.ct + (size_t)i * kH;
+      for (int c = 0; c < n_cls && c < kMaxClasses; ++c) {
+        const float* src = a.cscene + (size_t)(scene0 + c) * kH;
+#pragma unroll
+        for (int col = lane * 4; col < kH; col += 128) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(src + col));
+          const float4 v = __ldg(reinterpret_cast<const float4*>(ctr + col));
+          *reinterpret_cast<float4*>(dst + c * kH + col) = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_c0 + buf * 8);
+    };
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 0; s < n_steps; ++s, ++it) {
         const uint32_t ph = it & 1;
+        if (s == 0) write_comb(it & 1, tile, a.first_step);
         mbar_wait(bar_x, ph);
         tc_fence_after();
         if (lane == 0) {
@@ -264,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           tc_commit(bar_d1);
         }
         __syncwarp();
+        if (s + 1 < n_steps) write_comb((it + 1) & 1, tile, a.first_step - s - 1);
         mbar_wait(bar_h1, ph);
         tc_fence_after();
         if (lane == 0) {
@@ -300,16 +326,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       const long long rrow = live ? row : (long long)a.N - 1;
       const int scene0 = (int)(((long long)tile * kTileM) / a.rows_per_scene);
       const int cls = (int)(rrow / a.rows_per_scene) - scene0;
-      // per-tile scene bias rows -> smem (the previous tile's readers are past their last use: they
-      // have all arrived on bar_x of the final step, which the loop below waits for implicitly)
-      {
-        const int t = warp * 32 + lane;  // 256 epilogue threads
-        const long long last_row = ((long long)tile * kTileM + kTileM - 1 < a.N ? (long long)tile * kTileM + kTileM - 1 : (long long)a.N - 1);
-        const int n_cls = (int)(last_row / a.rows_per_scene) - scene0 + 1;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int c = 0; c < n_cls && c < kMaxClasses; ++c) cs[c * kH + t] = a.cscene[(size_t)(scene0 + c) * kH + t];
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
       // chain state: fp32 in registers for the whole reverse loop
       float x[20];
       const float* xr = a.xin + rrow * PSTL_XIN_LD;
@@ -336,12 +352,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       for (int s = 0; s < n_steps; ++s, ++it) {
         const uint32_t ph = it & 1;
         const int i = a.first_step - s;  // reverse step index (t == i)
-        const float* ctr = a.ct + (size_t)i * kH;
+        const float* comb = cs + (it & 1) * (kMaxClasses * kH) + cls * kH;
+        float zn[20];
         // ---- layers 1 and 2: D -> (+bias, relu, bf16) -> H ----
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
           tc_fence_after();
+          if (layer == 0) mbar_wait(bar_c0 + (it & 1) * 8, (it >> 1) & 1);
 #pragma unroll 1
           for (int ch = 0; ch < 4; ++ch) {
             const int col = half * 128 + ch * 32;
@@ -353,9 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
             for (int j = 0; j < 32; j += 4) {
               float4 b;
               if (layer == 0) {
-                const float4 b0 = *reinterpret_cast<const float4*>(cs + cls * kH + col + j);
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(ctr + col + j));
-                b = make_float4(b0.x + b1.x, b0.y + b1.y, b0.z + b1.z, b0.w + b1.w);
+                b = *reinterpret_cast<const float4*>(comb + col + j);
               } else {
                 b = *reinterpret_cast<const float4*>(b2s + col + j);
               }
@@ -368,6 +384,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(layer == 0 ? bar_h1 : bar_h2);
+          if (layer == 0) {
+            // this step's noise is drawn now, in the shadow of the layer-2 MMA
+            const int zi = a.steps - 1 - i;
+            const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 20; j += 4) {
+              zn[j] = zn[j + 1] = zn[j + 2] = zn[j + 3] = 0.f;
+              if (i > 1) {
+                if (zr) {
+                  const float4 zz = *reinterpret_cast<const float4*>(zr + j);
+                  zn[j] = zz.x; zn[j + 1] = zz.y; zn[j + 2] = zz.z; zn[j + 3] = zz.w;
+                } else {
+                  uint4 ctr4 = make_uint4((unsigned)(rrow & 0xffffffff), (unsigned)(rrow >> 32), (unsigned)((c0 + j) >> 2),
+                                          (unsigned)i + (unsigned)a.offset);
+                  const uint4 rn = pstl_philox(ctr4, make_uint2((unsigned)(a.seed & 0xffffffff), (unsigned)(a.seed >> 32)));
+                  pstl_box_muller(rn.x, rn.y, zn[j], zn[j + 1]);
+                  pstl_box_muller(rn.z, rn.w, zn[j + 2], zn[j + 3]);
+                }
+              }
+            }
+          }
         }
         // ---- layer 3: eps, posterior mean, noise, next x ----
         mbar_wait(bar_d3, ph);
@@ -377,29 +414,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         TMEM_LD_X4(tmem + lane_addr + kColD3 + c0 + 16, (r + 16));
         tmem_wait_ld();
         const float c1 = a.c1[i], c2 = a.c2[i], sb = a.sb[i];
-        const int zi = a.steps - 1 - i;
-        const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 20; j += 4) {
-          float z[4] = {0.f, 0.f, 0.f, 0.f};
-          if (i > 1) {
-            if (zr) {
-              const float4 zz = *reinterpret_cast<const float4*>(zr + j);
-              z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
-            } else {
-              uint4 ctr4 = make_uint4((unsigned)(rrow & 0xffffffff), (unsigned)(rrow >> 32), (unsigned)((c0 + j) >> 2),
-                                      (unsigned)i + (unsigned)a.offset);
-              const uint4 rn = pstl_philox(ctr4, make_uint2((unsigned)(a.seed & 0xffffffff), (unsigned)(a.seed >> 32)));
-              pstl_box_muller(rn.x, rn.y, z[0], z[1]);
-              pstl_box_muller(rn.z, rn.w, z[2], z[3]);
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float eps = __uint_as_float(r[j + e]) + b3s[c0 + j + e] + x[j + e];
-            const float mu = c2 * (x[j + e] - c1 * eps);
-            x[j + e] = mu + sb * z[e];
-          }
+        for (int j = 0; j < 20; ++j) {
+          const float eps = __uint_as_float(r[j]) + b3s[c0 + j] + x[j];
+          const float mu = c2 * (x[j] - c1 * eps);
+          x[j] = mu + sb * zn[j];
         }
         const int kidx = a.keep - i;
         if (a.iterates && kidx >= 0 && live) {

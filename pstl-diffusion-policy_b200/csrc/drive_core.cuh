@@ -26,18 +26,18 @@ PSTL_HD float pstl_linspace01(int k, int n) {
   return (k < n / 2) ? step * (float)k : 1.0f - step * (float)(n - k - 1);
 }
 
-#define PSTL_MAX_NL 8
+#define PSTL_NL 4  // --refined_nL (the only value built; checked on the host side)
 
 // utils.py:465-497 (num_W = 1): body-axis circle centres of a car and the common radius.
 struct PstlCircles {
-  float cx[PSTL_MAX_NL], cy[PSTL_MAX_NL];
-  float q[PSTL_MAX_NL];  // body-x offsets (needed for d centre / d heading)
-  float q_y;             // body-y offset (0 for car-shaped boxes)
+  float cx[PSTL_NL], cy[PSTL_NL];
+  float q[PSTL_NL];  // body-x offsets (needed for d centre / d heading)
+  float q_y;         // body-y offset (0 for car-shaped boxes)
   float r;
 };
 
-PSTL_HD void pstl_car_circles(float x, float y, float c, float sn, float L, float W, int nL, PstlCircles& out) {
-  const float r_l = L / (float)nL / 2.f;
+PSTL_HD void pstl_car_circles(float x, float y, float c, float sn, float L, float W, PstlCircles& out) {
+  const float r_l = L / (float)PSTL_NL / 2.f;
   const float r_w = W / 1.f / 2.f;
   const float r = fminf(fmaxf(r_l, r_w), W / 2.f);
   const float x1 = L / 2.f, x2 = -L / 2.f;
@@ -45,8 +45,9 @@ PSTL_HD void pstl_car_circles(float x, float y, float c, float sn, float L, floa
   const float ys = (y3 + r) * (1.f - 0.f) + (y2 - r) * 0.f;  // linspace(0,1,1) = [0]
   out.r = r;
   out.q_y = ys;
-  for (int k = 0; k < nL; ++k) {
-    const float al = pstl_linspace01(k, nL);
+#pragma unroll
+  for (int k = 0; k < PSTL_NL; ++k) {
+    const float al = pstl_linspace01(k, PSTL_NL);
     const float xs = (x2 + r) * (1.f - al) + (x1 - r) * al;
     out.q[k] = xs;
     out.cx[k] = xs * c - ys * sn + x;
@@ -54,39 +55,59 @@ PSTL_HD void pstl_car_circles(float x, float y, float c, float sn, float L, floa
   }
 }
 
+// Neighbour at one time step as the scene accessors hand it out.
+struct PstlNei {
+  float cx[PSTL_NL], cy[PSTL_NL];
+  float r, valid;
+};
+
 // utils.py:499-510 + nusc_train.py:142-148 for ONE neighbour: clipped clearance term and, when
 // grad != nullptr, d term / d (ego x, y, th).
-PSTL_HD float pstl_pair_clearance(const PstlCircles& e, float ec, float es, const float* ncx, const float* ncy,
-                                  float nr, float valid, int nL, float* grad /*3 or null*/) {
+PSTL_HD float pstl_pair_clearance(const PstlCircles& e, float ec, float es, const PstlNei& n, float* grad /*3 or null*/) {
   float best = INFINITY;
   int bi = 0, bj = 0;
-  for (int i = 0; i < nL; ++i)
-    for (int j = 0; j < nL; ++j) {
-      const float dx = e.cx[i] - ncx[j], dy = e.cy[i] - ncy[j];
+#pragma unroll
+  for (int i = 0; i < PSTL_NL; ++i)
+#pragma unroll
+    for (int j = 0; j < PSTL_NL; ++j) {
+      const float dx = e.cx[i] - n.cx[j], dy = e.cy[i] - n.cy[j];
       const float d2 = dx * dx + dy * dy;
       if (d2 < best) { best = d2; bi = i; bj = j; }
     }
   const float mind = sqrtf(best);  // sqrt is monotone: min of norms == norm at the min square
-  const float car = mind - e.r - nr;
+  const float car = mind - e.r - n.r;
   const float clipped = fminf(fmaxf(car, -5.f), 20.f);
-  const float term = clipped * valid + (1.f - valid) * 100.f;
+  const float term = clipped * n.valid + (1.f - n.valid) * 100.f;
   if (grad) {
     float gx = 0.f, gy = 0.f, gth = 0.f;
     if (car >= -5.f && car <= 20.f) {
-      const float dx = e.cx[bi] - ncx[bj], dy = e.cy[bi] - ncy[bj];
-      const float ux = dx / mind, uy = dy / mind;  // NaN when coincident, as torch.norm's backward
-      gx = ux * valid;
-      gy = uy * valid;
+      float ex = 0.f, ey = 0.f, nx = 0.f, ny = 0.f, q = 0.f;
+#pragma unroll
+      for (int i = 0; i < PSTL_NL; ++i) {
+        if (i == bi) { ex = e.cx[i]; ey = e.cy[i]; q = e.q[i]; }
+        if (i == bj) { nx = n.cx[i]; ny = n.cy[i]; }
+      }
+      const float ux = (ex - nx) / mind, uy = (ey - ny) / mind;  // NaN when coincident, as torch.norm's backward
+      gx = ux * n.valid;
+      gy = uy * n.valid;
       // centre = (x + q c - qy s, y + q s + qy c): d/dth = (-q s - qy c, q c - qy s)
-      gth = (ux * (-e.q[bi] * es - e.q_y * ec) + uy * (e.q[bi] * ec - e.q_y * es)) * valid;
+      gth = (ux * (-q * es - e.q_y * ec) + uy * (q * ec - e.q_y * es)) * n.valid;
     }
     grad[0] = gx; grad[1] = gy; grad[2] = gth;
   }
   return term;
 }
 
-// nusc_api.py:693-735: signed lateral distance and heading error of pose p to polyline lane
-// (nseg points of [x,y,th], element stride ls floats between consecutive components' rows).
+// Exact cull for a neighbour with valid == 1: every circle centre lies within L/2 - r of the car
+// centre, so  car_dist >= |C_ego - C_nei| - L_ego/2 - reach_nei  with reach = L_nei/2.  If that bound
+// (less a rounding margin) is not below min(best, 20) the neighbour cannot lower the running minimum
+// and its clipped term is exactly 20 when the bound exceeds 20.
+PSTL_HD bool pstl_cull_neighbour(float dx, float dy, float ego_half_len, float reach, float best) {
+  const float R = fminf(best, 20.f) + ego_half_len + reach + 1e-3f;
+  return R > 0.f && (dx * dx + dy * dy) >= R * R;
+}
+
+// nusc_api.py:693-735: signed lateral distance and heading error of pose p to polyline lane.
 // part (3 floats or null): d dist/d px, d dist/d py, d ang/d pth.
 template <class LaneAcc>
 PSTL_HD void pstl_lane_pred(float px, float py, float pth, const LaneAcc& lane, int nseg, int clip_dist,

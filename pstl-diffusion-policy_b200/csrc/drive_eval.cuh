@@ -6,20 +6,26 @@
 #include "stl_program.h"
 
 // Scene accessor concept:
-//   float lane(int l, int j, int f)                       lane l point j component f
-//   void  nei_circles(int k, int t, float* cx, float* cy, float& r, float& valid)
+//   float lane(int l, int j, int f)                      lane l point j component f
+//   void  nei_meta(int k, int t, float& cx, float& cy, float& reach, float& valid)   car centre, L/2
+//   void  nei(int k, int t, PstlNei& out)                circle centres, radius, valid
 struct PstlSceneGlobal {
-  const float* nei;  // (K,T,7) of this row's scene
+  const float* neib;  // (K,T,7) of this row's scene
   const float* ln[3];
-  int K, T, nL;
+  int K, T;
   PSTL_HD float lane(int l, int j, int f) const { return ln[l][j * 3 + f]; }
-  PSTL_HD void nei_circles(int k, int t, float* cx, float* cy, float& r, float& valid) const {
-    const float* p = nei + ((size_t)k * T + t) * 7;
+  PSTL_HD void nei_meta(int k, int t, float& cx, float& cy, float& reach, float& valid) const {
+    const float* p = neib + ((size_t)k * T + t) * 7;
+    valid = p[0]; cx = p[1]; cy = p[2]; reach = p[5] / 2.f;
+  }
+  PSTL_HD void nei(int k, int t, PstlNei& out) const {
+    const float* p = neib + ((size_t)k * T + t) * 7;
     PstlCircles c;
-    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], nL, c);
-    for (int i = 0; i < nL; ++i) { cx[i] = c.cx[i]; cy[i] = c.cy[i]; }
-    r = c.r;
-    valid = p[0];
+    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], c);
+#pragma unroll
+    for (int i = 0; i < PSTL_NL; ++i) { out.cx[i] = c.cx[i]; out.cy[i] = c.cy[i]; }
+    out.r = c.r;
+    out.valid = p[0];
   }
 };
 
@@ -30,7 +36,7 @@ struct PstlLaneAcc {
 
 struct PstlEvalCfg {
   float dt, tau, ego_L, ego_W, w_scale, a_scale;
-  int clip_controls, clip_dist, hard, nL, nseg, K, T;
+  int clip_controls, clip_dist, hard, nseg, K, T;
 };
 
 struct PstlLeafFused {
@@ -76,15 +82,21 @@ PSTL_HD void pstl_scaled_control(const float* u, int t, const PstlEvalCfg& c, fl
   }
 }
 
+PSTL_HD int pstl_need_pose(const PstlProgView& P) {
+  int n = 0;
+  for (int b = 0; b < PSTL_N_BASE_SIGNALS; ++b) n = P.base_need[b] > n ? P.base_need[b] : n;
+  return n;
+}
+
 // Forward: fills the value tape (and the partial block pt when GRAD) and returns the score.
 // u: controls of this row (T*2 floats, pre-scale) or nullptr; ego: pre-rolled states (stride es) or nullptr.
-template <class Scene, bool GRAD>
+template <class Scene, bool GRAD, bool FAST>
 PSTL_HD float pstl_eval_traj(const PstlProgView& P, const Scene& sc, const PstlEvalCfg& c, PstlPose s,
                              const float* u, const float* ego, int es, const float* stlp, float* vt, float* pt,
                              int stride) {
   const int T = c.T;
-  int need_pose = 0;
-  for (int b = 0; b < PSTL_N_BASE_SIGNALS; ++b) need_pose = P.base_need[b] > need_pose ? P.base_need[b] : need_pose;
+  const int need_pose = pstl_need_pose(P);
+  const float ego_half = c.ego_L / 2.f;
 #define VT(off) vt[(size_t)(off) * stride]
 #define PT(row, t) pt[(size_t)((row) * T + (t)) * stride]
   for (int t = 0; t < need_pose; ++t) {
@@ -110,19 +122,30 @@ PSTL_HD float pstl_eval_traj(const PstlProgView& P, const Scene& sc, const PstlE
     }
     if (t < P.base_need[PSTL_SIG_NEI]) {
       PstlCircles e;
-      pstl_car_circles(s.x, s.y, cs, sn, c.ego_L, c.ego_W, c.nL, e);
-      float best = INFINITY, bg[3] = {0.f, 0.f, 0.f};
+      pstl_car_circles(s.x, s.y, cs, sn, c.ego_L, c.ego_W, e);
+      float best = INFINITY, bg0 = 0.f, bg1 = 0.f, bg2 = 0.f;
       for (int k = 0; k < c.K; ++k) {
-        float ncx[PSTL_MAX_NL], ncy[PSTL_MAX_NL], nr, valid, g[3];
-        sc.nei_circles(k, t, ncx, ncy, nr, valid);
-        const float term = pstl_pair_clearance(e, cs, sn, ncx, ncy, nr, valid, c.nL, GRAD ? g : nullptr);
+        float ncx, ncy, reach, valid;
+        sc.nei_meta(k, t, ncx, ncy, reach, valid);
+        if (valid == 0.f) {  // clip(d)*0 + (1-0)*100 (zero-padded rows, nusc_api.py:615,639)
+          if (100.f < best) { best = 100.f; bg0 = bg1 = bg2 = 0.f; }
+          continue;
+        }
+        if (valid == 1.f && pstl_cull_neighbour(s.x - ncx, s.y - ncy, ego_half, reach, best)) {
+          if (20.f < best) { best = 20.f; bg0 = bg1 = bg2 = 0.f; }  // clipped at 20, zero gradient
+          continue;
+        }
+        PstlNei nb;
+        sc.nei(k, t, nb);
+        float g[3];
+        const float term = pstl_pair_clearance(e, cs, sn, nb, GRAD ? g : nullptr);
         if (term < best) {  // torch.min(dim=1): first minimal index
           best = term;
-          if (GRAD) { bg[0] = g[0]; bg[1] = g[1]; bg[2] = g[2]; }
+          if (GRAD) { bg0 = g[0]; bg1 = g[1]; bg2 = g[2]; }
         }
       }
       VT(P.base_off[PSTL_SIG_NEI] + t) = best;
-      if (GRAD) { PT(12, t) = bg[0]; PT(13, t) = bg[1]; PT(14, t) = bg[2]; }
+      if (GRAD) { PT(12, t) = bg0; PT(13, t) = bg1; PT(14, t) = bg2; }
     }
     if (!ego && t + 1 < need_pose) {
       float w, a;
@@ -131,14 +154,15 @@ PSTL_HD float pstl_eval_traj(const PstlProgView& P, const Scene& sc, const PstlE
     }
   }
   PstlLeafFused leaf{&P, vt, stride, stlp};
-  pstl_interp_fwd(P, vt, stride, c.tau, c.hard, leaf);
+  pstl_interp_fwd<FAST>(P, vt, stride, c.tau, c.hard, leaf);
   return VT(P.ops[P.n_ops - 1].out_off);
 #undef VT
 #undef PT
 }
 
-// Reverse: after pstl_eval_traj<.., true>.  gscore = d loss / d score.  Writes d loss / d controls
+// Reverse: after pstl_eval_traj<.., true, ..>.  gscore = d loss / d score.  Writes d loss / d controls
 // (pre-scale, T*2 floats, row stride 1) when gu != nullptr, d loss / d ego (T*4) when ge != nullptr.
+template <bool FAST>
 PSTL_HD void pstl_eval_traj_bwd(const PstlProgView& P, const PstlEvalCfg& c, const float* u, const float* stlp,
                                 float gscore, const float* vt, float* gt, const float* pt, int stride, float* gu,
                                 float* ge) {
@@ -147,12 +171,12 @@ PSTL_HD void pstl_eval_traj_bwd(const PstlProgView& P, const PstlEvalCfg& c, con
 #define PT(row, t) pt[(size_t)((row) * T + (t)) * stride]
   for (int i = 0; i < P.val_floats; ++i) GT(i) = 0.f;
   GT(P.ops[P.n_ops - 1].out_off) = gscore;
+  PstlLeafFused leaf{&P, vt, stride, stlp};
   PstlLeafFusedGrad lg{&P, gt, stride, stlp};
-  pstl_interp_bwd(P, vt, gt, stride, c.tau, c.hard, lg);
+  pstl_interp_bwd<FAST>(P, vt, gt, stride, c.tau, c.hard, leaf, lg);
   // adjoint of the pose at every step from the base-signal adjoints
   float ax = 0.f, ay = 0.f, ath = 0.f, av = 0.f;  // adjoint of s_{t+1} accumulated so far
-  int need_pose = 0;
-  for (int b = 0; b < PSTL_N_BASE_SIGNALS; ++b) need_pose = P.base_need[b] > need_pose ? P.base_need[b] : need_pose;
+  const int need_pose = pstl_need_pose(P);
   for (int t = need_pose; t < T; ++t) {  // poses the formula never reads
     if (ge) { ge[t * 4 + 0] = 0.f; ge[t * 4 + 1] = 0.f; ge[t * 4 + 2] = 0.f; ge[t * 4 + 3] = 0.f; }
     if (gu) { gu[2 * t] = 0.f; gu[2 * t + 1] = 0.f; }

@@ -45,20 +45,38 @@ struct PstlLse {
   PSTL_HD void init() { m = PSTL_NEG_INF; s = 0.f; }
 };
 
+// FAST selects the SFU intrinsics (ex2/lg2 based, ~2 ulp) inside the fused scoring kernels, where
+// arguments are tau-scaled and the result is divided by tau again; the node API keeps expf/logf.
+template <bool FAST>
+PSTL_HD float pstl_exp(float x) {
+#if defined(__CUDA_ARCH__)
+  if (FAST) return __expf(x);
+#endif
+  return expf(x);
+}
+template <bool FAST>
+PSTL_HD float pstl_log(float x) {
+#if defined(__CUDA_ARCH__)
+  if (FAST) return __logf(x);
+#endif
+  return logf(x);
+}
+
+template <bool FAST>
 PSTL_HD float pstl_lse_finish(float m, float s) {
   // torch: maxes_squeezed = where(|max|==inf, 0, max); log(sum(exp(x-maxes_squeezed))) + maxes_squeezed
-  return logf(s) + m;
+  return pstl_log<FAST>(s) + m;
 }
 
 // two-pass reduction over n values fetched by functor f(j) (already scaled by +-tau)
-template <class F>
+template <bool FAST, class F>
 PSTL_HD float pstl_lse_n(int n, F f) {
   float m = PSTL_NEG_INF;
   for (int j = 0; j < n; ++j) m = fmaxf(m, f(j));
   if (isinf(m)) m = 0.f;
   float s = 0.f;
-  for (int j = 0; j < n; ++j) s += expf(f(j) - m);
-  return pstl_lse_finish(m, s);
+  for (int j = 0; j < n; ++j) s += pstl_exp<FAST>(f(j) - m);
+  return pstl_lse_finish<FAST>(m, s);
 }
 
 PSTL_HD float pstl_logaddexp(float a, float b) {
@@ -73,10 +91,15 @@ PSTL_HD int pstl_clipi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? h
 // ----------------------------------------------------------------------------------------
 // forward.  Leaf must provide: float signal(int p, int t); float pred(int a0, int a1, int t).
 // ----------------------------------------------------------------------------------------
-template <class Leaf>
+template <bool FAST = false, class Leaf>
 PSTL_HD void pstl_interp_fwd(const PstlProgView& P, float* tape, int stride, float tau, int hard, Leaf& leaf) {
   const int T = P.T;
 #define TP(off) tape[(size_t)(off) * stride]
+  // typed predicate leaves are not materialised: consumers evaluate them from the base signals
+  auto IN = [&](int idx, int t) -> float {
+    const PstlROp& p = P.ops[idx];
+    return (p.op == PSTL_OP_PRED) ? leaf.pred(p.a0, p.a1, t) : TP(p.out_off + t);
+  };
   for (int i = 0; i < P.n_ops; ++i) {
     const PstlROp o = P.ops[i];
     const int oo = o.out_off;
@@ -85,18 +108,17 @@ PSTL_HD void pstl_interp_fwd(const PstlProgView& P, float* tape, int stride, flo
         for (int t = 0; t < o.n_out; ++t) TP(oo + t) = leaf.signal(o.a0, t);
         break;
       case PSTL_OP_PRED:
-        for (int t = 0; t < o.n_out; ++t) TP(oo + t) = leaf.pred(o.a0, o.a1, t);
+        if (oo >= 0)
+          for (int t = 0; t < o.n_out; ++t) TP(oo + t) = leaf.pred(o.a0, o.a1, t);
         break;
       case PSTL_OP_NEG: {  // stl_d_lib.py:130-131
-        const int io = P.ops[o.in0].out_off;
-        for (int t = 0; t < o.n_out; ++t) TP(oo + t) = -TP(io + t);
+        for (int t = 0; t < o.n_out; ++t) TP(oo + t) = -IN(o.in0, t);
       } break;
       case PSTL_OP_SMIN2:
       case PSTL_OP_SMAX2: {  // stl_d_lib.py:21-26 (stack dim=1, logsumexp)
-        const int ia = P.ops[o.in0].out_off, ib = P.ops[o.in1].out_off;
         const float sg = (o.op == PSTL_OP_SMIN2) ? -1.f : 1.f;
         for (int t = 0; t < o.n_out; ++t) {
-          const float a = sg * TP(ia + t), b = sg * TP(ib + t);
+          const float a = sg * IN(o.in0, t), b = sg * IN(o.in1, t);
           float r;
           if (hard) {
             r = fmaxf(a, b);
@@ -104,7 +126,7 @@ PSTL_HD void pstl_interp_fwd(const PstlProgView& P, float* tape, int stride, flo
             const float xa = a * tau, xb = b * tau;
             float m = fmaxf(xa, xb);
             if (isinf(m)) m = 0.f;
-            r = pstl_lse_finish(m, expf(xa - m) + expf(xb - m)) / tau;
+            r = pstl_lse_finish<FAST>(m, pstl_exp<FAST>(xa - m) + pstl_exp<FAST>(xb - m)) / tau;
           }
           TP(oo + t) = sg * r;
         }
@@ -115,16 +137,15 @@ PSTL_HD void pstl_interp_fwd(const PstlProgView& P, float* tape, int stride, flo
           float r;
           if (hard) {
             r = PSTL_NEG_INF;
-            for (int j = 0; j < k; ++j) r = fmaxf(r, -TP(P.ops[P.klist[kb + j]].out_off + t));
+            for (int j = 0; j < k; ++j) r = fmaxf(r, -IN(P.klist[kb + j], t));
           } else {
-            r = pstl_lse_n(k, [&](int j) { return -TP(P.ops[P.klist[kb + j]].out_off + t) * tau; }) / tau;
+            r = pstl_lse_n<FAST>(k, [&](int j) { return -IN(P.klist[kb + j], t) * tau; }) / tau;
           }
           TP(oo + t) = -r;
         }
       } break;
       case PSTL_OP_WIN_SMIN:
       case PSTL_OP_WIN_SMAX: {  // stl_d_lib.py:151,164 window [t+ts, t+te) clipped to [0,T); empty -> -inf (:7-8,:16-17)
-        const int io = P.ops[o.in0].out_off;
         const float sg = (o.op == PSTL_OP_WIN_SMIN) ? -1.f : 1.f;
         for (int t = 0; t < o.n_out; ++t) {
           const int lo = pstl_clipi(t + o.a0, 0, T), hi = pstl_clipi(t + o.a1, 0, T);
@@ -135,26 +156,24 @@ PSTL_HD void pstl_interp_fwd(const PstlProgView& P, float* tape, int stride, flo
           float r;
           if (hard) {
             r = PSTL_NEG_INF;
-            for (int j = lo; j < hi; ++j) r = fmaxf(r, sg * TP(io + j));
+            for (int j = lo; j < hi; ++j) r = fmaxf(r, sg * IN(o.in0, j));
           } else {
-            r = pstl_lse_n(hi - lo, [&](int j) { return sg * TP(io + lo + j) * tau; }) / tau;
+            r = pstl_lse_n<FAST>(hi - lo, [&](int j) { return sg * IN(o.in0, lo + j) * tau; }) / tau;
           }
           TP(oo + t) = sg * r;
         }
       } break;
       case PSTL_OP_PREFIX_SMIN: {  // stl_d_lib.py:189
-        const int io = P.ops[o.in0].out_off;
         float acc = PSTL_NEG_INF;
         for (int t = 0; t < o.n_out; ++t) {
-          acc = pstl_logaddexp(acc, -TP(io + t) * tau);
+          acc = pstl_logaddexp(acc, -IN(o.in0, t) * tau);
           TP(oo + t) = -acc / tau;
         }
       } break;
       case PSTL_OP_SUFFIX_SMAX: {  // stl_d_lib.py:191
-        const int io = P.ops[o.in0].out_off;
         float acc = PSTL_NEG_INF;
         for (int t = T - 1; t >= 0; --t) {
-          acc = pstl_logaddexp(acc, TP(io + t) * tau);
+          acc = pstl_logaddexp(acc, IN(o.in0, t) * tau);
           if (t < o.n_out) TP(oo + t) = acc / tau;
         }
       } break;
@@ -171,12 +190,21 @@ PSTL_HD void pstl_interp_fwd(const PstlProgView& P, float* tape, int stride, flo
 // void signal(int p,int t,float g); void pred(int a0,int a1,int t,float g).
 // Soft-max weights are recomputed exactly as torch's logsumexp backward: exp(x*tau - lse).
 // ----------------------------------------------------------------------------------------
-template <class LeafGrad>
+template <bool FAST = false, class Leaf, class LeafGrad>
 PSTL_HD void pstl_interp_bwd(const PstlProgView& P, const float* vt, float* gt, int stride, float tau, int hard,
-                             LeafGrad& lg) {
+                             Leaf& leaf, LeafGrad& lg) {
   const int T = P.T;
 #define VT(off) vt[(size_t)(off) * stride]
 #define GT(off) gt[(size_t)(off) * stride]
+  auto IN = [&](int idx, int t) -> float {
+    const PstlROp& p = P.ops[idx];
+    return (p.op == PSTL_OP_PRED) ? leaf.pred(p.a0, p.a1, t) : VT(p.out_off + t);
+  };
+  auto ADDG = [&](int idx, int t, float g) {
+    const PstlROp& p = P.ops[idx];
+    if (p.op == PSTL_OP_PRED) lg.pred(p.a0, p.a1, t, g);
+    else GT(p.out_off + t) += g;
+  };
   for (int i = P.n_ops - 1; i >= 0; --i) {
     const PstlROp o = P.ops[i];
     const int oo = o.out_off;
@@ -185,30 +213,29 @@ PSTL_HD void pstl_interp_bwd(const PstlProgView& P, const float* vt, float* gt, 
         for (int t = 0; t < o.n_out; ++t) lg.signal(o.a0, t, GT(oo + t));
         break;
       case PSTL_OP_PRED:
-        for (int t = 0; t < o.n_out; ++t) lg.pred(o.a0, o.a1, t, GT(oo + t));
+        if (oo >= 0)
+          for (int t = 0; t < o.n_out; ++t) lg.pred(o.a0, o.a1, t, GT(oo + t));
         break;
       case PSTL_OP_NEG: {
-        const int io = P.ops[o.in0].out_off;
-        for (int t = 0; t < o.n_out; ++t) GT(io + t) -= GT(oo + t);
+        for (int t = 0; t < o.n_out; ++t) ADDG(o.in0, t, -GT(oo + t));
       } break;
       case PSTL_OP_SMIN2:
       case PSTL_OP_SMAX2: {
-        const int ia = P.ops[o.in0].out_off, ib = P.ops[o.in1].out_off;
         const float sg = (o.op == PSTL_OP_SMIN2) ? -1.f : 1.f;
         for (int t = 0; t < o.n_out; ++t) {
           const float g = GT(oo + t);
           if (g == 0.f) continue;
-          const float a = sg * VT(ia + t), b = sg * VT(ib + t);
+          const float a = sg * IN(o.in0, t), b = sg * IN(o.in1, t);
           if (hard) {  // torch.max(dim) routes to the first maximal index
-            if (a >= b) GT(ia + t) += g; else GT(ib + t) += g;
+            if (a >= b) ADDG(o.in0, t, g); else ADDG(o.in1, t, g);
           } else {
             const float xa = a * tau, xb = b * tau;
             float m = fmaxf(xa, xb);
             if (isinf(m)) m = 0.f;
-            const float lse = pstl_lse_finish(m, expf(xa - m) + expf(xb - m));
+            const float lse = pstl_lse_finish<FAST>(m, pstl_exp<FAST>(xa - m) + pstl_exp<FAST>(xb - m));
             // d out/d in = sg * (1/tau) * softmax * tau * sg = softmax weight
-            GT(ia + t) += g * expf(xa - lse);
-            GT(ib + t) += g * expf(xb - lse);
+            ADDG(o.in0, t, g * pstl_exp<FAST>(xa - lse));
+            ADDG(o.in1, t, g * pstl_exp<FAST>(xb - lse));
           }
         }
       } break;
@@ -219,24 +246,20 @@ PSTL_HD void pstl_interp_bwd(const PstlProgView& P, const float* vt, float* gt, 
           if (g == 0.f) continue;
           if (hard) {
             int bj = 0;
-            float bv = -VT(P.ops[P.klist[kb]].out_off + t);
+            float bv = -IN(P.klist[kb], t);
             for (int j = 1; j < k; ++j) {
-              const float v = -VT(P.ops[P.klist[kb + j]].out_off + t);
+              const float v = -IN(P.klist[kb + j], t);
               if (v > bv) { bv = v; bj = j; }
             }
-            GT(P.ops[P.klist[kb + bj]].out_off + t) += g;
+            ADDG(P.klist[kb + bj], t, g);
           } else {
-            const float lse = pstl_lse_n(k, [&](int j) { return -VT(P.ops[P.klist[kb + j]].out_off + t) * tau; });
-            for (int j = 0; j < k; ++j) {
-              const int io = P.ops[P.klist[kb + j]].out_off;
-              GT(io + t) += g * expf(-VT(io + t) * tau - lse);
-            }
+            const float lse = pstl_lse_n<FAST>(k, [&](int j) { return -IN(P.klist[kb + j], t) * tau; });
+            for (int j = 0; j < k; ++j) ADDG(P.klist[kb + j], t, g * pstl_exp<FAST>(-IN(P.klist[kb + j], t) * tau - lse));
           }
         }
       } break;
       case PSTL_OP_WIN_SMIN:
       case PSTL_OP_WIN_SMAX: {
-        const int io = P.ops[o.in0].out_off;
         const float sg = (o.op == PSTL_OP_WIN_SMIN) ? -1.f : 1.f;
         for (int t = 0; t < o.n_out; ++t) {
           const float g = GT(oo + t);
@@ -245,35 +268,33 @@ PSTL_HD void pstl_interp_bwd(const PstlProgView& P, const float* vt, float* gt, 
           if (hi <= lo) continue;
           if (hard) {
             int bj = lo;
-            float bv = sg * VT(io + lo);
+            float bv = sg * IN(o.in0, lo);
             for (int j = lo + 1; j < hi; ++j) {
-              const float v = sg * VT(io + j);
+              const float v = sg * IN(o.in0, j);
               if (v > bv) { bv = v; bj = j; }
             }
-            GT(io + bj) += g;
+            ADDG(o.in0, bj, g);
           } else {
-            const float lse = pstl_lse_n(hi - lo, [&](int j) { return sg * VT(io + lo + j) * tau; });
-            for (int j = lo; j < hi; ++j) GT(io + j) += g * expf(sg * VT(io + j) * tau - lse);
+            const float lse = pstl_lse_n<FAST>(hi - lo, [&](int j) { return sg * IN(o.in0, lo + j) * tau; });
+            for (int j = lo; j < hi; ++j) ADDG(o.in0, j, g * pstl_exp<FAST>(sg * IN(o.in0, j) * tau - lse));
           }
         }
       } break;
       case PSTL_OP_PREFIX_SMIN: {
         // out[t] = -LSE_{j<=t}(-x_j tau)/tau  ->  d out[t]/d x_j = exp(-x_j tau - lse_t)
-        const int io = P.ops[o.in0].out_off;
         for (int t = 0; t < o.n_out; ++t) {
           const float g = GT(oo + t);
           if (g == 0.f) continue;
           const float lse = -VT(oo + t) * tau;
-          for (int j = 0; j <= t; ++j) GT(io + j) += g * expf(-VT(io + j) * tau - lse);
+          for (int j = 0; j <= t; ++j) ADDG(o.in0, j, g * expf(-IN(o.in0, j) * tau - lse));
         }
       } break;
       case PSTL_OP_SUFFIX_SMAX: {
-        const int io = P.ops[o.in0].out_off;
         for (int t = 0; t < o.n_out; ++t) {
           const float g = GT(oo + t);
           if (g == 0.f) continue;
           const float lse = VT(oo + t) * tau;
-          for (int j = t; j < T; ++j) GT(io + j) += g * expf(VT(io + j) * tau - lse);
+          for (int j = t; j < T; ++j) ADDG(o.in0, j, g * expf(IN(o.in0, j) * tau - lse));
         }
       } break;
       default:

@@ -140,7 +140,7 @@ __global__ void k_stl_signals(const PstlProgView* __restrict__ dprog, const floa
     } else {
       for (int i = 0; i < F; ++i) gt[(size_t)i * stride] = 0.f;
       for (int t = 0; t < prog.need_t; ++t) gt[(size_t)(top.out_off + t) * stride] += grad_trace[(size_t)n * prog.need_t + t];
-      pstl_interp_bwd(prog, vt, gt, stride, tau, hard, leaf);
+      pstl_interp_bwd(prog, vt, gt, stride, tau, hard, leaf, leaf);
     }
   }
   if (BWD) {
@@ -199,16 +199,24 @@ extern "C" int pstl_stl_eval_signals_bwd(pstl_program_t prog, const float* sig, 
 // --------------------------------------------------------------------------------------
 // fused scoring
 // --------------------------------------------------------------------------------------
+#define PSTL_NEI_W 16  // floats per staged (neighbour, step): cx[4], cy[4], r, valid, centre x, y, L/2, pad
 struct SceneSmem {
-  const float* circ;  // (K,T,2nL+2): cx[nL], cy[nL], r, valid
+  const float* circ;  // (K,T,PSTL_NEI_W)
   const float* ln;    // (3,nseg,3)
-  int K, T, nL, nseg;
+  int K, T, nseg;
   __device__ float lane(int l, int j, int f) const { return ln[(l * nseg + j) * 3 + f]; }
-  __device__ void nei_circles(int k, int t, float* cx, float* cy, float& r, float& valid) const {
-    const float* p = circ + ((size_t)k * T + t) * (2 * nL + 2);
-    for (int i = 0; i < nL; ++i) { cx[i] = p[i]; cy[i] = p[nL + i]; }
-    r = p[2 * nL];
-    valid = p[2 * nL + 1];
+  __device__ void nei_meta(int k, int t, float& cx, float& cy, float& reach, float& valid) const {
+    const float4 m = *reinterpret_cast<const float4*>(circ + (k * T + t) * PSTL_NEI_W + 8);
+    const float4 m2 = *reinterpret_cast<const float4*>(circ + (k * T + t) * PSTL_NEI_W + 12);
+    valid = m.y; cx = m.z; cy = m.w; reach = m2.x;
+  }
+  __device__ void nei(int k, int t, PstlNei& out) const {
+    const float* p = circ + (k * T + t) * PSTL_NEI_W;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    out.cx[0] = a.x; out.cx[1] = a.y; out.cx[2] = a.z; out.cx[3] = a.w;
+    out.cy[0] = b.x; out.cy[1] = b.y; out.cy[2] = b.z; out.cy[3] = b.w;
+    out.r = p[8];
+    out.valid = p[9];
   }
 };
 
@@ -231,24 +239,24 @@ struct ScoreArgs {
 };
 
 __device__ __forceinline__ size_t scene_tile_floats(const PstlEvalCfg& c) {
-  return (size_t)c.K * c.T * (2 * c.nL + 2) + (size_t)3 * c.nseg * 3;
+  return (size_t)c.K * c.T * PSTL_NEI_W + (size_t)3 * c.nseg * 3;
 }
 
 // block-cooperative staging of one scene into shared memory
 __device__ void stage_scene(const ScoreArgs& a, int scene, float* tile) {
   const PstlEvalCfg& c = a.cfg;
-  const int W = 2 * c.nL + 2;
+  const int W = PSTL_NEI_W;
   float* circ = tile;
   float* ln = tile + (size_t)c.K * c.T * W;
   const float* nb = a.neighbors + (size_t)scene * c.K * c.T * 7;
   for (int e = threadIdx.x; e < c.K * c.T; e += blockDim.x) {
     const float* p = nb + (size_t)e * 7;
     PstlCircles cc;
-    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], c.nL, cc);
+    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], cc);
     float* o = circ + (size_t)e * W;
-    for (int i = 0; i < c.nL; ++i) { o[i] = cc.cx[i]; o[c.nL + i] = cc.cy[i]; }
-    o[2 * c.nL] = cc.r;
-    o[2 * c.nL + 1] = p[0];
+    for (int i = 0; i < PSTL_NL; ++i) { o[i] = cc.cx[i]; o[PSTL_NL + i] = cc.cy[i]; }
+    o[8] = cc.r; o[9] = p[0]; o[10] = p[1]; o[11] = p[2]; o[12] = p[5] / 2.f;
+    o[13] = o[14] = o[15] = 0.f;
   }
   for (int l = 0; l < 3; ++l) {
     const float* src = a.lanes[l] + (size_t)scene * c.nseg * 3;
@@ -268,7 +276,14 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
   const PstlEvalCfg c = a.cfg;
   const int B = blockDim.x;
   const int n0 = blockIdx.x * B;
-  const int n = n0 + threadIdx.x;
+  // rows of the pipeline cycle through the three formulas (n % 3): deal them to warps so that a warp
+  // interprets ONE program (purely a divergence optimisation; every thread still reads its own mode)
+  int li = threadIdx.x;
+  if (B % 96 == 0) {
+    const int g = li / 96, w = li - g * 96;
+    li = g * 96 + (w & 31) * 3 + (w >> 5);
+  }
+  const int n = n0 + li;
   float* tile = sm;
   float* tape0 = sm;
   if (SMEM_SCENE) {
@@ -300,11 +315,11 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
   const float* ego = a.ego ? a.ego + (size_t)n * T * a.ego_stride : nullptr;
   const int scene = n / a.rows_per_scene;
 
-  SceneSmem ss{tile, tile + (size_t)c.K * c.T * (2 * c.nL + 2), c.K, c.T, c.nL, c.nseg};
+  SceneSmem ss{tile, tile + (size_t)c.K * c.T * PSTL_NEI_W, c.K, c.T, c.nseg};
   PstlSceneGlobal sg;
-  sg.nei = a.neighbors + (size_t)scene * c.K * c.T * 7;
+  sg.neib = a.neighbors + (size_t)scene * c.K * c.T * 7;
   for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
-  sg.K = c.K; sg.T = c.T; sg.nL = c.nL;
+  sg.K = c.K; sg.T = c.T;
 
   if (!BWD) {
     float best = -INFINITY;
@@ -313,8 +328,8 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
       const float* u = a.controls ? a.controls + ((size_t)cand * a.N + n) * T * 2 : nullptr;
       float sc;
       if (m < 3) {
-        sc = SMEM_SCENE ? pstl_eval_traj<SceneSmem, false>(P, ss, c, s0, u, ego, a.ego_stride, stlp, vt, nullptr, stride)
-                        : pstl_eval_traj<PstlSceneGlobal, false>(P, sg, c, s0, u, ego, a.ego_stride, stlp, vt, nullptr, stride);
+        sc = SMEM_SCENE ? pstl_eval_traj<SceneSmem, false, true>(P, ss, c, s0, u, ego, a.ego_stride, stlp, vt, nullptr, stride)
+                        : pstl_eval_traj<PstlSceneGlobal, false, true>(P, sg, c, s0, u, ego, a.ego_stride, stlp, vt, nullptr, stride);
       } else {
         sc = (m == 3) ? 1.0f : 0.0f;  // nusc_train.py:322 outlier score; unknown mode selects nothing (:150-151)
       }
@@ -351,8 +366,8 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
       if (ge) for (int i = 0; i < T * 4; ++i) ge[i] = 0.f;
       return;
     }
-    const float sc = SMEM_SCENE ? pstl_eval_traj<SceneSmem, true>(P, ss, c, s0, u, ego, a.ego_stride, stlp, vt, pt, stride)
-                                : pstl_eval_traj<PstlSceneGlobal, true>(P, sg, c, s0, u, ego, a.ego_stride, stlp, vt, pt, stride);
+    const float sc = SMEM_SCENE ? pstl_eval_traj<SceneSmem, true, true>(P, ss, c, s0, u, ego, a.ego_stride, stlp, vt, pt, stride)
+                                : pstl_eval_traj<PstlSceneGlobal, true, true>(P, sg, c, s0, u, ego, a.ego_stride, stlp, vt, pt, stride);
     if (a.scores) a.scores[n] = sc;
     float g;
     if (a.grad_score) {
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
     } else {  // guidance loss (nusc_train.py:616-619): mean(relu(thres-score)*valid)/clip(mean(valid),1e-2)
       g = (a.thres - sc > 0.f) ? -a.valid[n] * a.inv_norm : 0.f;
     }
-    pstl_eval_traj_bwd(P, c, u, stlp, g, vt, gt, pt, stride, gu, ge);
+    pstl_eval_traj_bwd<true>(P, c, u, stlp, g, vt, gt, pt, stride, gu, ge);
   }
 }
 
@@ -370,7 +385,7 @@ static int fill_cfg(const pstl_scene_view* sv, const pstl_spec_params* sp, PstlE
   c->dt = sp->dt; c->tau = sp->tau; c->ego_L = sp->ego_L; c->ego_W = sp->ego_W;
   c->w_scale = sp->w_scale; c->a_scale = sp->a_scale;
   c->clip_controls = sp->clip_controls; c->clip_dist = sp->clip_dist; c->hard = sp->hard;
-  c->nL = 4; c->nseg = sv->nseg; c->K = sv->Knei; c->T = sv->T;
+  c->nseg = sv->nseg; c->K = sv->Knei; c->T = sv->T;
   return 0;
 }
 
@@ -384,14 +399,24 @@ static ScorePlan plan_score(pstl_program_t const* progs, const pstl_scene_view* 
   ScorePlan sp;
   sp.F = with_grad ? max3(progs[0]->h.grad_floats, progs[1]->h.grad_floats, progs[2]->h.grad_floats)
                    : max3(progs[0]->h.val_floats, progs[1]->h.val_floats, progs[2]->h.val_floats);
-  const size_t tile = (((size_t)sv->Knei * sv->T * 10 + (size_t)9 * sv->nseg + 3) & ~(size_t)3) * sizeof(float);
-  // one scene per block needs rows_per_scene to be a multiple of the block size
+  const size_t tile = (((size_t)sv->Knei * sv->T * PSTL_NEI_W + (size_t)9 * sv->nseg + 3) & ~(size_t)3) * sizeof(float);
+  // one scene per block: the block size must divide rows_per_scene
   sp.smem_scene = 0;
   const int prefer = with_grad ? 64 : 128;
   if (sv->rows_per_scene >= 32 && tile <= 96 * 1024) {
-    for (int b = prefer; b >= 32; b >>= 1)
-      if (sv->rows_per_scene % b == 0) {
-        sp.tp = plan_tape(sp.F, tile, b);  // a smaller power-of-two block still divides rows_per_scene
+    static const int cands[] = {192, 96, 128, 64, 32};
+    for (int b : cands) {
+      if (sv->rows_per_scene % b != 0) continue;
+      const size_t bytes = tile + (size_t)sp.F * (b + 1) * sizeof(float);
+      if (bytes > (size_t)kSmemBudget / 2 && b > 32) continue;  // keep at least two blocks per SM
+      if (bytes > (size_t)kSmemBudget) continue;
+      sp.tp.block = b; sp.tp.smem_tape = 1; sp.tp.smem_bytes = bytes;
+      sp.smem_scene = 1;
+      return sp;
+    }
+    for (int b : cands)
+      if (sv->rows_per_scene % b == 0) {  // tape too large for shared memory: workspace tape, scene tile stays
+        sp.tp.block = b; sp.tp.smem_tape = 0; sp.tp.smem_bytes = tile;
         sp.smem_scene = 1;
         return sp;
       }

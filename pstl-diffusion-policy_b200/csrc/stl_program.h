@@ -122,6 +122,8 @@ static inline int pstl_resolve_program(const pstl_op* ops, int n_ops, int n_sign
     if (o.op == PSTL_OP_SIGNAL) {  // staged signals are read in place
       o.out_off = o.a0 * T;
       o.n_out = 0;
+    } else if (o.op == PSTL_OP_PRED && i != n_ops - 1) {  // evaluated on the fly by the consumer
+      o.out_off = -1;
     } else {
       o.out_off = cur;
       cur += o.n_out;

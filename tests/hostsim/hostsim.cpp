@@ -27,7 +27,7 @@ extern "C" int hs_stl_signals(const pstl_op* ops, int n_ops, int P, int T, int n
     if (grad_trace && grad_sig) {
       std::fill(gt.begin(), gt.end(), 0.f);
       for (int t = 0; t < need_t; ++t) gt[top + t] += grad_trace[(size_t)n * need_t + t];
-      pstl_interp_bwd(pv, vt.data(), gt.data(), 1, tau, hard, leaf);
+      pstl_interp_bwd(pv, vt.data(), gt.data(), 1, tau, hard, leaf, leaf);
       for (int q = 0; q < P * T; ++q) grad_sig[(size_t)n * P * T + q] = gt[q];
     }
   }
@@ -44,7 +44,7 @@ extern "C" int hs_score(const pstl_op* const* ops3, const int* n_ops3, int T, in
   char err[256];
   for (int k = 0; k < 3; ++k)
     if (pstl_resolve_program(ops3[k], n_ops3[k], 0, T, 1, &pv[k], err, sizeof(err))) { fprintf(stderr, "%s\n", err); return -1; }
-  PstlEvalCfg c{dt, tau, 4.084f, 1.730f, w_scale, a_scale, clip_controls, 0, hard, 4, nseg, K, T};
+  PstlEvalCfg c{dt, tau, 4.084f, 1.730f, w_scale, a_scale, clip_controls, 0, hard, nseg, K, T};
   const float* ln[3] = {l0, l1, l2};
   for (int n = 0; n < N; ++n) {
     const int m = (int)mode[n];
@@ -53,9 +53,9 @@ extern "C" int hs_score(const pstl_op* const* ops3, const int* n_ops3, int T, in
     std::vector<float> tape(P.grad_floats);
     PstlSceneGlobal sg;
     const int scene = n / rows_per_scene;
-    sg.nei = neighbors + (size_t)scene * K * T * 7;
+    sg.neib = neighbors + (size_t)scene * K * T * 7;
     for (int l = 0; l < 3; ++l) sg.ln[l] = ln[l] + (size_t)scene * nseg * 3;
-    sg.K = K; sg.T = T; sg.nL = 4;
+    sg.K = K; sg.T = T;
     PstlPose s0{0, 0, 0, 0};
     if (state0) s0 = PstlPose{state0[n * 4], state0[n * 4 + 1], state0[n * 4 + 2], state0[n * 4 + 3]};
     const float* u = controls ? controls + (size_t)n * T * 2 : nullptr;
@@ -63,9 +63,9 @@ extern "C" int hs_score(const pstl_op* const* ops3, const int* n_ops3, int T, in
     float* vt = tape.data();
     float* gt = vt + P.val_floats;
     float* pt = vt + P.part_off;
-    scores[n] = pstl_eval_traj<PstlSceneGlobal, true>(P, sg, c, s0, u, e, es, stlp + (size_t)n * 6, vt, pt, 1);
+    scores[n] = pstl_eval_traj<PstlSceneGlobal, true, false>(P, sg, c, s0, u, e, es, stlp + (size_t)n * 6, vt, pt, 1);
     if (grad_score)
-      pstl_eval_traj_bwd(P, c, u, stlp + (size_t)n * 6, grad_score[n], vt, gt, pt, 1,
+      pstl_eval_traj_bwd<false>(P, c, u, stlp + (size_t)n * 6, grad_score[n], vt, gt, pt, 1,
                          grad_controls ? grad_controls + (size_t)n * T * 2 : nullptr,
                          grad_ego ? grad_ego + (size_t)n * T * 4 : nullptr);
   }
