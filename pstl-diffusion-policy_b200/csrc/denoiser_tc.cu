@@ -47,7 +47,9 @@ static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kColD = 0, kColH = 256, kColD3 = 384;
 
 struct TcState {
-  uint8_t* image;  // device: swizzled bf16 weight image (kWeightBytes)
+  uint8_t* image;    // device: swizzled bf16 weight image of policy_net (kWeightBytes)
+  uint8_t* image_r;  // same for rect_net (RefineNet head), or null
+  float* zeros;      // 256 zeros: the "time" bias row of the RefineNet pass
   int sm_count;
 };
 
@@ -194,6 +196,11 @@ struct TcArgs {
   int N, rows_per_scene, steps, first_step, last_step, keep, clip;
   float w_max, a_max;
   unsigned long long seed, offset;
+  // RefineNet pass (Net.rect_forward, reference nusc_model.py:209-233): one "step", no x update
+  int refine;
+  const float* u0;      // (N, 40) controls being refined
+  const float* scores;  // (N)
+  float* out;           // (N, 40)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_constant__ TcArgs a) {
@@ -391,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 20; j += 4) {
               zn[j] = zn[j + 1] = zn[j + 2] = zn[j + 3] = 0.f;
-              if (i > 1) {
+              if (i > 1 && !a.refine) {
                 if (zr) {
                   const float4 zz = *reinterpret_cast<const float4*>(zr + j);
                   zn[j] = zz.x; zn[j + 1] = zz.y; zn[j + 2] = zz.z; zn[j + 3] = zz.w;
@@ -413,6 +420,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         TMEM_LD_X16(tmem + lane_addr + kColD3 + c0, r);
         TMEM_LD_X4(tmem + lane_addr + kColD3 + c0 + 16, (r + 16));
         tmem_wait_ld();
+        if (a.refine) {
+          // tanh-interval rescale towards the remaining headroom, only for violating rows
+          const float viol = (a.scores[rrow] < 0.f) ? 1.f : 0.f;
+          const float* u0r = a.u0 + rrow * 40 + c0;
+          float* orow = a.out + rrow * 40 + c0;
+#pragma unroll
+          for (int j = 0; j < 20; ++j) {
+            const float rr = tanhf(__uint_as_float(r[j]) + b3s[c0 + j]);
+            const float init = u0r[j];
+            const float lim = (j & 1) ? a.a_max : a.w_max;  // c0 is even: parity of j is parity of the column
+            const float mk = (rr >= 0.f) ? 1.f : 0.f;
+            const float merged = (rr * (init - (-lim))) * (1.f - mk) + (rr * (lim - init)) * mk;
+            float o = init + merged * viol;
+            if (a.clip) o = fminf(fmaxf(o, -lim), lim);
+            if (live) orow[j] = o;
+          }
+          continue;
+        }
         const float c1 = a.c1[i], c2 = a.c2[i], sb = a.sb[i];
 #pragma unroll
         for (int j = 0; j < 20; ++j) {
@@ -441,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           if (lane == 0) mbar_arrive(bar_x);
         }
       }
-      if (live) {
+      if (live && !a.refine) {
         float* xw = a.xin + row * PSTL_XIN_LD;
 #pragma unroll
         for (int j = 0; j < 20; ++j) xw[c0 + j] = x[j];
@@ -472,11 +497,20 @@ int pstl_tc_create(pstl_denoiser* d) {
   }
   TcState* s = new TcState();
   s->sm_count = sms;
-  s->image = nullptr;
+  s->image = s->image_r = nullptr;
+  s->zeros = nullptr;
   PSTL_CUDA(cudaMalloc(&s->image, kWeightBytes));
   PSTL_CUDA(cudaMemset(s->image, 0, kWeightBytes));
+  PSTL_CUDA(cudaMalloc(&s->zeros, kH * sizeof(float)));
+  PSTL_CUDA(cudaMemset(s->zeros, 0, kH * sizeof(float)));
   k_build_image<<<(256 * 256 + 255) / 256, 256>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image);
   PSTL_LAUNCH_CHECK();
+  if (d->r1p && d->w.rect_hidden == kH) {
+    PSTL_CUDA(cudaMalloc(&s->image_r, kWeightBytes));
+    PSTL_CUDA(cudaMemset(s->image_r, 0, kWeightBytes));
+    k_build_image<<<(256 * 256 + 255) / 256, 256>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_r);
+    PSTL_LAUNCH_CHECK();
+  }
   PSTL_CUDA(cudaDeviceSynchronize());
   PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
   d->tc = s;
@@ -487,6 +521,8 @@ void pstl_tc_destroy(pstl_denoiser* d) {
   TcState* s = (TcState*)d->tc;
   if (!s) return;
   cudaFree(s->image);
+  cudaFree(s->image_r);
+  cudaFree(s->zeros);
   delete s;
   d->tc = nullptr;
 }
@@ -518,3 +554,25 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
 }
+
+// RefineNet head on the same engine: xin rows = [fused(40) | hl | stlp], one pass, tanh-interval epilogue
+int pstl_tc_refine(pstl_denoiser* d, const float* cscene, int rows_per_scene, const float* xin, int N, const float* u0,
+                   const float* scores, float w_max, float a_max, int clip_rect, float* out, cudaStream_t st) {
+  TcState* s = (TcState*)d->tc;
+  PSTL_CHECK_ARG(s && s->image_r, "RefineNet image not built");
+  PSTL_CHECK_ARG((kTileM + rows_per_scene - 1) / rows_per_scene + 1 <= kMaxClasses, "rows_per_scene too small for the tcgen05 tile");
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.image = s->image_r; a.cscene = cscene; a.ct = s->zeros; a.b2 = d->w.r2_b; a.b3 = d->w.r4_b;
+  a.xin = const_cast<float*>(xin);
+  a.N = N; a.rows_per_scene = rows_per_scene; a.steps = 2; a.first_step = 0; a.last_step = 0;  // one pass, ct row 0
+  a.clip = clip_rect; a.w_max = w_max; a.a_max = a_max;
+  a.refine = 1; a.u0 = u0; a.scores = scores; a.out = out;
+  const int n_tiles = (N + kTileM - 1) / kTileM;
+  const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
+  k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
+bool pstl_tc_has_refine(pstl_denoiser* d) { return d->tc && ((TcState*)d->tc)->image_r; }

@@ -43,17 +43,22 @@ struct PstlLeafFused {
   const PstlProgView* P;
   const float* vt;
   int stride;
-  const float* stlp;
+  float p[6];  // this row's pSTL parameters, read once
+  PSTL_HD PstlLeafFused(const PstlProgView* P_, const float* vt_, int stride_, const float* stlp)
+      : P(P_), vt(vt_), stride(stride_) {
+    for (int i = 0; i < 6; ++i) p[i] = stlp[i];
+  }
   PSTL_HD float signal(int, int) const { return 0.f; }
-  PSTL_HD float pred(int a0, int a1, int t) const {
+  // value[t] = (+-base[sid][t] +- stlp[pid]) / den   (include/pstl.h, PSTL_OP_PRED)
+  PSTL_HD PstlIn pred_in(int a0, int a1) const {
     const int sid = a0 & 0xff, pid = a1 & 0xff, den = (a1 >> 16) & 0xff;
-    float b = vt[(size_t)(P->base_off[sid] + t) * stride];
-    float p = stlp[pid];
-    if ((a0 >> 8) & 1) b = -b;
-    if ((a1 >> 8) & 1) p = -p;
-    float v = b + p;
-    if (den != PSTL_DEN_ONE) v = v / pstl_pred_den(den, stlp);
-    return v;
+    PstlIn r;
+    r.p = vt + (size_t)P->base_off[sid] * stride;
+    r.sb = ((a0 >> 8) & 1) ? -1.f : 1.f;
+    r.pp = ((a1 >> 8) & 1) ? -p[pid] : p[pid];
+    r.den = (den == PSTL_DEN_ONE) ? 1.f : pstl_pred_den(den, p);
+    r.pred = 1;
+    return r;
   }
 };
 
@@ -61,14 +66,15 @@ struct PstlLeafFusedGrad {
   const PstlProgView* P;
   float* gt;
   int stride;
-  const float* stlp;
+  const float* p;
   PSTL_HD void signal(int, int, float) const {}
-  PSTL_HD void pred(int a0, int a1, int t, float g) const {
-    if (g == 0.f) return;
+  PSTL_HD PstlOut pred_out(int a0, int a1) const {
     const int sid = a0 & 0xff, den = (a1 >> 16) & 0xff;
-    float w = ((a0 >> 8) & 1) ? -1.f : 1.f;
-    if (den != PSTL_DEN_ONE) w = w / pstl_pred_den(den, stlp);
-    gt[(size_t)(P->base_off[sid] + t) * stride] += g * w;
+    PstlOut r;
+    r.g = gt + (size_t)P->base_off[sid] * stride;
+    r.w = ((a0 >> 8) & 1) ? -1.f : 1.f;
+    if (den != PSTL_DEN_ONE) r.w = r.w / pstl_pred_den(den, p);
+    return r;
   }
 };
 
@@ -153,7 +159,7 @@ PSTL_HD float pstl_eval_traj(const PstlProgView& P, const Scene& sc, const PstlE
       s = pstl_unicycle_step(s, w, a, c.dt, cs, sn);
     }
   }
-  PstlLeafFused leaf{&P, vt, stride, stlp};
+  PstlLeafFused leaf(&P, vt, stride, stlp);
   pstl_interp_fwd<FAST>(P, vt, stride, c.tau, c.hard, leaf);
   return VT(P.ops[P.n_ops - 1].out_off);
 #undef VT
@@ -171,8 +177,8 @@ PSTL_HD void pstl_eval_traj_bwd(const PstlProgView& P, const PstlEvalCfg& c, con
 #define PT(row, t) pt[(size_t)((row) * T + (t)) * stride]
   for (int i = 0; i < P.val_floats; ++i) GT(i) = 0.f;
   GT(P.ops[P.n_ops - 1].out_off) = gscore;
-  PstlLeafFused leaf{&P, vt, stride, stlp};
-  PstlLeafFusedGrad lg{&P, gt, stride, stlp};
+  PstlLeafFused leaf(&P, vt, stride, stlp);
+  PstlLeafFusedGrad lg{&P, gt, stride, leaf.p};
   pstl_interp_bwd<FAST>(P, vt, gt, stride, c.tau, c.hard, leaf, lg);
   // adjoint of the pose at every step from the base-signal adjoints
   float ax = 0.f, ay = 0.f, ath = 0.f, av = 0.f;  // adjoint of s_{t+1} accumulated so far

@@ -235,6 +235,9 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
                    const float* sched, int steps, const float* noise, unsigned long long seed,
                    unsigned long long offset, float w_max, float a_max, int clip, int keep_last_k, float* iterates_out,
                    int first_step, int last_step, cudaStream_t st);
+int pstl_tc_refine(pstl_denoiser* d, const float* cscene, int rows_per_scene, const float* xin, int N, const float* u0,
+                   const float* scores, float w_max, float a_max, int clip_rect, float* out, cudaStream_t st);
+bool pstl_tc_has_refine(pstl_denoiser* d);
 
 extern "C" int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_denoiser_t* out) {
   PSTL_CHECK_ARG(w && out, "null argument");
@@ -497,6 +500,8 @@ extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_sce
   const long long gtot = (long long)(N / per) * T2;
   k_group_fuse<<<pstl_ceil_div(gtot, 256), 256, 0, st>>>(w.g, u0, w.xin, N, T2, n_randoms, per);
   PSTL_LAUNCH_CHECK();
+  if (d->precision == PSTL_PRECISION_BF16 && pstl_tc_has_refine(d) && (128 + rows_per_scene - 1) / rows_per_scene + 1 <= 8)
+    return pstl_tc_refine(d, w.cscene, rows_per_scene, w.xin, N, u0, scores, w_max, a_max, clip_rect, out, st);
   rc = mlp_hidden(d, w, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st);
   if (rc) return rc;
   lin_defaults(a);

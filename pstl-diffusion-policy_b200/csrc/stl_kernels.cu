@@ -86,9 +86,9 @@ static TapePlan plan_tape(int F, size_t extra, int prefer_block) {
 // --------------------------------------------------------------------------------------
 struct LeafNone {
   __device__ float signal(int, int) const { return 0.f; }
-  __device__ float pred(int, int, int) const { return 0.f; }
   __device__ void signal(int, int, float) const {}
-  __device__ void pred(int, int, int, float) const {}
+  __device__ PstlIn pred_in(int, int) const { return PstlIn{nullptr, 1.f, 0.f, 1.f, 0}; }
+  __device__ PstlOut pred_out(int, int) const { return PstlOut{nullptr, 0.f}; }
 };
 
 template <bool BWD>

@@ -121,8 +121,12 @@ class Net(nn.Module):
     def time_table(self, steps, device):
         """(steps, time_dim) table of pos_encoding(t), t = 0..steps-1, built on the host exactly as the
         reference builds each row, then uploaded once."""
-        t = torch.arange(steps, dtype=torch.long).reshape(steps, 1)
-        return self.pos_encoding(t, self.time_dim).to(device=device, dtype=torch.float32).contiguous()
+        key = (steps, str(device))
+        cache = self.__dict__.setdefault("_temb_cache", {})
+        if key not in cache:
+            t = torch.arange(steps, dtype=torch.long).reshape(steps, 1)
+            cache[key] = self.pos_encoding(t, self.time_dim).to(device=device, dtype=torch.float32).contiguous()
+        return cache[key]
 
     # --- encoders (reference nusc_model.py:55-95) ----------------------------------------
     def encode_feat(self, nn_input, ext=None):
@@ -213,7 +217,7 @@ class Net(nn.Module):
         u0 = _nv.f32(init_controls.reshape(n, a.nt * 2))
         _nv.require_cuda(u0, "init_controls")
         out = torch.empty((n, a.nt, 2), dtype=torch.float32, device=u0.device)
-        handle = self.native_handle("fp32")
+        handle = self.native_handle(getattr(a, "precision", "fp32"))
         L = _nv.lib()
         ws = _nv.workspace(L.pstl_denoiser_workspace_bytes(handle, n, bs, None), u0.device, "denoiser")
         _nv.check(L.pstl_refine(handle, _nv.fptr(_nv.f32(scene_feat)), bs, n // bs, _nv.fptr(_nv.f32(highlevel.reshape(n))),

@@ -604,6 +604,19 @@ class IterateList:
 
 
 _call_counter = [0]
+_sched_cache = {}
+
+
+def _host_schedule(beta, alpha, alpha_hat):
+    """(3,steps) fp32 host copy of the schedule, read back from the device once per coeffs tuple
+    (a per-call .cpu() would be a device synchronisation in the middle of the pipeline)."""
+    key = (beta.data_ptr(), alpha.data_ptr(), alpha_hat.data_ptr(), beta._version, beta.numel())
+    s = _sched_cache.get(key)
+    if s is None:
+        s = torch.stack([beta, alpha, alpha_hat], 0).to("cpu", torch.float32).contiguous()
+        _sched_cache.clear()
+        _sched_cache[key] = s
+    return s
 
 
 def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, coeffs=None, fastforward=False,
@@ -679,7 +692,7 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
         keepalive += [pack, sv, sp, pa, progs, states_flat_new]
     ws_bytes = L.pstl_denoiser_workspace_bytes(handle, n, bs, _nv.C.byref(gcfg) if gcfg is not None else None)
     ws = _nv.workspace(ws_bytes, noise.device, "denoiser")
-    sched = torch.stack([beta, alpha, alpha_hat], 0).to("cpu", torch.float32).contiguous()
+    sched = _host_schedule(beta, alpha, alpha_hat)
     temb = net.time_table(steps, noise.device)
     _call_counter[0] += 1
     _nv.check(L.pstl_denoiser_sample(

@@ -7,9 +7,9 @@
 
 struct LeafHost {
   float signal(int, int) const { return 0.f; }
-  float pred(int, int, int) const { return 0.f; }
   void signal(int, int, float) const {}
-  void pred(int, int, int, float) const {}
+  PstlIn pred_in(int, int) const { return PstlIn{nullptr, 1.f, 0.f, 1.f, 0}; }
+  PstlOut pred_out(int, int) const { return PstlOut{nullptr, 0.f}; }
 };
 
 extern "C" int hs_stl_signals(const pstl_op* ops, int n_ops, int P, int T, int need_t, const float* sig, int N,

@@ -379,3 +379,31 @@ def test_bf16_tcgen05_sampler_vs_fp32(bs, S_, steps):
     scale = torch.tensor([0.5, 5.0], device="cuda")  # compare in normalised units
     err = ((a - b) / scale).abs()
     assert err.max().item() < 2e-2, err.max().item()
+
+
+def test_bf16_refinenet_vs_fp32():
+    """RefineNet head on the tcgen05 engine vs the fp32 path (2e-2 in normalised units)"""
+    bs, S_, nt = 12, 64, 20
+    W = synthetic.make_weights(1007, nt=nt)
+    g = torch.Generator().manual_seed(77)
+    N = bs * S_ * 3
+    u0 = ((torch.rand(N, nt, 2, generator=g) * 2 - 1) * torch.tensor([0.45, 4.5])).cuda()
+    scores = (torch.rand(N, generator=g) - 0.7).cuda()
+    batch = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=5))
+    stlp = batch["pre_stlp"].reshape(bs, S_, 3, 6)[:, 0:1].repeat(1, S_, 1, 1).reshape(N, 6)
+    hl = torch.tensor([0.0, 1.0, 2.0], device="cuda").repeat(bs * S_)[:, None]
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        args = NT.default_args(n_randoms=S_, sampling_size=S_, precision=prec)
+        net = Net(args)
+        net.load_state_dict(W)
+        net = net.cuda()
+        with torch.no_grad():
+            feat = net.encode_feat(batch)
+        dense = feat.reshape(bs, 1, -1).expand(bs, S_ * 3, feat.shape[-1]).reshape(N, -1)
+        dense._pstl_scene_feat = feat
+        net.args.precision = prec
+        outs[prec] = net.rect_forward(dense, hl, stlp, u0, scores)
+    err = ((outs["bf16"] - outs["fp32"]) / torch.tensor([0.5, 5.0], device="cuda")).abs()
+    assert torch.equal(outs["bf16"][scores >= 0], u0[scores >= 0])
+    assert err.max().item() < 2e-2, err.max().item()
