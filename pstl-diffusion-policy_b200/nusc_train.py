@@ -98,6 +98,21 @@ def get_neighbor_trajs(neighbors, nt, dt, full=False):
 # scene-indexed containers
 # ---------------------------------------------------------------------------------------
 
+_mode_cache = {}
+
+
+def _mode_column(n_groups, device):
+    """(n_groups*3, 1) float column 0,1,2,0,1,2,... (highlevel_dense, reference :753); cached per shape"""
+    key = (int(n_groups), str(device))
+    t = _mode_cache.get(key)
+    if t is None:
+        t = torch.tensor([0.0, 1.0, 2.0]).repeat(n_groups).reshape(-1, 1).to(device)
+        if len(_mode_cache) > 8:
+            _mode_cache.clear()
+        _mode_cache[key] = t
+    return t
+
+
 class ScenePack:
     """Compact inputs of the scoring / guidance kernels for N = bs*S*3 chains
     (flat index n = (scene*S + sample)*3 + mode)."""
@@ -127,7 +142,7 @@ class ScenePack:
         state0 = dup(batch["ego_traj"][:, 0, :4], m)
         valids = torch.cat([batch["curr_id"], batch["left_id"], batch["right_id"]], dim=-1)
         valid = dup(valids, S).reshape(-1)
-        mode = torch.tensor([0.0, 1.0, 2.0], device=nei.device).repeat(bs * S)
+        mode = _mode_column(bs * S, nei.device).reshape(-1)
         return ScenePack(nei, [batch["currlane_wpts"], batch["leftlane_wpts"], batch["rightlane_wpts"]], state0,
                          stlp_dense.reshape(bs * m, 6), mode, valid, m)
 
@@ -362,8 +377,7 @@ def augment_batch_data(batch, the_stlp, args, n_randoms=None, stlp_dense=None):
                                   "pass stlp_dense or use --load_stlp")
     valids = torch.cat([batch["curr_id"], batch["left_id"], batch["right_id"]], dim=-1)
     batch["valids_dense"] = dup(valids, n_randoms).reshape(bs * n_randoms, 3)
-    batch["highlevel_dense"] = torch.tensor([0, 1.0, 2.0], device=valids.device).reshape(1, 3, 1).repeat(
-        bs * n_randoms, 1, 1).reshape(bs * m, 1).float()
+    batch["highlevel_dense"] = _mode_column(bs * n_randoms, valids.device)
     if "neighbor_trajs_aug" not in batch and "neighbors_traj" in batch:
         batch["neighbor_trajs_aug"] = batch["neighbors_traj"][..., :7]
     batch["_pstl_pack"] = ScenePack.from_batch(batch, batch["stlp_dense"], n_randoms)
