@@ -379,7 +379,30 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
   }
 }
 
+#include "score_warp.cuh"
+
 static int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+
+// forward scoring on the warp-per-trajectory kernel (T <= 31); returns 1 if it took the launch
+static int launch_score_warp(ScoreArgs& a, pstl_program_t const* progs, cudaStream_t st, int* took) {
+  *took = 0;
+  const PstlEvalCfg& c = a.cfg;
+  if (c.T > 31 || getenv("PSTL_SCORE_THREAD_KERNEL")) return PSTL_OK;
+  a.F = max3(progs[0]->h.n_ops, progs[1]->h.n_ops, progs[2]->h.n_ops);
+  const size_t stack_bytes = (size_t)8 * a.F * 32 * sizeof(float);
+  const size_t tile_bytes = ((((size_t)c.K * PSTL_SOA_F * c.T + (size_t)9 * c.nseg + 3) & ~(size_t)3)) * sizeof(float);
+  const bool smem_scene = a.rows_per_scene % PSTL_WARP_ROWS == 0 && tile_bytes + stack_bytes <= 64 * 1024;
+  const int grid = pstl_ceil_div(a.N, PSTL_WARP_ROWS);
+  if (smem_scene) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    k_score_warp<true><<<grid, 256, tile_bytes + stack_bytes, st>>>(a);
+  } else {
+    k_score_warp<false><<<grid, 256, stack_bytes, st>>>(a);
+  }
+  PSTL_LAUNCH_CHECK();
+  *took = 1;
+  return PSTL_OK;
+}
 
 static int fill_cfg(const pstl_scene_view* sv, const pstl_spec_params* sp, PstlEvalCfg* c) {
   c->dt = sp->dt; c->tau = sp->tau; c->ego_L = sp->ego_L; c->ego_W = sp->ego_W;
@@ -486,6 +509,9 @@ extern "C" int pstl_score_fused(pstl_program_t const* progs, const pstl_scene_vi
   a.ego_stride = ego_stride; a.stlp = stlp; a.N = N; a.C = ego_traj ? 1 : C;
   a.scores_all = scores_all; a.best_score = best_score; a.best_idx = best_idx;
   a.best_controls = best_controls; a.traj_out = traj_out; a.ws = (float*)workspace;
+  int took = 0;
+  rc = launch_score_warp(a, progs, (cudaStream_t)stream, &took);
+  if (rc || took) return rc;
   ScorePlan plan = plan_score(progs, scenes, N, 0);
   PSTL_CHECK_ARG(plan.tp.smem_tape || workspace, "workspace required (see pstl_score_workspace_bytes)");
   return launch_score<false>(a, plan, (cudaStream_t)stream);

@@ -1,0 +1,61 @@
+"""Auxiliary measurements of the other BASELINE configs (not the driver's bench line).
+   python tests/bench_configs.py guidance [scenes]     # config 3 shape: K=10, guidance last 10 steps, n_rolls 3
+   python tests/bench_configs.py dense [n] [T] [Knei]  # config 1/5 shape: compute_stl_dense on dense rows
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import pstl_b200  # noqa: E402,F401
+from pstl_b200 import synthetic  # noqa: E402
+from pstl_b200 import nusc_train as NT  # noqa: E402
+from pstl_b200.nusc_model import Net  # noqa: E402
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def guidance(scenes):
+    args = NT.default_args(NT.GUIDANCE_FLAGS, precision="bf16")
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007))
+    net = net.cuda()
+    b = {k: v.cuda() for k, v in synthetic.make_scene_batch(scenes, seed=3).items()}
+    stls, co = NT.build_stl_cache(args), NT.get_diffusion_coeffs(args)
+    ms = timeit(lambda: NT.sample_and_score(net, b, stls, co, args), reps=3, warm=1)
+    n = scenes * 64 * 3
+    out = NT.sample_and_score(net, b, stls, co, args)
+    print("config3 (Ours+guidance, K=10, n_rolls=3): scenes=%d chains=%d  %.2f ms/batch  %.3g chains/s  acc=%.3f"
+          % (scenes, n, ms, n / ms * 1e3, out["acc"].item()))
+
+
+def dense(n, T, K):
+    args = NT.default_args(nt=T)
+    x, idx, mask = synthetic.make_dense_stl_input(n, nt=T, n_neighbors=K, seed=7)
+    xc = {k: v.cuda() for k, v in x.items()}
+    idx, mask = idx.cuda(), mask.cuda()
+    stls = NT.build_stl_cache(args)
+    ms = timeit(lambda: NT.compute_stl_dense(xc, stls, idx, mask, args))
+    by = 16 * T + 28 * K * T + 36 * 15 + 24 + 8 + 4
+    print("dense compute_stl_dense: n=%d T=%d Knei=%d  %.3f ms  %.3g traj/s  %.1f GB/s algorithmic (%d B/traj)"
+          % (n, T, K, ms, n / ms * 1e3, n * by / ms / 1e6, by))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "guidance":
+        guidance(int(sys.argv[2]) if len(sys.argv) > 2 else 256)
+    else:
+        dense(*(int(a) for a in (sys.argv[2:5] + ["4096", "20", "8"][len(sys.argv) - 2:])))
