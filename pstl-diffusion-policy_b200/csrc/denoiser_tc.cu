@@ -24,21 +24,20 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kH = 256;        // hidden width (checked at create)
-constexpr int kK1 = 48;        // layer-1 depth: 40 + 7, padded to 3 UMMA K-steps
+constexpr int kK1 = 64;        // layer-1 depth: [x 40 | hl | stlp 6 | 0 | 8 one-hot class pairs] = 4 UMMA K-steps
 constexpr int kN3 = 48;        // layer-3 width padded to a multiple of 16
 constexpr int kMaxClasses = 8; // distinct scenes a 128-row tile may span
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarps + 1) * 32;
 
 // shared-memory image offsets (bytes)
-constexpr int kOffW1 = 0;                         // [256 x 64] bf16 SW128 (cols >= 48 unused)
+constexpr int kOffW1 = 0;                         // [256 x 64] bf16 SW128; cols 48..63 = per-step bias (hi,lo) per class
 constexpr int kOffW2 = kOffW1 + 256 * 128;        // 4 K-blocks of [256 x 64]
 constexpr int kOffW3 = kOffW2 + 4 * 256 * 128;    // 4 K-blocks of [48 x 64]
 constexpr int kWeightBytes = kOffW3 + 4 * kN3 * 128;
-constexpr int kOffX = kWeightBytes;               // [128 x 64] bf16 SW128
-constexpr int kOffCs = kOffX + kTileM * 128;      // comb[2][kMaxClasses][256] fp32: c_scene[scene] + c_t[step]
-constexpr int kOffB2 = kOffCs + 2 * kMaxClasses * kH * 4;
-constexpr int kOffB3 = kOffB2 + kH * 4;
+constexpr int kOffX = kWeightBytes;               // [128 x 64] bf16 SW128; cols 48..63 = one-hot class pairs
+constexpr int kOffB2 = kOffX + kTileM * 128;      // [256 x 16] bf16, K-major no-swizzle: (hi,lo) of b2 in every class pair
+constexpr int kOffB3 = kOffB2 + 256 * 16 * 2;
 constexpr int kOffBar = kOffB3 + 64 * 4;
 constexpr int kSmemBytes = kOffBar + 128;
 static_assert(kWeightBytes == 188416, "weight image size");
@@ -99,6 +98,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// K-major, no swizzle: 8x16B core matrices; LBO = bytes between K-adjacent cores, SBO = between 8-row groups
+__device__ __forceinline__ uint64_t make_desc_flat(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -152,6 +155,17 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+// byte offset of element (row, k) of the [256 x 16] no-swizzle bias tile (LBO 128, SBO 256)
+__host__ __device__ __forceinline__ int flat16_off(int row, int k) {
+  return (row >> 3) * 256 + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
+// (hi, lo) bf16 split of an fp32 value packed as {lo:16 | hi:16}: hi at the lower address
+__device__ __forceinline__ uint32_t split_bf16(float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
 }
 
 // byte offset of element (row, k) inside a [rows x 64] bf16 K-major SW128 block
@@ -212,10 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
   const uint32_t bar_w = smem_u32(&bars[0]), bar_x = smem_u32(&bars[1]), bar_d1 = smem_u32(&bars[2]),
                  bar_h1 = smem_u32(&bars[3]), bar_d2 = smem_u32(&bars[4]), bar_h2 = smem_u32(&bars[5]),
                  bar_d3 = smem_u32(&bars[6]);
-  const uint32_t bar_c0 = smem_u32(&bars[7]);  // two bias barriers, 8 bytes apart
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[10]);
-  float* cs = reinterpret_cast<float*>(smem + kOffCs);
-  float* b2s = reinterpret_cast<float*>(smem + kOffB2);
   float* b3s = reinterpret_cast<float*>(smem + kOffB3);
 
   if (warp == kEpiWarps) {
@@ -227,8 +238,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       mbar_init(bar_d2, 1);
       mbar_init(bar_h2, kEpiWarps);
       mbar_init(bar_d3, 1);
-      mbar_init(bar_c0, 1);
-      mbar_init(bar_c0 + 8, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -236,8 +245,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < kH; i += kThreads) b2s[i] = a.b2[i];
+  for (int n = threadIdx.x; n < kH; n += kThreads) {  // layer-2 bias tile: every class pair carries (hi, lo) of b2[n]
+    const uint32_t v = split_bf16(a.b2[n]);
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) *reinterpret_cast<uint32_t*>(smem + kOffB2 + flat16_off(n, 2 * c)) = v;
+  }
   for (int i = threadIdx.x; i < 64; i += kThreads) b3s[i] = i < 40 ? a.b3[i] : 0.f;
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -262,31 +276,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
     mbar_wait(bar_w, 0);
     const uint32_t id12 = make_idesc(kTileM, kH), id3 = make_idesc(kTileM, kN3);
     const uint64_t dX = make_desc(sbase + kOffX), dW1 = make_desc(sbase + kOffW1);
-    // layer-1 bias rows of a tile-step, comb[buf][class][col] = c_scene[scene0+class][col] + c_t[i][col],
-    // are prepared one step ahead by this otherwise idle warp
-    auto write_comb = [&](uint32_t buf, int tile, int i) {
+    // Biases ride on the tensor pipe.  The X tile carries, in columns 48..63, a pair of ones at the row's
+    // scene class; W1' columns 48..63 carry (hi, lo) bf16 halves of c_scene[scene0+class] + c_t[step], rewritten
+    // here (by this otherwise idle warp) once the previous layer-1 MMA has retired.  Layer 2 gets b2 through one
+    // extra K-step against the same one-hot columns.
+    auto write_bias_cols = [&](int tile, int i) {
       const long long r0 = (long long)tile * kTileM;
       const long long r1 = (r0 + kTileM - 1 < a.N) ? r0 + kTileM - 1 : (long long)a.N - 1;
       const int scene0 = (int)(r0 / a.rows_per_scene);
       const int n_cls = (int)(r1 / a.rows_per_scene) - scene0 + 1;
-      float* dst = cs + buf * (kMaxClasses * kH);
       const float* ctr = a.ct + (size_t)i * kH;
       for (int c = 0; c < n_cls && c < kMaxClasses; ++c) {
         const float* src = a.cscene + (size_t)(scene0 + c) * kH;
 #pragma unroll
-        for (int col = lane * 4; col < kH; col += 128) {
-          const float4 u = __ldg(reinterpret_cast<const float4*>(src + col));
-          const float4 v = __ldg(reinterpret_cast<const float4*>(ctr + col));
-          *reinterpret_cast<float4*>(dst + c * kH + col) = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
-        }
+        for (int n = lane; n < kH; n += 32)
+          *reinterpret_cast<uint32_t*>(smem + kOffW1 + sw128_off(n, 48 + 2 * c)) = split_bf16(__ldg(src + n) + __ldg(ctr + n));
       }
+      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_c0 + buf * 8);
     };
+    const uint64_t dXb = dX + 6;  // K-chunk 3 of the X tile (columns 48..63): 96 bytes into the swizzle atom
+    const uint64_t dB2 = make_desc_flat(sbase + kOffB2, 128, 256);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 0; s < n_steps; ++s, ++it) {
         const uint32_t ph = it & 1;
-        if (s == 0) write_comb(it & 1, tile, a.first_step);
+        if (s == 0) write_bias_cols(tile, a.first_step);
         mbar_wait(bar_x, ph);
         tc_fence_after();
         if (lane == 0) {
@@ -296,18 +310,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           tc_commit(bar_d1);
         }
         __syncwarp();
-        if (s + 1 < n_steps) write_comb((it + 1) & 1, tile, a.first_step - s - 1);
         mbar_wait(bar_h1, ph);
         tc_fence_after();
         if (lane == 0) {
+          mma_ss(tmem + kColD, dXb, dB2, id12, 0);  // D = onehot . b2
 #pragma unroll
           for (int k = 0; k < kH / 16; ++k) {
             const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)((k & 3) * 2);
-            mma_ts(tmem + kColD, tmem + kColH + k * 8, dB, id12, k > 0);
+            mma_ts(tmem + kColD, tmem + kColH + k * 8, dB, id12, 1);
           }
           tc_commit(bar_d2);
         }
         __syncwarp();
+        // layer-1 MMA of this step has retired (bar_h1 passed): next step's bias columns, in the layer-2 shadow
+        if (s + 1 < n_steps) write_bias_cols(tile, a.first_step - s - 1);
         mbar_wait(bar_h2, ph);
         tc_fence_after();
         if (lane == 0) {
@@ -347,10 +363,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         }
       };
       store_x_tile();
-      if (half == 1) {  // constant columns 40..47: hl, stlp(6), 0
+      if (half == 1) {  // constant columns 40..47: hl, stlp(6), 0 ; 48..63: ones at this row's scene class
 #pragma unroll
         for (int j = 0; j < 8; j += 2)
           *reinterpret_cast<__nv_bfloat162*>(xt + sw128_off(row_in_tile, 40 + j)) = __floats2bfloat162_rn(xr[40 + j], xr[41 + j]);
+#pragma unroll
+        for (int c = 0; c < kMaxClasses; ++c) {
+          const float one = (c == cls) ? 1.f : 0.f;
+          *reinterpret_cast<__nv_bfloat162*>(xt + sw128_off(row_in_tile, 48 + 2 * c)) = __floats2bfloat162_rn(one, one);
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -359,34 +380,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       for (int s = 0; s < n_steps; ++s, ++it) {
         const uint32_t ph = it & 1;
         const int i = a.first_step - s;  // reverse step index (t == i)
-        const float* comb = cs + (it & 1) * (kMaxClasses * kH) + cls * kH;
         float zn[20];
-        // ---- layers 1 and 2: D -> (+bias, relu, bf16) -> H ----
+        // ---- layers 1 and 2: D (bias already accumulated by the MMA) -> relu -> bf16 -> H ----
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
           tc_fence_after();
-          if (layer == 0) mbar_wait(bar_c0 + (it & 1) * 8, (it >> 1) & 1);
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            const int col = half * 128 + ch * 32;
-            uint32_t r[32];
-            TMEM_LD_X32(tmem + lane_addr + kColD + col, r);
-            tmem_wait_ld();
-            uint32_t p[16];
+          const uint32_t dsrc = tmem + lane_addr + kColD + half * 128, hdst = tmem + lane_addr + kColH + half * 64;
+          uint32_t ra[32], rb[32], p[16];
+          TMEM_LD_X32(dsrc, ra);
+          tmem_wait_ld();
+          TMEM_LD_X32(dsrc + 32, rb);  // in flight while chunk 0 is packed
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b;
-              if (layer == 0) {
-                b = *reinterpret_cast<const float4*>(comb + col + j);
-              } else {
-                b = *reinterpret_cast<const float4*>(b2s + col + j);
-              }
-              p[j / 2] = pack_relu_bf16(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y);
-              p[j / 2 + 1] = pack_relu_bf16(__uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
-            }
-            TMEM_ST_X16(tmem + lane_addr + kColH + col / 2, p);
-          }
+          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
+          TMEM_ST_X16(hdst, p);
+          tmem_wait_ld();
+          TMEM_LD_X32(dsrc + 64, ra);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
+          TMEM_ST_X16(hdst + 16, p);
+          tmem_wait_ld();
+          TMEM_LD_X32(dsrc + 96, rb);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
+          TMEM_ST_X16(hdst + 32, p);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
+          TMEM_ST_X16(hdst + 48, p);
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();

@@ -49,7 +49,9 @@ __device__ __forceinline__ float wbase_sel(const WBase& b, int sid) {
   }
 }
 
-__device__ __forceinline__ float wpred(const WBase& b, int a0, int a1, const float* p) {
+// value of a typed predicate leaf at this lane's time step.  Deliberately NOT inlined: the kernel is
+// instruction-cache bound if every consumer carries its own copy of the decode + IEEE division.
+__device__ __noinline__ float wpred(const WBase& b, int a0, int a1, const float* p) {
   const int sid = a0 & 0xff, pid = a1 & 0xff, den = (a1 >> 16) & 0xff;
   float x = wbase_sel(b, sid);
   if ((a0 >> 8) & 1) x = -x;
@@ -67,133 +69,89 @@ __device__ __forceinline__ float wget(const PstlProgView& P, int idx, const floa
   return (o.op == PSTL_OP_PRED) ? wpred(b, o.a0, o.a1, p) : st[idx * 32 + lane];
 }
 
+// inclusive scan of (max, sum) pairs towards lane 0 (dir = +1: suffix) or towards lane 31 (dir = -1: prefix)
+__device__ __noinline__ void wscan(float& m, float& s, int lane, int dir, int hard) {
+#pragma unroll 1
+  for (int off = 1; off < 32; off <<= 1) {
+    const int src = lane + dir * off;
+    const float m2 = __shfl_sync(0xffffffffu, m, src & 31), s2 = __shfl_sync(0xffffffffu, s, src & 31);
+    if (src >= 0 && src < 32) {
+      if (hard) m = fmaxf(m, m2);
+      else lse_merge(m, s, m2, s2);
+    }
+  }
+}
+
 // Interpret the program for one trajectory; returns the top-level robustness at t = 0 (all lanes).
-__device__ float warp_interp(const PstlProgView& P, float* st, int lane, int T, const WBase& b, const float* p,
-                             float tau, int hard) {
+__device__ __noinline__ float warp_interp(const PstlProgView& P, float* st, int lane, int T, const WBase& b,
+                                          const float* p, float tau, int hard) {
+  const float ts = hard ? 1.f : tau;  // scale applied before reductions
+#pragma unroll 1
   for (int i = 0; i < P.n_ops; ++i) {
     const PstlROp o = P.ops[i];
-    float out = 0.f;
-    switch (o.op) {
-      case PSTL_OP_PRED:
-        continue;  // evaluated by the consumer
-      case PSTL_OP_NEG:
-        out = -wget(P, o.in0, st, lane, b, p);
-        break;
-      case PSTL_OP_SMIN2:
-      case PSTL_OP_SMAX2: {
-        const float sg = (o.op == PSTL_OP_SMIN2) ? -1.f : 1.f;
-        const float x = sg * wget(P, o.in0, st, lane, b, p), y = sg * wget(P, o.in1, st, lane, b, p);
-        float r;
-        if (hard) {
-          r = fmaxf(x, y);
-        } else {
-          const float xa = x * tau, xb = y * tau;
-          float m = fmaxf(xa, xb);
-          if (isinf(m)) m = 0.f;
-          r = (__logf(__expf(xa - m) + __expf(xb - m)) + m) / tau;
-        }
-        out = sg * r;
-      } break;
-      case PSTL_OP_SMIN_K: {
-        const int k = o.a0, kb = o.a1;
-        float m = -INFINITY;
-        for (int j = 0; j < k; ++j) m = fmaxf(m, -wget(P, P.klist[kb + j], st, lane, b, p) * (hard ? 1.f : tau));
-        float r = m;
-        if (!hard) {
-          if (isinf(m)) m = 0.f;
-          float s = 0.f;
-          for (int j = 0; j < k; ++j) s += __expf(-wget(P, P.klist[kb + j], st, lane, b, p) * tau - m);
-          r = (__logf(s) + m) / tau;
-        }
-        out = -r;
-      } break;
-      case PSTL_OP_WIN_SMIN:
-      case PSTL_OP_WIN_SMAX: {
-        const float sg = (o.op == PSTL_OP_WIN_SMIN) ? -1.f : 1.f;
-        const float mine = (lane < T) ? sg * wget(P, o.in0, st, lane, b, p) * (hard ? 1.f : tau) : -INFINITY;
-        if (o.n_out == 1) {
-          // only t = 0 is consumed: one masked warp reduction over the window [clip(ts), clip(te))
-          const int lo = pstl_clipi(o.a0, 0, T), hi = pstl_clipi(o.a1, 0, T);
-          const bool in = lane >= lo && lane < hi;
-          float m = wmax(in ? mine : -INFINITY);
-          float r;
-          if (hi <= lo) {
-            r = -INFINITY;  // empty window: -inf for soft-min and soft-max alike (stl_d_lib.py:7-8,16-17)
-            out = r;
-            break;
-          }
-          if (hard) {
-            r = m;
-          } else {
-            if (isinf(m)) m = 0.f;
-            const float s = wsum(in ? __expf(mine - m) : 0.f);
-            r = (__logf(s) + m) / tau;
-          }
-          out = sg * r;
-        } else if (o.a0 == 0 && o.a1 >= T) {
-          // suffix windows [t, T): inclusive suffix scan of (max, sum) pairs
-          float m = mine, s = (lane < T) ? 1.f : 0.f;
+    if (o.op == PSTL_OP_PRED) continue;  // evaluated by the consumer
+    const bool is_min = (o.op == PSTL_OP_SMIN2 || o.op == PSTL_OP_SMIN_K || o.op == PSTL_OP_WIN_SMIN ||
+                         o.op == PSTL_OP_PREFIX_SMIN);
+    const float sg = is_min ? -1.f : 1.f;
+    float out;
+    if (o.op == PSTL_OP_NEG) {
+      out = -wget(P, o.in0, st, lane, b, p);
+    } else if (o.op == PSTL_OP_SMIN2 || o.op == PSTL_OP_SMAX2 || o.op == PSTL_OP_SMIN_K) {
+      // per-lane soft-min/max over k stacked children, accumulated as (max, sum) pairs
+      const bool two = o.op != PSTL_OP_SMIN_K;
+      const int k = two ? 2 : o.a0;
+      float m = -INFINITY, s = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < k; ++j) {
+        const int src = two ? (j == 0 ? o.in0 : o.in1) : P.klist[o.a1 + j];
+        const float x = sg * wget(P, src, st, lane, b, p) * ts;
+        if (hard) m = fmaxf(m, x);
+        else lse_merge(m, s, x, 1.f);
+      }
+      out = sg * (hard ? m : (__logf(s) + m) / tau);
+    } else {
+      // temporal operators: this lane's scaled input, then a reduction / scan across lanes
+      const float mine = (lane < T) ? sg * wget(P, o.in0, st, lane, b, p) * ts : -INFINITY;
+      float m = mine, s = (lane < T) ? 1.f : 0.f;
+      bool empty = false;
+      if (o.op == PSTL_OP_PREFIX_SMIN) {
+        wscan(m, s, lane, -1, 0);
+      } else if (o.op == PSTL_OP_SUFFIX_SMAX) {
+        wscan(m, s, lane, +1, 0);
+      } else if (o.n_out == 1) {
+        // only t = 0 is consumed: one masked warp reduction over the window [clip(ts), clip(te))
+        const int lo = pstl_clipi(o.a0, 0, T), hi = pstl_clipi(o.a1, 0, T);
+        const bool in = lane >= lo && lane < hi;
+        empty = hi <= lo;
+        const float M = wmax(in ? mine : -INFINITY);
+        const float mm = isinf(M) ? 0.f : M;
+        s = hard ? 0.f : wsum(in ? __expf(mine - mm) : 0.f);
+        m = hard ? M : mm;
+      } else if (o.a0 == 0 && o.a1 >= T) {
+        wscan(m, s, lane, +1, hard);  // suffix windows [t, T)
+      } else {
+        // general window [t+ts, t+te) clipped to [0,T): walk the window through shuffles
+        const int lo = pstl_clipi(lane + o.a0, 0, T), hi = pstl_clipi(lane + o.a1, 0, T);
+        int len = (lane < T) ? hi - lo : 0;
+        empty = hi <= lo;
 #pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const float m2 = __shfl_down_sync(0xffffffffu, m, off), s2 = __shfl_down_sync(0xffffffffu, s, off);
-            if (lane + off < 32) {
-              if (hard) m = fmaxf(m, m2);
-              else lse_merge(m, s, m2, s2);
-            }
+        for (int of = 16; of > 0; of >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, of));
+        m = -INFINITY; s = 0.f;
+#pragma unroll 1
+        for (int d = 0; d < len; ++d) {
+          const float x = __shfl_sync(0xffffffffu, mine, (lo + d) & 31);
+          if (lo + d < hi) {
+            if (hard) m = fmaxf(m, x);
+            else lse_merge(m, s, x, 1.f);
           }
-          const float r = hard ? m : (__logf(s) + m) / tau;
-          out = sg * r;
-        } else {
-          // general window [t+ts, t+te) clipped to [0,T): two passes over shuffled neighbours
-          const int lo = pstl_clipi(lane + o.a0, 0, T), hi = pstl_clipi(lane + o.a1, 0, T);
-          int wmaxlen = 0;
-          {
-            int len = (lane < T) ? hi - lo : 0;
-#pragma unroll
-            for (int of = 16; of > 0; of >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, of));
-            wmaxlen = len;
-          }
-          float m = -INFINITY;
-          for (int d = 0; d < wmaxlen; ++d) {
-            const float x = __shfl_sync(0xffffffffu, mine, (lo + d) & 31);
-            if (lo + d < hi) m = fmaxf(m, x);
-          }
-          float r = m;
-          if (!hard) {
-            float mm = isinf(m) ? 0.f : m;
-            float s = 0.f;
-            for (int d = 0; d < wmaxlen; ++d) {
-              const float x = __shfl_sync(0xffffffffu, mine, (lo + d) & 31);
-              if (lo + d < hi) s += __expf(x - mm);
-            }
-            r = (__logf(s) + mm) / tau;
-          }
-          out = (hi <= lo) ? -INFINITY : sg * r;
         }
-      } break;
-      case PSTL_OP_PREFIX_SMIN: {  // -logcumsumexp(-x tau)/tau : inclusive prefix scan
-        float m = (lane < T) ? -wget(P, o.in0, st, lane, b, p) * tau : -INFINITY, s = (lane < T) ? 1.f : 0.f;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const float m2 = __shfl_up_sync(0xffffffffu, m, off), s2 = __shfl_up_sync(0xffffffffu, s, off);
-          if (lane >= off) lse_merge(m, s, m2, s2);
-        }
-        out = -(__logf(s) + m) / tau;
-      } break;
-      case PSTL_OP_SUFFIX_SMAX: {
-        float m = (lane < T) ? wget(P, o.in0, st, lane, b, p) * tau : -INFINITY, s = (lane < T) ? 1.f : 0.f;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const float m2 = __shfl_down_sync(0xffffffffu, m, off), s2 = __shfl_down_sync(0xffffffffu, s, off);
-          if (lane + off < 32) lse_merge(m, s, m2, s2);
-        }
-        out = (__logf(s) + m) / tau;
-      } break;
-      default:
-        break;
+      }
+      // empty window: -inf for soft-min and soft-max alike (stl_d_lib.py:7-8,16-17)
+      const bool scan_only = (o.op == PSTL_OP_PREFIX_SMIN || o.op == PSTL_OP_SUFFIX_SMAX);
+      const float r = (hard && !scan_only) ? m : (__logf(s) + m) / tau;
+      out = empty ? -INFINITY : sg * r;
     }
     st[i * 32 + lane] = out;
-    __syncwarp();
   }
   const PstlROp& top = P.ops[P.n_ops - 1];
   const float mine = (top.op == PSTL_OP_PRED) ? wpred(b, top.a0, top.a1, p) : st[(P.n_ops - 1) * 32 + lane];
@@ -239,21 +197,25 @@ __device__ void stage_scene_soa(const ScoreArgs& a, int scene, float* tile) {
 }
 
 template <class Scene>
-__device__ __forceinline__ void warp_predicates(const PstlProgView& P, const Scene& sc, const PstlEvalCfg& c,
+__device__ __noinline__ void warp_predicates(const PstlProgView& P, const Scene& sc, const PstlEvalCfg& c,
                                                 const PstlPose& s, float cs, float sn, int t, WBase& b) {
   b.v = s.v;
   b.nei = 0.f;
 #pragma unroll
-  for (int l = 0; l < 3; ++l) {
-    b.d[l] = 0.f;
-    b.th[l] = 0.f;
+  for (int l = 0; l < 3; ++l) { b.d[l] = 0.f; b.th[l] = 0.f; }
+#pragma unroll 1
+  for (int l = 0; l < 3; ++l) {  // one copy of the lane search in the instruction stream
     const int sd = PSTL_SIG_D_CURR + 2 * l;
     if (t < P.base_need[sd] || t < P.base_need[sd + 1]) {
       struct L {
         const Scene* s; int l;
         __device__ float operator()(int j, int f) const { return s->lane(l, j, f); }
       } lacc{&sc, l};
-      pstl_lane_pred(s.x, s.y, s.th, lacc, c.nseg, c.clip_dist, b.d[l], b.th[l], nullptr);
+      float d, th;
+      pstl_lane_pred(s.x, s.y, s.th, lacc, c.nseg, c.clip_dist, d, th, nullptr);
+      if (l == 0) { b.d[0] = d; b.th[0] = th; }
+      else if (l == 1) { b.d[1] = d; b.th[1] = th; }
+      else { b.d[2] = d; b.th[2] = th; }
     }
   }
   if (t < P.base_need[PSTL_SIG_NEI]) {
@@ -323,12 +285,13 @@ __global__ void __launch_bounds__(256) k_score_warp(ScoreArgs a) {
     PstlPose bs = s0;
     for (int cand = 0; cand < a.C; ++cand) {
       PstlPose s = s0;
-      float w = 0.f, ac = 0.f;
+      float w = 0.f, ac = 0.f, cs, sn;
       if (a.ego) {
         if (lane < T) {
           const float* e = a.ego + ((size_t)n * T + lane) * a.ego_stride;
           s.x = e[0]; s.y = e[1]; s.th = e[2]; s.v = e[3];
         }
+        sincosf(s.th, &sn, &cs);
       } else {
         // lane t holds control t; states are prefix sums accumulated in the reference's order
         if (lane < T) {
@@ -345,7 +308,8 @@ __global__ void __launch_bounds__(256) k_score_warp(ScoreArgs a) {
           const float a_th = __shfl_sync(0xffffffffu, ith, j), a_v = __shfl_sync(0xffffffffu, iv, j);
           if (j < lane) { s.th = s.th + a_th; s.v = s.v + a_v; }
         }
-        const float ix = (s.v * cosf(s.th)) * c.dt, iy = (s.v * sinf(s.th)) * c.dt;
+        sincosf(s.th, &sn, &cs);
+        const float ix = (s.v * cs) * c.dt, iy = (s.v * sn) * c.dt;
         for (int j = 0; j < T; ++j) {
           const float a_x = __shfl_sync(0xffffffffu, ix, j), a_y = __shfl_sync(0xffffffffu, iy, j);
           if (j < lane) { s.x = s.x + a_x; s.y = s.y + a_y; }
@@ -354,7 +318,6 @@ __global__ void __launch_bounds__(256) k_score_warp(ScoreArgs a) {
       float sc;
       if (m < 3) {
         WBase b;
-        const float cs = cosf(s.th), sn = sinf(s.th);
         if (lane < T) {
           if (SMEM_SCENE) warp_predicates(P, ss, c, s, cs, sn, lane, b);
           else warp_predicates(P, sg, c, s, cs, sn, lane, b);
