@@ -147,6 +147,11 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
                "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])        \
                : "memory")
 
+#define TMEM_ST_X8(taddr, r)                                                                              \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), \
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])                     \
+               : "memory")
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -387,27 +392,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
           tc_fence_after();
           const uint32_t dsrc = tmem + lane_addr + kColD + half * 128, hdst = tmem + lane_addr + kColH + half * 64;
-          uint32_t ra[32], rb[32], p[16];
-          TMEM_LD_X32(dsrc, ra);
-          tmem_wait_ld();
-          TMEM_LD_X32(dsrc + 32, rb);  // in flight while chunk 0 is packed
+          // 8 chunks of 16 accumulator columns, the next chunk's TMEM load in flight while one is packed
+          uint32_t ra[16], rb[16], p[8];
+          TMEM_LD_X16(dsrc, ra);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
-          TMEM_ST_X16(hdst, p);
-          tmem_wait_ld();
-          TMEM_LD_X32(dsrc + 64, ra);
+          for (int ch = 0; ch < 8; ch += 2) {
+            tmem_wait_ld();
+            TMEM_LD_X16(dsrc + (ch + 1) * 16, rb);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
-          TMEM_ST_X16(hdst + 16, p);
-          tmem_wait_ld();
-          TMEM_LD_X32(dsrc + 96, rb);
+            for (int j = 0; j < 16; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
+            TMEM_ST_X8(hdst + ch * 8, p);
+            tmem_wait_ld();
+            if (ch + 2 < 8) TMEM_LD_X16(dsrc + (ch + 2) * 16, ra);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
-          TMEM_ST_X16(hdst + 32, p);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
-          TMEM_ST_X16(hdst + 48, p);
+            for (int j = 0; j < 16; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
+            TMEM_ST_X8(hdst + (ch + 1) * 8, p);
+          }
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
