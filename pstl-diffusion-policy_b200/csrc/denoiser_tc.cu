@@ -35,15 +35,16 @@ constexpr int kOffW1 = 0;                         // [256 x 64] bf16 SW128; cols
 constexpr int kOffW2 = kOffW1 + 256 * 128;        // 4 K-blocks of [256 x 64]
 constexpr int kOffW3 = kOffW2 + 4 * 256 * 128;    // 4 K-blocks of [48 x 64]
 constexpr int kWeightBytes = kOffW3 + 4 * kN3 * 128;
-constexpr int kOffX = kWeightBytes;               // [128 x 64] bf16 SW128; cols 48..63 = one-hot class pairs
-constexpr int kOffB2 = kOffX + kTileM * 128;      // [256 x 16] bf16, K-major no-swizzle: (hi,lo) of b2 in every class pair
+constexpr int kOffB2 = kWeightBytes;              // [256 x 16] bf16, K-major no-swizzle: (hi,lo) of b2 in every class pair
 constexpr int kOffB3 = kOffB2 + 256 * 16 * 2;
 constexpr int kOffBar = kOffB3 + 64 * 4;
 constexpr int kSmemBytes = kOffBar + 128;
 static_assert(kWeightBytes == 188416, "weight image size");
 static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
 
-constexpr uint32_t kColD = 0, kColH = 256, kColD3 = 384;
+constexpr uint32_t kColD = 0, kColH = 256, kColD3 = 384, kColX = 432;  // X: 32 columns = 64 bf16 of layer-1 input
+#define MSTAMP (a.dbg && blockIdx.x == 0 && it == 2 && lane == 0)
+#define STAMP (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0)
 
 struct TcState {
   uint8_t* image;    // device: swizzled bf16 weight image of policy_net (kWeightBytes)
@@ -152,6 +153,17 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])                     \
                : "memory")
 
+#define TMEM_ST_X4(taddr, r) \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory")
+#define TMEM_ST_X2(taddr, r) \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory")
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -220,12 +232,16 @@ struct TcArgs {
   const float* u0;      // (N, 40) controls being refined
   const float* scores;  // (N)
   float* out;           // (N, 40)
+  long long* dbg;       // optional clock64 timeline of one tile-step (PSTL_TC_DEBUG)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = smem_u32(smem);
+  // the shared-window address of the dynamic segment is uniform: keep the 1 KB alignment arithmetic on
+  // that integer so every UMMA descriptor stays in uniform registers (no per-issue R2UR / ELECT loop)
+  const uint32_t sraw = smem_u32(smem_raw);
+  const uint32_t sbase = (sraw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - sraw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   const uint32_t bar_w = smem_u32(&bars[0]), bar_x = smem_u32(&bars[1]), bar_d1 = smem_u32(&bars[2]),
@@ -260,7 +276,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  // all 512 columns are ours, so the allocation starts at lane 0 / column 0: a literal base keeps the
+  // TMEM operands of every tcgen05 instruction immediate
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
 
   if (warp == kEpiWarps && lane == 0) {
     // weights: one TMA bulk stream into the resident image
@@ -280,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
     // ================= MMA issuer: the whole warp walks the protocol, lane 0 issues =================
     mbar_wait(bar_w, 0);
     const uint32_t id12 = make_idesc(kTileM, kH), id3 = make_idesc(kTileM, kN3);
-    const uint64_t dX = make_desc(sbase + kOffX), dW1 = make_desc(sbase + kOffW1);
+    const uint64_t dW1 = make_desc(sbase + kOffW1);
     // Biases ride on the tensor pipe.  The X tile carries, in columns 48..63, a pair of ones at the row's
     // scene class; W1' columns 48..63 carry (hi, lo) bf16 halves of c_scene[scene0+class] + c_t[step], rewritten
     // here (by this otherwise idle warp) once the previous layer-1 MMA has retired.  Layer 2 gets b2 through one
@@ -300,36 +319,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       fence_proxy_async();
       __syncwarp();
     };
-    const uint64_t dXb = dX + 6;  // K-chunk 3 of the X tile (columns 48..63): 96 bytes into the swizzle atom
     const uint64_t dB2 = make_desc_flat(sbase + kOffB2, 128, 256);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 0; s < n_steps; ++s, ++it) {
         const uint32_t ph = it & 1;
         if (s == 0) write_bias_cols(tile, a.first_step);
         mbar_wait(bar_x, ph);
+        if (MSTAMP) a.dbg[0] = clock64();
         tc_fence_after();
         if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < kK1 / 16; ++k)  // advancing 32 B inside the 128 B swizzle atom
-            mma_ss(tmem + kColD, dX + (uint64_t)(k * 2), dW1 + (uint64_t)(k * 2), id12, k > 0);
+          for (int k = 0; k < kK1 / 16; ++k) {  // advancing 32 B inside the 128 B swizzle atom
+            mma_ts(tmem + kColD, tmem + kColX + k * 8, dW1 + (uint64_t)(k * 2), id12, k > 0);
+            if (MSTAMP) a.dbg[16 + k] = clock64();
+          }
           tc_commit(bar_d1);
+          if (MSTAMP) a.dbg[1] = clock64();
         }
         __syncwarp();
         mbar_wait(bar_h1, ph);
+        if (MSTAMP) a.dbg[2] = clock64();
         tc_fence_after();
         if (lane == 0) {
-          mma_ss(tmem + kColD, dXb, dB2, id12, 0);  // D = onehot . b2
+          mma_ts(tmem + kColD, tmem + kColX + 24, dB2, id12, 0);  // D = onehot(class) . b2
 #pragma unroll
           for (int k = 0; k < kH / 16; ++k) {
             const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)((k & 3) * 2);
             mma_ts(tmem + kColD, tmem + kColH + k * 8, dB, id12, 1);
           }
           tc_commit(bar_d2);
+          if (MSTAMP) a.dbg[3] = clock64();
         }
         __syncwarp();
         // layer-1 MMA of this step has retired (bar_h1 passed): next step's bias columns, in the layer-2 shadow
         if (s + 1 < n_steps) write_bias_cols(tile, a.first_step - s - 1);
         mbar_wait(bar_h2, ph);
+        if (MSTAMP) a.dbg[4] = clock64();
         tc_fence_after();
         if (lane == 0) {
 #pragma unroll
@@ -338,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
             mma_ts(tmem + kColD3, tmem + kColH + k * 8, dB, id3, k > 0);
           }
           tc_commit(bar_d3);
+          if (MSTAMP) a.dbg[5] = clock64();
         }
         __syncwarp();
       }
@@ -359,26 +385,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       const float* xr = a.xin + rrow * PSTL_XIN_LD;
 #pragma unroll
       for (int j = 0; j < 20; ++j) x[j] = xr[c0 + j];
-      uint8_t* xt = smem + kOffX;
-      auto store_x_tile = [&]() {
+      // the layer-1 operand lives in TMEM too (columns kColX..+32): bf16 pairs of [x | hl stlp 0 | class one-hots]
+      auto store_x = [&]() {
+        uint32_t px[10];
 #pragma unroll
-        for (int j = 0; j < 20; j += 2) {
-          const __nv_bfloat162 v = __floats2bfloat162_rn(x[j], x[j + 1]);
-          *reinterpret_cast<__nv_bfloat162*>(xt + sw128_off(row_in_tile, c0 + j)) = v;
-        }
+        for (int j = 0; j < 20; j += 2) px[j / 2] = pack_bf16(x[j], x[j + 1]);
+        TMEM_ST_X8(tmem + lane_addr + kColX + c0 / 2, px);
+        TMEM_ST_X2(tmem + lane_addr + kColX + c0 / 2 + 8, (px + 8));
       };
-      store_x_tile();
+      store_x();
       if (half == 1) {  // constant columns 40..47: hl, stlp(6), 0 ; 48..63: ones at this row's scene class
+        uint32_t pc[12];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2)
-          *reinterpret_cast<__nv_bfloat162*>(xt + sw128_off(row_in_tile, 40 + j)) = __floats2bfloat162_rn(xr[40 + j], xr[41 + j]);
+        for (int j = 0; j < 8; j += 2) pc[j / 2] = pack_bf16(xr[40 + j], xr[41 + j]);
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) {
-          const float one = (c == cls) ? 1.f : 0.f;
-          *reinterpret_cast<__nv_bfloat162*>(xt + sw128_off(row_in_tile, 48 + 2 * c)) = __floats2bfloat162_rn(one, one);
-        }
+        for (int c = 0; c < kMaxClasses; ++c) pc[4 + c] = (c == cls) ? 0x3F803F80u : 0u;
+        TMEM_ST_X4(tmem + lane_addr + kColX + 20, pc);
+        TMEM_ST_X8(tmem + lane_addr + kColX + 24, (pc + 4));
       }
-      fence_proxy_async();
+      tmem_wait_st();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_x);
 
@@ -390,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
+          if (STAMP) a.dbg[layer == 0 ? 8 : 11] = clock64();
           tc_fence_after();
           const uint32_t dsrc = tmem + lane_addr + kColD + half * 128, hdst = tmem + lane_addr + kColH + half * 64;
           // 8 chunks of 16 accumulator columns, the next chunk's TMEM load in flight while one is packed
@@ -412,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(layer == 0 ? bar_h1 : bar_h2);
+          if (STAMP) a.dbg[layer == 0 ? 9 : 12] = clock64();
           if (layer == 0) {
             // this step's noise is drawn now, in the shadow of the layer-2 MMA
             const int zi = a.steps - 1 - i;
@@ -432,10 +460,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
                 }
               }
             }
+            if (STAMP) a.dbg[10] = clock64();
           }
         }
         // ---- layer 3: eps, posterior mean, noise, next x ----
         mbar_wait(bar_d3, ph);
+        if (STAMP) a.dbg[13] = clock64();
         tc_fence_after();
         uint32_t r[20];
         TMEM_LD_X16(tmem + lane_addr + kColD3 + c0, r);
@@ -480,11 +510,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           }
         }
         if (s + 1 < n_steps) {
-          store_x_tile();
-          fence_proxy_async();
+          store_x();
+          tmem_wait_st();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_x);
+          if (STAMP) a.dbg[14] = clock64();
         }
       }
       if (live && !a.refine) {
@@ -571,7 +602,21 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   a.keep = keep_last_k; a.clip = clip; a.w_max = w_max; a.a_max = a_max; a.seed = seed; a.offset = offset;
   const int n_tiles = (N + kTileM - 1) / kTileM;
   const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
+  long long* dbg = nullptr;
+  if (getenv("PSTL_TC_DEBUG")) { cudaMalloc(&dbg, 32 * sizeof(long long)); cudaMemset(dbg, 0, 32 * sizeof(long long)); }
+  a.dbg = dbg;
   k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
+  if (dbg) {
+    cudaStreamSynchronize(st);
+    long long h[32];
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[pstl tc timeline, CTA 0, 3rd tile-step, cycles rel. to bar_x ready]\n  MMA : x %lld | mma1 issued %lld | h1 %lld | mma2 issued %lld | h2 %lld | mma3 issued %lld\n"
+                    "  EPI0: d1 %lld | epi1 done %lld | noise done %lld | d2 %lld | epi2 done %lld | d3 %lld | epi3 done %lld\n",
+            0LL, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0],
+            h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
+    fprintf(stderr, "  MMA1 issue stamps: %lld %lld %lld %lld\n", h[16] - h[0], h[17] - h[0], h[18] - h[0], h[19] - h[0]);
+    cudaFree(dbg);
+  }
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
 }

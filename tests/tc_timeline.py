@@ -1,0 +1,15 @@
+"""PSTL_TC_DEBUG=1 python tests/tc_timeline.py — print the clock64 timeline of one tile-step of k_denoiser_tc"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["PSTL_TC_DEBUG"] = "1"
+import torch
+import pstl_b200
+from pstl_b200 import synthetic, nusc_train as NT
+from pstl_b200.nusc_model import Net
+args = NT.default_args(precision="bf16")
+net = Net(args); net.load_state_dict(synthetic.make_weights(1007)); net = net.cuda()
+b = {k: v.cuda() for k, v in synthetic.make_scene_batch(256, seed=3).items()}
+for _ in range(2):
+    NT.sample_and_score(net, b, NT.build_stl_cache(args), NT.get_diffusion_coeffs(args), args)
+torch.cuda.synchronize()
