@@ -30,7 +30,7 @@ FLOP_PER_CHAIN = 99 * 2 * (47 * 256 + 256 * 256 + 256 * 40)  # minimal (hoisted)
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--scenes", type=int, default=1024, help="scenes per GPU per step")
@@ -49,34 +49,42 @@ def peaks():
         return 1400.0, 6650.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE
+    background `nvidia-smi -lms 200` process started before the warm-up and killed after the timed regions
+    (forking a fresh process per sample from a CUDA process stalls the launching thread)."""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.proc = index, None
 
-    def run(self):
+    def start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        if not self.rows:
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        rows = [[c.strip() for c in l.split(",")] for l in out.splitlines() if l.strip()]
+        rows = [r for r in rows if len(r) >= 7 and r[0].isdigit()]
+        busy = [r for r in rows if r[6].isdigit() and int(r[6]) > 0] or rows
+        if not busy:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in busy)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        mx = max(int(r[1]) for r in self.rows if r[1].isdigit())
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in busy)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(int(r[1]) for r in busy if r[1].isdigit()),
+                "reasons": reasons, "samples": len(busy)}
 
 
 def oracle_batch_time(scenes, reps, seed=4000):
@@ -192,18 +200,19 @@ def main():
             torch.cuda.current_stream().synchronize()
         return out
 
-    # sampler share (roofline numerator's time): events around the native sampler call
-    real_rollout = NT.diffusion_rollout
+    # roofline numerator's time: CUDA events immediately around the native sampler call
+    # (pstl_denoiser_sample = hoist GEMMs + input pack + the persistent tcgen05 kernel)
+    pending = {}
 
-    def timed_rollout(*aa, **kk):
-        e0, e1 = ev(), ev()
-        e0.record()
-        r = real_rollout(*aa, **kk)
-        e1.record()
-        samp_ms.append((e0, e1))
-        return r
+    def kernel_timer(name, is_start):
+        e = ev()
+        e.record()
+        if is_start:
+            pending[name] = e
+        else:
+            samp_ms.append((pending.pop(name), e))
 
-    NT.diffusion_rollout = timed_rollout
+    NT.KERNEL_TIMER = kernel_timer
 
     def barrier():
         torch.cuda.synchronize()
@@ -211,13 +220,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
     for i in range(a.warmup):
         step(i, False)
     barrier()
     samp_ms.clear()
-    clk = ClockSampler(local)
-    if rank == 0:
-        clk.start()
     e0, e1 = ev(), ev()
     e0.record()
     for i in range(a.steps):
@@ -236,7 +245,6 @@ def main():
         step(i, True)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    clk.stop_flag = True
     tm = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)

@@ -81,6 +81,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!done && ++spins > (1u << 24)) __trap();  // a protocol bug must fail the launch, not hang the GPU
   } while (!done);
 }
+// pure polling wait (mbarrier.test_wait never suspends the thread): used where a late wake-up of the
+// suspending try_wait was measured to cost ~1000 cycles per step (tc timeline)
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  unsigned spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();
+  } while (!done);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -229,6 +245,7 @@ struct TcArgs {
   unsigned long long seed, offset;
   // RefineNet pass (Net.rect_forward, reference nusc_model.py:209-233): one "step", no x update
   int refine;
+  int exp_skip_bias;    // timing experiment only (PSTL_TC_EXP=skipbias): results are wrong
   const float* u0;      // (N, 40) controls being refined
   const float* scores;  // (N)
   float* out;           // (N, 40)
@@ -324,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       for (int s = 0; s < n_steps; ++s, ++it) {
         const uint32_t ph = it & 1;
         if (s == 0) write_bias_cols(tile, a.first_step);
-        mbar_wait(bar_x, ph);
+        mbar_spin(bar_x, ph);
         if (MSTAMP) a.dbg[0] = clock64();
         tc_fence_after();
         if (lane == 0) {
@@ -334,10 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
             if (MSTAMP) a.dbg[16 + k] = clock64();
           }
           tc_commit(bar_d1);
-          if (MSTAMP) a.dbg[1] = clock64();
+          if (MSTAMP) { a.dbg[1] = clock64(); mbar_wait(bar_d1, ph); a.dbg[20] = clock64(); }
         }
         __syncwarp();
-        mbar_wait(bar_h1, ph);
+        mbar_spin(bar_h1, ph);
         if (MSTAMP) a.dbg[2] = clock64();
         tc_fence_after();
         if (lane == 0) {
@@ -352,8 +369,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         }
         __syncwarp();
         // layer-1 MMA of this step has retired (bar_h1 passed): next step's bias columns, in the layer-2 shadow
-        if (s + 1 < n_steps) write_bias_cols(tile, a.first_step - s - 1);
-        mbar_wait(bar_h2, ph);
+        if (s + 1 < n_steps && !a.exp_skip_bias) write_bias_cols(tile, a.first_step - s - 1);
+        mbar_spin(bar_h2, ph);
         if (MSTAMP) a.dbg[4] = clock64();
         tc_fence_after();
         if (lane == 0) {
@@ -412,10 +429,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         const uint32_t ph = it & 1;
         const int i = a.first_step - s;  // reverse step index (t == i)
         float zn[20];
+        // This step's noise z (20 normals per thread = 5 Philox calls) is drawn in the shadows of the three
+        // MMAs: 4 calls while the long layer-2 MMA runs, 1 while layer 3 runs (layer 1 is too short).  The Philox counter
+        // passes through an opaque asm at each site so the compiler cannot hoist the (barrier-independent)
+        // arithmetic to the top of the loop, where it would sit on the critical path.
+        const int zi = a.steps - 1 - i;
+        const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
+        const bool draw = i > 1 && !a.refine;
+        auto noise4 = [&](int j) {
+          unsigned step_ctr = (unsigned)i + (unsigned)a.offset;
+          asm volatile("" : "+r"(step_ctr)::"memory");
+          zn[j] = zn[j + 1] = zn[j + 2] = zn[j + 3] = 0.f;
+          if (draw) {
+            if (zr) {
+              const float4 zz = *reinterpret_cast<const float4*>(zr + j);
+              zn[j] = zz.x; zn[j + 1] = zz.y; zn[j + 2] = zz.z; zn[j + 3] = zz.w;
+            } else {
+              uint4 ctr4 = make_uint4((unsigned)(rrow & 0xffffffff), (unsigned)(rrow >> 32), (unsigned)((c0 + j) >> 2), step_ctr);
+              const uint4 rn = pstl_philox(ctr4, make_uint2((unsigned)(a.seed & 0xffffffff), (unsigned)(a.seed >> 32)));
+              pstl_box_muller(rn.x, rn.y, zn[j], zn[j + 1]);
+              pstl_box_muller(rn.z, rn.w, zn[j + 2], zn[j + 3]);
+            }
+          }
+        };
         // ---- layers 1 and 2: D (bias already accumulated by the MMA) -> relu -> bf16 -> H ----
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
-          mbar_wait(layer == 0 ? bar_d1 : bar_d2, ph);
+          if (STAMP && layer == 0) a.dbg[21] = clock64();
+          mbar_spin(layer == 0 ? bar_d1 : bar_d2, ph);
           if (STAMP) a.dbg[layer == 0 ? 8 : 11] = clock64();
           tc_fence_after();
           const uint32_t dsrc = tmem + lane_addr + kColD + half * 128, hdst = tmem + lane_addr + kColH + half * 64;
@@ -441,30 +482,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           if (lane == 0) mbar_arrive(layer == 0 ? bar_h1 : bar_h2);
           if (STAMP) a.dbg[layer == 0 ? 9 : 12] = clock64();
           if (layer == 0) {
-            // this step's noise is drawn now, in the shadow of the layer-2 MMA
-            const int zi = a.steps - 1 - i;
-            const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 20; j += 4) {
-              zn[j] = zn[j + 1] = zn[j + 2] = zn[j + 3] = 0.f;
-              if (i > 1 && !a.refine) {
-                if (zr) {
-                  const float4 zz = *reinterpret_cast<const float4*>(zr + j);
-                  zn[j] = zz.x; zn[j + 1] = zz.y; zn[j + 2] = zz.z; zn[j + 3] = zz.w;
-                } else {
-                  uint4 ctr4 = make_uint4((unsigned)(rrow & 0xffffffff), (unsigned)(rrow >> 32), (unsigned)((c0 + j) >> 2),
-                                          (unsigned)i + (unsigned)a.offset);
-                  const uint4 rn = pstl_philox(ctr4, make_uint2((unsigned)(a.seed & 0xffffffff), (unsigned)(a.seed >> 32)));
-                  pstl_box_muller(rn.x, rn.y, zn[j], zn[j + 1]);
-                  pstl_box_muller(rn.z, rn.w, zn[j + 2], zn[j + 3]);
-                }
-              }
-            }
+            noise4(0);
+            noise4(4);
+            noise4(8);
+            noise4(12);
             if (STAMP) a.dbg[10] = clock64();
+          } else {
+            noise4(16);
           }
         }
         // ---- layer 3: eps, posterior mean, noise, next x ----
-        mbar_wait(bar_d3, ph);
+        mbar_spin(bar_d3, ph);
         if (STAMP) a.dbg[13] = clock64();
         tc_fence_after();
         uint32_t r[20];
@@ -605,6 +633,7 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   long long* dbg = nullptr;
   if (getenv("PSTL_TC_DEBUG")) { cudaMalloc(&dbg, 32 * sizeof(long long)); cudaMemset(dbg, 0, 32 * sizeof(long long)); }
   a.dbg = dbg;
+  a.exp_skip_bias = getenv("PSTL_TC_EXP") != nullptr;
   k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
   if (dbg) {
     cudaStreamSynchronize(st);
@@ -614,7 +643,7 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
                     "  EPI0: d1 %lld | epi1 done %lld | noise done %lld | d2 %lld | epi2 done %lld | d3 %lld | epi3 done %lld\n",
             0LL, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0],
             h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
-    fprintf(stderr, "  MMA1 issue stamps: %lld %lld %lld %lld\n", h[16] - h[0], h[17] - h[0], h[18] - h[0], h[19] - h[0]);
+    fprintf(stderr, "  MMA1 issue stamps: %lld %lld %lld %lld  d1 seen by the issuing lane: %lld ; epilogue warp 0 starts waiting for d1 at %lld\n", h[16] - h[0], h[17] - h[0], h[18] - h[0], h[19] - h[0], h[20] - h[0], h[21] - h[0]);
     cudaFree(dbg);
   }
   PSTL_LAUNCH_CHECK();

@@ -107,6 +107,18 @@ PSTL_HD bool pstl_cull_neighbour(float dx, float dy, float ego_half_len, float r
   return R > 0.f && (dx * dx + dy * dy) >= R * R;
 }
 
+// The segment search only ranks d_j + d_{j+1}: a 1-ulp square root (MUFU.SQRT) changes the arg-min only
+// between sums that differ by rounding; every distance that reaches the output uses the IEEE sqrtf.
+PSTL_HD float pstl_sqrt_search(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+
 // nusc_api.py:693-735: signed lateral distance and heading error of pose p to polyline lane.
 // part (3 floats or null): d dist/d px, d dist/d py, d ang/d pth.
 template <class LaneAcc>
@@ -117,7 +129,7 @@ PSTL_HD void pstl_lane_pred(float px, float py, float pth, const LaneAcc& lane, 
   int bi = 0;
   for (int j = 0; j < nseg; ++j) {
     const float dx = px - lane(j, 0), dy = py - lane(j, 1);
-    const float d = sqrtf(dx * dx + dy * dy);
+    const float d = pstl_sqrt_search(dx * dx + dy * dy);
     if (j > 0) {
       const float sum = prev + d;
       if (sum < bestv) { bestv = sum; bi = j - 1; }

@@ -49,9 +49,9 @@ __device__ __forceinline__ float wbase_sel(const WBase& b, int sid) {
   }
 }
 
-// value of a typed predicate leaf at this lane's time step.  Deliberately NOT inlined: the kernel is
-// instruction-cache bound if every consumer carries its own copy of the decode + IEEE division.
-__device__ __noinline__ float wpred(const WBase& b, int a0, int a1, const float* p) {
+// value of a typed predicate leaf at this lane's time step (called from ONE place: the kernel is
+// instruction-cache bound if every consumer carries its own copy of the decode + IEEE division)
+__device__ __forceinline__ float wpred(const WBase& b, int a0, int a1, const float* p) {
   const int sid = a0 & 0xff, pid = a1 & 0xff, den = (a1 >> 16) & 0xff;
   float x = wbase_sel(b, sid);
   if ((a0 >> 8) & 1) x = -x;
@@ -65,8 +65,7 @@ __device__ __noinline__ float wpred(const WBase& b, int a0, int a1, const float*
 // value of op `idx` at this lane's time step
 __device__ __forceinline__ float wget(const PstlProgView& P, int idx, const float* st, int lane, const WBase& b,
                                       const float* p) {
-  const PstlROp& o = P.ops[idx];
-  return (o.op == PSTL_OP_PRED) ? wpred(b, o.a0, o.a1, p) : st[idx * 32 + lane];
+  return st[idx * 32 + lane];  // leaves were materialised by warp_interp's first pass
 }
 
 // inclusive scan of (max, sum) pairs towards lane 0 (dir = +1: suffix) or towards lane 31 (dir = -1: prefix)
@@ -89,7 +88,10 @@ __device__ __noinline__ float warp_interp(const PstlProgView& P, float* st, int 
 #pragma unroll 1
   for (int i = 0; i < P.n_ops; ++i) {
     const PstlROp o = P.ops[i];
-    if (o.op == PSTL_OP_PRED) continue;  // evaluated by the consumer
+    if (o.op == PSTL_OP_PRED) {  // a leaf is one word per lane here: materialise it
+      st[i * 32 + lane] = wpred(b, o.a0, o.a1, p);
+      continue;
+    }
     const bool is_min = (o.op == PSTL_OP_SMIN2 || o.op == PSTL_OP_SMIN_K || o.op == PSTL_OP_WIN_SMIN ||
                          o.op == PSTL_OP_PREFIX_SMIN);
     const float sg = is_min ? -1.f : 1.f;
@@ -153,9 +155,7 @@ __device__ __noinline__ float warp_interp(const PstlProgView& P, float* st, int 
     }
     st[i * 32 + lane] = out;
   }
-  const PstlROp& top = P.ops[P.n_ops - 1];
-  const float mine = (top.op == PSTL_OP_PRED) ? wpred(b, top.a0, top.a1, p) : st[(P.n_ops - 1) * 32 + lane];
-  return __shfl_sync(0xffffffffu, mine, 0);
+  return __shfl_sync(0xffffffffu, st[(P.n_ops - 1) * 32 + lane], 0);
 }
 
 // scene accessors (SoA tile in shared memory, or this row's raw tensors in global memory)
@@ -239,15 +239,16 @@ __device__ __noinline__ void warp_predicates(const PstlProgView& P, const Scene&
   }
 }
 
+// The three resolved programs travel as kernel parameters (constant bank): the interpreter's decode and
+// branching then run on uniform loads / the uniform datapath instead of per-thread shared-memory reads.
+struct WarpProgs {
+  PstlProgView p[3];
+};
+
 template <bool SMEM_SCENE>
-__global__ void __launch_bounds__(256) k_score_warp(ScoreArgs a) {
+__global__ void __launch_bounds__(256, 3) k_score_warp(const __grid_constant__ ScoreArgs a, const __grid_constant__ WarpProgs wp) {
   extern __shared__ float sm[];
-  __shared__ PstlProgView progs[3];
-  for (int k = 0; k < 3; ++k) {
-    const int* src = reinterpret_cast<const int*>(a.progs[k]);
-    int* dst = reinterpret_cast<int*>(&progs[k]);
-    for (int i = threadIdx.x; i < (int)(sizeof(PstlProgView) / 4); i += blockDim.x) dst[i] = src[i];
-  }
+  const PstlProgView* progs = wp.p;
   const PstlEvalCfg c = a.cfg;
   const int T = c.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -393,11 +393,13 @@ static int launch_score_warp(ScoreArgs& a, pstl_program_t const* progs, cudaStre
   const size_t tile_bytes = ((((size_t)c.K * PSTL_SOA_F * c.T + (size_t)9 * c.nseg + 3) & ~(size_t)3)) * sizeof(float);
   const bool smem_scene = a.rows_per_scene % PSTL_WARP_ROWS == 0 && tile_bytes + stack_bytes <= 64 * 1024;
   const int grid = pstl_ceil_div(a.N, PSTL_WARP_ROWS);
+  WarpProgs wp;
+  for (int k = 0; k < 3; ++k) wp.p[k] = progs[k]->h;
   if (smem_scene) {
     PSTL_CUDA(cudaFuncSetAttribute(k_score_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    k_score_warp<true><<<grid, 256, tile_bytes + stack_bytes, st>>>(a);
+    k_score_warp<true><<<grid, 256, tile_bytes + stack_bytes, st>>>(a, wp);
   } else {
-    k_score_warp<false><<<grid, 256, stack_bytes, st>>>(a);
+    k_score_warp<false><<<grid, 256, stack_bytes, st>>>(a, wp);
   }
   PSTL_LAUNCH_CHECK();
   *took = 1;

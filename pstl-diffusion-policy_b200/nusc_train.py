@@ -619,6 +619,7 @@ class IterateList:
 
 _call_counter = [0]
 _sched_cache = {}
+KERNEL_TIMER = None  # bench hook: callable(name, is_start) recording CUDA events around the native sampler call
 
 
 def _host_schedule(beta, alpha, alpha_hat):
@@ -709,6 +710,8 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
     sched = _host_schedule(beta, alpha, alpha_hat)
     temb = net.time_table(steps, noise.device)
     _call_counter[0] += 1
+    if KERNEL_TIMER is not None:
+        KERNEL_TIMER("sampler", True)
     _nv.check(L.pstl_denoiser_sample(
         handle, _nv.fptr(_nv.f32(scene_feat)), bs, rows_per_scene, _nv.fptr(hl), _nv.fptr(stlp), n,
         _nv.C.c_void_p(sched.data_ptr()), _nv.fptr(temb), steps, _nv.fptr(x_T), _nv.fptr(z),
@@ -716,6 +719,8 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
         _nv.C.c_float(args.mul_w_max), _nv.C.c_float(args.mul_a_max), int(bool(args.diffusion_clip)), K,
         _nv.C.byref(gcfg) if gcfg is not None else None, _nv.fptr(iterates), None, _nv.ptr(ws), _nv.stream()),
         "pstl_denoiser_sample")
+    if KERNEL_TIMER is not None:
+        KERNEL_TIMER("sampler", False)
     diffused_result = iterates[-1]
     dense_feature = None
     if return_feature:
