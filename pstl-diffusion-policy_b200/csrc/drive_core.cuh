@@ -119,8 +119,41 @@ PSTL_HD float pstl_sqrt_search(float x) {
 #endif
 }
 
-// nusc_api.py:693-735: signed lateral distance and heading error of pose p to polyline lane.
+// nusc_api.py:693-735, after the segment search: signed lateral distance (triangle area / base) and
+// heading error of pose p to the segment (x2,y2,th2)-(x3,y3).
 // part (3 floats or null): d dist/d px, d dist/d py, d ang/d pth.
+PSTL_HD void pstl_lane_finish(float px, float py, float pth, float x2, float y2, float th2, float x3, float y3,
+                              int clip_dist, float& dist, float& ang, float* part) {
+  const float area = px * (y2 - y3) + x2 * (y3 - py) + x3 * (py - y2);
+  const float bx = x2 - x3, by = y2 - y3;
+  const float base = sqrtf(bx * bx + by * by);
+  const float ex = px - x2, ey = py - y2;
+  const float q = ex * ex + ey * ey;
+  const float l2 = sqrtf(fmaxf(q, 1e-3f));
+  const float ok = (base != 0.f) ? 1.f : 0.f;
+  const float den = fmaxf(base, 1e-7f);
+  float d0 = ok * area / den + (1.f - ok) * l2;
+  float gdx = 0.f, gdy = 0.f;
+  if (part) {
+    gdx = ok * (y2 - y3) / den;
+    gdy = ok * (x3 - x2) / den;
+    if (ok == 0.f && q >= 1e-3f) { gdx += ex / l2; gdy += ey / l2; }
+  }
+  if (clip_dist) {
+    if (d0 < -5.f || d0 > 5.f) { gdx = 0.f; gdy = 0.f; }
+    d0 = fminf(fmaxf(d0, -5.f), 5.f);
+  }
+  const float u = th2 - pth;
+  dist = d0;
+  ang = 1.f - cosf(u);
+  if (part) {
+    part[0] = gdx;
+    part[1] = gdy;
+    part[2] = -sinf(u);
+  }
+}
+
+// nusc_api.py:693-735: closest segment by arg-min of d_j + d_{j+1} (first minimum), then pstl_lane_finish.
 template <class LaneAcc>
 PSTL_HD void pstl_lane_pred(float px, float py, float pth, const LaneAcc& lane, int nseg, int clip_dist,
                             float& dist, float& ang, float* part) {
@@ -136,30 +169,8 @@ PSTL_HD void pstl_lane_pred(float px, float py, float pth, const LaneAcc& lane, 
     }
     prev = d;
   }
-  const float x2 = lane(bi, 0), y2 = lane(bi, 1), x3 = lane(bi + 1, 0), y3 = lane(bi + 1, 1);
-  const float area = px * (y2 - y3) + x2 * (y3 - py) + x3 * (py - y2);
-  const float bx = x2 - x3, by = y2 - y3;
-  const float base = sqrtf(bx * bx + by * by);
-  const float ex = px - x2, ey = py - y2;
-  const float q = ex * ex + ey * ey;
-  const float l2 = sqrtf(fmaxf(q, 1e-3f));
-  const float ok = (base != 0.f) ? 1.f : 0.f;
-  const float den = fmaxf(base, 1e-7f);
-  float d0 = ok * area / den + (1.f - ok) * l2;
-  float gdx = ok * (y2 - y3) / den, gdy = ok * (x3 - x2) / den;
-  if (ok == 0.f && q >= 1e-3f) { gdx += ex / l2; gdy += ey / l2; }
-  if (clip_dist) {
-    if (d0 < -5.f || d0 > 5.f) { gdx = 0.f; gdy = 0.f; }
-    d0 = fminf(fmaxf(d0, -5.f), 5.f);
-  }
-  const float u = lane(bi, 2) - pth;
-  dist = d0;
-  ang = 1.f - cosf(u);
-  if (part) {
-    part[0] = gdx;
-    part[1] = gdy;
-    part[2] = -sinf(u);
-  }
+  pstl_lane_finish(px, py, pth, lane(bi, 0), lane(bi, 1), lane(bi, 2), lane(bi + 1, 0), lane(bi + 1, 1), clip_dist,
+                   dist, ang, part);
 }
 
 // decode helpers for PSTL_OP_PRED

@@ -1,0 +1,345 @@
+// score_stream.cuh — streaming forward scorer: ONE thread per trajectory, ONE pass over the rollout.
+//
+// For programs with a PstlPlan (stl_program.h: [ListAnd of] R1_[lo,hi) [R2_suffix] X) the robustness at
+// t = 0 needs no trace tape: while the Euler rollout advances, every term keeps an online log-sum-exp
+// accumulator (max, sum) in two registers; only the terms with an inner suffix operator park X(t) in a
+// shared-memory column and are folded by one backward sweep after the rollout.  All threads of a block
+// are at the same time step of the same scene, so every scene read (lane points, neighbour circles) is a
+// warp-uniform shared-memory broadcast, and warps are dealt rows of one formula (rows cycle through the
+// three modes), so term decoding is uniform too.
+//
+// Replaces, per row: generate_trajs (nusc_train.py:39-49), prep_stl_cache (:74-93), the three formula
+// calls of compute_stl_dense (:318-323) and the best-of-K max/gather (:992-1007).
+//
+// Soft reductions run in the base-2 domain: x2 = x * (+-tau * log2 e), e = ex2(-|x2 - m|), result
+// (lg2(s) + m) * ln2 / tau.  Mathematically torch.logsumexp; rounding differs by a few ulp of the result.
+#pragma once
+#include "drive_eval.cuh"
+
+#define PSTL_STREAM_NEI_F4 4  // float4 per staged (neighbour, step): cx[4] | cy[4] | valid, centre x, y, L/2 | r
+
+PSTL_HD float pstl_ex2(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return exp2f(x);
+#endif
+}
+PSTL_HD float pstl_lg2(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return log2f(x);
+#endif
+}
+
+#define PSTL_LSE2_INIT (-3.402823466e+38f)
+
+// online log-sum-exp in base 2: exactly one of the two rescale factors is 1, so one ex2 per element
+PSTL_HD void pstl_lse2_add(float& m, float& s, float x) {
+  const float d = x - m;
+  const float e = pstl_ex2(-fabsf(d));
+  s = (d > 0.f) ? s * e + 1.f : s + e;
+  m = fmaxf(m, x);
+}
+
+struct PstlF4 {
+  float x, y, z, w;
+};
+
+// scene accessors of the streaming scorer
+struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
+  const float* neib;            // (K,T,7)
+  const float* ln[3];           // (nseg,3)
+  int T;
+  PSTL_HD PstlF4 lane_pt(int l, int j) const {
+    const float* p = ln[l] + j * 3;
+    return PstlF4{p[0], p[1], p[2], 0.f};
+  }
+  PSTL_HD void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& reach) const {
+    const float* p = neib + ((size_t)k * T + t) * 7;
+    valid = p[0]; cx = p[1]; cy = p[2]; reach = p[5] / 2.f;
+  }
+  PSTL_HD void nei(int k, int t, PstlNei& out) const {
+    const float* p = neib + ((size_t)k * T + t) * 7;
+    PstlCircles c;
+    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], c);
+    for (int i = 0; i < PSTL_NL; ++i) { out.cx[i] = c.cx[i]; out.cy[i] = c.cy[i]; }
+    out.r = c.r;
+    out.valid = p[0];
+  }
+};
+
+PSTL_HD float pstl_plan_leaf(const PstlLeafC& l, float v, float d, float th, float nei, const float* p) {
+  const float base = (l.c == 0) ? v : (l.c == 1) ? d : (l.c == 2) ? th : nei;
+  float x = l.sb * base + l.sp * p[l.pid];  // signs are +-1: exact
+  if (l.den != PSTL_DEN_ONE) x = x / pstl_pred_den(l.den, p);
+  return x;
+}
+
+// One trajectory through rollout -> predicates -> plan.  u: this row's controls (T*2, pre-scale) or null;
+// ego: pre-rolled states (stride es) or null; p: this row's six pSTL parameters; tape: this row's column
+// base, element (col, t) at tape[(col * T + t) * tstride].
+template <class Scene>
+PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose s, const float* u,
+                               const float* ego, int es, const float* p, float* tape, int tstride) {
+  const int T = c.T;
+  const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
+  const float back = 0.6931471805599453f / c.tau;  // ln2 / tau
+  const float ego_half = c.ego_L / 2.f;
+  float am[PSTL_MAX_TERMS], as[PSTL_MAX_TERMS];
+#pragma unroll
+  for (int k = 0; k < PSTL_MAX_TERMS; ++k) { am[k] = PSTL_LSE2_INIT; as[k] = 0.f; }
+
+#pragma unroll 1
+  for (int t = 0; t < pl.need_pose; ++t) {
+    if (ego) {
+      const float* e = ego + (size_t)t * es;
+      s.x = e[0]; s.y = e[1]; s.th = e[2]; s.v = e[3];
+    }
+    float sn, cs;
+#if defined(__CUDA_ARCH__)
+    sincosf(s.th, &sn, &cs);
+#else
+    sn = sinf(s.th); cs = cosf(s.th);
+#endif
+    float d = 0.f, th = 0.f, nei = 0.f;
+    if (t < pl.need_lane) {
+      // nusc_api.py:693-712: closest segment = first arg-min of d_j + d_{j+1}
+      const int l = pl.lane;
+      PstlF4 q = sc.lane_pt(l, 0);
+      float dx = s.x - q.x, dy = s.y - q.y;
+      float prev = pstl_sqrt_search(dx * dx + dy * dy);
+      float bestv = INFINITY;
+      int bi = 0;
+      for (int j = 1; j < c.nseg; ++j) {
+        q = sc.lane_pt(l, j);
+        dx = s.x - q.x; dy = s.y - q.y;
+        const float dj = pstl_sqrt_search(dx * dx + dy * dy);
+        const float sum = prev + dj;
+        if (sum < bestv) { bestv = sum; bi = j - 1; }
+        prev = dj;
+      }
+      const PstlF4 p2 = sc.lane_pt(l, bi), p3 = sc.lane_pt(l, bi + 1);
+      pstl_lane_finish(s.x, s.y, s.th, p2.x, p2.y, p2.z, p3.x, p3.y, c.clip_dist, d, th, nullptr);
+    }
+    if (t < pl.need_nei) {
+      // utils.py:465-526 + nusc_train.py:142-148 with exact culling (drive_core.cuh)
+      PstlCircles e;
+      pstl_car_circles(s.x, s.y, cs, sn, c.ego_L, c.ego_W, e);
+      float best = INFINITY;
+      for (int k = 0; k < c.K; ++k) {
+        float valid, ncx, ncy, reach;
+        sc.nei_meta(k, t, valid, ncx, ncy, reach);
+        if (valid == 0.f) { best = fminf(best, 100.f); continue; }
+        if (valid == 1.f && pstl_cull_neighbour(s.x - ncx, s.y - ncy, ego_half, reach, best)) {
+          best = fminf(best, 20.f);
+          continue;
+        }
+        PstlNei nb;
+        sc.nei(k, t, nb);
+        best = fminf(best, pstl_pair_clearance(e, cs, sn, nb, nullptr));
+      }
+      nei = best;
+    }
+#pragma unroll
+    for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
+      if (k < pl.n_terms) {
+        const PstlTerm& tm = pl.terms[k];
+        if (tm.inner != 0 || (t >= tm.lo && t < tm.hi)) {
+          float x = pstl_plan_leaf(tm.a, s.v, d, th, nei, p);
+          if (tm.pair != 0) {  // soft-min / soft-max of two leaves (stl_d_lib.py:21-26)
+            const float g = (float)tm.pair * k2;
+            const float xa = x * g, xb = pstl_plan_leaf(tm.b, s.v, d, th, nei, p) * g;
+            const float m = fmaxf(xa, xb);
+            x = (pstl_lg2(1.f + pstl_ex2(-fabsf(xa - xb))) + m) * ((float)tm.pair * back);
+          }
+          if (tm.inner != 0) tape[(size_t)(tm.tape * T + t) * tstride] = x;
+          else pstl_lse2_add(am[k], as[k], x * ((float)tm.outer * k2));
+        }
+      }
+    }
+    if (!ego && t + 1 < pl.need_pose) {
+      float w, a;
+      pstl_scaled_control(u, t, c, w, a);
+      s = pstl_unicycle_step(s, w, a, c.dt, cs, sn);
+    }
+  }
+
+  // terms with an inner suffix operator: y(t) = R2_{t' >= t} X(t') by one backward sweep, folded into R1
+#pragma unroll
+  for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
+    if (k < pl.n_terms && pl.terms[k].inner != 0) {
+      const PstlTerm& tm = pl.terms[k];
+      const float gi = (float)tm.inner * k2;
+      const float go = (float)(tm.inner * tm.outer);  // y2 = (lg2 s + m) * inner ; outer argument = y2 * inner * outer
+      float m = PSTL_LSE2_INIT, sm = 0.f;
+#pragma unroll 1
+      for (int t = T - 1; t >= tm.lo; --t) {
+        pstl_lse2_add(m, sm, tape[(size_t)(tm.tape * T + t) * tstride] * gi);
+        if (t < tm.hi) pstl_lse2_add(am[k], as[k], (pstl_lg2(sm) + m) * go);
+      }
+    }
+  }
+
+  // top level (stl_d_lib.py:97-112): ListAnd = soft-min over the terms; empty window -> -inf (:7-8,16-17)
+  float top_m = PSTL_LSE2_INIT, top_s = 0.f, single = 0.f;
+  bool empty = false;
+#pragma unroll
+  for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
+    if (k < pl.n_terms) {
+      const PstlTerm& tm = pl.terms[k];
+      if (tm.hi <= tm.lo) empty = true;
+      const float y2 = (pstl_lg2(as[k]) + am[k]) * (float)tm.outer;  // term value * tau * log2 e
+      single = y2;
+      pstl_lse2_add(top_m, top_s, -y2);
+    }
+  }
+  if (empty) return -INFINITY;
+  if (!pl.listand) return single * back;
+  return -((pstl_lg2(top_s) + top_m) * back);
+}
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------
+struct StreamSceneSmem {
+  const float4* nb;  // [K*T][PSTL_STREAM_NEI_F4]
+  const float4* ln;  // [3][nseg] (x, y, theta, 0)
+  int T, nseg;
+  __device__ __forceinline__ PstlF4 lane_pt(int l, int j) const {
+    const float4 q = ln[l * nseg + j];
+    return PstlF4{q.x, q.y, q.z, q.w};
+  }
+  __device__ __forceinline__ void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& reach) const {
+    const float4 q = nb[(k * T + t) * PSTL_STREAM_NEI_F4 + 2];
+    valid = q.x; cx = q.y; cy = q.z; reach = q.w;
+  }
+  __device__ __forceinline__ void nei(int k, int t, PstlNei& o) const {
+    const float4* q = nb + (k * T + t) * PSTL_STREAM_NEI_F4;
+    const float4 a = q[0], b = q[1];
+    o.cx[0] = a.x; o.cx[1] = a.y; o.cx[2] = a.z; o.cx[3] = a.w;
+    o.cy[0] = b.x; o.cy[1] = b.y; o.cy[2] = b.z; o.cy[3] = b.w;
+    o.valid = q[2].x;
+    o.r = q[3].x;
+  }
+};
+
+__device__ __forceinline__ size_t stream_tile_f4(const PstlEvalCfg& c) {
+  return (size_t)c.K * c.T * PSTL_STREAM_NEI_F4 + (size_t)3 * c.nseg;
+}
+
+__device__ void stream_stage_scene(const ScoreArgs& a, int scene, float4* tile) {
+  const PstlEvalCfg& c = a.cfg;
+  const float* nb = a.neighbors + (size_t)scene * c.K * c.T * 7;
+  for (int e = threadIdx.x; e < c.K * c.T; e += blockDim.x) {
+    const float* p = nb + (size_t)e * 7;
+    PstlCircles cc;
+    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], cc);
+    float4* o = tile + (size_t)e * PSTL_STREAM_NEI_F4;
+    o[0] = make_float4(cc.cx[0], cc.cx[1], cc.cx[2], cc.cx[3]);
+    o[1] = make_float4(cc.cy[0], cc.cy[1], cc.cy[2], cc.cy[3]);
+    o[2] = make_float4(p[0], p[1], p[2], p[5] / 2.f);
+    o[3] = make_float4(cc.r, 0.f, 0.f, 0.f);
+  }
+  float4* ln = tile + (size_t)c.K * c.T * PSTL_STREAM_NEI_F4;
+  for (int e = threadIdx.x; e < 3 * c.nseg; e += blockDim.x) {
+    const int l = e / c.nseg, j = e - l * c.nseg;
+    const float* src = a.lanes[l] + ((size_t)scene * c.nseg + j) * 3;
+    ln[e] = make_float4(src[0], src[1], src[2], 0.f);
+  }
+}
+
+struct StreamPlans {
+  PstlPlan p[3];
+};
+
+#define PSTL_STREAM_BLOCK_MAX 192
+
+template <bool SMEM_SCENE>
+__global__ void __launch_bounds__(PSTL_STREAM_BLOCK_MAX, SMEM_SCENE ? 5 : 4)
+k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ StreamPlans sp) {
+  extern __shared__ float4 sm4[];
+  const PstlEvalCfg c = a.cfg;
+  const int B = blockDim.x, T = c.T;
+  const int n0 = blockIdx.x * B;
+  // rows of the pipeline cycle through the three formulas (n % 3): deal them to warps so that a warp
+  // evaluates ONE plan (a divergence optimisation only; every thread still reads its own mode)
+  int li = threadIdx.x;
+  if (B % 96 == 0) {
+    const int g = li / 96, w = li - g * 96;
+    li = g * 96 + (w & 31) * 3 + (w >> 5);
+  }
+  const int n = n0 + li;
+  float4* tile = sm4;
+  float* tape = reinterpret_cast<float*>(sm4);
+  if (SMEM_SCENE) {
+    stream_stage_scene(a, n0 / a.rows_per_scene, tile);
+    tape = reinterpret_cast<float*>(sm4 + stream_tile_f4(c));
+    __syncthreads();
+  }
+  tape += threadIdx.x;
+  const bool live = n < a.N;
+  int m = 4;
+  if (live) {
+    const float md = a.mode[n];
+    m = (md == 0.f) ? 0 : (md == 1.f) ? 1 : (md == 2.f) ? 2 : (md == 3.f) ? 3 : 4;
+  }
+  const int nn = live ? n : 0;
+  PstlPose s0{0.f, 0.f, 0.f, 0.f};
+  if (a.state0) {
+    const float4 q = *reinterpret_cast<const float4*>(a.state0 + (size_t)nn * 4);
+    s0 = PstlPose{q.x, q.y, q.z, q.w};
+  }
+  const float* stlp = a.stlp + (size_t)nn * 6;
+  const float* ego = a.ego ? a.ego + (size_t)nn * T * a.ego_stride : nullptr;
+  const int scene = nn / a.rows_per_scene;
+  StreamSceneSmem ss{tile, tile + (size_t)c.K * T * PSTL_STREAM_NEI_F4, T, c.nseg};
+  PstlStreamSceneGlobal sg;
+  sg.neib = a.neighbors + (size_t)scene * c.K * T * 7;
+  for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
+  sg.T = T;
+
+  float best = -INFINITY;
+  int bi = 0;
+#pragma unroll 1
+  for (int cand = 0; cand < a.C; ++cand) {
+    const float* u = a.controls ? a.controls + ((size_t)cand * a.N + nn) * T * 2 : nullptr;
+    float sc = (m == 3) ? 1.0f : 0.0f;  // nusc_train.py:322 outlier score; unknown mode selects nothing (:150-151)
+#pragma unroll 1
+    for (int mm = 0; mm < 3; ++mm) {
+      if (!__any_sync(0xffffffffu, m == mm)) continue;
+      if (m == mm) {
+        sc = SMEM_SCENE ? pstl_stream_eval(sp.p[mm], ss, c, s0, u, ego, a.ego_stride, stlp, tape, B)
+                        : pstl_stream_eval(sp.p[mm], sg, c, s0, u, ego, a.ego_stride, stlp, tape, B);
+      }
+    }
+    if (live && a.scores_all) a.scores_all[(size_t)cand * a.N + n] = sc;
+    if (cand == 0 || sc > best) { best = sc; bi = cand; }  // torch.max(dim=0): first maximum
+  }
+  if (!live) return;
+  if (a.best_score) a.best_score[n] = best;
+  if (a.best_idx) a.best_idx[n] = bi;
+  if ((a.best_controls || a.traj_out) && a.controls) {
+    const float* u = a.controls + ((size_t)bi * a.N + n) * T * 2;
+    PstlPose s = s0;
+    for (int t = 0; t < T; ++t) {
+      float w, ac;
+      pstl_scaled_control(u, t, c, w, ac);
+      if (a.best_controls) *reinterpret_cast<float2*>(a.best_controls + ((size_t)n * T + t) * 2) = make_float2(w, ac);
+      if (a.traj_out) {
+        *reinterpret_cast<float4*>(a.traj_out + ((size_t)n * (T + 1) + t) * 4) = make_float4(s.x, s.y, s.th, s.v);
+        float sn, cs;
+        sincosf(s.th, &sn, &cs);
+        s = pstl_unicycle_step(s, w, ac, c.dt, cs, sn);
+      }
+    }
+    if (a.traj_out) *reinterpret_cast<float4*>(a.traj_out + ((size_t)n * (T + 1) + T) * 4) = make_float4(s.x, s.y, s.th, s.v);
+  }
+}
+#endif  // __CUDACC__

@@ -14,6 +14,7 @@
 struct pstl_program {
   PstlProgView h;        // host copy
   PstlProgView* d;       // device copy
+  PstlPlan plan;         // closed form for the streaming scorer (valid == 0: interpreter only)
 };
 
 static const int kSmemBudget = 200 * 1024;
@@ -33,6 +34,7 @@ extern "C" int pstl_program_create(const pstl_op* postfix, int n_ops, int n_sign
     return PSTL_ERR_ARG;
   }
   p->d = nullptr;
+  pstl_make_plan(p->h, &p->plan);
   cudaError_t e = cudaMalloc(&p->d, sizeof(PstlProgView));
   if (e == cudaSuccess) e = cudaMemcpy(p->d, &p->h, sizeof(PstlProgView), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -380,6 +382,13 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
 }
 
 #include "score_warp.cuh"
+#include "score_stream.cuh"
+
+// PSTL_SCORE_KERNEL=stream|warp|thread pins the forward scoring kernel (tests compare the three)
+static bool score_kernel_forced(const char* name) {
+  const char* e = getenv("PSTL_SCORE_KERNEL");
+  return e && strcmp(e, name) == 0;
+}
 
 static int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 
@@ -387,7 +396,7 @@ static int max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ?
 static int launch_score_warp(ScoreArgs& a, pstl_program_t const* progs, cudaStream_t st, int* took) {
   *took = 0;
   const PstlEvalCfg& c = a.cfg;
-  if (c.T > 31 || getenv("PSTL_SCORE_THREAD_KERNEL")) return PSTL_OK;
+  if (c.T > 31 || score_kernel_forced("thread")) return PSTL_OK;
   a.F = max3(progs[0]->h.n_ops, progs[1]->h.n_ops, progs[2]->h.n_ops);
   const size_t stack_bytes = (size_t)8 * a.F * 32 * sizeof(float);
   const size_t tile_bytes = ((((size_t)c.K * PSTL_SOA_F * c.T + (size_t)9 * c.nseg + 3) & ~(size_t)3)) * sizeof(float);
@@ -400,6 +409,55 @@ static int launch_score_warp(ScoreArgs& a, pstl_program_t const* progs, cudaStre
     k_score_warp<true><<<grid, 256, tile_bytes + stack_bytes, st>>>(a, wp);
   } else {
     k_score_warp<false><<<grid, 256, stack_bytes, st>>>(a, wp);
+  }
+  PSTL_LAUNCH_CHECK();
+  *took = 1;
+  return PSTL_OK;
+}
+
+// forward scoring on the streaming kernel (all three programs have a plan, soft semantics);
+// sets *took when it owned the launch
+static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaStream_t st, int* took) {
+  *took = 0;
+  const PstlEvalCfg& c = a.cfg;
+  if (c.hard || score_kernel_forced("warp") || score_kernel_forced("thread")) return PSTL_OK;
+  StreamPlans sp;
+  int n_tapes = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (!progs[k]->plan.valid) return PSTL_OK;
+    sp.p[k] = progs[k]->plan;
+    n_tapes = progs[k]->plan.n_tapes > n_tapes ? progs[k]->plan.n_tapes : n_tapes;
+  }
+  const size_t tile_bytes = ((size_t)c.K * c.T * PSTL_STREAM_NEI_F4 + (size_t)3 * c.nseg) * sizeof(float4);
+  const size_t budget = 100 * 1024;
+  int block = 0;
+  bool smem_scene = false;
+  if (a.rows_per_scene % 32 == 0 && tile_bytes <= budget / 2) {  // one scene per block, staged in shared memory
+    static const int cands[] = {192, 96, 128, 64, 32};
+    for (int b : cands)
+      if (a.rows_per_scene % b == 0 && tile_bytes + (size_t)b * n_tapes * c.T * sizeof(float) <= budget) {
+        block = b;
+        smem_scene = true;
+        break;
+      }
+  }
+  if (!block) {
+    static const int cands[] = {128, 64, 32};
+    for (int b : cands)
+      if ((size_t)b * n_tapes * c.T * sizeof(float) <= budget / 2) {
+        block = b;
+        break;
+      }
+  }
+  if (!block) return PSTL_OK;
+  const size_t smem = (smem_scene ? tile_bytes : 0) + (size_t)block * n_tapes * c.T * sizeof(float);
+  const int grid = pstl_ceil_div(a.N, block);
+  if (smem_scene) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<true><<<grid, block, smem, st>>>(a, sp);
+  } else {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<false><<<grid, block, smem, st>>>(a, sp);
   }
   PSTL_LAUNCH_CHECK();
   *took = 1;
@@ -512,6 +570,8 @@ extern "C" int pstl_score_fused(pstl_program_t const* progs, const pstl_scene_vi
   a.scores_all = scores_all; a.best_score = best_score; a.best_idx = best_idx;
   a.best_controls = best_controls; a.traj_out = traj_out; a.ws = (float*)workspace;
   int took = 0;
+  rc = launch_score_stream(a, progs, (cudaStream_t)stream, &took);
+  if (rc || took) return rc;
   rc = launch_score_warp(a, progs, (cudaStream_t)stream, &took);
   if (rc || took) return rc;
   ScorePlan plan = plan_score(progs, scenes, N, 0);

@@ -135,3 +135,112 @@ static inline int pstl_resolve_program(const pstl_op* ops, int n_ops, int n_sign
   return 0;
 #undef FAIL
 }
+
+// ----------------------------------------------------------------------------------------
+// Plan: closed form of a resolved driving program of the shape
+//     [ListAnd of]  R1_{t in [lo,hi)} [ R2_{t' in [t,T)} ]  X(t)        (only t = 0 consumed)
+// with R1, R2 in {soft-min (Always), soft-max (Eventually)} and X a typed predicate leaf or a
+// soft-min/max of two typed leaves — the whole spec of build_stl_cache (nusc_train.py:95-140).
+// The streaming scorer (score_stream.cuh) evaluates such a program in ONE pass over the rollout with
+// two registers per term; anything else runs on the postfix interpreter kernels.
+// ----------------------------------------------------------------------------------------
+#define PSTL_MAX_TERMS 8
+#define PSTL_MAX_TAPES 4
+struct PstlLeafC {
+  int c;      // canonical base signal: 0 speed, 1 lane distance, 2 lane heading error, 3 neighbour clearance
+  int pid;    // stlp column
+  int den;    // PSTL_DEN_*
+  float sb, sp;  // +-1
+};
+struct PstlTerm {
+  PstlLeafC a, b;
+  int pair;    // 0: X = a ; -1: soft-min(a,b) ; +1: soft-max(a,b)
+  int inner;   // 0: none ; -1 / +1: soft-min / soft-max over the suffix [t, T)
+  int outer;   // -1 / +1: soft-min / soft-max over [lo, hi) evaluated at t = 0
+  int lo, hi;  // clipped to [0, T]
+  int tape;    // tape column of X(t) for terms with an inner operator, else -1
+};
+struct PstlPlan {
+  int valid, n_terms, listand;
+  int lane;       // lane (0 curr, 1 left, 2 right) the distance / heading leaves refer to, -1: none
+  int n_tapes;
+  int need_pose, need_lane, need_nei;  // leading steps for which the pose / lane search / clearance are read
+  PstlTerm terms[PSTL_MAX_TERMS];
+};
+
+static inline bool pstl_plan_leaf(const PstlProgView& P, int idx, PstlLeafC* out, int* lane) {
+  const PstlROp& o = P.ops[idx];
+  if (o.op != PSTL_OP_PRED) return false;
+  const int sid = o.a0 & 0xff;
+  if (sid == PSTL_SIG_V) out->c = 0;
+  else if (sid == PSTL_SIG_NEI) out->c = 3;
+  else {
+    const int l = (sid - PSTL_SIG_D_CURR) / 2;
+    if (*lane >= 0 && *lane != l) return false;  // one lane search per program
+    *lane = l;
+    out->c = 1 + (sid - PSTL_SIG_D_CURR) % 2;
+  }
+  out->sb = ((o.a0 >> 8) & 1) ? -1.f : 1.f;
+  out->pid = o.a1 & 0xff;
+  out->sp = ((o.a1 >> 8) & 1) ? -1.f : 1.f;
+  out->den = (o.a1 >> 16) & 0xff;
+  return true;
+}
+
+static inline bool pstl_plan_x(const PstlProgView& P, int idx, PstlTerm* t, int* lane) {
+  const PstlROp& o = P.ops[idx];
+  if (o.op == PSTL_OP_SMIN2 || o.op == PSTL_OP_SMAX2) {
+    t->pair = (o.op == PSTL_OP_SMIN2) ? -1 : 1;
+    return pstl_plan_leaf(P, o.in0, &t->a, lane) && pstl_plan_leaf(P, o.in1, &t->b, lane);
+  }
+  t->pair = 0;
+  t->b = PstlLeafC{0, 0, 0, 1.f, 1.f};
+  return pstl_plan_leaf(P, idx, &t->a, lane);
+}
+
+static inline bool pstl_plan_term(const PstlProgView& P, int idx, PstlTerm* t, int* lane, int* n_tapes) {
+  const PstlROp& o = P.ops[idx];
+  if ((o.op != PSTL_OP_WIN_SMIN && o.op != PSTL_OP_WIN_SMAX) || o.n_out != 1) return false;
+  t->outer = (o.op == PSTL_OP_WIN_SMIN) ? -1 : 1;
+  t->lo = pstl_clipi(o.a0, 0, P.T);
+  t->hi = pstl_clipi(o.a1, 0, P.T);
+  t->tape = -1;
+  const PstlROp& c = P.ops[o.in0];
+  if ((c.op == PSTL_OP_WIN_SMIN || c.op == PSTL_OP_WIN_SMAX) && c.a0 == 0 && c.a1 >= P.T) {
+    t->inner = (c.op == PSTL_OP_WIN_SMIN) ? -1 : 1;
+    if (*n_tapes >= PSTL_MAX_TAPES) return false;
+    t->tape = (*n_tapes)++;
+    return pstl_plan_x(P, c.in0, t, lane);
+  }
+  t->inner = 0;
+  return pstl_plan_x(P, o.in0, t, lane);
+}
+
+static inline void pstl_make_plan(const PstlProgView& P, PstlPlan* pl) {
+  memset(pl, 0, sizeof(*pl));
+  pl->lane = -1;
+  if (P.need_t != 1 || P.n_signals != 0) return;
+  const PstlROp& top = P.ops[P.n_ops - 1];
+  int lane = -1, n_tapes = 0;
+  if (top.op == PSTL_OP_SMIN_K) {
+    if (top.a0 > PSTL_MAX_TERMS) return;
+    for (int j = 0; j < top.a0; ++j)
+      if (!pstl_plan_term(P, P.klist[top.a1 + j], &pl->terms[j], &lane, &n_tapes)) return;
+    pl->n_terms = top.a0;
+    pl->listand = 1;
+  } else {
+    if (!pstl_plan_term(P, P.n_ops - 1, &pl->terms[0], &lane, &n_tapes)) return;
+    pl->n_terms = 1;
+  }
+  pl->lane = lane;
+  pl->n_tapes = n_tapes;
+  pl->need_lane = 0;
+  if (lane >= 0) {
+    const int sd = PSTL_SIG_D_CURR + 2 * lane;
+    pl->need_lane = P.base_need[sd] > P.base_need[sd + 1] ? P.base_need[sd] : P.base_need[sd + 1];
+  }
+  pl->need_nei = P.base_need[PSTL_SIG_NEI];
+  pl->need_pose = 0;
+  for (int b = 0; b < PSTL_N_BASE_SIGNALS; ++b) pl->need_pose = P.base_need[b] > pl->need_pose ? P.base_need[b] : pl->need_pose;
+  pl->valid = 1;
+}

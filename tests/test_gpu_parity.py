@@ -407,3 +407,50 @@ def test_bf16_refinenet_vs_fp32():
     err = ((outs["bf16"] - outs["fp32"]) / torch.tensor([0.5, 5.0], device="cuda")).abs()
     assert torch.equal(outs["bf16"][scores >= 0], u0[scores >= 0])
     assert err.max().item() < 2e-2, err.max().item()
+
+
+def test_three_forward_scorers_agree():
+    """the three forward scoring kernels (streaming plan, warp interpreter, thread-per-trajectory tape kernel)
+    agree on the driving spec — dense rows and scene-indexed best-of-K"""
+    x, idx, mask = synthetic.make_dense_stl_input(3000, seed=1011)
+    args = NT.default_args()
+    stls = NT.build_stl_cache(args)
+    outs = []
+    try:
+        for kern in ("stream", "warp", "thread"):
+            os.environ["PSTL_SCORE_KERNEL"] = kern
+            _, sc, _ = NT.compute_stl_dense(cuda(x), stls, idx.cuda(), mask.cuda(), args)
+            outs.append(sc.clone())
+    finally:
+        os.environ.pop("PSTL_SCORE_KERNEL", None)
+    close(outs[0], outs[1], rtol=2e-6)
+    close(outs[0], outs[2], rtol=2e-6)
+    close(outs[0], O.stl_scores(dict(x), idx[:, 0], 100.0))
+    # scene-indexed pack, 5 candidates: scores_all / best_idx / best_controls / traj
+    S = 32
+    b = cuda(synthetic.make_scene_batch(6, n_randoms=S, seed=1012))
+    a2 = NT.default_args(n_randoms=S, sampling_size=S)
+    nb = NT.LazyBatch({k: b[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+                                         "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp")})
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    pack = NT.augment_batch_data(nb, None, a2, n_randoms=S)["_pstl_pack"]
+    g = torch.Generator().manual_seed(5)
+    cand = (torch.rand(5, pack.N, 20, 2, generator=g) * 2 - 1).cuda() * torch.tensor([0.5, 5.0], device="cuda")
+    progs = NT._fused_programs(NT.build_stl_cache(a2), 20)
+    want = ("scores_all", "best_score", "best_idx", "best_controls", "traj")
+    res = {}
+    try:
+        for kern in ("stream", "warp", "thread"):
+            os.environ["PSTL_SCORE_KERNEL"] = kern
+            res[kern] = {k: v.clone() for k, v in NT.score_pack(pack, cand, a2, progs, want=want).items()}
+    finally:
+        os.environ.pop("PSTL_SCORE_KERNEL", None)
+    for kern in ("warp", "thread"):
+        close(res["stream"]["scores_all"], res[kern]["scores_all"], rtol=2e-6)
+        sa = res[kern]["scores_all"]
+        top2 = sa.topk(2, dim=0).values
+        clear = (top2[0] - top2[1]) > 1e-4
+        assert torch.equal(res["stream"]["best_idx"][clear], res[kern]["best_idx"][clear])
+        same = res["stream"]["best_idx"] == res[kern]["best_idx"]
+        assert torch.equal(res["stream"]["best_controls"][same], res[kern]["best_controls"][same])
+        close(res["stream"]["traj"][same], res[kern]["traj"][same], rtol=1e-6)

@@ -104,5 +104,11 @@ def test_fused_dense_scores_and_grads(golden_dir, tag, n, nt, knei, seed):
                      fp(scores), None, fp(gego))
     assert rc == 0
     close(scores, sc_ref)
+    # the streaming plan evaluator (score_stream.cuh) on the same rows
+    s2 = np.zeros(n, np.float32)
+    rc = hs.hs_score_stream(ops3, nops, nt, knei, 15, fp(nei), fp(l0), fp(l1), fp(l2), 1, fp(mode), None, None, fp(ego), 4,
+                            fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(1.0), C.c_float(1.0), 0, fp(s2))
+    assert rc == 0
+    close(s2, sc_ref)
     gref = G[tag + "|grad_ego"]
     np.testing.assert_allclose(gego, gref, rtol=2e-4, atol=2e-4 * np.abs(gref).max())
