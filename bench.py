@@ -37,6 +37,7 @@ def parse():
     p.add_argument("--precision", default=os.environ.get("PSTL_PRECISION", "auto"), choices=["auto", "fp32", "bf16"])
     p.add_argument("--cpu-scenes", type=int, default=32, help="scenes per CPU-baseline batch")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     return p.parse_args()
 
 
@@ -186,12 +187,19 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
     samp_ms = []
 
+    # the public call: NT.CapturedPipeline replays sample_and_score as one CUDA graph (static shapes);
+    # --eager launches the same kernels one by one from Python
+    runner = None if a.eager else NT.CapturedPipeline(net, stls, coeffs, args, resident[0])
+    L = native.lib()
+
     def step(i, e2e):
-        if e2e:
-            b = {k: host[i % n_host][k].to(dev, non_blocking=True) for k in need}
+        b = host[i % n_host] if e2e else resident[i % n_host]
+        if runner is not None:
+            out = runner(b)  # copies the batch (pinned host or device) into the graph's static inputs, replays
         else:
-            b = resident[i % n_host]
-        out = NT.sample_and_score(net, b, stls, coeffs, args)
+            if e2e:
+                b = {k: b[k].to(dev, non_blocking=True) for k in need}
+            out = NT.sample_and_score(net, b, stls, coeffs, args)
         if world > 1:
             sharding.gather_scores(out["scores"], out["best_idx"])
         if e2e:
@@ -212,7 +220,14 @@ def main():
         else:
             samp_ms.append((pending.pop(name), e))
 
-    NT.KERNEL_TIMER = kernel_timer
+    if runner is None:
+        NT.KERNEL_TIMER = kernel_timer
+    # our kernels per step, counted by the library itself around one eager step
+    torch.cuda.synchronize()
+    c0 = L.pstl_launch_count()
+    NT.sample_and_score(net, resident[0], stls, coeffs, args)
+    torch.cuda.synchronize()
+    launches = int(L.pstl_launch_count() - c0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,6 +250,16 @@ def main():
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
+    if runner is not None:
+        # CUDA events cannot be read back from inside a replayed graph: the dominant kernel is timed by the same
+        # events around the same native call over a second pass of the same K steps, launched eagerly
+        NT.KERNEL_TIMER = kernel_timer
+        samp_ms.clear()
+        for i in range(a.steps):
+            flush.zero_()
+            NT.sample_and_score(net, resident[i % n_host], stls, coeffs, args)
+        barrier()
+        NT.KERNEL_TIMER = None
     sampler_ms = sum(x.elapsed_time(y) for x, y in samp_ms) / max(1, len(samp_ms))
     # end to end: pinned host inputs -> H2D -> pipeline -> D2H of scores + selected indices
     step(0, True)
@@ -258,10 +283,6 @@ def main():
     e2e_val = world * N / (e2e_ms / a.steps / 1e3)
     tf_peak, hbm_peak, src = peaks()
     achieved = FLOP_PER_CHAIN * N / (sampler_ms / 1e3) / 1e12
-    if precision == "fp32":
-        launches = 3 + 99 * 3 + 1 + 10 + 1  # hoist(2)+pack, 3 GEMM-kernels/step, best-of-K, RefineNet(10), final score
-    else:
-        launches = 3 + 1 + 1 + 10 + 1
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if precision == "fp32" else "bf16 (denoiser operands; fp32 accumulate, fp32 STL/rollout)",
@@ -270,6 +291,7 @@ def main():
                                    "%d scenes x 64 samples x 3 modes = %d chains per GPU per step" % (a.scenes, N),
                        "scenes_per_gpu": a.scenes, "chains_per_gpu": N, "multi_cands": K, "precision": precision,
                        "noise": "in-kernel Philox", "l2": "flushed between timed steps (160 MB write)",
+                       "launch": "eager" if runner is None else "CUDA graph replay of sample_and_score (NT.CapturedPipeline)",
                        "parallelism": "scene-sharded x%d, NCCL all-gather of scores" % world},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches * a.steps,
@@ -277,8 +299,10 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": None,
                          "kernel": "denoiser reverse loop (%s)" % precision,
-                         "note": "minimal hoisted FLOP count 17.39 MFLOP/chain / sampler time %.3f ms; peak = %s bf16 sustained"
-                                 % (sampler_ms, src)}}
+                         "note": "minimal hoisted FLOP count 17.39 MFLOP/chain / sampler time %.3f ms (CUDA events around "
+                                 "pstl_denoiser_sample, %s); peak = %s bf16 sustained"
+                                 % (sampler_ms, "timed region" if runner is None else "eager pass of the same K steps after "
+                                    "the graph-replay region", src)}}
     if not a.no_cpu_baseline:
         n, times = oracle_batch_time(a.cpu_scenes, 3)
         best = min(times[1:]) if len(times) > 1 else times[0]

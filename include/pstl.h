@@ -34,6 +34,8 @@ const char* pstl_last_error(void);
 /* library / device facts: returns sm count, writes compute capability major*10+minor */
 int pstl_device_info(int* sm_count, int* cc);
 int pstl_version(void);
+/* kernels launched by this library since load (bench.py reports it as gpu_launches) */
+unsigned long long pstl_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * STL formula programs (replaces the recursive node evaluation of stl_d_lib.py:70-203).
@@ -174,6 +176,12 @@ typedef struct {
 
 int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_denoiser_t* out);
 int pstl_denoiser_destroy(pstl_denoiser_t d);
+
+/* Philox offset word in DEVICE memory (or NULL to clear): the sampler adds *device_counter to the
+ * `offset` argument of pstl_denoiser_sample when it draws noise.  A CUDA graph that captured the
+ * sampler bumps this word in-graph so every replay draws fresh normals (upstream: randn_like per
+ * step, nusc_train.py:627). */
+int pstl_denoiser_set_noise_counter(pstl_denoiser_t d, const uint64_t* device_counter);
 
 typedef struct {
   const float* valid;    /* (N) lane validity mask of the guidance loss                       */

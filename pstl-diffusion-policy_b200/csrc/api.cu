@@ -1,4 +1,6 @@
 // api.cu — error state, device facts
+#include <atomic>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -11,6 +13,10 @@ void pstl_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* pstl_last_error(void) { return g_err; }
+
+static std::atomic<unsigned long long> g_launches{0};
+void pstl_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" unsigned long long pstl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int pstl_version(void) { return 100; }
 

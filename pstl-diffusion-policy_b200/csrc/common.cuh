@@ -8,6 +8,7 @@
 #include "../../include/pstl.h"
 
 void pstl_set_error(const char* fmt, ...);
+void pstl_count_launch(void);  // api.cu: kernels launched by this library (pstl_launch_count)
 
 #define PSTL_CHECK_ARG(cond, msg)                   \
   do {                                              \
@@ -33,6 +34,7 @@ void pstl_set_error(const char* fmt, ...);
       pstl_set_error("%s: launch failed -> %s", __func__, cudaGetErrorString(e_));    \
       return PSTL_ERR_CUDA;                                                           \
     }                                                                                 \
+    pstl_count_launch();                                                              \
   } while (0)
 
 static inline int pstl_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -243,6 +243,7 @@ struct TcArgs {
   int N, rows_per_scene, steps, first_step, last_step, keep, clip;
   float w_max, a_max;
   unsigned long long seed, offset;
+  const unsigned long long* offset_dev;  // optional device word added to offset (graph replays draw fresh noise)
   // RefineNet pass (Net.rect_forward, reference nusc_model.py:209-233): one "step", no x update
   int refine;
   int exp_skip_bias;    // timing experiment only (PSTL_TC_EXP=skipbias): results are wrong
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
     const int row_in_tile = q * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     const int c0 = half * 20;  // this thread's 20 state columns
+    const unsigned off_base = (unsigned)a.offset + (a.offset_dev ? (unsigned)__ldg(a.offset_dev) : 0u);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long row = (long long)tile * kTileM + row_in_tile;
       const bool live = row < a.N;
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
         const bool draw = i > 1 && !a.refine;
         auto noise4 = [&](int j) {
-          unsigned step_ctr = (unsigned)i + (unsigned)a.offset;
+          unsigned step_ctr = (unsigned)i + off_base;
           asm volatile("" : "+r"(step_ctr)::"memory");
           zn[j] = zn[j + 1] = zn[j + 2] = zn[j + 3] = 0.f;
           if (draw) {
@@ -627,7 +629,7 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
     a.sb[i] = sqrtf(beta[i]);
   }
   a.N = N; a.rows_per_scene = rows_per_scene; a.steps = steps; a.first_step = first_step; a.last_step = last_step;
-  a.keep = keep_last_k; a.clip = clip; a.w_max = w_max; a.a_max = a_max; a.seed = seed; a.offset = offset;
+  a.keep = keep_last_k; a.clip = clip; a.w_max = w_max; a.a_max = a_max; a.seed = seed; a.offset = offset; a.offset_dev = d->offset_dev;
   const int n_tiles = (N + kTileM - 1) / kTileM;
   const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
   long long* dbg = nullptr;

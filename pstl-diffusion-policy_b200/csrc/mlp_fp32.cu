@@ -24,6 +24,7 @@ struct LinArgs {
   float c1, c2, sqrt_beta;
   const float* z;
   unsigned long long seed, offset;
+  const unsigned long long* offset_dev;
   int step, noise_mode;  // 0: none, 1: injected, 2: philox
   float* xio; int ldxio;
   float* mu_out;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) k_linear(LinArgs a) {
         } else {
           float z = 0.f;
           if (a.noise_mode == 1) z = a.z[m * a.Nout + n];
-          else if (a.noise_mode == 2) z = pstl_noise_at(a.seed, a.offset, a.step, m, n);
+          else if (a.noise_mode == 2) z = pstl_noise_at(a.seed, a.offset + (a.offset_dev ? *a.offset_dev : 0ull), a.step, m, n);
           const float xn = mu + a.sqrt_beta * z;
           a.xio[m * a.ldxio + n] = xn;
           if (a.iter_out) {  // normalize_diff, nusc_train.py:647-655
@@ -200,15 +201,15 @@ __global__ void k_group_fuse(const float* __restrict__ g, const float* __restric
 
 __global__ void k_finish_step(const float* __restrict__ mu, float* __restrict__ xin, const float* __restrict__ z,
                               long long N, int T2, float sqrt_beta, int noise_mode, unsigned long long seed,
-                              unsigned long long offset, int step, float* __restrict__ iter_out, float w_max,
-                              float a_max, int clip) {
+                              unsigned long long offset, const unsigned long long* __restrict__ offset_dev, int step,
+                              float* __restrict__ iter_out, float w_max, float a_max, int clip) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * T2) return;
   const long long n = i / T2;
   const int c = (int)(i - n * T2);
   float zz = 0.f;
   if (noise_mode == 1) zz = z[i];
-  else if (noise_mode == 2) zz = pstl_noise_at(seed, offset, step, n, c);
+  else if (noise_mode == 2) zz = pstl_noise_at(seed, offset + (offset_dev ? *offset_dev : 0ull), step, n, c);
   const float xn = mu[i] + sqrt_beta * zz;
   xin[n * PSTL_XIN_LD + c] = xn;
   if (iter_out) {
@@ -251,6 +252,7 @@ extern "C" int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_d
   d->kin = d->T2 + 7;
   d->w1p = d->r1p = nullptr;
   d->tc = nullptr;
+  d->offset_dev = nullptr;
   const int in1 = w->feat_dim + d->T2 + w->time_dim + 7;  // 303
   const size_t f = sizeof(float);
   cudaError_t e = cudaMalloc(&d->w1p, (size_t)w->hidden * d->kin * f);
@@ -292,6 +294,12 @@ extern "C" int pstl_denoiser_destroy(pstl_denoiser_t d) {
   cudaFree(d->w1p);
   cudaFree(d->r1p);
   delete d;
+  return PSTL_OK;
+}
+
+extern "C" int pstl_denoiser_set_noise_counter(pstl_denoiser_t d, const uint64_t* device_counter) {
+  PSTL_CHECK_ARG(d, "null handle");
+  d->offset_dev = reinterpret_cast<const unsigned long long*>(device_counter);
   return PSTL_OK;
 }
 
@@ -433,7 +441,7 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
     a.c2 = 1.0f / sqrtf(alpha[i]);
     a.sqrt_beta = sqrtf(beta[i]);
     a.z = (noise && i > 1) ? noise + (size_t)zi * NT2 : nullptr;
-    a.seed = seed; a.offset = offset; a.step = i; a.noise_mode = noise_mode;
+    a.seed = seed; a.offset = offset; a.offset_dev = d->offset_dev; a.step = i; a.noise_mode = noise_mode;
     a.xio = w.xin; a.ldxio = PSTL_XIN_LD;
     a.mu_out = guided ? w.g : nullptr;
     a.iter_out = guided ? nullptr : it_out;
@@ -452,7 +460,7 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
                                 m, v, anchor, w.gws, stream);
       if (rc) break;
       k_finish_step<<<pstl_ceil_div((long long)NT2, 256), 256, 0, st>>>(w.g, w.xin, a.z, N, T2, a.sqrt_beta, noise_mode,
-                                                                       seed, offset, i, it_out, w_max, a_max, clip);
+                                                                       seed, offset, d->offset_dev, i, it_out, w_max, a_max, clip);
       cudaError_t le = cudaGetLastError();
       if (le != cudaSuccess) { rc = PSTL_ERR_CUDA; pstl_set_error("k_finish_step: %s", cudaGetErrorString(le)); break; }
     }

@@ -22,7 +22,7 @@ EXPORTS = [
     "pstl_program_tape_floats", "pstl_stl_workspace_bytes", "pstl_stl_eval_signals", "pstl_stl_eval_signals_bwd",
     "pstl_score_workspace_bytes", "pstl_score_fused", "pstl_score_fused_bwd", "pstl_guidance_step",
     "pstl_denoiser_create", "pstl_denoiser_destroy", "pstl_denoiser_workspace_bytes", "pstl_denoiser_sample",
-    "pstl_denoiser_eps", "pstl_refine", "pstl_rollout", "pstl_rollout_bwd", "pstl_predicates", "pstl_linear",
+    "pstl_denoiser_eps", "pstl_denoiser_set_noise_counter", "pstl_launch_count", "pstl_refine", "pstl_rollout", "pstl_rollout_bwd", "pstl_predicates", "pstl_linear",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
     except OSError as e:  # pragma: no cover
         raise PstlNativeError("cannot load %s: %s" % (LIB_PATH, e))
     L.pstl_last_error.restype = C.c_char_p
+    L.pstl_launch_count.restype = C.c_ulonglong
     for name in ("pstl_stl_workspace_bytes", "pstl_score_workspace_bytes", "pstl_denoiser_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
     _lib = L

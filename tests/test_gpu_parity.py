@@ -454,3 +454,32 @@ def test_three_forward_scorers_agree():
         same = res["stream"]["best_idx"] == res[kern]["best_idx"]
         assert torch.equal(res["stream"]["best_controls"][same], res[kern]["best_controls"][same])
         close(res["stream"]["traj"][same], res[kern]["traj"][same], rtol=1e-6)
+
+
+def test_captured_pipeline_replays_fresh_noise_and_new_inputs():
+    """CUDA-graph replay of sample_and_score: every replay draws fresh noise, reads the batch it is given, and
+    its scores are the eager scorer's scores of the controls it returns"""
+    S_ = 64
+    args = NT.default_args(precision="bf16", n_randoms=S_, sampling_size=S_)
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007))
+    net = net.cuda()
+    stls, co = NT.build_stl_cache(args), NT.get_diffusion_coeffs(args)
+    progs = NT._fused_programs(stls, args.nt)
+    b1 = cuda(synthetic.make_scene_batch(4, n_randoms=S_, seed=31))
+    b2 = cuda(synthetic.make_scene_batch(4, n_randoms=S_, seed=32))
+    runner = NT.CapturedPipeline(net, stls, co, args, b1)
+    o1 = {k: v.clone() for k, v in runner(b1).items() if isinstance(v, torch.Tensor)}
+    o2 = {k: v.clone() for k, v in runner(b1).items() if isinstance(v, torch.Tensor)}
+    o3 = {k: v.clone() for k, v in runner(b2).items() if isinstance(v, torch.Tensor)}
+    assert (o1["final_iterate"] - o2["final_iterate"]).abs().max().item() > 1e-3  # fresh z per replay
+    for b, o in ((b1, o2), (b2, o3)):
+        nb = NT.LazyBatch({k: b[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+                                             "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp")})
+        nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+        pack = NT.augment_batch_data(nb, None, args, n_randoms=S_)["_pstl_pack"]
+        sc = NT.score_pack(pack, o["controls"], args, progs)["best_score"]
+        assert torch.equal(sc, o["scores"])
+        assert torch.isfinite(o["scores"]).all()
+    # the z stream has unit variance: x_0 of a random-init net stays O(1)
+    assert 0.05 < o1["final_iterate"].std().item() < 50.0
