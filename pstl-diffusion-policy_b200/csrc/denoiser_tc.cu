@@ -58,6 +58,17 @@ struct TcState {
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a converged warp (ptxas keeps the guarded tcgen05 issue on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         mbar_spin(bar_x, ph);
         if (MSTAMP) a.dbg[0] = clock64();
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kK1 / 16; ++k) {  // advancing 32 B inside the 128 B swizzle atom
             mma_ts(tmem + kColD, tmem + kColX + k * 8, dW1 + (uint64_t)(k * 2), id12, k > 0);
@@ -358,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         mbar_spin(bar_h1, ph);
         if (MSTAMP) a.dbg[2] = clock64();
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           mma_ts(tmem + kColD, tmem + kColX + 24, dB2, id12, 0);  // D = onehot(class) . b2
 #pragma unroll
           for (int k = 0; k < kH / 16; ++k) {
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         mbar_spin(bar_h2, ph);
         if (MSTAMP) a.dbg[4] = clock64();
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kH / 16; ++k) {
             const uint64_t dB = make_desc(sbase + kOffW3 + (k >> 2) * (kN3 * 128)) + (uint64_t)((k & 3) * 2);

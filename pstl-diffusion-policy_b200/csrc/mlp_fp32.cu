@@ -36,57 +36,73 @@ struct LinArgs {
   const float* scores;
 };
 
-#define BM 128
 #define BN 64
 #define BK 16
 
-template <int EPI>
+// Tiled SGEMM with fused epilogues.  TMR rows x 4 columns per thread (block tile 16*TMR x 64); the next K-slab is
+// fetched into registers while the current one is multiplied.  Every output element is one fmaf chain over k in
+// ascending order, whatever the tile shape, so results do not depend on the batch size or the tile chosen.
+template <int EPI, int TMR>
 __global__ void __launch_bounds__(256) k_linear(LinArgs a) {
-  __shared__ __align__(16) float As[BK][BM + 4];
+  constexpr int BM_ = 16 * TMR;
+  constexpr int APT = BM_ * BK / 256;  // A elements per thread per slab (8 or 2)
+  __shared__ __align__(16) float As[BK][BM_ + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const long long m0 = (long long)blockIdx.x * BM;
+  const long long m0 = (long long)blockIdx.x * BM_;
   const int n0 = blockIdx.y * BN;
-  float acc[8][4];
+  float acc[TMR][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TMR; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int ar = tid >> 1, ak = (tid & 1) * 8;  // A: row ar, k-offset ak..ak+7
-  const int br = tid >> 2, bk = (tid & 3) * 4;  // B: row br, k-offset bk..bk+3
+  const int ar = tid / (BK / APT), ak = (tid % (BK / APT)) * APT;  // A: row ar, k-offset ak..ak+APT-1
+  const int br = tid >> 2, bk = (tid & 3) * 4;                      // B: row br, k-offset bk..bk+3
   const long long am = m0 + ar;
   const int bn = n0 + br;
-  for (int k0 = 0; k0 < a.K; k0 += BK) {
+  float ra[APT], rb4[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < APT; ++j) {
       const int k = k0 + ak + j;
-      As[ak + j][ar] = (am < a.M && k < a.K) ? a.X[am * a.ldx + k] : 0.f;
+      ra[j] = (am < a.M && k < a.K) ? a.X[am * a.ldx + k] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + bk + j;
-      Bs[bk + j][br] = (bn < a.Nout && k < a.K) ? a.W[(long long)bn * a.ldw + k] : 0.f;
+      rb4[j] = (bn < a.Nout && k < a.K) ? a.W[(long long)bn * a.ldw + k] : 0.f;
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < a.K; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < APT; ++j) As[ak + j][ar] = ra[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Bs[bk + j][br] = rb4[j];
     __syncthreads();
+    if (k0 + BK < a.K) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      float av[TMR];
+#pragma unroll
+      for (int i = 0; i < TMR; i += 2) {
+        const float2 t2 = *reinterpret_cast<const float2*>(&As[kk][ty * TMR + i]);
+        av[i] = t2.x; av[i + 1] = t2.y;
+      }
       const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < TMR; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long long m = m0 + ty * 8 + i;
+  for (int i = 0; i < TMR; ++i) {
+    const long long m = m0 + ty * TMR + i;
     if (m >= a.M) continue;
     const float* rb = a.rowbias ? a.rowbias + (m / a.rows_per_group) * a.ldrb : nullptr;
 #pragma unroll
@@ -143,8 +159,14 @@ static void lin_defaults(LinArgs& a) { memset(&a, 0, sizeof(a)); a.rows_per_grou
 template <int EPI>
 static int launch_linear(const LinArgs& a, cudaStream_t st) {
   if (a.M <= 0) return PSTL_OK;
-  dim3 grid(pstl_ceil_div(a.M, BM), pstl_ceil_div(a.Nout, BN));
-  k_linear<EPI><<<grid, 256, 0, st>>>(a);
+  // small problems: 32-row tiles so the grid covers the SMs
+  if ((long long)pstl_ceil_div(a.M, 128) * pstl_ceil_div(a.Nout, BN) < 296) {
+    dim3 grid(pstl_ceil_div(a.M, 32), pstl_ceil_div(a.Nout, BN));
+    k_linear<EPI, 2><<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid(pstl_ceil_div(a.M, 128), pstl_ceil_div(a.Nout, BN));
+    k_linear<EPI, 8><<<grid, 256, 0, st>>>(a);
+  }
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
 }
@@ -196,6 +218,129 @@ __global__ void k_group_fuse(const float* __restrict__ g, const float* __restric
   for (int j = 0; j < per; ++j) {
     const long long n = (b * R + sh * per + j) * 3 + m;
     xin[n * PSTL_XIN_LD + c] = u0[n * T2 + c] + mx;
+  }
+}
+
+// RefineNet front end in one launch (nusc_model.py:186-204): merge_net (T2 -> 32 -> 32 -> T2, ReLU) on every chain of
+// one scene, max over the `per` samples of each (shard, mode) group, fused = u0 + pooled, packed with [hl | stlp | 0]
+// into the engine's input rows.  One block per scene, one thread per chain for the MLP (weights and the scene's
+// controls in shared memory), then a coalesced cooperative write of the packed rows.  The sums run k-ascending
+// through fmaf with the bias added last, exactly like k_linear.
+#define PSTL_MERGE_H 32
+__global__ void __launch_bounds__(256) k_merge_fuse(const float* __restrict__ u0, const float* __restrict__ w0,
+                                                    const float* __restrict__ b0, const float* __restrict__ w2,
+                                                    const float* __restrict__ b2, const float* __restrict__ w4,
+                                                    const float* __restrict__ b4, const float* __restrict__ hl,
+                                                    const float* __restrict__ stlp, float* __restrict__ xin, int T2, int R,
+                                                    int per) {
+  extern __shared__ __align__(16) float smf[];
+  constexpr int MH = PSTL_MERGE_H;
+  const int rows = 3 * R, ld = T2 + 1;
+  const int T2p = (T2 + 3) & ~3;
+  float* W0t = smf;                 // [T2][MH]   transposed: the inner index is the output unit (LDS.128 = 4 units)
+  float* W2t = W0t + T2 * MH;       // [MH][MH]
+  float* W4t = W2t + MH * MH;       // [MH][T2p]
+  float* B0 = W4t + MH * T2p;       // MH
+  float* B2 = B0 + MH;              // MH
+  float* B4 = B2 + MH;              // T2p
+  float* X = B4 + T2p;              // [rows][ld]: controls in, merge_net output over them (row r belongs to thread r)
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * rows;
+  // all global reads are float4 and issued before their first use (T2 % 4 == 0, checked by the launcher)
+  const int T2q = T2 / 4;
+#pragma unroll 4
+  for (int i = tid; i < MH * T2q; i += blockDim.x) {  // w0 (MH, T2) row-major -> W0t[k][j]
+    const float4 v = reinterpret_cast<const float4*>(w0)[i];
+    const int j = i / T2q, k = (i - j * T2q) * 4;
+    W0t[k * MH + j] = v.x; W0t[(k + 1) * MH + j] = v.y; W0t[(k + 2) * MH + j] = v.z; W0t[(k + 3) * MH + j] = v.w;
+  }
+#pragma unroll 4
+  for (int i = tid; i < T2 * (MH / 4); i += blockDim.x) {  // w4 (T2, MH) row-major -> W4t[in][c]
+    const float4 v = reinterpret_cast<const float4*>(w4)[i];
+    const int c = i / (MH / 4), j = (i - c * (MH / 4)) * 4;
+    W4t[j * T2p + c] = v.x; W4t[(j + 1) * T2p + c] = v.y; W4t[(j + 2) * T2p + c] = v.z; W4t[(j + 3) * T2p + c] = v.w;
+  }
+  for (int i = tid; i < MH * (MH / 4); i += blockDim.x) {  // w2 (MH, MH) -> W2t[k][j]
+    const float4 v = reinterpret_cast<const float4*>(w2)[i];
+    const int j = i / (MH / 4), k = (i - j * (MH / 4)) * 4;
+    W2t[k * MH + j] = v.x; W2t[(k + 1) * MH + j] = v.y; W2t[(k + 2) * MH + j] = v.z; W2t[(k + 3) * MH + j] = v.w;
+  }
+  for (int i = tid; i < MH; i += blockDim.x) { B0[i] = b0[i]; B2[i] = b2[i]; }
+  for (int i = tid; i < T2; i += blockDim.x) B4[i] = b4[i];
+  const float4* u4 = reinterpret_cast<const float4*>(u0 + row0 * T2);
+#pragma unroll 8
+  for (int i = tid; i < rows * T2q; i += blockDim.x) {
+    const float4 v = u4[i];
+    const int r = i / T2q, k = (i - r * T2q) * 4;
+    float* x = X + r * ld + k;
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  }
+  __syncthreads();
+  for (int r = tid; r < rows; r += blockDim.x) {
+    float h1[MH], h2[MH];
+#pragma unroll
+    for (int j = 0; j < MH; ++j) { h1[j] = 0.f; h2[j] = 0.f; }
+    for (int k = 0; k < T2; ++k) {
+      const float x = X[r * ld + k];
+#pragma unroll
+      for (int j = 0; j < MH; j += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(W0t + k * MH + j);
+        h1[j] = fmaf(x, w.x, h1[j]); h1[j + 1] = fmaf(x, w.y, h1[j + 1]);
+        h1[j + 2] = fmaf(x, w.z, h1[j + 2]); h1[j + 3] = fmaf(x, w.w, h1[j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MH; ++j) h1[j] = fmaxf(h1[j] + B0[j], 0.f);
+#pragma unroll
+    for (int k = 0; k < MH; ++k) {
+#pragma unroll
+      for (int j = 0; j < MH; j += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(W2t + k * MH + j);
+        h2[j] = fmaf(h1[k], w.x, h2[j]); h2[j + 1] = fmaf(h1[k], w.y, h2[j + 1]);
+        h2[j + 2] = fmaf(h1[k], w.z, h2[j + 2]); h2[j + 3] = fmaf(h1[k], w.w, h2[j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MH; ++j) h2[j] = fmaxf(h2[j] + B2[j], 0.f);
+    for (int c = 0; c < T2; c += 4) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int k = 0; k < MH; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(W4t + k * T2p + c);
+        a0 = fmaf(h2[k], w.x, a0); a1 = fmaf(h2[k], w.y, a1); a2 = fmaf(h2[k], w.z, a2); a3 = fmaf(h2[k], w.w, a3);
+      }
+      X[r * ld + c] = a0 + B4[c];
+      if (c + 1 < T2) X[r * ld + c + 1] = a1 + B4[c + 1];
+      if (c + 2 < T2) X[r * ld + c + 2] = a2 + B4[c + 2];
+      if (c + 3 < T2) X[r * ld + c + 3] = a3 + B4[c + 3];
+    }
+  }
+  __syncthreads();
+  constexpr int LQ = PSTL_XIN_LD / 4;
+  float4* o4 = reinterpret_cast<float4*>(xin + row0 * PSTL_XIN_LD);
+#pragma unroll 4
+  for (int i = tid; i < rows * LQ; i += blockDim.x) {
+    const int r = i / LQ, c = (i - r * LQ) * 4;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < T2) {
+      const float4 uu = u4[r * T2q + c / 4];
+      const int ri = r / 3, m = r - ri * 3, sh = ri / per;
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      for (int j = 0; j < per; ++j) {
+        const float* g = X + ((sh * per + j) * 3 + m) * ld + c;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mx[e] = fmaxf(mx[e], g[e]);
+      }
+      o[0] = uu.x + mx[0]; o[1] = uu.y + mx[1]; o[2] = uu.z + mx[2]; o[3] = uu.w + mx[3];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cc = c + e;
+        if (cc == T2) o[e] = hl[row0 + r];
+        else if (cc < T2 + 7) o[e] = stlp[(row0 + r) * 6 + (cc - T2 - 1)];
+      }
+    }
+    o4[i] = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -490,24 +635,34 @@ extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_sce
   const int inr = d->w.feat_dim + 7 + T2;
   int rc = hoist(d->w.r0_w, inr, d->w.r0_b, H, scene_feat, n_scenes, d->w.feat_dim, w.cscene, nullptr, 0, 0, 0, nullptr, st);
   if (rc) return rc;
-  // merge_net on every chain (nusc_model.py:186)
-  LinArgs a;
-  lin_defaults(a);
-  a.X = u0; a.ldx = T2; a.W = d->w.m0_w; a.ldw = T2; a.bias = d->w.m0_b; a.Y = w.h1; a.ldy = MH; a.M = N; a.K = T2; a.Nout = MH; a.act = 1;
-  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
-  lin_defaults(a);
-  a.X = w.h1; a.ldx = MH; a.W = d->w.m2_w; a.ldw = MH; a.bias = d->w.m2_b; a.Y = w.h2; a.ldy = MH; a.M = N; a.K = MH; a.Nout = MH; a.act = 1;
-  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
-  lin_defaults(a);
-  a.X = w.h2; a.ldx = MH; a.W = d->w.m4_w; a.ldw = MH; a.bias = d->w.m4_b; a.Y = w.g; a.ldy = T2; a.M = N; a.K = MH; a.Nout = T2;
-  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
-  const long long tot = (long long)N * PSTL_XIN_LD;
-  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(nullptr, 0, hl, stlp, w.xin, N, T2);
-  PSTL_LAUNCH_CHECK();
   const int per = n_randoms / n_shards;
-  const long long gtot = (long long)(N / per) * T2;
-  k_group_fuse<<<pstl_ceil_div(gtot, 256), 256, 0, st>>>(w.g, u0, w.xin, N, T2, n_randoms, per);
-  PSTL_LAUNCH_CHECK();
+  const int T2p = (T2 + 3) & ~3;
+  const size_t merge_smem = sizeof(float) * ((size_t)MH * T2 + MH * MH + (size_t)MH * T2p + 2 * MH + T2p + (size_t)3 * n_randoms * (T2 + 1));
+  LinArgs a;
+  if (MH == PSTL_MERGE_H && T2 % 4 == 0 && merge_smem <= 160 * 1024) {
+    // merge_net + shard max-pool + fuse + pack: one launch, one block per scene
+    PSTL_CUDA(cudaFuncSetAttribute(k_merge_fuse, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    k_merge_fuse<<<N / (3 * n_randoms), 256, merge_smem, st>>>(u0, d->w.m0_w, d->w.m0_b, d->w.m2_w, d->w.m2_b, d->w.m4_w,
+                                                            d->w.m4_b, hl, stlp, w.xin, T2, n_randoms, per);
+    PSTL_LAUNCH_CHECK();
+  } else {
+    // merge_net on every chain (nusc_model.py:186)
+    lin_defaults(a);
+    a.X = u0; a.ldx = T2; a.W = d->w.m0_w; a.ldw = T2; a.bias = d->w.m0_b; a.Y = w.h1; a.ldy = MH; a.M = N; a.K = T2; a.Nout = MH; a.act = 1;
+    if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+    lin_defaults(a);
+    a.X = w.h1; a.ldx = MH; a.W = d->w.m2_w; a.ldw = MH; a.bias = d->w.m2_b; a.Y = w.h2; a.ldy = MH; a.M = N; a.K = MH; a.Nout = MH; a.act = 1;
+    if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+    lin_defaults(a);
+    a.X = w.h2; a.ldx = MH; a.W = d->w.m4_w; a.ldw = MH; a.bias = d->w.m4_b; a.Y = w.g; a.ldy = T2; a.M = N; a.K = MH; a.Nout = T2;
+    if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+    const long long tot = (long long)N * PSTL_XIN_LD;
+    k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(nullptr, 0, hl, stlp, w.xin, N, T2);
+    PSTL_LAUNCH_CHECK();
+    const long long gtot = (long long)(N / per) * T2;
+    k_group_fuse<<<pstl_ceil_div(gtot, 256), 256, 0, st>>>(w.g, u0, w.xin, N, T2, n_randoms, per);
+    PSTL_LAUNCH_CHECK();
+  }
   if (d->precision == PSTL_PRECISION_BF16 && pstl_tc_has_refine(d) && (128 + rows_per_scene - 1) / rows_per_scene + 1 <= 8)
     return pstl_tc_refine(d, w.cscene, rows_per_scene, w.xin, N, u0, scores, w_max, a_max, clip_rect, out, st);
   rc = mlp_hidden(d, w, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st);

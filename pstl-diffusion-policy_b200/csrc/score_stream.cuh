@@ -52,17 +52,24 @@ struct PstlF4 {
 };
 
 // scene accessors of the streaming scorer
+//   lane_pt(l, j)                         lane l point j as (x, y, theta, -)
+//   nei_begin(t, count, init)             neighbours to visit at step t and the initial running minimum
+//                                         (100 when a zero-valid neighbour was dropped from the list)
+//   nei_meta(slot, t, valid, cx, cy, rsum) car centre and  L_ego/2 + L_nei/2 + 1e-3  (cull radius less min(best,20))
+//   nei(slot, t, out)                     circle centres, radius, valid
 struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
   const float* neib;            // (K,T,7)
   const float* ln[3];           // (nseg,3)
-  int T;
+  int K, T;
+  float ego_half;
   PSTL_HD PstlF4 lane_pt(int l, int j) const {
     const float* p = ln[l] + j * 3;
     return PstlF4{p[0], p[1], p[2], 0.f};
   }
-  PSTL_HD void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& reach) const {
+  PSTL_HD void nei_begin(int, int& count, float& init) const { count = K; init = INFINITY; }
+  PSTL_HD void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& rsum) const {
     const float* p = neib + ((size_t)k * T + t) * 7;
-    valid = p[0]; cx = p[1]; cy = p[2]; reach = p[5] / 2.f;
+    valid = p[0]; cx = p[1]; cy = p[2]; rsum = ego_half + p[5] / 2.f + 1e-3f;
   }
   PSTL_HD void nei(int k, int t, PstlNei& out) const {
     const float* p = neib + ((size_t)k * T + t) * 7;
@@ -74,6 +81,13 @@ struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
   }
 };
 
+// Exact cull (see pstl_cull_neighbour): rsum = L_ego/2 + L_nei/2 + margin
+PSTL_HD bool pstl_cull_neighbour_r(float dx, float dy, float rsum, float best) {
+  const float R = fminf(best, 20.f) + rsum;
+  return R > 0.f && (dx * dx + dy * dy) >= R * R;
+}
+
+// value of a typed leaf (include/pstl.h, PSTL_OP_PRED): (sb*base + sp*stlp[pid]) / den
 PSTL_HD float pstl_plan_leaf(const PstlLeafC& l, float v, float d, float th, float nei, const float* p) {
   const float base = (l.c == 0) ? v : (l.c == 1) ? d : (l.c == 2) ? th : nei;
   float x = l.sb * base + l.sp * p[l.pid];  // signs are +-1: exact
@@ -84,16 +98,35 @@ PSTL_HD float pstl_plan_leaf(const PstlLeafC& l, float v, float d, float th, flo
 // One trajectory through rollout -> predicates -> plan.  u: this row's controls (T*2, pre-scale) or null;
 // ego: pre-rolled states (stride es) or null; p: this row's six pSTL parameters; tape: this row's column
 // base, element (col, t) at tape[(col * T + t) * tstride].
+//
+// A single-leaf term  R_t (sb*b_t + q)/den  is shift-invariant:  = q/den + R_t (sb*b_t/den), so inside the
+// time loop such a term costs one multiply by its per-row factor g = +-tau*log2(e)/den and one online
+// accumulator update; q/den is added once after the loop.  Two-leaf (And/Or) terms evaluate X(t) in full.
 template <class Scene>
 PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose s, const float* u,
                                const float* ego, int es, const float* p, float* tape, int tstride) {
   const int T = c.T;
   const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
   const float back = 0.6931471805599453f / c.tau;  // ln2 / tau
-  const float ego_half = c.ego_L / 2.f;
-  float am[PSTL_MAX_TERMS], as[PSTL_MAX_TERMS];
+  float am[PSTL_MAX_TERMS], as[PSTL_MAX_TERMS], g2[PSTL_MAX_TERMS];
 #pragma unroll
-  for (int k = 0; k < PSTL_MAX_TERMS; ++k) { am[k] = PSTL_LSE2_INIT; as[k] = 0.f; }
+  for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
+    am[k] = PSTL_LSE2_INIT; as[k] = 0.f; g2[k] = 0.f;
+    if (k < pl.n_terms) {
+      const PstlTerm& tm = pl.terms[k];
+      if (tm.pair == 0) {
+        // single leaf: accumulate (or tape) b_t * g2 ; the operator sign joins g2 only when there is no inner operator
+        float g = tm.a.sb * k2;
+        if (tm.a.den != PSTL_DEN_ONE) g = g / pstl_pred_den(tm.a.den, p);
+        g2[k] = (tm.inner == 0) ? g * (float)tm.outer : g;
+      }
+    }
+  }
+
+  float rg_nei = 0.f;  // 1 / g2 of the clearance term (negative), see the value-aware bound below
+#pragma unroll
+  for (int k = 0; k < PSTL_MAX_TERMS; ++k)
+    if (k == pl.nei_term) rg_nei = 1.f / g2[k];
 
 #pragma unroll 1
   for (int t = 0; t < pl.need_pose; ++t) {
@@ -128,21 +161,50 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
       pstl_lane_finish(s.x, s.y, s.th, p2.x, p2.y, p2.z, p3.x, p3.y, c.clip_dist, d, th, nullptr);
     }
     if (t < pl.need_nei) {
-      // utils.py:465-526 + nusc_train.py:142-148 with exact culling (drive_core.cuh)
-      PstlCircles e;
-      pstl_car_circles(s.x, s.y, cs, sn, c.ego_L, c.ego_W, e);
-      float best = INFINITY;
-      for (int k = 0; k < c.K; ++k) {
-        float valid, ncx, ncy, reach;
-        sc.nei_meta(k, t, valid, ncx, ncy, reach);
-        if (valid == 0.f) { best = fminf(best, 100.f); continue; }
-        if (valid == 1.f && pstl_cull_neighbour(s.x - ncx, s.y - ncy, ego_half, reach, best)) {
-          best = fminf(best, 20.f);
-          continue;
+      // utils.py:465-526 + nusc_train.py:142-148 with exact culling (drive_core.cuh).
+      // Value-aware bound: when the clearance only feeds soft-min terms  G_t(nei_t - q)  (pl.nei_term >= 0), a
+      // step whose clearance exceeds that term's running minimum by more than 36 / (tau log2 e) adds less than
+      // 2^-36 to a sum >= 1 — nothing in fp32 — so neighbours that cannot come closer than thr are skipped.
+      float thr = 20.f;
+#pragma unroll
+      for (int k = 0; k < PSTL_MAX_TERMS; ++k)
+        if (k == pl.nei_term) thr = fminf(thr, (am[k] - 36.f) * rg_nei);
+      if (pl.nei_term < 0) thr = 20.f;
+      int cnt;
+      float best;
+      sc.nei_begin(t, cnt, best);
+      // pass 1 (branch-free): which neighbours can be closer than thr at all
+      unsigned cand = 0u;
+      for (int k = 0; k < cnt; ++k) {
+        float valid, ncx, ncy, rsum;
+        sc.nei_meta(k, t, valid, ncx, ncy, rsum);
+        const float dx = s.x - ncx, dy = s.y - ncy;
+        const float R = thr + rsum;
+        const bool far = (valid == 1.f) && (R > 0.f) && (dx * dx + dy * dy >= R * R);
+        if (valid == 0.f) best = fminf(best, 100.f);
+        else if (far) best = fminf(best, thr);   // its clipped clearance is >= thr (== 20 when thr == 20)
+        else cand |= 1u << (k & 31);
+        if ((k & 31) == 31 || k == cnt - 1) {
+          // pass 2: the survivors, nearest first, re-tested against the running minimum
+          if (cand) {
+            PstlCircles e;
+            pstl_car_circles(s.x, s.y, cs, sn, c.ego_L, c.ego_W, e);
+            const int k0 = k & ~31;
+            while (cand) {
+#if defined(__CUDA_ARCH__)
+              const int b = __ffs(cand) - 1;
+#else
+              const int b = __builtin_ctz(cand);
+#endif
+              cand &= cand - 1u;
+              sc.nei_meta(k0 + b, t, valid, ncx, ncy, rsum);
+              if (valid == 1.f && pstl_cull_neighbour_r(s.x - ncx, s.y - ncy, rsum, best)) continue;
+              PstlNei nb;
+              sc.nei(k0 + b, t, nb);
+              best = fminf(best, pstl_pair_clearance(e, cs, sn, nb, nullptr));
+            }
+          }
         }
-        PstlNei nb;
-        sc.nei(k, t, nb);
-        best = fminf(best, pstl_pair_clearance(e, cs, sn, nb, nullptr));
       }
       nei = best;
     }
@@ -151,15 +213,18 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
       if (k < pl.n_terms) {
         const PstlTerm& tm = pl.terms[k];
         if (tm.inner != 0 || (t >= tm.lo && t < tm.hi)) {
-          float x = pstl_plan_leaf(tm.a, s.v, d, th, nei, p);
-          if (tm.pair != 0) {  // soft-min / soft-max of two leaves (stl_d_lib.py:21-26)
+          float x2;  // X(t) in tau*log2(e) units (single leaf: without its constant q/den)
+          if (tm.pair == 0) {
+            const float base = (tm.a.c == 0) ? s.v : (tm.a.c == 1) ? d : (tm.a.c == 2) ? th : nei;
+            x2 = base * g2[k];
+          } else {  // soft-min / soft-max of two leaves (stl_d_lib.py:21-26)
             const float g = (float)tm.pair * k2;
-            const float xa = x * g, xb = pstl_plan_leaf(tm.b, s.v, d, th, nei, p) * g;
-            const float m = fmaxf(xa, xb);
-            x = (pstl_lg2(1.f + pstl_ex2(-fabsf(xa - xb))) + m) * ((float)tm.pair * back);
+            const float xa = pstl_plan_leaf(tm.a, s.v, d, th, nei, p) * g, xb = pstl_plan_leaf(tm.b, s.v, d, th, nei, p) * g;
+            x2 = (pstl_lg2(1.f + pstl_ex2(-fabsf(xa - xb))) + fmaxf(xa, xb)) * (float)tm.pair;
+            if (tm.inner == 0) x2 = x2 * (float)tm.outer;
           }
-          if (tm.inner != 0) tape[(size_t)(tm.tape * T + t) * tstride] = x;
-          else pstl_lse2_add(am[k], as[k], x * ((float)tm.outer * k2));
+          if (tm.inner != 0) tape[(size_t)(tm.tape * T + t) * tstride] = x2;
+          else pstl_lse2_add(am[k], as[k], x2);
         }
       }
     }
@@ -175,8 +240,8 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
   for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
     if (k < pl.n_terms && pl.terms[k].inner != 0) {
       const PstlTerm& tm = pl.terms[k];
-      const float gi = (float)tm.inner * k2;
-      const float go = (float)(tm.inner * tm.outer);  // y2 = (lg2 s + m) * inner ; outer argument = y2 * inner * outer
+      const float gi = (float)tm.inner;
+      const float go = (float)(tm.inner * tm.outer);  // y2 = (lg2 s + m) * inner ; outer argument = y2 * outer
       float m = PSTL_LSE2_INIT, sm = 0.f;
 #pragma unroll 1
       for (int t = T - 1; t >= tm.lo; --t) {
@@ -194,7 +259,12 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
     if (k < pl.n_terms) {
       const PstlTerm& tm = pl.terms[k];
       if (tm.hi <= tm.lo) empty = true;
-      const float y2 = (pstl_lg2(as[k]) + am[k]) * (float)tm.outer;  // term value * tau * log2 e
+      float y2 = (pstl_lg2(as[k]) + am[k]) * (float)tm.outer;  // term value * tau * log2 e
+      if (tm.pair == 0) {  // the leaf's constant, q/den
+        float q = tm.a.sp * p[tm.a.pid];
+        if (tm.a.den != PSTL_DEN_ONE) q = q / pstl_pred_den(tm.a.den, p);
+        y2 = y2 + q * k2;
+      }
       single = y2;
       pstl_lse2_add(top_m, top_s, -y2);
     }
@@ -209,19 +279,25 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
 // kernel
 // ---------------------------------------------------------------------------------------
 struct StreamSceneSmem {
-  const float4* nb;  // [K*T][PSTL_STREAM_NEI_F4]
-  const float4* ln;  // [3][nseg] (x, y, theta, 0)
-  int T, nseg;
+  const float4* nb;   // [T][K slots][PSTL_STREAM_NEI_F4], valid neighbours only, nearest (to the scene's ego) first
+  const float2* hdr;  // [T] (count, initial minimum)
+  const float4* ln;   // [3][nseg] (x, y, theta, 0)
+  int K, T, nseg;
   __device__ __forceinline__ PstlF4 lane_pt(int l, int j) const {
     const float4 q = ln[l * nseg + j];
     return PstlF4{q.x, q.y, q.z, q.w};
   }
-  __device__ __forceinline__ void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& reach) const {
-    const float4 q = nb[(k * T + t) * PSTL_STREAM_NEI_F4 + 2];
-    valid = q.x; cx = q.y; cy = q.z; reach = q.w;
+  __device__ __forceinline__ void nei_begin(int t, int& count, float& init) const {
+    const float2 h = hdr[t];
+    count = __float_as_int(h.x);
+    init = h.y;
+  }
+  __device__ __forceinline__ void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& rsum) const {
+    const float4 q = nb[(t * K + k) * PSTL_STREAM_NEI_F4 + 2];
+    valid = q.x; cx = q.y; cy = q.z; rsum = q.w;
   }
   __device__ __forceinline__ void nei(int k, int t, PstlNei& o) const {
-    const float4* q = nb + (k * T + t) * PSTL_STREAM_NEI_F4;
+    const float4* q = nb + (t * K + k) * PSTL_STREAM_NEI_F4;
     const float4 a = q[0], b = q[1];
     o.cx[0] = a.x; o.cx[1] = a.y; o.cx[2] = a.z; o.cx[3] = a.w;
     o.cy[0] = b.x; o.cy[1] = b.y; o.cy[2] = b.z; o.cy[3] = b.w;
@@ -230,28 +306,63 @@ struct StreamSceneSmem {
   }
 };
 
-__device__ __forceinline__ size_t stream_tile_f4(const PstlEvalCfg& c) {
-  return (size_t)c.K * c.T * PSTL_STREAM_NEI_F4 + (size_t)3 * c.nseg;
+// shared-memory tile of one scene, in float4 units: neighbours | lanes | per-step headers (+ sort keys)
+__host__ __device__ __forceinline__ size_t stream_tile_f4(int K, int T, int nseg) {
+  return (size_t)K * T * PSTL_STREAM_NEI_F4 + (size_t)3 * nseg + (size_t)(T + 1) / 2 + (size_t)(K * T + 3) / 4;
 }
 
-__device__ void stream_stage_scene(const ScoreArgs& a, int scene, float4* tile) {
+// Block-cooperative staging.  Per step the valid neighbours are compacted and ordered nearest-first with
+// respect to the constant-velocity prediction of the block's first row, so the running minimum tightens early
+// and the exact cull rejects most of the rest (ordering and compaction never change the minimum itself).
+__device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4* tile) {
   const PstlEvalCfg& c = a.cfg;
-  const float* nb = a.neighbors + (size_t)scene * c.K * c.T * 7;
-  for (int e = threadIdx.x; e < c.K * c.T; e += blockDim.x) {
-    const float* p = nb + (size_t)e * 7;
-    PstlCircles cc;
-    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], cc);
-    float4* o = tile + (size_t)e * PSTL_STREAM_NEI_F4;
-    o[0] = make_float4(cc.cx[0], cc.cx[1], cc.cx[2], cc.cx[3]);
-    o[1] = make_float4(cc.cy[0], cc.cy[1], cc.cy[2], cc.cy[3]);
-    o[2] = make_float4(p[0], p[1], p[2], p[5] / 2.f);
-    o[3] = make_float4(cc.r, 0.f, 0.f, 0.f);
+  const int K = c.K, T = c.T;
+  float4* ln = tile + (size_t)K * T * PSTL_STREAM_NEI_F4;
+  float2* hdr = reinterpret_cast<float2*>(ln + 3 * c.nseg);
+  float* keys = reinterpret_cast<float*>(ln + 3 * c.nseg + (T + 1) / 2);
+  const float* nb = a.neighbors + (size_t)scene * K * T * 7;
+  // reference point of the ordering heuristic
+  float rx = 0.f, ry = 0.f, rvx = 0.f, rvy = 0.f;
+  if (a.state0) {
+    const float* s0 = a.state0 + (size_t)n0 * 4;
+    rx = s0[0]; ry = s0[1];
+    rvx = s0[3] * cosf(s0[2]) * c.dt; rvy = s0[3] * sinf(s0[2]) * c.dt;
   }
-  float4* ln = tile + (size_t)c.K * c.T * PSTL_STREAM_NEI_F4;
+  for (int e = threadIdx.x; e < K * T; e += blockDim.x) {
+    const int k = e / T, t = e - k * T;
+    const float* p = nb + (size_t)e * 7;
+    float px = rx + rvx * (float)t, py = ry + rvy * (float)t;
+    if (a.ego) { const float* q = a.ego + ((size_t)n0 * T + t) * a.ego_stride; px = q[0]; py = q[1]; }
+    const float dx = p[1] - px, dy = p[2] - py;
+    keys[t * K + k] = (p[0] != 0.f) ? dx * dx + dy * dy : INFINITY;
+  }
   for (int e = threadIdx.x; e < 3 * c.nseg; e += blockDim.x) {
     const int l = e / c.nseg, j = e - l * c.nseg;
     const float* src = a.lanes[l] + ((size_t)scene * c.nseg + j) * 3;
     ln[e] = make_float4(src[0], src[1], src[2], 0.f);
+  }
+  __syncthreads();
+  const float ego_half = c.ego_L / 2.f;
+  for (int e = threadIdx.x; e < K * T; e += blockDim.x) {
+    const int k = e / T, t = e - k * T;
+    const float* kt = keys + t * K;
+    const float key = kt[k];
+    int rank = 0, n_valid = 0;
+    for (int j = 0; j < K; ++j) {
+      const float kj = kt[j];
+      n_valid += (kj != INFINITY) ? 1 : 0;
+      rank += (kj < key || (kj == key && j < k)) ? 1 : 0;
+    }
+    if (k == 0) hdr[t] = make_float2(__int_as_float(n_valid), n_valid < K ? 100.f : INFINITY);
+    if (key == INFINITY) continue;  // valid == 0: clip(d)*0 + (1-0)*100, folded into the initial minimum
+    const float* p = nb + (size_t)e * 7;
+    PstlCircles cc;
+    pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], cc);
+    float4* o = tile + (size_t)(t * K + rank) * PSTL_STREAM_NEI_F4;
+    o[0] = make_float4(cc.cx[0], cc.cx[1], cc.cx[2], cc.cx[3]);
+    o[1] = make_float4(cc.cy[0], cc.cy[1], cc.cy[2], cc.cy[3]);
+    o[2] = make_float4(p[0], p[1], p[2], ego_half + p[5] / 2.f + 1e-3f);
+    o[3] = make_float4(cc.r, 0.f, 0.f, 0.f);
   }
 }
 
@@ -261,8 +372,8 @@ struct StreamPlans {
 
 #define PSTL_STREAM_BLOCK_MAX 192
 
-template <bool SMEM_SCENE>
-__global__ void __launch_bounds__(PSTL_STREAM_BLOCK_MAX, SMEM_SCENE ? 5 : 4)
+template <bool SMEM_SCENE, int MINB>
+__global__ void __launch_bounds__(PSTL_STREAM_BLOCK_MAX, MINB)
 k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ StreamPlans sp) {
   extern __shared__ float4 sm4[];
   const PstlEvalCfg c = a.cfg;
@@ -279,8 +390,8 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
   float4* tile = sm4;
   float* tape = reinterpret_cast<float*>(sm4);
   if (SMEM_SCENE) {
-    stream_stage_scene(a, n0 / a.rows_per_scene, tile);
-    tape = reinterpret_cast<float*>(sm4 + stream_tile_f4(c));
+    stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile);
+    tape = reinterpret_cast<float*>(sm4 + stream_tile_f4(c.K, T, c.nseg));
     __syncthreads();
   }
   tape += threadIdx.x;
@@ -299,11 +410,12 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
   const float* stlp = a.stlp + (size_t)nn * 6;
   const float* ego = a.ego ? a.ego + (size_t)nn * T * a.ego_stride : nullptr;
   const int scene = nn / a.rows_per_scene;
-  StreamSceneSmem ss{tile, tile + (size_t)c.K * T * PSTL_STREAM_NEI_F4, T, c.nseg};
+  const float4* tile_ln = tile + (size_t)c.K * T * PSTL_STREAM_NEI_F4;
+  StreamSceneSmem ss{tile, reinterpret_cast<const float2*>(tile_ln + 3 * c.nseg), tile_ln, c.K, T, c.nseg};
   PstlStreamSceneGlobal sg;
   sg.neib = a.neighbors + (size_t)scene * c.K * T * 7;
   for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
-  sg.T = T;
+  sg.K = c.K; sg.T = T; sg.ego_half = c.ego_L / 2.f;
 
   float best = -INFINITY;
   int bi = 0;

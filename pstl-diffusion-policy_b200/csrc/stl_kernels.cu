@@ -428,7 +428,7 @@ static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaSt
     sp.p[k] = progs[k]->plan;
     n_tapes = progs[k]->plan.n_tapes > n_tapes ? progs[k]->plan.n_tapes : n_tapes;
   }
-  const size_t tile_bytes = ((size_t)c.K * c.T * PSTL_STREAM_NEI_F4 + (size_t)3 * c.nseg) * sizeof(float4);
+  const size_t tile_bytes = stream_tile_f4(c.K, c.T, c.nseg) * sizeof(float4);
   const size_t budget = 100 * 1024;
   int block = 0;
   bool smem_scene = false;
@@ -452,12 +452,16 @@ static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaSt
   if (!block) return PSTL_OK;
   const size_t smem = (smem_scene ? tile_bytes : 0) + (size_t)block * n_tapes * c.T * sizeof(float);
   const int grid = pstl_ceil_div(a.N, block);
-  if (smem_scene) {
-    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    k_score_stream<true><<<grid, block, smem, st>>>(a, sp);
+  const char* mb = getenv("PSTL_STREAM_MINB");
+  if (smem_scene && !(mb && atoi(mb) == 5)) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<true, 4><<<grid, block, smem, st>>>(a, sp);
+  } else if (smem_scene) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<true, 5><<<grid, block, smem, st>>>(a, sp);
   } else {
-    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    k_score_stream<false><<<grid, block, smem, st>>>(a, sp);
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<false, 4><<<grid, block, smem, st>>>(a, sp);
   }
   PSTL_LAUNCH_CHECK();
   *took = 1;

@@ -165,6 +165,8 @@ struct PstlPlan {
   int lane;       // lane (0 curr, 1 left, 2 right) the distance / heading leaves refer to, -1: none
   int n_tapes;
   int need_pose, need_lane, need_nei;  // leading steps for which the pose / lane search / clearance are read
+  int nei_term;   // >= 0: the clearance signal feeds exactly this term and it is  Always_[lo,hi) (nei - q)/den
+                  // (soft-min, positive sign, no And/Or, no inner operator); -1 otherwise
   PstlTerm terms[PSTL_MAX_TERMS];
 };
 
@@ -242,5 +244,16 @@ static inline void pstl_make_plan(const PstlProgView& P, PstlPlan* pl) {
   pl->need_nei = P.base_need[PSTL_SIG_NEI];
   pl->need_pose = 0;
   for (int b = 0; b < PSTL_N_BASE_SIGNALS; ++b) pl->need_pose = P.base_need[b] > pl->need_pose ? P.base_need[b] : pl->need_pose;
+  // the value-aware neighbour bound of the streaming scorer applies only to a lone  G(nei - q)  term
+  int uses = 0, idx = -1;
+  for (int k = 0; k < pl->n_terms; ++k) {
+    const PstlTerm& t = pl->terms[k];
+    const bool a_nei = t.a.c == 3, b_nei = t.pair != 0 && t.b.c == 3;
+    if (a_nei || b_nei) {
+      ++uses;
+      if (a_nei && t.pair == 0 && t.inner == 0 && t.outer == -1 && t.a.sb == 1.f && t.lo == 0) idx = k;
+    }
+  }
+  pl->nei_term = (uses == 1) ? idx : -1;
   pl->valid = 1;
 }

@@ -636,7 +636,7 @@ def _host_schedule(beta, alpha, alpha_hat):
 
 def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, coeffs=None, fastforward=False,
                       n_randoms=None, return_feature=False, mono=False, tmp_stlp=None, guidance_extras=None,
-                      maximize=False):
+                      maximize=False, scene_feature_only=False):
     """DDPM reverse loop i = steps-1..1 with t == i (reference :557-645): ONE native call that runs all
     steps (eps-MLP, posterior update, noise, optional STL guidance) instead of ~100 launches per step.
 
@@ -725,7 +725,12 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
     dense_feature = None
     if return_feature:
         k = scene_feat.shape[-1]
-        dense_feature = scene_feat.reshape(bs, 1, k).expand(bs, rows_per_scene, k).reshape(-1, k)
+        if scene_feature_only:
+            # callers inside this package only read the per-scene rows: skip the (N, 224) replication
+            # (176 MB at 196,608 chains) that upstream's dense feature costs
+            dense_feature = scene_feat.reshape(bs, 1, k).expand(bs, rows_per_scene, k)
+        else:
+            dense_feature = scene_feat.reshape(bs, 1, k).expand(bs, rows_per_scene, k).reshape(-1, k)
         dense_feature._pstl_scene_feat = scene_feat
     if args.diff_full:
         final_list = IterateList(steps, iterates)
@@ -754,7 +759,7 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     guidance_extras = (new_batch, pack.state0, stls_cac) if args.guidance else None
     progs = _fused_programs(stls_cac, args.nt)
     res = diffusion_rollout(noise, net, new_batch, highlevel_new, None, args, coeffs, n_randoms=S,
-                            return_feature=True, guidance_extras=guidance_extras)
+                            return_feature=True, guidance_extras=guidance_extras, scene_feature_only=True)
     if args.diff_full:
         nn_controls, feature, nn_list = res
     else:
