@@ -14,8 +14,13 @@
 //     epilogue: eps = D3 + b3 + x ; mu ; x <- mu + sqrt(beta) z (Philox or injected) ; the fp32 state
 //               never leaves registers; its bf16 image goes back to the X tile for the next step and,
 //               in the last K steps, the normalised controls go to HBM.
-// TMEM columns: D [0,256)  H [256,384)  D3 [384,432).   Warps 0-7: epilogue (lane quarter = warp%4,
-// column half = warp/4); warp 8: barrier init, TMEM alloc, weight load and the single MMA-issuing lane.
+// Every layer is issued as two N=128 halves with their own completion barriers, and the epilogue warps are
+// split the same way (lane quarter = warp%4, column half = warp/4), so the epilogue of half 0 runs under the MMA
+// of half 1, layer 2 starts on the first half of H1 while the second is still being packed, and layer 3 is
+// half issued before the last hidden columns exist.
+// TMEM columns: D [0,256)  H1 [256,384)  H2 [384,512);  D3 aliases H1[0,48) (dead once layer 2 retired) and the
+// layer-1 operand X aliases H2[0,32) (dead once layer 3 retired).  Warp 8: barrier init, TMEM alloc, weight load
+// and the MMA-issuing lane.
 #include <cuda_bf16.h>
 
 #include "mlp_common.cuh"
@@ -28,7 +33,7 @@ constexpr int kK1 = 64;        // layer-1 depth: [x 40 | hl | stlp 6 | 0 | 8 one
 constexpr int kN3 = 48;        // layer-3 width padded to a multiple of 16
 constexpr int kMaxClasses = 8; // distinct scenes a 128-row tile may span
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarps + 1) * 32;
+constexpr int kThreads = (kEpiWarps + 2) * 32;  // + MMA warp + bias warp
 
 // shared-memory image offsets (bytes)
 constexpr int kOffW1 = 0;                         // [256 x 64] bf16 SW128; cols 48..63 = per-step bias (hi,lo) per class
@@ -42,7 +47,7 @@ constexpr int kSmemBytes = kOffBar + 128;
 static_assert(kWeightBytes == 188416, "weight image size");
 static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
 
-constexpr uint32_t kColD = 0, kColH = 256, kColD3 = 384, kColX = 432;  // X: 32 columns = 64 bf16 of layer-1 input
+constexpr uint32_t kColD = 0, kColH1 = 256, kColH2 = 384, kColD3 = 256, kColX = 384;  // X: 32 columns = 64 bf16 of layer-1 input
 #define MSTAMP (a.dbg && blockIdx.x == 0 && it == 2 && lane == 0)
 #define STAMP (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0)
 
@@ -273,21 +278,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
   uint8_t* smem = smem_raw + (sbase - sraw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  // d*/h* barriers come in pairs: [+0] column half 0, [+8 bytes] column half 1
   const uint32_t bar_w = smem_u32(&bars[0]), bar_x = smem_u32(&bars[1]), bar_d1 = smem_u32(&bars[2]),
-                 bar_h1 = smem_u32(&bars[3]), bar_d2 = smem_u32(&bars[4]), bar_h2 = smem_u32(&bars[5]),
-                 bar_d3 = smem_u32(&bars[6]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[10]);
+                 bar_h1 = smem_u32(&bars[4]), bar_d2 = smem_u32(&bars[6]), bar_h2 = smem_u32(&bars[8]),
+                 bar_d3 = smem_u32(&bars[10]), bar_b = smem_u32(&bars[11]);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[14]);
   float* b3s = reinterpret_cast<float*>(smem + kOffB3);
 
   if (warp == kEpiWarps) {
     if (lane == 0) {
       mbar_init(bar_w, 1);
       mbar_init(bar_x, kEpiWarps);
-      mbar_init(bar_d1, 1);
-      mbar_init(bar_h1, kEpiWarps);
-      mbar_init(bar_d2, 1);
-      mbar_init(bar_h2, kEpiWarps);
+      for (uint32_t h = 0; h < 2; ++h) {
+        mbar_init(bar_d1 + 8 * h, 1);
+        mbar_init(bar_h1 + 8 * h, kEpiWarps / 2);
+        mbar_init(bar_d2 + 8 * h, 1);
+        mbar_init(bar_h2 + 8 * h, kEpiWarps / 2);
+      }
       mbar_init(bar_d3, 1);
+      mbar_init(bar_b, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -324,15 +333,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
   const int n_steps = a.first_step - a.last_step + 1;
   uint32_t it = 0;  // tile-steps done by this CTA: every barrier completes once per tile-step
 
-  if (warp == kEpiWarps) {
-    // ================= MMA issuer: the whole warp walks the protocol, lane 0 issues =================
-    mbar_wait(bar_w, 0);
-    const uint32_t id12 = make_idesc(kTileM, kH), id3 = make_idesc(kTileM, kN3);
-    const uint64_t dW1 = make_desc(sbase + kOffW1);
-    // Biases ride on the tensor pipe.  The X tile carries, in columns 48..63, a pair of ones at the row's
-    // scene class; W1' columns 48..63 carry (hi, lo) bf16 halves of c_scene[scene0+class] + c_t[step], rewritten
-    // here (by this otherwise idle warp) once the previous layer-1 MMA has retired.  Layer 2 gets b2 through one
-    // extra K-step against the same one-hot columns.
+  if (warp == kEpiWarps + 1) {
+    // ================= bias warp: W1' columns 48..63 for the next tile-step =================
+    // It may overwrite them as soon as the layer-1 MMAs of the previous tile-step have retired (d1[1]).
     auto write_bias_cols = [&](int tile, int i) {
       const long long r0 = (long long)tile * kTileM;
       const long long r1 = (r0 + kTileM - 1 < a.N) ? r0 + kTileM - 1 : (long long)a.N - 1;
@@ -348,52 +351,98 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       fence_proxy_async();
       __syncwarp();
     };
+    mbar_wait(bar_w, 0);  // the weight image (whose bias columns are zero) must have landed first
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int s = 0; s < n_steps; ++s, ++it) {
+        if (it > 0) mbar_wait(bar_d1 + 8, (it - 1) & 1);
+        if (!a.exp_skip_bias || s == 0) write_bias_cols(tile, a.first_step - s);
+        if (lane == 0) mbar_arrive(bar_b);
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // ================= MMA issuer: the whole warp walks the protocol, one elected lane issues =================
+    mbar_wait(bar_w, 0);
+    const uint32_t idh = make_idesc(kTileM, kH / 2), id3 = make_idesc(kTileM, kN3);
+    const uint64_t dW1 = make_desc(sbase + kOffW1);
+    // Biases ride on the tensor pipe.  The X tile carries, in columns 48..63, a pair of ones at the row's
+    // scene class; W1' columns 48..63 carry (hi, lo) bf16 halves of c_scene[scene0+class] + c_t[step], rewritten
+    // by the bias warp once the previous layer-1 MMA has retired (bar_b).  Layer 2 gets b2 through one extra
+    // K-step against the same one-hot columns.
     const uint64_t dB2 = make_desc_flat(sbase + kOffB2, 128, 256);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 0; s < n_steps; ++s, ++it) {
         const uint32_t ph = it & 1;
-        if (s == 0) write_bias_cols(tile, a.first_step);
+        mbar_spin(bar_b, ph);
         mbar_spin(bar_x, ph);
         if (MSTAMP) a.dbg[0] = clock64();
         tc_fence_after();
         if (elect_one()) {
+          // layer 1, column halves 0 and 1 (W1' rows 128.. start 16 KB into the block: +1024 in descriptor units)
 #pragma unroll
-          for (int k = 0; k < kK1 / 16; ++k) {  // advancing 32 B inside the 128 B swizzle atom
-            mma_ts(tmem + kColD, tmem + kColX + k * 8, dW1 + (uint64_t)(k * 2), id12, k > 0);
-            if (MSTAMP) a.dbg[16 + k] = clock64();
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int k = 0; k < kK1 / 16; ++k)  // advancing 32 B inside the 128 B swizzle atom
+              mma_ts(tmem + kColD + h * 128, tmem + kColX + k * 8, dW1 + (uint64_t)(h * 1024 + k * 2), idh, k > 0);
+            tc_commit(bar_d1 + 8 * h);
           }
-          tc_commit(bar_d1);
-          if (MSTAMP) { a.dbg[1] = clock64(); mbar_wait(bar_d1, ph); a.dbg[20] = clock64(); }
         }
         __syncwarp();
+        if (MSTAMP) a.dbg[1] = clock64();
+        // layer 2, half 0, first eight K-steps: needs H1[:, 0:128) only
         mbar_spin(bar_h1, ph);
         if (MSTAMP) a.dbg[2] = clock64();
         tc_fence_after();
         if (elect_one()) {
-          mma_ts(tmem + kColD, tmem + kColX + 24, dB2, id12, 0);  // D = onehot(class) . b2
+          mma_ts(tmem + kColD, tmem + kColX + 24, dB2, idh, 0);  // D = onehot(class) . b2
 #pragma unroll
-          for (int k = 0; k < kH / 16; ++k) {
+          for (int k = 0; k < 8; ++k) {
             const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)((k & 3) * 2);
-            mma_ts(tmem + kColD, tmem + kColH + k * 8, dB, id12, 1);
+            mma_ts(tmem + kColD, tmem + kColH1 + k * 8, dB, idh, 1);
           }
-          tc_commit(bar_d2);
-          if (MSTAMP) a.dbg[3] = clock64();
         }
         __syncwarp();
-        // layer-1 MMA of this step has retired (bar_h1 passed): next step's bias columns, in the layer-2 shadow
-        if (s + 1 < n_steps && !a.exp_skip_bias) write_bias_cols(tile, a.first_step - s - 1);
+        mbar_spin(bar_h1 + 8, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          // the bias of half 1 goes first: it is the last reader of X, which E2 (after d2[0]) overwrites
+          mma_ts(tmem + kColD + 128, tmem + kColX + 24, dB2 + (uint64_t)256, idh, 0);
+#pragma unroll
+          for (int k = 8; k < 16; ++k) {
+            const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)((k & 3) * 2);
+            mma_ts(tmem + kColD, tmem + kColH1 + k * 8, dB, idh, 1);
+          }
+          tc_commit(bar_d2);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)(1024 + (k & 3) * 2);
+            mma_ts(tmem + kColD + 128, tmem + kColH1 + k * 8, dB, idh, 1);
+          }
+          tc_commit(bar_d2 + 8);
+        }
+        __syncwarp();
+        if (MSTAMP) a.dbg[3] = clock64();
         mbar_spin(bar_h2, ph);
         if (MSTAMP) a.dbg[4] = clock64();
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kH / 16; ++k) {
+          for (int k = 0; k < 8; ++k) {
             const uint64_t dB = make_desc(sbase + kOffW3 + (k >> 2) * (kN3 * 128)) + (uint64_t)((k & 3) * 2);
-            mma_ts(tmem + kColD3, tmem + kColH + k * 8, dB, id3, k > 0);
+            mma_ts(tmem + kColD3, tmem + kColH2 + k * 8, dB, id3, k > 0);
+          }
+        }
+        __syncwarp();
+        mbar_spin(bar_h2 + 8, ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 8; k < 16; ++k) {
+            const uint64_t dB = make_desc(sbase + kOffW3 + (k >> 2) * (kN3 * 128)) + (uint64_t)((k & 3) * 2);
+            mma_ts(tmem + kColD3, tmem + kColH2 + k * 8, dB, id3, 1);
           }
           tc_commit(bar_d3);
-          if (MSTAMP) a.dbg[5] = clock64();
         }
+        if (MSTAMP) a.dbg[5] = clock64();
         __syncwarp();
       }
     }
@@ -416,23 +465,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 #pragma unroll
       for (int j = 0; j < 20; ++j) x[j] = xr[c0 + j];
       // the layer-1 operand lives in TMEM too (columns kColX..+32): bf16 pairs of [x | hl stlp 0 | class one-hots]
+      // constant columns 40..47: hl, stlp(6), 0 ; 48..63: ones at this row's scene class.  X shares its columns
+      // with H2, so the whole operand is rewritten every step (the half-1 warps carry the constants).
+      uint32_t pc[12];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) pc[j / 2] = pack_bf16(xr[40 + j], xr[41 + j]);
+#pragma unroll
+      for (int c = 0; c < kMaxClasses; ++c) pc[4 + c] = (c == cls) ? 0x3F803F80u : 0u;
       auto store_x = [&]() {
         uint32_t px[10];
 #pragma unroll
         for (int j = 0; j < 20; j += 2) px[j / 2] = pack_bf16(x[j], x[j + 1]);
         TMEM_ST_X8(tmem + lane_addr + kColX + c0 / 2, px);
         TMEM_ST_X2(tmem + lane_addr + kColX + c0 / 2 + 8, (px + 8));
+        if (half == 1) {
+          TMEM_ST_X4(tmem + lane_addr + kColX + 20, pc);
+          TMEM_ST_X8(tmem + lane_addr + kColX + 24, (pc + 4));
+        }
       };
       store_x();
-      if (half == 1) {  // constant columns 40..47: hl, stlp(6), 0 ; 48..63: ones at this row's scene class
-        uint32_t pc[12];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) pc[j / 2] = pack_bf16(xr[40 + j], xr[41 + j]);
-#pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) pc[4 + c] = (c == cls) ? 0x3F803F80u : 0u;
-        TMEM_ST_X4(tmem + lane_addr + kColX + 20, pc);
-        TMEM_ST_X8(tmem + lane_addr + kColX + 24, (pc + 4));
-      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -469,10 +520,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           if (STAMP && layer == 0) a.dbg[21] = clock64();
-          mbar_spin(layer == 0 ? bar_d1 : bar_d2, ph);
+          mbar_spin((layer == 0 ? bar_d1 : bar_d2) + 8 * half, ph);
           if (STAMP) a.dbg[layer == 0 ? 8 : 11] = clock64();
           tc_fence_after();
-          const uint32_t dsrc = tmem + lane_addr + kColD + half * 128, hdst = tmem + lane_addr + kColH + half * 64;
+          const uint32_t dsrc = tmem + lane_addr + kColD + half * 128;
+          const uint32_t hdst = tmem + lane_addr + (layer == 0 ? kColH1 : kColH2) + half * 64;
           // 8 chunks of 16 accumulator columns, the next chunk's TMEM load in flight while one is packed
           uint32_t ra[16], rb[16], p[8];
           TMEM_LD_X16(dsrc, ra);
@@ -492,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(layer == 0 ? bar_h1 : bar_h2);
+          if (lane == 0) mbar_arrive((layer == 0 ? bar_h1 : bar_h2) + 8 * half);
           if (STAMP) a.dbg[layer == 0 ? 9 : 12] = clock64();
           if (layer == 0) {
             noise4(0);
@@ -652,11 +704,10 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
     cudaStreamSynchronize(st);
     long long h[32];
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[pstl tc timeline, CTA 0, 3rd tile-step, cycles rel. to bar_x ready]\n  MMA : x %lld | mma1 issued %lld | h1 %lld | mma2 issued %lld | h2 %lld | mma3 issued %lld\n"
+    fprintf(stderr, "[pstl tc timeline, CTA 0, 3rd tile-step, cycles rel. to bar_x ready]\n  MMA : x %lld | mma1 issued %lld | h1[0] %lld | mma2 issued %lld | h2[0] %lld | mma3 issued %lld\n"
                     "  EPI0: d1 %lld | epi1 done %lld | noise done %lld | d2 %lld | epi2 done %lld | d3 %lld | epi3 done %lld\n",
             0LL, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0],
             h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
-    fprintf(stderr, "  MMA1 issue stamps: %lld %lld %lld %lld  d1 seen by the issuing lane: %lld ; epilogue warp 0 starts waiting for d1 at %lld\n", h[16] - h[0], h[17] - h[0], h[18] - h[0], h[19] - h[0], h[20] - h[0], h[21] - h[0]);
     cudaFree(dbg);
   }
   PSTL_LAUNCH_CHECK();
