@@ -493,26 +493,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         const uint32_t ph = it & 1;
         const int i = a.first_step - s;  // reverse step index (t == i)
         float zn[20];
-        // This step's noise z (20 normals per thread = 5 Philox calls) is drawn in the shadows of the three
-        // MMAs: 4 calls while the long layer-2 MMA runs, 1 while layer 3 runs (layer 1 is too short).  The Philox counter
-        // passes through an opaque asm at each site so the compiler cannot hoist the (barrier-independent)
-        // arithmetic to the top of the loop, where it would sit on the critical path.
+        // This step's noise z (20 normals per thread = 5 Philox calls) is drawn in ONE block right after this warp
+        // has handed H1 over, i.e. in the shadow of the layer-2 MMA of its column half.  The five counter chains are
+        // independent and interleave (a single Philox4x32-10 call is a ~200-cycle dependent chain); the step counter
+        // passes through an opaque asm so the compiler cannot hoist the (barrier-independent) arithmetic to the top
+        // of the loop, where it would sit on the critical path.
         const int zi = a.steps - 1 - i;
         const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
         const bool draw = i > 1 && !a.refine;
-        auto noise4 = [&](int j) {
+        auto draw_noise = [&]() {
           unsigned step_ctr = (unsigned)i + off_base;
           asm volatile("" : "+r"(step_ctr)::"memory");
-          zn[j] = zn[j + 1] = zn[j + 2] = zn[j + 3] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 20; ++j) zn[j] = 0.f;
           if (draw) {
             if (zr) {
-              const float4 zz = *reinterpret_cast<const float4*>(zr + j);
-              zn[j] = zz.x; zn[j + 1] = zz.y; zn[j + 2] = zz.z; zn[j + 3] = zz.w;
+#pragma unroll
+              for (int j = 0; j < 20; j += 4) {
+                const float4 zz = *reinterpret_cast<const float4*>(zr + j);
+                zn[j] = zz.x; zn[j + 1] = zz.y; zn[j + 2] = zz.z; zn[j + 3] = zz.w;
+              }
             } else {
-              uint4 ctr4 = make_uint4((unsigned)(rrow & 0xffffffff), (unsigned)(rrow >> 32), (unsigned)((c0 + j) >> 2), step_ctr);
-              const uint4 rn = pstl_philox(ctr4, make_uint2((unsigned)(a.seed & 0xffffffff), (unsigned)(a.seed >> 32)));
-              pstl_box_muller(rn.x, rn.y, zn[j], zn[j + 1]);
-              pstl_box_muller(rn.z, rn.w, zn[j + 2], zn[j + 3]);
+              const uint2 key = make_uint2((unsigned)(a.seed & 0xffffffff), (unsigned)(a.seed >> 32));
+              uint4 rn[5];
+#pragma unroll
+              for (int q = 0; q < 5; ++q)
+                rn[q] = pstl_philox(make_uint4((unsigned)(rrow & 0xffffffff), (unsigned)(rrow >> 32), (unsigned)(c0 / 4 + q), step_ctr), key);
+#pragma unroll
+              for (int q = 0; q < 5; ++q) {
+                pstl_box_muller(rn[q].x, rn[q].y, zn[4 * q], zn[4 * q + 1]);
+                pstl_box_muller(rn[q].z, rn[q].w, zn[4 * q + 2], zn[4 * q + 3]);
+              }
             }
           }
         };
@@ -547,13 +558,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           if (lane == 0) mbar_arrive((layer == 0 ? bar_h1 : bar_h2) + 8 * half);
           if (STAMP) a.dbg[layer == 0 ? 9 : 12] = clock64();
           if (layer == 0) {
-            noise4(0);
-            noise4(4);
-            noise4(8);
-            noise4(12);
+            draw_noise();
             if (STAMP) a.dbg[10] = clock64();
-          } else {
-            noise4(16);
           }
         }
         // ---- layer 3: eps, posterior mean, noise, next x ----

@@ -44,9 +44,12 @@ __device__ __forceinline__ uint4 pstl_philox(uint4 ctr, uint2 key) {
 }
 
 __device__ __forceinline__ void pstl_box_muller(unsigned a, unsigned b, float& z0, float& z1) {
-  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]: never denormal, never 0
   const float u2 = (float)b * 2.3283064365386963e-10f;
-  const float r = sqrtf(-2.0f * __logf(u1));
+  // r = sqrt(-2 ln u1) through the SFU (lg2 / sqrt approximations, ~2 ulp): noise, not arithmetic that has a reference
+  float l2, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   z0 = r * c;
