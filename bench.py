@@ -41,6 +41,17 @@ def parse():
     return p.parse_args()
 
 
+def measured_traffic(chains):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json);
+    None when the workload differs from the captured one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["k_denoiser_tc"]
+        return t["dram_read_bytes"] + t["dram_write_bytes"] if t["chains"] == chains else None
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -63,7 +74,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -146,6 +157,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PSTL_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     native.lib()  # fail loudly if the CUDA library is missing
 
@@ -201,7 +213,7 @@ def main():
                 b = {k: b[k].to(dev, non_blocking=True) for k in need}
             out = NT.sample_and_score(net, b, stls, coeffs, args)
         if world > 1:
-            sharding.gather_scores(out["scores"], out["best_idx"])
+            sharding.gather_scores(out["scores"], out["best_idx"], equal_sizes=True)
         if e2e:
             host_scores.copy_(out["scores"], non_blocking=True)
             host_idx.copy_(out["best_idx"], non_blocking=True)
@@ -297,7 +309,7 @@ def main():
             "gpu_launches": launches * a.steps,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": None,
+                         "frac": achieved / tf_peak, "traffic": measured_traffic(N) if precision == "bf16" else None,
                          "kernel": "denoiser reverse loop (%s)" % precision,
                          "note": "minimal hoisted FLOP count 17.39 MFLOP/chain / sampler time %.3f ms (CUDA events around "
                                  "pstl_denoiser_sample, %s); peak = %s bf16 sustained"

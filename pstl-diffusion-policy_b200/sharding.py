@@ -40,12 +40,20 @@ def guidance_normaliser(valid_local, group=None):
     return n_total, float(part[0].item()) / n_total
 
 
-def gather_scores(scores_local, best_idx_local=None, group=None):
+def gather_scores(scores_local, best_idx_local=None, group=None, equal_sizes=False):
     """all-gather per-chain scores (and int32 selected-candidate indices) in rank order.
-    Shards may differ by one scene, so sizes are exchanged first and tensors padded."""
+    Shards may differ by one scene, so sizes are exchanged first and tensors padded; a caller that knows
+    every rank holds the same number of chains passes ``equal_sizes`` and gets one collective per tensor
+    with no host read-back."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return scores_local, best_idx_local
     world = dist.get_world_size(group)
+    if equal_sizes and scores_local.is_cuda:
+        def gather_eq(t):
+            out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t.reshape(-1).contiguous(), group=group)
+            return out
+        return gather_eq(scores_local), (gather_eq(best_idx_local) if best_idx_local is not None else None)
     n = torch.tensor([scores_local.numel()], device=scores_local.device, dtype=torch.int64)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)

@@ -106,3 +106,15 @@ extern "C" int hs_score_stream(const pstl_op* const* ops3, const int* n_ops3, in
   }
   return 0;
 }
+
+// plan recognition (stl_program.h): out = {valid, n_terms, listand, lane, n_tapes, need_pose, need_lane, need_nei, nei_term}
+extern "C" int hs_plan_info(const pstl_op* ops, int n_ops, int T, int* out) {
+  PstlProgView pv;
+  PstlPlan pl;
+  char err[256];
+  if (pstl_resolve_program(ops, n_ops, 0, T, 1, &pv, err, sizeof(err))) { fprintf(stderr, "%s\n", err); return -1; }
+  pstl_make_plan(pv, &pl);
+  const int v[9] = {pl.valid, pl.n_terms, pl.listand, pl.lane, pl.n_tapes, pl.need_pose, pl.need_lane, pl.need_nei, pl.nei_term};
+  for (int i = 0; i < 9; ++i) out[i] = v[i];
+  return 0;
+}

@@ -483,3 +483,23 @@ def test_captured_pipeline_replays_fresh_noise_and_new_inputs():
         assert torch.isfinite(o["scores"]).all()
     # the z stream has unit variance: x_0 of a random-init net stays O(1)
     assert 0.05 < o1["final_iterate"].std().item() < 50.0
+
+
+@pytest.mark.parametrize("n,nt,knei,seed", [(64, 200, 64, 1021), (96, 100, 32, 1022), (130, 31, 3, 1023)])
+def test_config5_corners_dense_scores_vs_oracle(n, nt, knei, seed):
+    """BASELINE config 5 corners (horizon up to 200 steps, up to 64 neighbours) through the dense drop-in API:
+    the streaming scorer on raw per-row tensors vs the oracle, and vs the interpreter kernels"""
+    x, idx, mask = synthetic.make_dense_stl_input(n, nt=nt, n_neighbors=knei, seed=seed)
+    args = NT.default_args(nt=nt)
+    stls = NT.build_stl_cache(args)
+    ref = O.stl_scores(dict(x), idx[:, 0], 100.0)
+    outs = {}
+    try:
+        for kern in ("stream", "thread"):
+            os.environ["PSTL_SCORE_KERNEL"] = kern
+            _, sc, _ = NT.compute_stl_dense(cuda(x), stls, idx.cuda(), mask.cuda(), args)
+            outs[kern] = sc.clone()
+    finally:
+        os.environ.pop("PSTL_SCORE_KERNEL", None)
+    close(outs["stream"], ref)
+    close(outs["thread"], ref)

@@ -112,3 +112,88 @@ def test_fused_dense_scores_and_grads(golden_dir, tag, n, nt, knei, seed):
     close(s2, sc_ref)
     gref = G[tag + "|grad_ego"]
     np.testing.assert_allclose(gego, gref, rtol=2e-4, atol=2e-4 * np.abs(gref).max())
+
+
+def _typed_leaves(nt):
+    """typed predicate leaves of the driving spec (nusc_train.build_stl_cache) for hand-built formulas"""
+    from pstl_b200 import nusc_train as NT
+    P = S.AP.predicate
+    one = lambda x: 1.0
+    return {
+        "vmin": P(one, native.SIG_V, 0, NT.I_VMIN, 1),
+        "vmax": P(one, native.SIG_V, 1, NT.I_VMAX, 0),
+        "dmin_l": P(one, native.SIG_D_LEFT, 0, NT.I_DMIN, 1),
+        "dmax_l": P(one, native.SIG_D_LEFT, 1, NT.I_DMAX, 0),
+        "th_l": P(one, native.SIG_TH_LEFT, 1, NT.I_THMAX, 0, native.DEN_THMAX),
+        "dmin_c": P(one, native.SIG_D_CURR, 0, NT.I_DMIN, 1),
+        "safe": P(one, native.SIG_NEI, 0, NT.I_DSAFE, 1),
+        "safe_n": P(one, native.SIG_NEI, 0, NT.I_DSAFE, 1, native.DEN_SFACTOR),
+        "unsafe": P(one, native.SIG_NEI, 1, NT.I_DSAFE, 0),
+    }
+
+
+def _plan_info(hs, f, nt):
+    ops = S.compile_formula(f, fused=True)[0]
+    out = (C.c_int * 9)()
+    assert hs.hs_plan_info(ops_array(ops), len(ops), nt, out) == 0
+    return dict(zip(("valid", "n_terms", "listand", "lane", "n_tapes", "need_pose", "need_lane", "need_nei", "nei_term"), out))
+
+
+def test_plan_recognition():
+    """which programs the streaming scorer takes (stl_program.h: pstl_make_plan)"""
+    hs = load()
+    nt = 20
+    infos = [_plan_info(hs, f, nt) for f in build_stl_cache(default_args(nt=nt))]
+    assert [i["valid"] for i in infos] == [1, 1, 1]
+    assert [i["lane"] for i in infos] == [0, 1, 2]
+    assert [i["n_tapes"] for i in infos] == [0, 2, 2]
+    assert [i["n_terms"] for i in infos] == [6, 5, 5]
+    assert all(i["nei_term"] == i["n_terms"] - 1 and i["need_pose"] == nt for i in infos)
+    L = _typed_leaves(nt)
+    A, E = S.Always, S.Eventually
+    assert _plan_info(hs, A(0, 7, L["vmin"]), nt) == dict(valid=1, n_terms=1, listand=0, lane=-1, n_tapes=0, need_pose=7,
+                                                           need_lane=0, need_nei=0, nei_term=-1)
+    # not of the closed form: inner window that is not a suffix, negation, two lanes in one program, Until
+    assert _plan_info(hs, A(0, nt, E(0, 5, L["vmin"])), nt)["valid"] == 0
+    assert _plan_info(hs, A(0, nt, S.Not(L["vmin"])), nt)["valid"] == 0
+    assert _plan_info(hs, S.ListAnd([A(0, nt, L["dmin_l"]), A(0, nt, L["dmin_c"])]), nt)["valid"] == 0
+    assert _plan_info(hs, S.Until(0, nt, L["vmin"], L["vmax"]), nt)["valid"] == 0
+    # the value-aware neighbour bound only for a lone soft-min  nei - q  term
+    assert _plan_info(hs, S.ListAnd([A(0, nt, L["safe"]), A(0, nt, L["vmin"])]), nt)["nei_term"] == 0
+    assert _plan_info(hs, S.ListAnd([A(0, nt, L["unsafe"]), A(0, nt, L["vmin"])]), nt)["nei_term"] == -1
+    assert _plan_info(hs, S.ListAnd([E(0, nt, L["safe"]), A(0, nt, L["vmin"])]), nt)["nei_term"] == -1
+    assert _plan_info(hs, S.ListAnd([A(0, nt, L["safe"]), A(0, 5, L["safe_n"])]), nt)["nei_term"] == -1
+
+
+def test_stream_plan_equals_interpreter_on_variant_specs():
+    """streaming closed form == postfix interpreter for hand-built formulas of the plan shape
+    (clipped / shifted windows, Or pairs, soft-max outer operators, single-term programs, normalised leaves)"""
+    hs = load()
+    n, nt, knei = 96, 20, 8
+    x, idx, mask = synthetic.make_dense_stl_input(n, nt=nt, n_neighbors=knei, seed=77)
+    L = _typed_leaves(nt)
+    A, E = S.Always, S.Eventually
+    variants = [
+        [S.ListAnd([A(2, 15, L["vmin"]), E(0, 7, L["vmax"]), E(3, 9, A(0, nt, S.And(L["dmin_l"], L["dmax_l"]))),
+                    A(0, nt, L["safe_n"])])] * 3,
+        [S.ListAnd([E(0, nt // 2, E(0, nt, S.Or(L["dmin_l"], L["th_l"]))), A(-3, 30, L["th_l"]), A(0, nt, L["safe"])])] * 3,
+        [A(0, nt, L["safe"]), E(1, 6, A(0, nt, L["th_l"])), S.ListAnd([A(5, 5, L["vmin"]), A(0, nt, L["vmax"])])],
+        [S.ListAnd([A(0, nt, L["unsafe"]), A(0, 9, L["dmin_c"])]), E(0, nt, L["safe"]),
+         S.ListAnd([A(0, nt, A(0, nt, L["safe"])), A(0, nt, L["vmin"])])],
+    ]
+    f = lambda t: np.ascontiguousarray(t.numpy(), np.float32)
+    nei, l0, l1, l2 = f(x["neighbors"]), f(x["currlane_wpts"]), f(x["leftlane_wpts"]), f(x["rightlane_wpts"])
+    ego, stlp, mode = f(x["ego_traj"]), f(x["stlp"][:, 0]), f(idx[:, 0])
+    for stls in variants:
+        progs = [S.compile_formula(g, fused=True)[0] for g in stls]
+        arrs = [ops_array(p) for p in progs]
+        ops3 = (C.c_void_p * 3)(*[C.cast(a, C.c_void_p) for a in arrs])
+        nops = (C.c_int * 3)(*[len(p) for p in progs])
+        ref, got = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        assert hs.hs_score(ops3, nops, nt, knei, 15, fp(nei), fp(l0), fp(l1), fp(l2), 1, fp(mode), None, None, fp(ego), 4,
+                           fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(1.0), C.c_float(1.0), 0, 0, None,
+                           fp(ref), None, None) == 0
+        assert hs.hs_score_stream(ops3, nops, nt, knei, 15, fp(nei), fp(l0), fp(l1), fp(l2), 1, fp(mode), None, None,
+                                  fp(ego), 4, fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(1.0),
+                                  C.c_float(1.0), 0, fp(got)) == 0
+        close(got, ref)
