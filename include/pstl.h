@@ -247,6 +247,19 @@ int pstl_predicates(const pstl_scene_view* scenes, float ego_L, float ego_W, int
 int pstl_linear(const float* x, const float* w, const float* b, int M, int K, int Nout, int act, float* y,
                 pstl_stream_t stream);
 
+/* Scene-encoder glue (Net.encode_feat, nusc_model.py:55-95).
+ * pstl_encoder_inputs: ego (n_scenes rows of >= 6 floats [x,y,th,v,L,W], row stride ego_row_stride), neighbors
+ * (n_scenes,Knei,7), three lanes (n_scenes,nseg,3) and their validity ids (n_scenes) -> the inputs of the three encoder
+ * MLPs after the ego-frame transform normalize_xyth (nusc_model.py:238-263): ego_in (n_scenes,6), nei_in
+ * (n_scenes*Knei,7), lane_in (n_scenes*3, nseg*3) (first point, then differences of consecutive points).
+ * pstl_encoder_pool: feature (n_scenes,7F) = [ego | min_k nei | mean_k nei | max_k nei | lanes] from the MLP outputs. */
+int pstl_encoder_inputs(const float* ego, int ego_row_stride, const float* neighbors, const float* lane_c,
+                        const float* lane_l, const float* lane_r, const float* id_c, const float* id_l,
+                        const float* id_r, int n_scenes, int Knei, int nseg, float* ego_in, float* nei_in,
+                        float* lane_in, pstl_stream_t stream);
+int pstl_encoder_pool(const float* ego_feat, const float* nei_feat, const float* lane_feat, int n_scenes, int Knei,
+                      int F, float* feature, pstl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

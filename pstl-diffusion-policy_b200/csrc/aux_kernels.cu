@@ -107,3 +107,104 @@ extern "C" int pstl_predicates(const pstl_scene_view* sv, float ego_L, float ego
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
 }
+
+// --------------------------------------------------------------------------------------
+// scene-encoder glue (Net.encode_feat, reference nusc_model.py:55-95): the ego-frame transform of every
+// neighbour / lane point and the input layouts of the three encoder MLPs in ONE launch (upstream: ~90
+// elementwise launches), and the neighbour pooling + feature concatenation in another.  Products and sums
+// round separately, as the PyTorch expressions do (-fmad=false).
+// --------------------------------------------------------------------------------------
+// normalize_xyth (reference nusc_model.py:238-263); valid < 0 means "no valid factor"
+__device__ __forceinline__ void enc_normalize(float x, float y, float th, float bx, float by, float bth, float valid,
+                                              bool has_valid, float& xr, float& yr, float& tr) {
+  const float xt = has_valid ? x - bx * valid : x - bx;
+  const float yt = has_valid ? y - by * valid : y - by;
+  const float c = cosf(bth), s = sinf(bth);
+  xr = xt * c + yt * s;
+  yr = (-xt) * s + yt * c;
+  tr = has_valid ? th - bth * valid : th - bth;
+}
+
+// items per scene: [0] ego, [1, 1+K) neighbours, [1+K, 1+K+3*nseg) lane points
+__global__ void k_encoder_inputs(const float* __restrict__ ego, int ego_stride, const float* __restrict__ nei,
+                                 const float* __restrict__ l0, const float* __restrict__ l1, const float* __restrict__ l2,
+                                 const float* __restrict__ id0, const float* __restrict__ id1,
+                                 const float* __restrict__ id2, int n_scenes, int K, int nseg,
+                                 float* __restrict__ ego_in, float* __restrict__ nei_in, float* __restrict__ lane_in) {
+  const int per = 1 + K + 3 * nseg;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_scenes * per) return;
+  const int b = (int)(i / per), it = (int)(i - (long long)b * per);
+  const float* e = ego + (size_t)b * ego_stride;
+  const float bx = e[0], by = e[1], bth = e[2];
+  if (it == 0) {
+    float xr, yr, tr;
+    enc_normalize(e[0], e[1], e[2], bx, by, bth, 0.f, false, xr, yr, tr);
+    float* o = ego_in + (size_t)b * 6;
+    o[0] = xr; o[1] = yr; o[2] = tr; o[3] = e[3]; o[4] = e[4]; o[5] = e[5];
+  } else if (it < 1 + K) {
+    const int k = it - 1;
+    const float* p = nei + ((size_t)b * K + k) * 7;
+    float xr, yr, tr;
+    enc_normalize(p[1], p[2], p[3], bx, by, bth, p[0], true, xr, yr, tr);
+    float* o = nei_in + ((size_t)b * K + k) * 7;
+    o[0] = p[0]; o[1] = xr; o[2] = yr; o[3] = tr; o[4] = p[4]; o[5] = p[5]; o[6] = p[6];
+  } else {
+    const int q = it - 1 - K, l = q / nseg, j = q - l * nseg;
+    const float* lane = (l == 0 ? l0 : (l == 1 ? l1 : l2)) + (size_t)b * nseg * 3;
+    const float valid = (l == 0 ? id0 : (l == 1 ? id1 : id2))[b];
+    float xr, yr, tr;
+    enc_normalize(lane[j * 3], lane[j * 3 + 1], lane[j * 3 + 2], bx, by, bth, valid, true, xr, yr, tr);
+    if (j > 0) {  // points after the first enter as differences of the NORMALISED points
+      float px, py, pt;
+      enc_normalize(lane[(j - 1) * 3], lane[(j - 1) * 3 + 1], lane[(j - 1) * 3 + 2], bx, by, bth, valid, true, px, py, pt);
+      xr = xr - px; yr = yr - py; tr = tr - pt;
+    }
+    float* o = lane_in + (((size_t)b * 3 + l) * nseg + j) * 3;
+    o[0] = xr; o[1] = yr; o[2] = tr;
+  }
+}
+
+extern "C" int pstl_encoder_inputs(const float* ego, int ego_row_stride, const float* neighbors, const float* lane_c,
+                                   const float* lane_l, const float* lane_r, const float* id_c, const float* id_l,
+                                   const float* id_r, int n_scenes, int Knei, int nseg, float* ego_in, float* nei_in,
+                                   float* lane_in, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(ego && neighbors && lane_c && lane_l && lane_r && id_c && id_l && id_r && ego_in && nei_in && lane_in,
+                 "null argument");
+  PSTL_CHECK_ARG(ego_row_stride >= 6 && Knei >= 0 && nseg >= 1, "bad shape");
+  if (n_scenes <= 0) return PSTL_OK;
+  const long long tot = (long long)n_scenes * (1 + Knei + 3 * nseg);
+  k_encoder_inputs<<<pstl_ceil_div(tot, 128), 128, 0, (cudaStream_t)stream>>>(
+      ego, ego_row_stride, neighbors, lane_c, lane_l, lane_r, id_c, id_l, id_r, n_scenes, Knei, nseg, ego_in, nei_in, lane_in);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
+// feature (bs, 7F) = [ego | min_k nei | mean_k nei | max_k nei | lane curr | left | right]  (nusc_model.py:88-93)
+__global__ void k_encoder_pool(const float* __restrict__ ego_f, const float* __restrict__ nei_f,
+                               const float* __restrict__ lane_f, int n_scenes, int K, int F, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_scenes * F) return;
+  const int b = (int)(i / F), f = (int)(i - (long long)b * F);
+  float mn = INFINITY, mx = -INFINITY, sum = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float v = nei_f[((size_t)b * K + k) * F + f];
+    mn = fminf(mn, v); mx = fmaxf(mx, v); sum += v;
+  }
+  float* o = out + (size_t)b * 7 * F;
+  o[f] = ego_f[(size_t)b * F + f];
+  o[F + f] = mn;
+  o[2 * F + f] = sum * (1.0f / (float)K);
+  o[3 * F + f] = mx;
+  for (int l = 0; l < 3; ++l) o[(4 + l) * F + f] = lane_f[((size_t)b * 3 + l) * F + f];
+}
+
+extern "C" int pstl_encoder_pool(const float* ego_feat, const float* nei_feat, const float* lane_feat, int n_scenes,
+                                 int Knei, int F, float* feature, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(ego_feat && nei_feat && lane_feat && feature && Knei >= 1 && F >= 1, "bad argument");
+  if (n_scenes <= 0) return PSTL_OK;
+  k_encoder_pool<<<pstl_ceil_div((long long)n_scenes * F, 128), 128, 0, (cudaStream_t)stream>>>(
+      ego_feat, nei_feat, lane_feat, n_scenes, Knei, F, feature);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}

@@ -131,6 +131,8 @@ class Net(nn.Module):
     # --- encoders (reference nusc_model.py:55-95) ----------------------------------------
     def encode_feat(self, nn_input, ext=None):
         bs = nn_input["ego_traj"].shape[0]
+        if nn_input["ego_traj"].is_cuda and not torch.is_grad_enabled():
+            return self._encode_feat_native(nn_input)
         ego = nn_input["ego_traj"][:, 0]
         ego_un = ego.unsqueeze(1)
         neis_ = nn_input["neighbors"]
@@ -147,6 +149,33 @@ class Net(nn.Module):
                              dim=-1)
         lanes_feat = self._mlp(self.lane_encoder, lanes_input).reshape(bs, -1)
         return torch.cat([ego_feat, nei_feat, lanes_feat], dim=-1)
+
+    def _encode_feat_native(self, nn_input):
+        """encode_feat on the GPU without autograd: one launch builds the three encoder inputs (ego-frame transform,
+        lane differences), the MLPs run on pstl_linear, one launch pools the neighbours and concatenates."""
+        ego_traj = _nv.f32(nn_input["ego_traj"])
+        bs, K = ego_traj.shape[0], nn_input["neighbors"].shape[1]
+        nei = _nv.f32(nn_input["neighbors"])
+        lanes = [_nv.f32(nn_input["%slane_wpts" % k]) for k in ("curr", "left", "right")]
+        ids = [_nv.f32(nn_input["%s_id" % k].reshape(bs)) for k in ("curr", "left", "right")]
+        nseg = lanes[0].shape[1]
+        dev = ego_traj.device
+        ego_in = torch.empty((bs, 6), dtype=torch.float32, device=dev)
+        nei_in = torch.empty((bs * K, 7), dtype=torch.float32, device=dev)
+        lane_in = torch.empty((bs * 3, nseg * self.lane_dim), dtype=torch.float32, device=dev)
+        L = _nv.lib()
+        _nv.check(L.pstl_encoder_inputs(_nv.fptr(ego_traj), ego_traj.shape[1] * ego_traj.shape[2], _nv.fptr(nei),
+                                        _nv.fptr(lanes[0]), _nv.fptr(lanes[1]), _nv.fptr(lanes[2]), _nv.fptr(ids[0]),
+                                        _nv.fptr(ids[1]), _nv.fptr(ids[2]), bs, K, nseg, _nv.fptr(ego_in),
+                                        _nv.fptr(nei_in), _nv.fptr(lane_in), _nv.stream()), "pstl_encoder_inputs")
+        ego_f = self._mlp(self.ego_encoder, ego_in)
+        nei_f = self._mlp(self.neighbor_encoder, nei_in)
+        lane_f = self._mlp(self.lane_encoder, lane_in)
+        F = ego_f.shape[-1]
+        feat = torch.empty((bs, 7 * F), dtype=torch.float32, device=dev)
+        _nv.check(L.pstl_encoder_pool(_nv.fptr(ego_f), _nv.fptr(nei_f), _nv.fptr(lane_f), bs, K, F, _nv.fptr(feat),
+                                      _nv.stream()), "pstl_encoder_pool")
+        return feat
 
     def _mlp(self, seq, x):
         """encoder MLP.  Inference on the GPU goes through pstl_linear (row-independent summation order,

@@ -503,3 +503,23 @@ def test_config5_corners_dense_scores_vs_oracle(n, nt, knei, seed):
         os.environ.pop("PSTL_SCORE_KERNEL", None)
     close(outs["stream"], ref)
     close(outs["thread"], ref)
+
+
+def test_native_encoder_glue_vs_oracle_and_torch_path():
+    """Net.encode_feat without autograd = pstl_encoder_inputs + pstl_linear MLPs + pstl_encoder_pool; with autograd it
+    is the PyTorch expression of the reference.  Both against the oracle's encode_scene."""
+    args = NT.default_args(n_randoms=16, sampling_size=16)
+    W = synthetic.make_weights(1007)
+    net = Net(args)
+    net.load_state_dict(W)
+    net = net.cuda()
+    b = synthetic.make_scene_batch(37, n_randoms=16, seed=41)
+    bc = cuda(b)
+    ref = O.encode_scene(W, b)
+    with torch.no_grad():
+        f_native = net.encode_feat(bc)
+    with torch.enable_grad():
+        f_torch = net.encode_feat(bc)
+    close(f_native, ref, what="native feature")
+    close(f_torch, ref, what="torch feature")
+    close(f_native, f_torch.detach(), rtol=2e-6, what="native vs torch")
