@@ -255,6 +255,7 @@ struct TcArgs {
   float* xin;           // (N, 48): [x(40) | hl | stlp(6) | 0], x updated in place at the end
   const float* noise;   // injected z (steps-2, N, 40) or null
   float* iterates;      // (keep, N, 40) or null
+  float* mu_out;        // (N, 40) or null: single guided step — write the posterior mean, leave x alone
   float c1[128], c2[128], sb[128];  // per reverse step i: (1-a)/sqrt(1-abar), 1/sqrt(a), sqrt(beta)
   int N, rows_per_scene, steps, first_step, last_step, keep, clip;
   float w_max, a_max;
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         // of the loop, where it would sit on the critical path.
         const int zi = a.steps - 1 - i;
         const float* zr = (a.noise && i > 1) ? a.noise + ((size_t)zi * a.N + rrow) * 40 + c0 : nullptr;
-        const bool draw = i > 1 && !a.refine;
+        const bool draw = i > 1 && !a.refine && !a.mu_out;
         auto draw_noise = [&]() {
           unsigned step_ctr = (unsigned)i + off_base;
           asm volatile("" : "+r"(step_ctr)::"memory");
@@ -589,6 +590,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           continue;
         }
         const float c1 = a.c1[i], c2 = a.c2[i], sb = a.sb[i];
+        if (a.mu_out) {  // guided step: the mean goes to the guidance kernels, which add the noise afterwards
+          float* mo = a.mu_out + rrow * 40 + c0;
+#pragma unroll
+          for (int j = 0; j < 20; ++j) {
+            const float eps = __uint_as_float(r[j]) + b3s[c0 + j] + x[j];
+            if (live) mo[j] = c2 * (x[j] - c1 * eps);
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 20; ++j) {
           const float eps = __uint_as_float(r[j]) + b3s[c0 + j] + x[j];
@@ -617,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           if (STAMP) a.dbg[14] = clock64();
         }
       }
-      if (live && !a.refine) {
+      if (live && !a.refine && !a.mu_out) {
         float* xw = a.xin + row * PSTL_XIN_LD;
 #pragma unroll
         for (int j = 0; j < 20; ++j) xw[c0 + j] = x[j];
@@ -682,7 +692,7 @@ void pstl_tc_destroy(pstl_denoiser* d) {
 int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, const float* ct, float* xin, int N,
                    const float* sched, int steps, const float* noise, unsigned long long seed,
                    unsigned long long offset, float w_max, float a_max, int clip, int keep_last_k, float* iterates_out,
-                   int first_step, int last_step, cudaStream_t st) {
+                   int first_step, int last_step, float* mu_out, cudaStream_t st) {
   TcState* s = (TcState*)d->tc;
   PSTL_CHECK_ARG(s, "engine not created");
   PSTL_CHECK_ARG(steps <= 128, "at most 128 diffusion steps");
@@ -691,6 +701,7 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   memset(&a, 0, sizeof(a));
   a.image = s->image; a.cscene = cscene; a.ct = ct; a.b2 = d->w.p2_b; a.b3 = d->w.p4_b; a.xin = xin;
   a.noise = noise; a.iterates = keep_last_k > 0 ? iterates_out : nullptr;
+  a.mu_out = mu_out;
   const float *beta = sched, *alpha = sched + steps, *abar = sched + 2 * steps;
   for (int i = 1; i < steps; ++i) {
     a.c1[i] = (1.0f - alpha[i]) / sqrtf(1.0f - abar[i]);

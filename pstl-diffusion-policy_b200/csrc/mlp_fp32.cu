@@ -380,7 +380,7 @@ void pstl_tc_destroy(pstl_denoiser* d);
 int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, const float* ct, float* xin, int N,
                    const float* sched, int steps, const float* noise, unsigned long long seed,
                    unsigned long long offset, float w_max, float a_max, int clip, int keep_last_k, float* iterates_out,
-                   int first_step, int last_step, cudaStream_t st);
+                   int first_step, int last_step, float* mu_out, cudaStream_t st);
 int pstl_tc_refine(pstl_denoiser* d, const float* cscene, int rows_per_scene, const float* xin, int N, const float* u0,
                    const float* scores, float w_max, float a_max, int clip_rect, float* out, cudaStream_t st);
 bool pstl_tc_has_refine(pstl_denoiser* d);
@@ -565,16 +565,19 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
     const int lo = guidance ? (guidance->before + 1 > 1 ? guidance->before + 1 : 1) : 1;
     if (lo <= steps - 1) {
       rc = pstl_tc_sample(d, w.cscene, rows_per_scene, w.ct, w.xin, N, sched, steps, noise, seed, offset, w_max, a_max,
-                          clip, keep_last_k, iterates_out, steps - 1, lo, st);
+                          clip, keep_last_k, iterates_out, steps - 1, lo, nullptr, st);
       if (rc) return rc;
       tc_from = lo;
     }
   }
 
+  const bool tc_guided = d->precision == PSTL_PRECISION_BF16 && tc_from < steps;  // engine usable for this shape
   for (int i = tc_from - 1; i >= 1; --i) {
-    rc = mlp_hidden(d, w, N, rows_per_scene, d->w1p, H, w.ct + (size_t)i * H, d->w.p2_w, d->w.p2_b, st);
-    if (rc) break;
     const bool guided = guidance && i <= guidance->before;
+    if (!(guided && tc_guided)) {
+      rc = mlp_hidden(d, w, N, rows_per_scene, d->w1p, H, w.ct + (size_t)i * H, d->w.p2_w, d->w.p2_b, st);
+      if (rc) break;
+    }
     const int zi = steps - 1 - i;  // index into the injected z stream (i = steps-1 first)
     const int noise_mode = (i > 1) ? (noise ? 1 : 2) : 0;
     const int kidx = keep_last_k - i;  // iterate after step i is the (i)-th from the end
@@ -591,7 +594,11 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
     a.mu_out = guided ? w.g : nullptr;
     a.iter_out = guided ? nullptr : it_out;
     a.w_max = w_max; a.a_max = a_max; a.clip = clip;
-    rc = launch_linear<EPI_DDPM>(a, st);
+    if (guided && tc_guided)  // one reverse step on the tcgen05 engine, posterior mean into w.g
+      rc = pstl_tc_sample(d, w.cscene, rows_per_scene, w.ct, w.xin, N, sched, steps, nullptr, seed, offset, w_max, a_max, clip,
+                          0, nullptr, i, i, w.g, st);
+    else
+      rc = launch_linear<EPI_DDPM>(a, st);
     if (rc) break;
     if (guided) {
       float* m = w.adam;

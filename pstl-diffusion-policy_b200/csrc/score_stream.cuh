@@ -102,13 +102,29 @@ PSTL_HD float pstl_plan_leaf(const PstlLeafC& l, float v, float d, float th, flo
 // A single-leaf term  R_t (sb*b_t + q)/den  is shift-invariant:  = q/den + R_t (sb*b_t/den), so inside the
 // time loop such a term costs one multiply by its per-row factor g = +-tau*log2(e)/den and one online
 // accumulator update; q/den is added once after the loop.  Two-leaf (And/Or) terms evaluate X(t) in full.
-template <class Scene>
-PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose s, const float* u,
-                               const float* ego, int es, const float* p, float* tape, int tstride) {
+//
+// GRAD: the pass also records, per step, what the reverse sweep (pstl_stream_bwd) needs — cos, sin, v, the three
+// other base signals and the partial derivatives of the lane / clearance predicates — in tape columns 0..11; the
+// X(t) column of an inner-operator term moves to 12 + 2*tm.tape and the next column receives
+// L_t = lse2_{t' >= t}(inner * X2(t')) for t in [lo, hi).
+#define PSTL_STREAM_GRAD_COLS 12
+PSTL_HD int pstl_stream_xcol(const PstlTerm& tm, bool grad) { return grad ? PSTL_STREAM_GRAD_COLS + 2 * tm.tape : tm.tape; }
+
+struct PstlStreamAcc {
+  float am[PSTL_MAX_TERMS], as[PSTL_MAX_TERMS], g2[PSTL_MAX_TERMS];
+  float top_m, top_s;
+};
+
+template <bool GRAD, class Scene>
+PSTL_HD float pstl_stream_fwd(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose s, const float* u,
+                              const float* ego, int es, const float* p, float* tape, int tstride, PstlStreamAcc& A) {
   const int T = c.T;
   const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
   const float back = 0.6931471805599453f / c.tau;  // ln2 / tau
-  float am[PSTL_MAX_TERMS], as[PSTL_MAX_TERMS], g2[PSTL_MAX_TERMS];
+  float (&am)[PSTL_MAX_TERMS] = A.am;
+  float (&as)[PSTL_MAX_TERMS] = A.as;
+  float (&g2)[PSTL_MAX_TERMS] = A.g2;
+#define PSTL_TAPE(col, t) tape[(size_t)((col) * T + (t)) * tstride]
 #pragma unroll
   for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
     am[k] = PSTL_LSE2_INIT; as[k] = 0.f; g2[k] = 0.f;
@@ -158,7 +174,9 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
         prev = dj;
       }
       const PstlF4 p2 = sc.lane_pt(l, bi), p3 = sc.lane_pt(l, bi + 1);
-      pstl_lane_finish(s.x, s.y, s.th, p2.x, p2.y, p2.z, p3.x, p3.y, c.clip_dist, d, th, nullptr);
+      float part[3];
+      pstl_lane_finish(s.x, s.y, s.th, p2.x, p2.y, p2.z, p3.x, p3.y, c.clip_dist, d, th, GRAD ? part : nullptr);
+      if (GRAD) { PSTL_TAPE(6, t) = part[0]; PSTL_TAPE(7, t) = part[1]; PSTL_TAPE(8, t) = part[2]; }
     }
     if (t < pl.need_nei) {
       // utils.py:465-526 + nusc_train.py:142-148 with exact culling (drive_core.cuh).
@@ -171,7 +189,7 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
         if (k == pl.nei_term) thr = fminf(thr, (am[k] - 36.f) * rg_nei);
       if (pl.nei_term < 0) thr = 20.f;
       int cnt;
-      float best;
+      float best, bg0 = 0.f, bg1 = 0.f, bg2 = 0.f;  // partials of the minimal term (first minimum, as torch.min)
       sc.nei_begin(t, cnt, best);
       // pass 1 (branch-free): which neighbours can be closer than thr at all
       unsigned cand = 0u;
@@ -181,9 +199,12 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
         const float dx = s.x - ncx, dy = s.y - ncy;
         const float R = thr + rsum;
         const bool far = (valid == 1.f) && (R > 0.f) && (dx * dx + dy * dy >= R * R);
-        if (valid == 0.f) best = fminf(best, 100.f);
-        else if (far) best = fminf(best, thr);   // its clipped clearance is >= thr (== 20 when thr == 20)
-        else cand |= 1u << (k & 31);
+        if (valid == 0.f || far) {  // 100, or a clipped clearance >= thr (== 20 when thr == 20): zero gradient
+          const float ph = (valid == 0.f) ? 100.f : thr;
+          if (ph < best) { best = ph; bg0 = bg1 = bg2 = 0.f; }
+        } else {
+          cand |= 1u << (k & 31);
+        }
         if ((k & 31) == 31 || k == cnt - 1) {
           // pass 2: the survivors, nearest first, re-tested against the running minimum
           if (cand) {
@@ -201,12 +222,22 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
               if (valid == 1.f && pstl_cull_neighbour_r(s.x - ncx, s.y - ncy, rsum, best)) continue;
               PstlNei nb;
               sc.nei(k0 + b, t, nb);
-              best = fminf(best, pstl_pair_clearance(e, cs, sn, nb, nullptr));
+              float g[3];
+              const float term = pstl_pair_clearance(e, cs, sn, nb, GRAD ? g : nullptr);
+              if (term < best) {
+                best = term;
+                if (GRAD) { bg0 = g[0]; bg1 = g[1]; bg2 = g[2]; }
+              }
             }
           }
         }
       }
       nei = best;
+      if (GRAD) { PSTL_TAPE(9, t) = bg0; PSTL_TAPE(10, t) = bg1; PSTL_TAPE(11, t) = bg2; }
+    }
+    if (GRAD) {
+      PSTL_TAPE(0, t) = cs; PSTL_TAPE(1, t) = sn; PSTL_TAPE(2, t) = s.v;
+      PSTL_TAPE(3, t) = d; PSTL_TAPE(4, t) = th; PSTL_TAPE(5, t) = nei;
     }
 #pragma unroll
     for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
@@ -223,7 +254,7 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
             x2 = (pstl_lg2(1.f + pstl_ex2(-fabsf(xa - xb))) + fmaxf(xa, xb)) * (float)tm.pair;
             if (tm.inner == 0) x2 = x2 * (float)tm.outer;
           }
-          if (tm.inner != 0) tape[(size_t)(tm.tape * T + t) * tstride] = x2;
+          if (tm.inner != 0) PSTL_TAPE(pstl_stream_xcol(tm, GRAD), t) = x2;
           else pstl_lse2_add(am[k], as[k], x2);
         }
       }
@@ -243,10 +274,15 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
       const float gi = (float)tm.inner;
       const float go = (float)(tm.inner * tm.outer);  // y2 = (lg2 s + m) * inner ; outer argument = y2 * outer
       float m = PSTL_LSE2_INIT, sm = 0.f;
+      const int xc = pstl_stream_xcol(tm, GRAD);
 #pragma unroll 1
       for (int t = T - 1; t >= tm.lo; --t) {
-        pstl_lse2_add(m, sm, tape[(size_t)(tm.tape * T + t) * tstride] * gi);
-        if (t < tm.hi) pstl_lse2_add(am[k], as[k], (pstl_lg2(sm) + m) * go);
+        pstl_lse2_add(m, sm, PSTL_TAPE(xc, t) * gi);
+        if (t < tm.hi) {
+          const float Lt = pstl_lg2(sm) + m;
+          if (GRAD) PSTL_TAPE(xc + 1, t) = Lt;
+          pstl_lse2_add(am[k], as[k], Lt * go);
+        }
       }
     }
   }
@@ -269,10 +305,143 @@ PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEv
       pstl_lse2_add(top_m, top_s, -y2);
     }
   }
+  A.top_m = top_m; A.top_s = top_s;
   if (empty) return -INFINITY;
   if (!pl.listand) return single * back;
   return -((pstl_lg2(top_s) + top_m) * back);
 }
+
+template <class Scene>
+PSTL_HD float pstl_stream_eval(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose s, const float* u,
+                               const float* ego, int es, const float* p, float* tape, int tstride) {
+  PstlStreamAcc A;
+  return pstl_stream_fwd<false>(pl, sc, c, s, u, ego, es, p, tape, tstride, A);
+}
+
+// floats of tape per trajectory for the forward+reverse pair
+PSTL_HD int pstl_stream_grad_floats(int n_tapes, int T) { return (PSTL_STREAM_GRAD_COLS + 2 * n_tapes) * T; }
+
+// Reverse sweep after pstl_stream_fwd<true>: d loss / d controls (gu, T*2, pre-scale; may be null) and
+// d loss / d ego states (ge, T*4; may be null) for gscore = d loss / d score.
+//   score = -lse2_k(-y2_k)/k2                       W_k  = softmax_k(-y2_k)
+//   y2_k  = outer * lse2_t(outer * X2_k(t))          p(t) = 2^(outer X2(t) - m_k) / s_k
+//   inner terms: d y2_k / d X2(t') = 2^(z(t')) * sum_{t <= t'} 2^((go - 1) L_t - m_k - lg2 s_k),  z = inner * X2
+// (one prefix pass in the log domain), then the adjoint of the Euler rollout exactly as pstl_eval_traj_bwd.
+PSTL_HD void pstl_stream_bwd(const PstlPlan& pl, const PstlEvalCfg& c, const float* u, const float* p, float gscore,
+                             bool finite, const PstlStreamAcc& A, float* tape, int tstride, float* gu, float* ge) {
+  const int T = c.T;
+  const float k2 = c.tau * 1.4426950408889634f;
+  const float back = 0.6931471805599453f / c.tau;
+  float W[PSTL_MAX_TERMS];
+#pragma unroll
+  for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
+    W[k] = 0.f;
+    if (k < pl.n_terms && finite) {
+      const PstlTerm& tm = pl.terms[k];
+      float y2 = (pstl_lg2(A.as[k]) + A.am[k]) * (float)tm.outer;
+      if (tm.pair == 0) {
+        float q = tm.a.sp * p[tm.a.pid];
+        if (tm.a.den != PSTL_DEN_ONE) q = q / pstl_pred_den(tm.a.den, p);
+        y2 = y2 + q * k2;
+      }
+      W[k] = pl.listand ? gscore * pstl_ex2(-y2 - A.top_m) / A.top_s : gscore;
+    }
+  }
+  // inner-operator terms: prefix pass, X column + 1 becomes d y2_k / d X2(t)
+#pragma unroll
+  for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
+    if (k < pl.n_terms && pl.terms[k].inner != 0) {
+      const PstlTerm& tm = pl.terms[k];
+      const int xc = pstl_stream_xcol(tm, true);
+      const float gi = (float)tm.inner, go1 = (float)(tm.inner * tm.outer) - 1.f;
+      const float norm = A.am[k] + pstl_lg2(A.as[k]);
+      float cm = PSTL_LSE2_INIT, cs = 0.f;
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        float g = 0.f;
+        if (t >= tm.lo) {
+          if (t < tm.hi) pstl_lse2_add(cm, cs, go1 * PSTL_TAPE(xc + 1, t) - norm);
+          g = cs * pstl_ex2(gi * PSTL_TAPE(xc, t) + cm);
+        }
+        PSTL_TAPE(xc + 1, t) = g;
+      }
+    }
+  }
+  const int need_pose = pl.need_pose;
+  for (int t = need_pose; t < T; ++t) {  // poses the formula never reads
+    if (ge) { ge[t * 4 + 0] = 0.f; ge[t * 4 + 1] = 0.f; ge[t * 4 + 2] = 0.f; ge[t * 4 + 3] = 0.f; }
+    if (gu) { gu[2 * t] = 0.f; gu[2 * t + 1] = 0.f; }
+  }
+  float ax = 0.f, ay = 0.f, ath = 0.f, av = 0.f;  // adjoint of s_{t+1} accumulated so far
+#pragma unroll 1
+  for (int t = need_pose - 1; t >= 0; --t) {
+    const float v = PSTL_TAPE(2, t), d = PSTL_TAPE(3, t), th = PSTL_TAPE(4, t), nei = PSTL_TAPE(5, t);
+    float G[4] = {0.f, 0.f, 0.f, 0.f};  // d loss / d (v, lane distance, heading error, clearance) at step t
+#pragma unroll
+    for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
+      if (k < pl.n_terms && W[k] != 0.f) {
+        const PstlTerm& tm = pl.terms[k];
+        const bool in = tm.inner != 0 ? (t >= tm.lo) : (t >= tm.lo && t < tm.hi);
+        if (in) {
+          const int xc = pstl_stream_xcol(tm, true);
+          if (tm.pair == 0) {
+            const float base = (tm.a.c == 0) ? v : (tm.a.c == 1) ? d : (tm.a.c == 2) ? th : nei;
+            // d X / d base = sb / den = g2 / k2 (times outer where g2 carries it)
+            float w, dxb;
+            if (tm.inner != 0) { w = PSTL_TAPE(xc + 1, t); dxb = A.g2[k] * back; }
+            else { w = pstl_ex2(base * A.g2[k] - A.am[k]) / A.as[k]; dxb = A.g2[k] * back * (float)tm.outer; }
+            const float gb = W[k] * w * dxb;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) G[q] += (tm.a.c == q) ? gb : 0.f;
+          } else {
+            const float g = (float)tm.pair * k2;
+            const float xa = pstl_plan_leaf(tm.a, v, d, th, nei, p) * g, xb = pstl_plan_leaf(tm.b, v, d, th, nei, p) * g;
+            const float l = pstl_lg2(1.f + pstl_ex2(-fabsf(xa - xb))) + fmaxf(xa, xb);
+            float w;
+            if (tm.inner != 0) w = PSTL_TAPE(xc + 1, t);
+            else w = pstl_ex2(l * (float)(tm.pair * tm.outer) - A.am[k]) / A.as[k];
+            const float gx = W[k] * w;  // d loss / d X(t)
+            float da = tm.a.sb, db = tm.b.sb;
+            if (tm.a.den != PSTL_DEN_ONE) da = da / pstl_pred_den(tm.a.den, p);
+            if (tm.b.den != PSTL_DEN_ONE) db = db / pstl_pred_den(tm.b.den, p);
+            const float ga = gx * pstl_ex2(xa - l) * da, gb = gx * pstl_ex2(xb - l) * db;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) G[q] += ((tm.a.c == q) ? ga : 0.f) + ((tm.b.c == q) ? gb : 0.f);
+          }
+        }
+      }
+    }
+    float lx = 0.f, ly = 0.f, lth = 0.f;
+    const float lv = G[0];
+    if (t < pl.need_lane) {
+      lx += G[1] * PSTL_TAPE(6, t);
+      ly += G[1] * PSTL_TAPE(7, t);
+      lth += G[2] * PSTL_TAPE(8, t);
+    }
+    if (t < pl.need_nei && G[3] != 0.f) {
+      lx += G[3] * PSTL_TAPE(9, t); ly += G[3] * PSTL_TAPE(10, t); lth += G[3] * PSTL_TAPE(11, t);
+    }
+    if (ge) { ge[t * 4 + 0] = lx; ge[t * 4 + 1] = ly; ge[t * 4 + 2] = lth; ge[t * 4 + 3] = lv; }
+    if (gu) {
+      // controls at step t move s_{t+1}: d th_{t+1}/d w_t = dt, d v_{t+1}/d a_t = dt
+      float gw = ath * c.dt * c.w_scale, ga = av * c.dt * c.a_scale;
+      if (c.clip_controls) {
+        const float w = u[2 * t] * c.w_scale, a = u[2 * t + 1] * c.a_scale;
+        if (w < -c.w_scale || w > c.w_scale) gw = 0.f;
+        if (a < -c.a_scale || a > c.a_scale) ga = 0.f;
+      }
+      gu[2 * t] = gw;
+      gu[2 * t + 1] = ga;
+      // A_t = lambda_t + J_t^T A_{t+1}
+      const float cs = PSTL_TAPE(0, t), sn = PSTL_TAPE(1, t);
+      const float nth = ath + ax * (-(v * sn) * c.dt) + ay * ((v * cs) * c.dt);
+      const float nv = av + ax * (cs * c.dt) + ay * (sn * c.dt);
+      ax += lx; ay += ly; ath = nth + lth; av = nv + lv;
+    }
+  }
+}
+#undef PSTL_TAPE
+
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------
@@ -452,6 +621,73 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
       }
     }
     if (a.traj_out) *reinterpret_cast<float4*>(a.traj_out + ((size_t)n * (T + 1) + T) * 4) = make_float4(s.x, s.y, s.th, s.v);
+  }
+}
+
+// Reverse mode (guidance, autograd of compute_stl_dense): forward with the per-step record in a global tape
+// (element-major, stride N: coalesced), then pstl_stream_bwd.  C == 1.
+template <bool SMEM_SCENE>
+__global__ void __launch_bounds__(PSTL_STREAM_BLOCK_MAX, 3)
+k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ StreamPlans sp) {
+  extern __shared__ float4 sm4[];
+  const PstlEvalCfg c = a.cfg;
+  const int B = blockDim.x, T = c.T;
+  const int n0 = blockIdx.x * B;
+  int li = threadIdx.x;
+  if (B % 96 == 0) {
+    const int g = li / 96, w = li - g * 96;
+    li = g * 96 + (w & 31) * 3 + (w >> 5);
+  }
+  const int n = n0 + li;
+  float4* tile = sm4;
+  if (SMEM_SCENE) {
+    stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile);
+    __syncthreads();
+  }
+  const bool live = n < a.N;
+  int m = 4;
+  if (live) {
+    const float md = a.mode[n];
+    m = (md == 0.f) ? 0 : (md == 1.f) ? 1 : (md == 2.f) ? 2 : (md == 3.f) ? 3 : 4;
+  }
+  const int nn = live ? n : 0;
+  PstlPose s0{0.f, 0.f, 0.f, 0.f};
+  if (a.state0) {
+    const float4 q = *reinterpret_cast<const float4*>(a.state0 + (size_t)nn * 4);
+    s0 = PstlPose{q.x, q.y, q.z, q.w};
+  }
+  const float* stlp = a.stlp + (size_t)nn * 6;
+  const float* ego = a.ego ? a.ego + (size_t)nn * T * a.ego_stride : nullptr;
+  const float* u = a.controls ? a.controls + (size_t)nn * T * 2 : nullptr;
+  float* gu = a.grad_controls ? a.grad_controls + (size_t)nn * T * 2 : nullptr;
+  float* ge = a.grad_ego ? a.grad_ego + (size_t)nn * T * 4 : nullptr;
+  float* tape = a.ws + nn;
+  const int scene = nn / a.rows_per_scene;
+  const float4* tile_ln = tile + (size_t)c.K * T * PSTL_STREAM_NEI_F4;
+  StreamSceneSmem ss{tile, reinterpret_cast<const float2*>(tile_ln + 3 * c.nseg), tile_ln, c.K, T, c.nseg};
+  PstlStreamSceneGlobal sg;
+  sg.neib = a.neighbors + (size_t)scene * c.K * T * 7;
+  for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
+  sg.K = c.K; sg.T = T; sg.ego_half = c.ego_L / 2.f;
+
+  if (live && m >= 3) {
+    if (a.scores) a.scores[n] = (m == 3) ? 1.0f : 0.0f;
+    if (gu) for (int i = 0; i < T * 2; ++i) gu[i] = 0.f;
+    if (ge) for (int i = 0; i < T * 4; ++i) ge[i] = 0.f;
+  }
+#pragma unroll 1
+  for (int mm = 0; mm < 3; ++mm) {
+    if (!__any_sync(0xffffffffu, m == mm)) continue;
+    if (m == mm) {
+      PstlStreamAcc A;
+      const float sc = SMEM_SCENE ? pstl_stream_fwd<true>(sp.p[mm], ss, c, s0, u, ego, a.ego_stride, stlp, tape, a.N, A)
+                                  : pstl_stream_fwd<true>(sp.p[mm], sg, c, s0, u, ego, a.ego_stride, stlp, tape, a.N, A);
+      if (a.scores) a.scores[n] = sc;
+      float g;
+      if (a.grad_score) g = a.grad_score[n];
+      else g = (a.thres - sc > 0.f) ? -a.valid[n] * a.inv_norm : 0.f;  // guidance loss, nusc_train.py:616-619
+      pstl_stream_bwd(sp.p[mm], c, u, stlp, g, sc != -INFINITY, A, tape, a.N, gu, ge);
+    }
   }
 }
 #endif  // __CUDACC__

@@ -468,6 +468,44 @@ static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaSt
   return PSTL_OK;
 }
 
+// reverse-mode scoring on the streaming kernel; sets *took when it owned the launch
+static size_t stream_bwd_ws_floats(pstl_program_t const* progs, int N, int T) {
+  int n_tapes = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (!progs[k]->plan.valid) return 0;
+    n_tapes = progs[k]->plan.n_tapes > n_tapes ? progs[k]->plan.n_tapes : n_tapes;
+  }
+  return (size_t)pstl_stream_grad_floats(n_tapes, T) * N;
+}
+
+static int launch_score_stream_bwd(ScoreArgs& a, pstl_program_t const* progs, cudaStream_t st, int* took) {
+  *took = 0;
+  const PstlEvalCfg& c = a.cfg;
+  if (c.hard || score_kernel_forced("warp") || score_kernel_forced("thread") || !a.ws) return PSTL_OK;
+  if (!stream_bwd_ws_floats(progs, a.N, c.T)) return PSTL_OK;
+  StreamPlans sp;
+  for (int k = 0; k < 3; ++k) sp.p[k] = progs[k]->plan;
+  const size_t tile_bytes = stream_tile_f4(c.K, c.T, c.nseg) * sizeof(float4);
+  const size_t budget = 100 * 1024;
+  int block = 128;
+  bool smem_scene = false;
+  if (a.rows_per_scene % 32 == 0 && tile_bytes <= budget) {
+    static const int cands[] = {192, 96, 128, 64, 32};
+    for (int b : cands)
+      if (a.rows_per_scene % b == 0) { block = b; smem_scene = true; break; }
+  }
+  const int grid = pstl_ceil_div(a.N, block);
+  if (smem_scene) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream_bwd<true><<<grid, block, tile_bytes, st>>>(a, sp);
+  } else {
+    k_score_stream_bwd<false><<<grid, block, 0, st>>>(a, sp);
+  }
+  PSTL_LAUNCH_CHECK();
+  *took = 1;
+  return PSTL_OK;
+}
+
 static int fill_cfg(const pstl_scene_view* sv, const pstl_spec_params* sp, PstlEvalCfg* c) {
   c->dt = sp->dt; c->tau = sp->tau; c->ego_L = sp->ego_L; c->ego_W = sp->ego_W;
   c->w_scale = sp->w_scale; c->a_scale = sp->a_scale;
@@ -518,8 +556,9 @@ extern "C" size_t pstl_score_workspace_bytes(pstl_program_t const* progs, int N,
   const int F = with_grad ? max3(progs[0]->h.grad_floats, progs[1]->h.grad_floats, progs[2]->h.grad_floats)
                           : max3(progs[0]->h.val_floats, progs[1]->h.val_floats, progs[2]->h.val_floats);
   TapePlan t = plan_tape(F, 96 * 1024, 32);
-  (void)T;
-  return t.smem_tape ? 0 : (size_t)F * N * sizeof(float);
+  const size_t interp = t.smem_tape ? 0 : (size_t)F * N * sizeof(float);
+  const size_t stream = with_grad ? stream_bwd_ws_floats(progs, N, T) * sizeof(float) : 0;
+  return interp > stream ? interp : stream;
 }
 
 template <bool BWD>
@@ -601,6 +640,9 @@ extern "C" int pstl_score_fused_bwd(pstl_program_t const* progs, const pstl_scen
   a.grad_score = grad_score; a.scores = scores;
   a.grad_controls = ego_traj ? nullptr : grad_controls; a.grad_ego = ego_traj ? grad_ego : nullptr;
   a.ws = (float*)workspace;
+  int took = 0;
+  rc = launch_score_stream_bwd(a, progs, (cudaStream_t)stream, &took);
+  if (rc || took) return rc;
   ScorePlan plan = plan_score(progs, scenes, N, 1);
   PSTL_CHECK_ARG(plan.tp.smem_tape || workspace, "workspace required (see pstl_score_workspace_bytes)");
   return launch_score<true>(a, plan, (cudaStream_t)stream);
@@ -653,9 +695,14 @@ extern "C" int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_
   base_args(a, progs, scenes, sp);
   a.mode = mode; a.state0 = state0; a.controls = mu; a.stlp = stlp; a.N = N; a.C = 1;
   a.valid = valid; a.thres = thres; a.inv_norm = inv_norm; a.grad_controls = grad; a.ws = tape;
-  ScorePlan plan = plan_score(progs, scenes, N, 1);
-  rc = launch_score<true>(a, plan, (cudaStream_t)stream);
+  int took = 0;
+  rc = launch_score_stream_bwd(a, progs, (cudaStream_t)stream, &took);
   if (rc) return rc;
+  if (!took) {
+    ScorePlan plan = plan_score(progs, scenes, N, 1);
+    rc = launch_score<true>(a, plan, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   const size_t n = (size_t)N * T * 2;
   // torch computes the bias corrections in Python doubles, then applies them to fp32 tensors
   const double bc1 = 1.0 - pow(0.9, (double)(iter + 1)), bc2 = 1.0 - pow(0.999, (double)(iter + 1));

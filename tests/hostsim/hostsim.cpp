@@ -118,3 +118,48 @@ extern "C" int hs_plan_info(const pstl_op* ops, int n_ops, int T, int* out) {
   for (int i = 0; i < 9; ++i) out[i] = v[i];
   return 0;
 }
+
+// streaming forward + reverse sweep (score_stream.cuh) on the same inputs as hs_score
+extern "C" int hs_score_stream_grad(const pstl_op* const* ops3, const int* n_ops3, int T, int K, int nseg,
+                                    const float* neighbors, const float* l0, const float* l1, const float* l2,
+                                    int rows_per_scene, const float* mode, const float* state0, const float* controls,
+                                    const float* ego, int es, const float* stlp, int N, float dt, float tau,
+                                    float w_scale, float a_scale, int clip_controls, const float* grad_score,
+                                    float* scores, float* grad_controls, float* grad_ego) {
+  PstlProgView pv[3];
+  PstlPlan pl[3];
+  char err[256];
+  for (int k = 0; k < 3; ++k) {
+    if (pstl_resolve_program(ops3[k], n_ops3[k], 0, T, 1, &pv[k], err, sizeof(err))) { fprintf(stderr, "%s\n", err); return -1; }
+    pstl_make_plan(pv[k], &pl[k]);
+    if (!pl[k].valid) return -2;
+  }
+  PstlEvalCfg c{dt, tau, 4.084f, 1.730f, w_scale, a_scale, clip_controls, 0, 0, nseg, K, T};
+  const float* ln[3] = {l0, l1, l2};
+  std::vector<float> tape((size_t)pstl_stream_grad_floats(PSTL_MAX_TAPES, T));
+  for (int n = 0; n < N; ++n) {
+    const int m = (int)mode[n];
+    float* gu = grad_controls ? grad_controls + (size_t)n * T * 2 : nullptr;
+    float* ge = grad_ego ? grad_ego + (size_t)n * T * 4 : nullptr;
+    if (m < 0 || m > 2) {
+      scores[n] = (m == 3) ? 1.f : 0.f;
+      if (gu) std::fill(gu, gu + 2 * T, 0.f);
+      if (ge) std::fill(ge, ge + 4 * T, 0.f);
+      continue;
+    }
+    PstlStreamSceneGlobal sg;
+    const int scene = n / rows_per_scene;
+    sg.neib = neighbors + (size_t)scene * K * T * 7;
+    for (int l = 0; l < 3; ++l) sg.ln[l] = ln[l] + (size_t)scene * nseg * 3;
+    sg.K = K; sg.T = T; sg.ego_half = c.ego_L / 2.f;
+    PstlPose s0{0, 0, 0, 0};
+    if (state0) s0 = PstlPose{state0[n * 4], state0[n * 4 + 1], state0[n * 4 + 2], state0[n * 4 + 3]};
+    const float* u = controls ? controls + (size_t)n * T * 2 : nullptr;
+    const float* e = ego ? ego + (size_t)n * T * es : nullptr;
+    PstlStreamAcc A;
+    const float sc = pstl_stream_fwd<true>(pl[m], sg, c, s0, u, e, es, stlp + (size_t)n * 6, tape.data(), 1, A);
+    scores[n] = sc;
+    pstl_stream_bwd(pl[m], c, u, stlp + (size_t)n * 6, grad_score[n], sc != -INFINITY, A, tape.data(), 1, gu, ge);
+  }
+  return 0;
+}

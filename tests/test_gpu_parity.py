@@ -523,3 +523,19 @@ def test_native_encoder_glue_vs_oracle_and_torch_path():
     close(f_native, ref, what="native feature")
     close(f_torch, ref, what="torch feature")
     close(f_native, f_torch.detach(), rtol=2e-6, what="native vs torch")
+
+
+def test_bf16_guided_steps_on_tcgen05_vs_fp32():
+    """'Ours+guidance' with the bf16 engine (the guided reverse steps take their posterior mean from one-step launches of
+    the tcgen05 kernel, gradients from the streaming reverse-mode scorer) against the fp32 path on the same injected noise.
+    Guidance moves mu by lr*g/(|g|+1e-8) per step, which turns rounding-level gradient differences of the few rows with
+    |g| ~ 1e-8 into lr-sized moves: the bound is on the bulk plus a loose maximum (10 steps x lr = 0.1)."""
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        out, _, _, _ = _run_pipeline(NT.GUIDANCE_FLAGS, 2002, precision=prec)
+        outs[prec] = out["final_iterate"].clone()
+    scale = torch.tensor([0.5, 5.0], device="cuda")
+    err = ((outs["bf16"] - outs["fp32"]) / scale).abs().flatten()
+    assert torch.isfinite(outs["bf16"]).all()
+    q50, q95, mx = torch.quantile(err, 0.5).item(), torch.quantile(err, 0.95).item(), err.max().item()
+    assert q50 < 2e-3 and q95 < 2e-2 and mx < 0.25, (q50, q95, mx)

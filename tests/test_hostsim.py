@@ -112,6 +112,14 @@ def test_fused_dense_scores_and_grads(golden_dir, tag, n, nt, knei, seed):
     close(s2, sc_ref)
     gref = G[tag + "|grad_ego"]
     np.testing.assert_allclose(gego, gref, rtol=2e-4, atol=2e-4 * np.abs(gref).max())
+    # streaming forward + reverse sweep
+    s3, g3 = np.zeros(n, np.float32), np.zeros((n, nt, 4), np.float32)
+    rc = hs.hs_score_stream_grad(ops3, nops, nt, knei, 15, fp(nei), fp(l0), fp(l1), fp(l2), 1, fp(mode), None, None, fp(ego),
+                                 4, fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(1.0), C.c_float(1.0), 0, fp(gs),
+                                 fp(s3), None, fp(g3))
+    assert rc == 0
+    close(s3, sc_ref)
+    np.testing.assert_allclose(g3, gref, rtol=2e-4, atol=2e-4 * np.abs(gref).max())
 
 
 def _typed_leaves(nt):
@@ -197,3 +205,19 @@ def test_stream_plan_equals_interpreter_on_variant_specs():
                                   fp(ego), 4, fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(1.0),
                                   C.c_float(1.0), 0, fp(got)) == 0
         close(got, ref)
+        # reverse mode through the rollout: d score / d controls (scaled + clipped controls, as the guidance call)
+        g = torch.Generator().manual_seed(3)
+        ctl = np.ascontiguousarray(((torch.rand(n, nt, 2, generator=g) * 2.4 - 1.2)).numpy(), np.float32)
+        s0 = np.ascontiguousarray(ego[:, 0, :4])
+        ones = np.ones(n, np.float32)
+        sa, sb = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        ga, gb = np.zeros((n, nt, 2), np.float32), np.zeros((n, nt, 2), np.float32)
+        assert hs.hs_score(ops3, nops, nt, knei, 15, fp(nei), fp(l0), fp(l1), fp(l2), 1, fp(mode), fp(s0), fp(ctl), None, 0,
+                           fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(0.5), C.c_float(5.0), 1, 0, fp(ones),
+                           fp(sa), fp(ga), None) == 0
+        assert hs.hs_score_stream_grad(ops3, nops, nt, knei, 15, fp(nei), fp(l0), fp(l1), fp(l2), 1, fp(mode), fp(s0), fp(ctl),
+                                       None, 0, fp(stlp), n, C.c_float(0.5), C.c_float(100.0), C.c_float(0.5), C.c_float(5.0),
+                                       1, fp(ones), fp(sb), fp(gb), None) == 0
+        close(sb, sa)
+        fin = np.isfinite(sa)
+        np.testing.assert_allclose(gb[fin], ga[fin], rtol=2e-4, atol=2e-4 * max(1e-6, np.abs(ga[fin]).max()))
