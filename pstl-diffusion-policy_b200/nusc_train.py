@@ -823,7 +823,23 @@ class CapturedPipeline:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._body()
-        self.launches_per_replay = None
+        # double buffering of the inputs: `prefetch` fills a staging copy on its own stream while a replay runs
+        self.staging = {k: torch.empty_like(t) for k, t in self.static_in.items()}
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staged = torch.cuda.Event()
+        self._staging_free = torch.cuda.Event()
+        self._staging_free.record(torch.cuda.current_stream(dev))
+        self._have_prefetch = False
+
+    def prefetch(self, batch):
+        """Start copying the NEXT batch (pinned host or device tensors) into the staging inputs on a separate stream;
+        the copy overlaps whatever the main stream is running.  The next ``runner()`` call consumes it."""
+        self._copy_stream.wait_event(self._staging_free)
+        with torch.cuda.stream(self._copy_stream):
+            for k, t in self.staging.items():
+                t.copy_(batch[k], non_blocking=True)
+            self._staged.record(self._copy_stream)
+        self._have_prefetch = True
 
     def _body(self):
         handle = self.net.native_handle(getattr(self.args, "precision", "fp32"))
@@ -833,10 +849,20 @@ class CapturedPipeline:
         with torch.no_grad():
             return sample_and_score(self.net, self.static_in, self.stls, self.coeffs, self.args)
 
-    def __call__(self, batch):
-        for k, t in self.static_in.items():
-            if batch[k] is not t:
-                t.copy_(batch[k], non_blocking=True)
+    def __call__(self, batch=None):
+        cur = torch.cuda.current_stream()
+        if batch is None:
+            if not self._have_prefetch:
+                raise ValueError("CapturedPipeline(): no batch given and nothing prefetched")
+            cur.wait_event(self._staged)
+            for k, t in self.static_in.items():
+                t.copy_(self.staging[k], non_blocking=True)  # device to device, a few microseconds
+            self._staging_free.record(cur)
+            self._have_prefetch = False
+        else:
+            for k, t in self.static_in.items():
+                if batch[k] is not t:
+                    t.copy_(batch[k], non_blocking=True)
         self.graph.replay()
         return self.out
 

@@ -539,3 +539,26 @@ def test_bf16_guided_steps_on_tcgen05_vs_fp32():
     assert torch.isfinite(outs["bf16"]).all()
     q50, q95, mx = torch.quantile(err, 0.5).item(), torch.quantile(err, 0.95).item(), err.max().item()
     assert q50 < 2e-3 and q95 < 2e-2 and mx < 0.25, (q50, q95, mx)
+
+
+def test_captured_pipeline_prefetch_matches_direct_call():
+    """prefetch(batch) + runner() reads the prefetched batch: its scores are the eager scorer's scores of that batch"""
+    S_ = 64
+    args = NT.default_args(precision="bf16", n_randoms=S_, sampling_size=S_)
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007))
+    net = net.cuda()
+    stls, co = NT.build_stl_cache(args), NT.get_diffusion_coeffs(args)
+    progs = NT._fused_programs(stls, args.nt)
+    hb = [{k: v.pin_memory() for k, v in synthetic.make_scene_batch(4, n_randoms=S_, seed=s).items()} for s in (51, 52)]
+    runner = NT.CapturedPipeline(net, stls, co, args, cuda(hb[0]))
+    runner.prefetch(hb[1])
+    out = {k: v.clone() for k, v in runner().items() if isinstance(v, torch.Tensor)}
+    b = cuda(hb[1])
+    nb = NT.LazyBatch({k: b[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+                                         "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp")})
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    pack = NT.augment_batch_data(nb, None, args, n_randoms=S_)["_pstl_pack"]
+    assert torch.equal(NT.score_pack(pack, out["controls"], args, progs)["best_score"], out["scores"])
+    with pytest.raises(ValueError):
+        runner()
