@@ -789,6 +789,18 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     return out
 
 
+def closed_loop_pick(scores_all, ego_controls, ego_trajs):
+    """candidate selection of the closed-loop simulator (reference nusc_sim.py:677-683): chains are rows
+    ``n = sample*3 + mode`` of ONE scene; modes 1, 2 (lane changes) are masked to -1e4 and the global arg-max wins
+    (first maximum).  Returns (index into the n rows, highest score, controls (1,T,2), trajectory (1,T+1,4)).
+    The mask is applied to a copy (upstream overwrites its score tensor in place)."""
+    n = scores_all.shape[0]
+    cube = scores_all.reshape(n // 3, 3).clone()
+    cube[:, 1:3] = -10000
+    total_idx = torch.argmax(cube)
+    return total_idx, cube.flatten()[total_idx], ego_controls[total_idx].unsqueeze(0), ego_trajs[total_idx].unsqueeze(0)
+
+
 class CapturedPipeline:
     """``sample_and_score`` captured ONCE into a CUDA graph and replayed per batch (static shapes): the
     ~170 kernel launches of a batch become one ``cudaGraphLaunch``, so the GPU is no longer paced by the

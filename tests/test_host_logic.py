@@ -179,3 +179,18 @@ def test_world_size_2_gloo_sharding_and_gather():
     for p in ps:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_closed_loop_pick_masks_lane_change_modes():
+    """reference nusc_sim.py:677-683"""
+    g = torch.Generator().manual_seed(0)
+    sc = torch.randn(64 * 3, generator=g)
+    sc[5 * 3 + 1] = 50.0          # a lane-change row with the best raw score must not win
+    sc[7 * 3] = sc[11 * 3] = 9.0  # tie between two mode-0 rows: first maximum
+    u, tr = torch.randn(192, 20, 2, generator=g), torch.randn(192, 21, 4, generator=g)
+    idx, best, cu, ct = NT.closed_loop_pick(sc, u, tr)
+    cube = sc.reshape(64, 3).clone()
+    cube[:, 1:3] = -10000
+    assert int(idx) == int(torch.argmax(cube)) == 21 and float(best) == 9.0
+    assert cu.shape == (1, 20, 2) and ct.shape == (1, 21, 4) and torch.equal(cu[0], u[21])
+    assert sc[5 * 3 + 1] == 50.0  # input untouched
