@@ -247,6 +247,20 @@ int pstl_predicates(const pstl_scene_view* scenes, float ego_L, float ego_W, int
 int pstl_linear(const float* x, const float* w, const float* b, int M, int K, int Nout, int act, float* y,
                 pstl_stream_t stream);
 
+/* Three-layer ReLU MLP of the scene encoders in one launch (nusc_model.py:82-91, hidden width 256):
+ * y (M,out) = W4 relu(W2 relu(W0 x + b0) + b2) + b4, weights (out_features, in_features) row-major as in nn.Linear.
+ * Same summation order as three pstl_linear calls. */
+int pstl_mlp3(const float* x, int M, int in_dim, const float* w0, const float* b0, const float* w2, const float* b2,
+              const float* w4, const float* b4, int hidden, int out_dim, float* y, pstl_stream_t stream);
+/* Several independent MLPs of that shape in ONE grid (the ego / neighbour / lane encoders side by side). */
+#define PSTL_MLP3_MAX 4
+typedef struct {
+  const float *x, *w0, *b0, *w2, *b2, *w4, *b4;
+  float* y;
+  int M, in_dim, hidden, out_dim;
+} pstl_mlp3_problem;
+int pstl_mlp3_batch(const pstl_mlp3_problem* problems, int n, pstl_stream_t stream);
+
 /* Scene-encoder glue (Net.encode_feat, nusc_model.py:55-95).
  * pstl_encoder_inputs: ego (n_scenes rows of >= 6 floats [x,y,th,v,L,W], row stride ego_row_stride), neighbors
  * (n_scenes,Knei,7), three lanes (n_scenes,nseg,3) and their validity ids (n_scenes) -> the inputs of the three encoder

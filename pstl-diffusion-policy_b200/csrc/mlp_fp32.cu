@@ -181,6 +181,162 @@ extern "C" int pstl_linear(const float* x, const float* w, const float* b, int M
 }
 
 // --------------------------------------------------------------------------------------
+// Three-layer ReLU MLP in one launch (the scene encoders, reference nusc_model.py:82-91: in -> 256 -> 256 -> out):
+// a block owns 32 rows and keeps their activations in shared memory ([k][row], so a thread reads its rows of one
+// k with float4 loads); the weights stream through 16-deep K slabs with the next slab prefetched into registers.
+// Each output is one fmaf chain over k ascending with the bias added last — bit-identical to three k_linear calls.
+// --------------------------------------------------------------------------------------
+#define MLP3_ROWS 32
+#define MLP3_H 256
+#define MLP3_LDA (MLP3_ROWS + 4)
+#define MLP3_LDW (MLP3_H + 4)
+
+// One layer: acc[RT][4] = sum_k A[k][row(s)] * W[col][k] over K; W (NR, K) row-major in global memory, NR = 256
+// (thread = 8 rows x 4 columns) or NR <= 32 padded to 32 (thread = 1 row x 4 columns).  Slab loads are coalesced:
+// 16 consecutive threads read the 16 consecutive k of one weight row.
+template <int NR, int RT>
+__device__ __forceinline__ void mlp3_layer(const float* __restrict__ As, int K, const float* __restrict__ W, int n_rows,
+                                           float* __restrict__ Ws, float (&acc)[RT][4]) {
+  constexpr int PER = NR * BK / 256;  // slab elements per thread (16 or 2)
+  constexpr int TXN = NR / 4;         // threads along the columns
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
+#pragma unroll
+  for (int i = 0; i < RT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float rw[PER];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = tid + 256 * i, n = e / BK, kk = e % BK;
+      rw[i] = (n < n_rows && k0 + kk < K) ? W[(size_t)n * K + k0 + kk] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    __syncthreads();  // previous slab fully consumed
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int e = tid + 256 * i;
+      Ws[(e % BK) * MLP3_LDW + e / BK] = rw[i];
+    }
+    __syncthreads();
+    if (k0 + BK < K) fetch(k0 + BK);
+    const int kn = (K - k0 < BK) ? K - k0 : BK;
+#pragma unroll 4
+    for (int kk = 0; kk < kn; ++kk) {
+      float av[RT];
+      if constexpr (RT == 8) {
+        const float4 a0 = *reinterpret_cast<const float4*>(As + (k0 + kk) * MLP3_LDA + ty * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(As + (k0 + kk) * MLP3_LDA + ty * 8 + 4);
+        av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+        av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+      } else {
+        av[0] = As[(k0 + kk) * MLP3_LDA + ty];
+      }
+      const float4 b0 = *reinterpret_cast<const float4*>(Ws + kk * MLP3_LDW + tx * 4);
+      const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+}
+
+struct Mlp3Problem {
+  const float *x, *w0, *b0, *w2, *b2, *w4, *b4;
+  float* y;
+  int M, in_dim, out_dim, block0;  // block0: first block of this problem in the grid
+};
+struct Mlp3Batch {
+  Mlp3Problem p[PSTL_MLP3_MAX];
+  int n;
+};
+
+// up to PSTL_MLP3_MAX independent MLPs in one grid (the three scene encoders run side by side)
+__global__ void __launch_bounds__(256) k_mlp3(const __grid_constant__ Mlp3Batch batch) {
+  extern __shared__ __align__(16) float sm3[];
+  float* As = sm3;                         // [256][MLP3_LDA]: layer input, k-major
+  float* Ws = As + MLP3_H * MLP3_LDA;      // [16][MLP3_LDW]
+  const int tid = threadIdx.x;
+  int pi = 0;
+  for (int i = 1; i < batch.n; ++i)
+    if ((int)blockIdx.x >= batch.p[i].block0) pi = i;
+  const Mlp3Problem& P = batch.p[pi];
+  const float* __restrict__ x = P.x;
+  const float *w0 = P.w0, *b0 = P.b0, *w2 = P.w2, *b2 = P.b2, *w4 = P.w4, *b4 = P.b4;
+  float* __restrict__ y = P.y;
+  const int M = P.M, in_dim = P.in_dim, out_dim = P.out_dim;
+  const long long m0 = (long long)((int)blockIdx.x - P.block0) * MLP3_ROWS;
+  for (int i = tid; i < MLP3_ROWS * in_dim; i += 256) {
+    const int r = i / in_dim, k = i - r * in_dim;
+    As[k * MLP3_LDA + r] = (m0 + r < M) ? x[(m0 + r) * in_dim + k] : 0.f;
+  }
+  // layers 1 and 2 (ReLU), outputs back into As as the next layer's input
+#pragma unroll 1
+  for (int layer = 0; layer < 2; ++layer) {
+    float acc[8][4];
+    const int tx = tid & 63, ty = tid >> 6;
+    __syncthreads();
+    mlp3_layer<MLP3_H, 8>(As, layer == 0 ? in_dim : MLP3_H, layer == 0 ? w0 : w2, MLP3_H, Ws, acc);
+    const float* bias = layer == 0 ? b0 : b2;
+    __syncthreads();  // every thread is done reading As
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = tx * 4 + j;
+      const float bb = bias[n];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[n * MLP3_LDA + ty * 8 + i] = fmaxf(acc[i][j] + bb, 0.f);
+    }
+  }
+  __syncthreads();
+  // layer 3: out_dim <= 32 columns, thread = (row tid/8, columns (tid%8)*4..+3)
+  float acc3[1][4];
+  mlp3_layer<32, 1>(As, MLP3_H, w4, out_dim, Ws, acc3);
+  const int r = tid >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = (tid & 7) * 4 + j;
+    if (n < out_dim && m0 + r < M) y[(m0 + r) * out_dim + n] = acc3[0][j] + b4[n];
+  }
+}
+
+// y_i (M_i, out_i) = W4 relu(W2 relu(W0 x_i + b0) + b2) + b4 for n independent problems; hidden width 256
+extern "C" int pstl_mlp3_batch(const pstl_mlp3_problem* probs, int n, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(probs && n >= 1 && n <= PSTL_MLP3_MAX, "1..PSTL_MLP3_MAX problems");
+  Mlp3Batch b;
+  memset(&b, 0, sizeof(b));
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    const pstl_mlp3_problem& q = probs[i];
+    PSTL_CHECK_ARG(q.x && q.w0 && q.b0 && q.w2 && q.b2 && q.w4 && q.b4 && q.y, "null argument");
+    PSTL_CHECK_ARG(q.hidden == MLP3_H && q.in_dim >= 1 && q.in_dim <= MLP3_H && q.out_dim >= 1 && q.out_dim <= 32,
+                   "pstl_mlp3 is built for hidden = 256, out <= 32");
+    if (q.M <= 0) continue;
+    Mlp3Problem& p = b.p[b.n++];
+    p.x = q.x; p.w0 = q.w0; p.b0 = q.b0; p.w2 = q.w2; p.b2 = q.b2; p.w4 = q.w4; p.b4 = q.b4; p.y = q.y;
+    p.M = q.M; p.in_dim = q.in_dim; p.out_dim = q.out_dim; p.block0 = blocks;
+    blocks += pstl_ceil_div(q.M, MLP3_ROWS);
+  }
+  if (!blocks) return PSTL_OK;
+  const size_t smem = sizeof(float) * ((size_t)MLP3_H * MLP3_LDA + (size_t)BK * MLP3_LDW);
+  PSTL_CUDA(cudaFuncSetAttribute(k_mlp3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mlp3<<<blocks, 256, smem, (cudaStream_t)stream>>>(b);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
+extern "C" int pstl_mlp3(const float* x, int M, int in_dim, const float* w0, const float* b0, const float* w2,
+                         const float* b2, const float* w4, const float* b4, int hidden, int out_dim, float* y,
+                         pstl_stream_t stream) {
+  pstl_mlp3_problem q;
+  q.x = x; q.w0 = w0; q.b0 = b0; q.w2 = w2; q.b2 = b2; q.w4 = w4; q.b4 = b4; q.y = y;
+  q.M = M; q.in_dim = in_dim; q.hidden = hidden; q.out_dim = out_dim;
+  return pstl_mlp3_batch(&q, 1, stream);
+}
+
+// --------------------------------------------------------------------------------------
 // small helper kernels
 // --------------------------------------------------------------------------------------
 // xin[n] = [x (T2) | hl | stlp(6) | 0]

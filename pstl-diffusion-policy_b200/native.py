@@ -23,7 +23,7 @@ EXPORTS = [
     "pstl_score_workspace_bytes", "pstl_score_fused", "pstl_score_fused_bwd", "pstl_guidance_step",
     "pstl_denoiser_create", "pstl_denoiser_destroy", "pstl_denoiser_workspace_bytes", "pstl_denoiser_sample",
     "pstl_denoiser_eps", "pstl_denoiser_set_noise_counter", "pstl_launch_count", "pstl_refine", "pstl_rollout", "pstl_rollout_bwd", "pstl_predicates", "pstl_linear", "pstl_encoder_inputs",
-    "pstl_encoder_pool",
+    "pstl_encoder_pool", "pstl_mlp3", "pstl_mlp3_batch",
 ]
 
 
@@ -53,6 +53,11 @@ _W_FIELDS = ["p0_w", "p0_b", "p2_w", "p2_b", "p4_w", "p4_b", "m0_w", "m0_b", "m2
 class Weights(C.Structure):
     _fields_ = [(f, C.c_void_p) for f in _W_FIELDS] + [(f, C.c_int) for f in
                                                         ("hidden", "rect_hidden", "merge_hidden", "feat_dim", "time_dim", "T")]
+
+
+class Mlp3Problem(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in ("x", "w0", "b0", "w2", "b2", "w4", "b4", "y")] + \
+               [(f, C.c_int) for f in ("M", "in_dim", "hidden", "out_dim")]
 
 
 class GuidanceCfg(C.Structure):

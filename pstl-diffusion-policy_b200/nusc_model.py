@@ -168,14 +168,33 @@ class Net(nn.Module):
                                         _nv.fptr(lanes[0]), _nv.fptr(lanes[1]), _nv.fptr(lanes[2]), _nv.fptr(ids[0]),
                                         _nv.fptr(ids[1]), _nv.fptr(ids[2]), bs, K, nseg, _nv.fptr(ego_in),
                                         _nv.fptr(nei_in), _nv.fptr(lane_in), _nv.stream()), "pstl_encoder_inputs")
-        ego_f = self._mlp(self.ego_encoder, ego_in)
-        nei_f = self._mlp(self.neighbor_encoder, nei_in)
-        lane_f = self._mlp(self.lane_encoder, lane_in)
+        ego_f, nei_f, lane_f = self._mlp_batch([(self.ego_encoder, ego_in), (self.neighbor_encoder, nei_in),
+                                                (self.lane_encoder, lane_in)])
         F = ego_f.shape[-1]
         feat = torch.empty((bs, 7 * F), dtype=torch.float32, device=dev)
         _nv.check(L.pstl_encoder_pool(_nv.fptr(ego_f), _nv.fptr(nei_f), _nv.fptr(lane_f), bs, K, F, _nv.fptr(feat),
                                       _nv.stream()), "pstl_encoder_pool")
         return feat
+
+    def _mlp_batch(self, jobs):
+        """several encoder MLPs in one launch (pstl_mlp3_batch) when they have the built shape, else one by one"""
+        ok = all(len(seq) == 5 and seq[0].out_features == 256 and seq[2].out_features == 256 and
+                 seq[0].in_features <= 256 and seq[4].out_features <= 32 for seq, _ in jobs)
+        if not ok or len(jobs) > 4:
+            return [self._mlp(seq, x) for seq, x in jobs]
+        probs = (_nv.Mlp3Problem * len(jobs))()
+        keep, outs = [], []
+        for i, (seq, x) in enumerate(jobs):
+            h = _nv.f32(x.reshape(-1, x.shape[-1]))
+            ws = [_nv.f32(getattr(seq[li], k)) for li in (0, 2, 4) for k in ("weight", "bias")]
+            y = torch.empty((h.shape[0], seq[4].out_features), dtype=torch.float32, device=h.device)
+            keep += [h] + ws
+            p = probs[i]
+            p.x, p.w0, p.b0, p.w2, p.b2, p.w4, p.b4 = [t.data_ptr() for t in [h] + ws]
+            p.y, p.M, p.in_dim, p.hidden, p.out_dim = y.data_ptr(), h.shape[0], h.shape[1], 256, seq[4].out_features
+            outs.append(y)
+        _nv.check(_nv.lib().pstl_mlp3_batch(probs, len(jobs), _nv.stream()), "pstl_mlp3_batch")
+        return outs
 
     def _mlp(self, seq, x):
         """encoder MLP.  Inference on the GPU goes through pstl_linear (row-independent summation order,
@@ -186,6 +205,13 @@ class Net(nn.Module):
         lead = x.shape[:-1]
         h = _nv.f32(x.reshape(-1, x.shape[-1]))
         L = _nv.lib()
+        if len(seq) == 5 and seq[0].out_features == 256 and seq[2].out_features == 256 and seq[0].in_features <= 256 \
+                and seq[4].out_features <= 32:
+            ws = [_nv.f32(getattr(seq[li], k)) for li in (0, 2, 4) for k in ("weight", "bias")]
+            y = torch.empty((h.shape[0], seq[4].out_features), dtype=torch.float32, device=h.device)
+            _nv.check(L.pstl_mlp3(_nv.fptr(h), h.shape[0], h.shape[1], *[_nv.fptr(t) for t in ws], 256,
+                                  seq[4].out_features, _nv.fptr(y), _nv.stream()), "pstl_mlp3")
+            return y.reshape(*lead, -1)
         for li in (0, 2, 4):
             w, b = _nv.f32(seq[li].weight), _nv.f32(seq[li].bias)
             y = torch.empty((h.shape[0], w.shape[0]), dtype=torch.float32, device=h.device)

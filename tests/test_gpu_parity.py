@@ -562,3 +562,26 @@ def test_captured_pipeline_prefetch_matches_direct_call():
     assert torch.equal(NT.score_pack(pack, out["controls"], args, progs)["best_score"], out["scores"])
     with pytest.raises(ValueError):
         runner()
+
+
+@pytest.mark.parametrize("m,in_dim", [(1, 6), (37, 7), (3072, 45), (8192, 7)])
+def test_mlp3_is_bit_identical_to_three_linear_calls(m, in_dim):
+    """pstl_mlp3 (one launch, activations in shared memory) == pstl_linear x 3 (same fmaf order), and close to torch"""
+    g = torch.Generator().manual_seed(m + in_dim)
+    seq = torch.nn.Sequential(torch.nn.Linear(in_dim, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+                              torch.nn.Linear(256, 32)).cuda()
+    x = torch.randn(m, in_dim, generator=g).cuda()
+    L = native.lib()
+    h = x
+    for li in (0, 2, 4):
+        w, b = seq[li].weight.detach().contiguous(), seq[li].bias.detach().contiguous()
+        y = torch.empty((m, w.shape[0]), device="cuda")
+        native.check(L.pstl_linear(native.fptr(h), native.fptr(w), native.fptr(b), m, h.shape[1], w.shape[0], int(li != 4),
+                                   native.fptr(y), native.stream()), "pstl_linear")
+        h = y
+    ws = [getattr(seq[li], k).detach().contiguous() for li in (0, 2, 4) for k in ("weight", "bias")]
+    out = torch.empty((m, 32), device="cuda")
+    native.check(L.pstl_mlp3(native.fptr(x), m, in_dim, *[native.fptr(t) for t in ws], 256, 32, native.fptr(out),
+                             native.stream()), "pstl_mlp3")
+    assert torch.equal(out, h)
+    close(out, seq(x).detach(), rtol=1e-5)
