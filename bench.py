@@ -157,7 +157,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PSTL_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner there at every debug level
+        if "PSTL_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["PSTL_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=dev)
     native.lib()  # fail loudly if the CUDA library is missing
 
