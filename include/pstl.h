@@ -247,6 +247,17 @@ int pstl_predicates(const pstl_scene_view* scenes, float ego_L, float ego_W, int
 int pstl_linear(const float* x, const float* w, const float* b, int M, int K, int Nout, int act, float* y,
                 pstl_stream_t stream);
 
+/* One iteration of the trajectory optimisation that produces the training targets (nusc_train.py:287-316, 1303-1325):
+ *   loss = sum_n relu(thres - score_n) valid_n * inv_norm + reg * (mean relu(w^2 - w_max^2) + mean relu(a^2 - a_max^2))
+ *   params <- Adam_step(params, d loss / d params)        (torch.optim.Adam defaults, bias correction of step iter+1)
+ * params (N,T,2) physical controls (sp->w_scale = a_scale = 1, clip_controls = 0), updated in place; adam_m / adam_v (N,T,2)
+ * zeroed by the caller before iter 0; scores (N, may be NULL) receives the robustness of the params BEFORE the step.
+ * workspace: N*T*2 floats + pstl_score_workspace_bytes(progs, N, T, 1). */
+int pstl_trajopt_step(pstl_program_t const* progs, const pstl_scene_view* scenes, const pstl_spec_params* sp,
+                      const float* mode, const float* state0, const float* stlp, const float* valid, int N, float thres,
+                      float inv_norm, float reg, float w_max, float a_max, float lr, int iter, float* params,
+                      float* adam_m, float* adam_v, float* scores, void* workspace, pstl_stream_t stream);
+
 /* Three-layer ReLU MLP of the scene encoders in one launch (nusc_model.py:82-91, hidden width 256):
  * y (M,out) = W4 relu(W2 relu(W0 x + b0) + b2) + b4, weights (out_features, in_features) row-major as in nn.Linear.
  * Same summation order as three pstl_linear calls. */

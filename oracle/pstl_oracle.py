@@ -423,3 +423,44 @@ def pipeline(W, b, x_T, noises, S=64, K=5, n_rolls=0, refinenet=True, steps=100,
     m = d["dense_valids"].reshape(-1)
     out.update(controls=u, scores=sc, trajs=tr, acc=mask_mean((sc > 0).float(), m))
     return out
+
+
+def trajopt(b, S, nt, dt, iters, lr=0.005, thres=0.01, reg=10.0, w_max=0.5, a_max=5.0, tau=100.0, record=None):
+    """Trajectory optimisation of the stored control parameters (nusc_train.py:287-316, 1303-1325):
+    ``iters`` Adam steps on  mean(relu(thres - score) * valid) / clip(mean(valid), 1e-3)
+    + reg * (mean(relu(w^2 - w_max^2)) + mean(relu(a^2 - a_max^2))),  controls ``b["params"]`` (bs,S,3,nt,2) used as is
+    (no scaling, no clipping), pSTL parameters ``pre_stlp`` per chain (training layout, :742).
+    Returns (params (N,nt,2), scores of the last evaluated iterate (N,)).  ``record(ii, loss, dense_loss, reg_loss,
+    scores, grad_or_None, params_after)`` is called every iteration."""
+    bs = b["currlane_wpts"].shape[0]
+    m = S * 3
+    N = bs * m
+    dup = lambda x: x.unsqueeze(1).repeat((1, m) + (1,) * (x.dim() - 1)).reshape((-1,) + x.shape[1:])
+    dense = {"neighbors": dup(b["neighbors_traj"][..., :7]), "currlane_wpts": dup(b["currlane_wpts"]),
+             "leftlane_wpts": dup(b["leftlane_wpts"]), "rightlane_wpts": dup(b["rightlane_wpts"]),
+             "stlp": b["pre_stlp"].reshape(N, 1, 6)}
+    valid = torch.cat([b["curr_id"], b["left_id"], b["right_id"]], -1).unsqueeze(1).repeat(1, S, 1).reshape(bs * S, 3)
+    s0 = dup(b["ego_traj"][:, 0, :4])
+    p = b["params"].reshape(N, nt, 2).clone().requires_grad_()
+    opt = torch.optim.Adam([p], lr=lr)
+    spec = driving_spec(nt)
+    scores = None
+    for ii in range(iters):
+        tr = rollout(s0, p, dt)
+        x = dict(dense)
+        x["ego_traj"] = tr[:, :-1]
+        x = predicates(x)
+        # formula i is evaluated on every row and column i of the (bs*S, 3) view is kept (:293-295)
+        dense_scores = torch.stack([stl_eval(f, x, tau)[:, 0].reshape(bs * S, 3)[:, i] for i, f in enumerate(spec)], -1)
+        dense_loss = torch.mean(torch.relu(thres - dense_scores) * valid) / torch.clip(torch.mean(valid), 1e-3)
+        reg_loss = (torch.mean(torch.relu(p[..., 0] ** 2 - w_max ** 2)) + torch.mean(torch.relu(p[..., 1] ** 2 - a_max ** 2))) * reg
+        loss = dense_loss + reg_loss
+        opt.zero_grad()
+        loss.backward()
+        g = p.grad.detach().clone()
+        opt.step()
+        scores = dense_scores.detach().reshape(-1)
+        if record is not None:
+            record(ii, loss.item(), dense_loss.item(), reg_loss.item(), scores, g, p.detach().clone())
+    return p.detach(), scores
+

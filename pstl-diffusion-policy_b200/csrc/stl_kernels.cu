@@ -711,3 +711,61 @@ extern "C" int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
 }
+
+// --------------------------------------------------------------------------------------
+// trajectory optimisation (nusc_train.py:287-316, 1303-1325): loss gradient (fused reverse-mode scorer) + control
+// regulariser + one torch.optim.Adam step (single-tensor arithmetic, as k_guidance_apply) on the stored controls
+// --------------------------------------------------------------------------------------
+__global__ void k_trajopt_adam(const float* __restrict__ g, float* __restrict__ p, float* __restrict__ m,
+                               float* __restrict__ v, size_t n, float step_size, float bc2_sqrt, float reg_over_numel,
+                               float w_max2, float a_max2) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float b2 = 0.999f, eps = 1e-8f;
+  const float w1 = (float)(1.0 - 0.9), w2 = (float)(1.0 - 0.999);
+  const float x = p[i];
+  // d/dx reg * mean(relu(x^2 - lim^2)): MeanBackward (grad / numel), relu mask, PowBackward (grad * (2 x))
+  const float lim2 = (i & 1) ? a_max2 : w_max2;
+  float gi = g[i];
+  if (x * x - lim2 > 0.f) gi += reg_over_numel * (2.f * x);
+  const float mi = m[i] + w1 * (gi - m[i]);
+  const float vi = v[i] * b2 + (w2 * gi) * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = x + ((-step_size) * mi) / denom;
+}
+
+extern "C" int pstl_trajopt_step(pstl_program_t const* progs, const pstl_scene_view* scenes, const pstl_spec_params* sp,
+                                 const float* mode, const float* state0, const float* stlp, const float* valid, int N,
+                                 float thres, float inv_norm, float reg, float w_max, float a_max, float lr, int iter,
+                                 float* params, float* adam_m, float* adam_v, float* scores, void* workspace,
+                                 pstl_stream_t stream) {
+  int rc = check_score_args(progs, scenes, sp, mode, stlp, N);
+  if (rc) return rc;
+  PSTL_CHECK_ARG(state0 && valid && params && adam_m && adam_v && workspace, "null argument");
+  if (N <= 0) return PSTL_OK;
+  const int T = scenes->T;
+  float* grad = (float*)workspace;            // workspace: [grad (N,T,2)] [tape]
+  float* tape = grad + (size_t)N * T * 2;
+  ScoreArgs a;
+  base_args(a, progs, scenes, sp);
+  a.mode = mode; a.state0 = state0; a.controls = params; a.stlp = stlp; a.N = N; a.C = 1;
+  a.valid = valid; a.thres = thres; a.inv_norm = inv_norm; a.grad_controls = grad; a.scores = scores; a.ws = tape;
+  int took = 0;
+  rc = launch_score_stream_bwd(a, progs, (cudaStream_t)stream, &took);
+  if (rc) return rc;
+  if (!took) {
+    ScorePlan plan = plan_score(progs, scenes, N, 1);
+    rc = launch_score<true>(a, plan, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  const size_t n = (size_t)N * T * 2;
+  const double bc1 = 1.0 - pow(0.9, (double)(iter + 1)), bc2 = 1.0 - pow(0.999, (double)(iter + 1));
+  const float numel = (float)((size_t)N * T);
+  k_trajopt_adam<<<pstl_ceil_div((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(
+      grad, params, adam_m, adam_v, n, (float)((double)lr / bc1), (float)sqrt(bc2), reg / numel, w_max * w_max, a_max * a_max);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+

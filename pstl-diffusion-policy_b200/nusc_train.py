@@ -789,6 +789,48 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     return out
 
 
+def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):
+    """Trajectory optimisation of the stored control parameters (reference nusc_train.py:287-316, 1303-1325):
+    ``iters`` (default ``args.traj_opt_iters``) Adam steps, lr ``args.trajopt_lr``, on
+    ``mean(relu(stl_trajopt_thres - score) * valid) / clip(mean(valid), 1e-3) + reg_loss * (mean relu(w^2 - w_max^2) + ...)``.
+    ``batch_cuda`` is a scene batch after ``augment_batch_data`` (training layout: ``stlp_dense`` from ``pre_stlp``);
+    ``params`` defaults to ``batch_cuda["params"]`` (bs, n_randoms, 3, nt, 2).  Every iteration is two launches: the
+    fused rollout + STL reverse-mode kernel and the regulariser + Adam update (upstream: ~600 autograd launches).
+    Returns (optimised params, same shape; scores (N,) of the iterate BEFORE the last step, as upstream logs them).
+    ``record(ii, scores)`` is called after every iteration when given (forces no sync by itself)."""
+    iters = int(args.traj_opt_iters if iters is None else iters)
+    p0 = batch_cuda["params"] if params is None else params
+    _nv.require_cuda(p0, "params")
+    S, nt = args.n_randoms, args.nt
+    bs = batch_cuda["currlane_wpts"].shape[0]
+    N = bs * S * 3
+    pack = batch_cuda.get("_pstl_pack")
+    if pack is None:
+        pack = ScenePack.from_batch(batch_cuda, batch_cuda["stlp_dense"], S)
+    progs = _fused_programs(stls_cac, nt)
+    if progs is None:
+        raise NotImplementedError("trajopt needs the typed spec of build_stl_cache")
+    p = _nv.f32(p0.reshape(N, nt, 2)).clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    scores = torch.empty((N,), dtype=torch.float32, device=p.device)
+    L = _nv.lib()
+    pa = _nv.prog_array(progs)
+    sv, sp = pack.view(), _spec(args)
+    ws = _nv.workspace(N * nt * 2 * 4 + L.pstl_score_workspace_bytes(pa, N, nt, 1), p.device, "trajopt")
+    # one scalar per call, computed on the device side of the host API (valid is a batch constant)
+    inv_norm = 1.0 / (N * max(float(pack.valid.mean().item()), 1e-3))
+    for ii in range(iters):
+        _nv.check(L.pstl_trajopt_step(pa, _nv.C.byref(sv), _nv.C.byref(sp), _nv.fptr(pack.mode), _nv.fptr(pack.state0),
+                                      _nv.fptr(pack.stlp), _nv.fptr(pack.valid), N, _nv.C.c_float(args.stl_trajopt_thres),
+                                      _nv.C.c_float(inv_norm), _nv.C.c_float(args.reg_loss), _nv.C.c_float(args.mul_w_max),
+                                      _nv.C.c_float(args.mul_a_max), _nv.C.c_float(args.trajopt_lr), ii, _nv.fptr(p),
+                                      _nv.fptr(m), _nv.fptr(v), _nv.fptr(scores), _nv.ptr(ws), _nv.stream()),
+                  "pstl_trajopt_step")
+        if record is not None:
+            record(ii, scores)
+    return p.reshape(p0.shape), scores
+
+
 def closed_loop_pick(scores_all, ego_controls, ego_trajs):
     """candidate selection of the closed-loop simulator (reference nusc_sim.py:677-683): chains are rows
     ``n = sample*3 + mode`` of ONE scene; modes 1, 2 (lane changes) are masked to -1e4 and the global arg-max wins

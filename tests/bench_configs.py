@@ -1,6 +1,7 @@
 """Auxiliary measurements of the other BASELINE configs (not the driver's bench line).
    python tests/bench_configs.py guidance [scenes]     # config 3 shape: K=10, guidance last 10 steps, n_rolls 3
    python tests/bench_configs.py dense [n] [T] [Knei]  # config 1/5 shape: compute_stl_dense on dense rows
+   python tests/bench_configs.py trajopt [scenes] [iters]  # trajectory-optimisation iterations
 """
 import os
 import sys
@@ -54,8 +55,24 @@ def dense(n, T, K):
           % (n, T, K, ms, n / ms * 1e3, n * by / ms / 1e6, by))
 
 
+def trajopt(scenes, iters):
+    """trajectory optimisation (nusc_train.py:1303-1325): iterations/s on scenes x 64 x 3 stored control sequences"""
+    args = NT.default_args()
+    b = {k: v.cuda() for k, v in synthetic.make_scene_batch(scenes, seed=5).items()}
+    nb = NT.LazyBatch(dict(b))
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    nb = NT.augment_batch_data(nb, None, args)
+    stls = NT.build_stl_cache(args)
+    ms = timeit(lambda: NT.trajopt(nb, stls, args, iters=iters), reps=2, warm=1)
+    n = scenes * 64 * 3
+    print("trajopt: scenes=%d trajectories=%d  %d Adam iterations in %.1f ms = %.3f ms/iteration  (%.3g trajectory-gradients/s)"
+          % (scenes, n, iters, ms, ms / iters, n * iters / ms * 1e3))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "guidance":
+    if sys.argv[1] == "trajopt":
+        trajopt(int(sys.argv[2]) if len(sys.argv) > 2 else 256, int(sys.argv[3]) if len(sys.argv) > 3 else 100)
+    elif sys.argv[1] == "guidance":
         guidance(int(sys.argv[2]) if len(sys.argv) > 2 else 256)
     else:
         dense(*(int(a) for a in (sys.argv[2:5] + ["4096", "20", "8"][len(sys.argv) - 2:])))

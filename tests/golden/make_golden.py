@@ -180,12 +180,58 @@ def gen_pipeline():
     np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
 
 
+TRAJOPT_FLAGS = ["-e", "e1_trajopt", "--diffusion", "--load_stlp", "--flex", "--skip_nusc_load", "--trajopt_only"]
+
+
+def gen_trajopt(iters=15, bs=2, S=16, seed=2003):
+    """The reference's trajectory-optimisation loop (nusc_train.py:1303-1325): generate_trajs ->
+    pre_prepare_stl_cache -> compute_trajopt_loss_lite -> Adam(lr=trajopt_lr), driven on one synthetic batch."""
+    T, args = ref_shim.load(TRAJOPT_FLAGS + ["--n_randoms", str(S)])
+    nt = args.nt
+    batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=seed)
+    out = {"in_checksum": np.array([checksum(batch[k]) for k in sorted(batch)])}
+    stls = T.build_stl_cache(args)
+    b = {k: v.clone() for k, v in batch.items()}
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    gt_stlp = b["pre_stlp"].reshape(bs, S, 3, 6)[:, 0, 0]  # any (bs,6): --load_stlp takes the dense pSTL from pre_stlp
+    b = T.augment_batch_data(b, gt_stlp, args)
+    states = b["ego_traj"][:, 0, :4]
+    dense_states = states.unsqueeze(1).unsqueeze(1).repeat(1, S, 3, 1)
+    real_md = T.napi.measure_diversity
+    z = torch.zeros(())
+    T.napi.measure_diversity = lambda *a, **k: (z, z, [np.zeros(1)], [np.zeros(1)])
+    try:
+        params = b["params"] = b["params"].clone().requires_grad_()
+        opt = torch.optim.Adam([params], lr=args.trajopt_lr)
+        for ii in range(iters):
+            trajs = T.generate_trajs(dense_states, params, args.dt)
+            cache = T.pre_prepare_stl_cache(b)
+            res = T.compute_trajopt_loss_lite(params, trajs, stls, cache, ii, iters)
+            loss, dense_loss, reg_loss, dense_scores = res[0], res[1], res[2], res[5]
+            out["loss|%d" % ii] = np.array([loss.item(), dense_loss.item(), reg_loss.item()])
+            if ii in (0, iters - 1):
+                out["scores|%d" % ii] = dense_scores.detach().reshape(-1).numpy().copy()
+            opt.zero_grad()
+            loss.backward()
+            if ii == 0:
+                out["grad|0"] = params.grad.detach().reshape(-1, nt, 2).numpy().copy()
+            opt.step()
+            if ii in (0, 4, iters - 1):
+                out["params|%d" % ii] = params.detach().reshape(-1, nt, 2).numpy().copy()
+    finally:
+        T.napi.measure_diversity = real_md
+    out["hyper"] = np.array([args.trajopt_lr, args.stl_trajopt_thres, args.reg_loss, args.mul_w_max, args.mul_a_max, iters])
+    np.savez_compressed(os.path.join(HERE, "trajopt.npz"), **out)
+    print("trajopt:", len(out), "arrays; loss", out["loss|0"], "->", out["loss|%d" % (iters - 1)])
+
+
 def main():
     torch.set_num_threads(8)
     T, args = ref_shim.load(ref_shim.OURS_FLAGS)
     gen_stl_kats()
     gen_dense(T, args)
     gen_pipeline()
+    gen_trajopt()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

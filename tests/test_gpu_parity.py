@@ -585,3 +585,35 @@ def test_mlp3_is_bit_identical_to_three_linear_calls(m, in_dim):
                              native.stream()), "pstl_mlp3")
     assert torch.equal(out, h)
     close(out, seq(x).detach(), rtol=1e-5)
+
+
+def test_trajopt_golden(golden_dir):
+    """nusc_train.trajopt (fused reverse-mode scorer + regulariser + Adam per iteration) against the reference's
+    trajectory-optimisation loop (tests/golden/trajopt.npz, nusc_train.py:1303-1325)"""
+    G = np.load(os.path.join(golden_dir, "trajopt.npz"))
+    lr, thres, reg, w_max, a_max, iters = [float(v) for v in G["hyper"]]
+    iters = int(iters)
+    bs, S_, nt = 2, 16, 20
+    args = NT.default_args(n_randoms=S_, sampling_size=S_, trajopt_lr=lr, stl_trajopt_thres=thres, reg_loss=reg)
+    b = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=2003))
+    nb = NT.LazyBatch(dict(b))
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    nb = NT.augment_batch_data(nb, None, args)  # training layout: one pSTL row per chain from pre_stlp
+    stls = NT.build_stl_cache(args)
+    snap = {}
+
+    def record(ii, scores):
+        if ii in (0, iters - 1):
+            snap["scores|%d" % ii] = scores.clone()
+
+    for k in (1, 5, iters):
+        p, _ = NT.trajopt(nb, stls, args, iters=k, record=record if k == iters else None)
+        snap["params|%d" % (k - 1)] = p.reshape(-1, nt, 2).clone()
+    close(snap["scores|0"], G["scores|0"])
+    close(snap["params|0"], G["params|0"])
+    for ii in (4, iters - 1):
+        err = (snap["params|%d" % ii].cpu().numpy() - G["params|%d" % ii])
+        err = np.abs(err)
+        assert np.percentile(err, 99) < 1e-5 and err.max() < 2 * lr * (ii + 1), (ii, np.percentile(err, 99), err.max())
+    err = np.abs(snap["scores|%d" % (iters - 1)].cpu().numpy() - G["scores|%d" % (iters - 1)])
+    assert np.percentile(err, 99) < 1e-4 * max(1.0, np.abs(G["scores|%d" % (iters - 1)]).max())
