@@ -258,6 +258,14 @@ int pstl_trajopt_step(pstl_program_t const* progs, const pstl_scene_view* scenes
                       float inv_norm, float reg, float w_max, float a_max, float lr, int iter, float* params,
                       float* adam_m, float* adam_v, float* scores, void* workspace, pstl_stream_t stream);
 
+/* Diversity metrics of the sampling test (measure_diversity, nusc_api.py:817-877), per (scene, lane mode):
+ * std_out (n_scenes,3) = mean over the 2*nt way-point features of the population std over the samples with score > 0
+ * (0 when none); vol_out (n_scenes,3) = sum over the steps of the convex-hull area of those samples' (x,y) (0 when the
+ * lane is invalid, fewer than three samples are accepted or they are collinear).
+ * trajs (n_scenes,m,3,2*nt) [x0,y0,x1,y1,...], scores / valids (n_scenes,m,3), m <= 128. */
+int pstl_diversity(const float* trajs, const float* scores, const float* valids, int n_scenes, int m, int nt,
+                   float* std_out, float* vol_out, pstl_stream_t stream);
+
 /* Three-layer ReLU MLP of the scene encoders in one launch (nusc_model.py:82-91, hidden width 256):
  * y (M,out) = W4 relu(W2 relu(W0 x + b0) + b2) + b4, weights (out_features, in_features) row-major as in nn.Linear.
  * Same summation order as three pstl_linear calls. */

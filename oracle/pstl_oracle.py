@@ -464,3 +464,31 @@ def trajopt(b, S, nt, dt, iters, lr=0.005, thres=0.01, reg=10.0, w_max=0.5, a_ma
             record(ii, loss.item(), dense_loss.item(), reg_loss.item(), scores, g, p.detach().clone())
     return p.detach(), scores
 
+
+def diversity(trajs, scores, valids, nt):
+    """measure_diversity (nusc_api.py:817-877) restated with plain loops: per (scene, lane) the mean over the 2*nt
+    way-point features of the population std over the samples with score > 0, and the summed scipy ConvexHull area of
+    those samples' positions over the steps (0 on any Qhull error, for invalid lanes and when nothing is accepted).
+    Returns (std (bs,3) float32, vol (bs,3) float64, ma_std_avg, ma_vol_avg)."""
+    import numpy as np
+    from scipy.spatial import ConvexHull
+    tr = trajs.detach().cpu().numpy().astype(np.float32)
+    acc = (scores.detach().cpu().numpy() > 0)
+    val = valids.detach().cpu().numpy()[:, 0, :] != 0
+    bs, m = tr.shape[0], tr.shape[1]
+    std = np.zeros((bs, 3), np.float32)
+    vol = np.zeros((bs, 3), np.float64)
+    for b in range(bs):
+        for l in range(3):
+            sel = tr[b, acc[b, :, l], l]            # (n_acc, 2*nt)
+            if sel.shape[0] > 0:
+                std[b, l] = np.mean(np.std(sel, axis=0))
+            if val[b, l] and sel.shape[0] > 0:
+                for t in range(nt):
+                    try:
+                        vol[b, l] += ConvexHull(sel[:, 2 * t:2 * t + 2]).volume
+                    except Exception:
+                        pass
+    n = max(int(val.sum()), 1)
+    return std, vol, float((std * val).sum() / n), float((vol * val).sum() / n)
+

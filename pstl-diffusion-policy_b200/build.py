@@ -22,6 +22,7 @@ UNITS = {
     "aux_kernels.cu": ["-fmad=false"],
     "mlp_fp32.cu": [],
     "denoiser_tc.cu": [],
+    "metrics.cu": [],
 }
 
 

@@ -922,8 +922,10 @@ class CapturedPipeline:
 
 
 def run_sampling_test(stls_cac, data_loader, net, coeffs, args, result_queue=None, thread_nusc=None):
-    """open-loop sampling test over ``data_loader`` (any iterable of batch dicts).  Metrics that need the
-    NuScenes map / scipy hulls are out of scope; acc, scene_acc and the timed region are reported."""
+    """open-loop sampling test over ``data_loader`` (any iterable of batch dicts): the timed region, then the metrics of
+    the reference's report line (acc, scene_acc, ade, fde, std, vol; area / entropies with --run_sampling_test's
+    extra_diversity) computed on the device (``pstl_b200.metrics``).  Visualisation is out of scope."""
+    from . import metrics as M
     meters = {}
     results = []
     for bi, batch in enumerate(data_loader):
@@ -935,10 +937,25 @@ def run_sampling_test(stls_cac, data_loader, net, coeffs, args, result_queue=Non
         out = sample_and_score(net, batch_cuda, stls_cac, coeffs, args)
         torch.cuda.synchronize()
         t2 = time.time()
-        for k, v in (("acc", out["acc"].item()), ("scene_acc", out["scene_acc"].item()), ("time", t2 - t1)):
+        S, nt = args.sampling_size, args.nt
+        bs = batch_cuda["ego_traj"].shape[0]
+        trajs, valid = out["trajs"], out["pack"].valid.reshape(bs, S, 3)
+        ma_std, ma_vol, _, _ = M.measure_diversity(trajs[:, :-1, :2].reshape(bs, S, 3, nt * 2), out["scores"].reshape(bs, S, 3),
+                                                   valid, nt)
+        ade, fde = M.compute_ade_fde(batch_cuda["ego_traj"][..., :4], trajs[:, :-1, :4], valid)
+        vals = [("acc", out["acc"].item()), ("scene_acc", out["scene_acc"].item()), ("ade", ade.item()), ("fde", fde.item()),
+                ("std", float(ma_std)), ("vol", float(ma_vol)), ("time", t2 - t1)]
+        if getattr(args, "extra_diversity", False):
+            ex = M.measure_extra_diversity(trajs[:, :-1].reshape(bs, S, 3, nt * 4), out["scores"].reshape(bs, S, 3), valid, nt,
+                                           out["controls"].reshape(bs, S, 3, nt * 2), -args.mul_w_max, args.mul_w_max,
+                                           -args.mul_a_max, args.mul_a_max)
+            vals += [(k, v.item()) for k, v in ex.items()]
+        for k, v in vals:
             meters.setdefault(k, []).append(v)
-        print("###[%02d] NN acc:%.3f scene_acc:%.3f ||| T:%.3f" % (bi, np.mean(meters["acc"]),
-                                                                   np.mean(meters["scene_acc"]), np.mean(meters["time"])))
+        mean = lambda k: float(np.mean(meters[k])) if k in meters else float("nan")
+        print("###[%02d] NN acc:%.3f scene_acc:%.3f ade:%.3f fde:%.3f std:%.3f vol:%.3f area:%.3f s:%.3f u:%.3f ||| T:%.3f"
+              % (bi, mean("acc"), mean("scene_acc"), mean("ade"), mean("fde"), mean("std"), mean("vol"), mean("area"),
+                 mean("ent_s"), mean("ent_wa"), mean("time")))
         results.append(out)
     return meters, results
 

@@ -225,6 +225,51 @@ def gen_trajopt(iters=15, bs=2, S=16, seed=2003):
     print("trajopt:", len(out), "arrays; loss", out["loss|0"], "->", out["loss|%d" % (iters - 1)])
 
 
+def metric_inputs(bs=5, m=16, nt=20, seed=2004):
+    """trajectories / scores / validity for the diversity metrics: rollouts of the synthetic parameter bank, a random
+    accept pattern that includes a lane with nothing accepted, one with two samples and one with collinear samples"""
+    b = synthetic.make_scene_batch(bs, nt=nt, n_randoms=m, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    s0 = b["ego_traj"][:, 0, :4].unsqueeze(1).unsqueeze(1).repeat(1, m, 3, 1)
+    u = b["params"]
+    tr = [s0]
+    for t in range(nt):
+        c = tr[-1]
+        ds = torch.stack([c[..., 3] * torch.cos(c[..., 2]), c[..., 3] * torch.sin(c[..., 2]), u[..., t, 0], u[..., t, 1]], -1)
+        tr.append(c + ds * 0.5)
+    trajs = torch.stack(tr, -2)                                  # (bs, m, 3, nt+1, 4)
+    scores = torch.rand(bs, m, 3, generator=g) - 0.4
+    scores[0, :, 1] = -1.0                                        # nothing accepted
+    scores[1, :, 2] = -1.0
+    scores[1, :2, 2] = 1.0                                        # two samples: no hull
+    trajs[2, :, 0, :, 1] = trajs[2, :, 0, :, 0] * 0.5 + 1.0       # collinear positions at every step
+    valids = torch.cat([b["curr_id"], b["left_id"], b["right_id"]], -1).unsqueeze(1).repeat(1, m, 1)
+    return b, trajs, scores, valids, u
+
+
+def gen_metrics(bs=5, m=16, nt=20, seed=2004):
+    """nusc_api.measure_diversity / measure_extra_diversity, utils.compute_entropy and nusc_train.compute_ade_fde of the
+    unmodified reference on synthetic trajectories"""
+    T, args = ref_shim.load(ref_shim.OURS_FLAGS + ["--n_randoms", str(m), "--sampling_size", str(m)])
+    b, trajs, scores, valids, u = metric_inputs(bs, m, nt, seed)
+    out = {"in_checksum": np.array([checksum(trajs), checksum(scores), checksum(valids)])}
+    xy = trajs[..., :-1, :2].reshape(bs, m, 3, nt * 2)
+    r = T.napi.measure_diversity(xy, scores, valids, nt)
+    out["ma_std"], out["ma_vol"] = np.array(r[0]), np.array(r[1])
+    for i in range(4):
+        out["std_list|%d" % i] = np.asarray(r[2][i], dtype=np.float64)
+        out["vol_list|%d" % i] = np.asarray(r[3][i], dtype=np.float64)
+    ex = T.napi.measure_extra_diversity(trajs[..., :-1, :].reshape(bs, m, 3, nt * 4), scores, valids, nt,
+                                        u.reshape(bs, m, 3, nt * 2), -args.mul_w_max, args.mul_w_max, -args.mul_a_max,
+                                        args.mul_a_max)
+    for k, v in ex.items():
+        out["extra|" + k] = np.array(float(v))
+    ade, fde = T.compute_ade_fde(b["ego_traj"][..., :4], trajs[..., :-1, :4], valids)
+    out["ade_fde"] = np.array([float(ade), float(fde)])
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+    print("metrics:", {k: (v.tolist() if v.size < 4 else v.shape) for k, v in out.items()})
+
+
 def main():
     torch.set_num_threads(8)
     T, args = ref_shim.load(ref_shim.OURS_FLAGS)
@@ -232,6 +277,7 @@ def main():
     gen_dense(T, args)
     gen_pipeline()
     gen_trajopt()
+    gen_metrics()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

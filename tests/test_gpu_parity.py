@@ -617,3 +617,35 @@ def test_trajopt_golden(golden_dir):
         assert np.percentile(err, 99) < 1e-5 and err.max() < 2 * lr * (ii + 1), (ii, np.percentile(err, 99), err.max())
     err = np.abs(snap["scores|%d" % (iters - 1)].cpu().numpy() - G["scores|%d" % (iters - 1)])
     assert np.percentile(err, 99) < 1e-4 * max(1.0, np.abs(G["scores|%d" % (iters - 1)]).max())
+
+
+def test_diversity_metrics_on_device(golden_dir):
+    """pstl_diversity (masked std + convex-hull areas in one kernel) and the device tensor-op metrics against the
+    reference's host-side nusc_api.measure_diversity / measure_extra_diversity (tests/golden/metrics.npz) and the oracle"""
+    from make_golden import metric_inputs
+    from pstl_b200 import metrics as M
+    G = np.load(os.path.join(golden_dir, "metrics.npz"))
+    bs, m, nt = 5, 16, 20
+    b, trajs, scores, valids, u = metric_inputs(bs, m, nt, 2004)
+    xy = trajs[..., :-1, :2].reshape(bs, m, 3, nt * 2)
+    ma_std, ma_vol, std_list, vol_list = M.measure_diversity(xy.cuda(), scores.cuda(), valids.cuda(), nt)
+    np.testing.assert_allclose(ma_std, G["ma_std"], rtol=1e-5)
+    np.testing.assert_allclose(ma_vol, G["ma_vol"], rtol=1e-5)
+    for i in range(4):
+        np.testing.assert_allclose(std_list[i], G["std_list|%d" % i], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(vol_list[i], G["vol_list|%d" % i], rtol=1e-5, atol=1e-6)
+    ex = M.measure_extra_diversity(trajs[..., :-1, :].reshape(bs, m, 3, nt * 4).cuda(), scores.cuda(), valids.cuda(), nt,
+                                   u.reshape(bs, m, 3, nt * 2).cuda(), -0.5, 0.5, -5.0, 5.0)
+    for k in ("ent_s", "ent_w", "ent_a", "ent_wa", "area"):
+        np.testing.assert_allclose(float(ex[k]), G["extra|" + k], rtol=1e-5)
+    # a larger random case against the oracle (scipy hulls)
+    g = torch.Generator().manual_seed(8)
+    tr2 = torch.randn(23, 64, 3, 40, generator=g).cumsum(-1)
+    sc2 = torch.rand(23, 64, 3, generator=g) - 0.6
+    va2 = (torch.rand(23, 1, 3, generator=g) > 0.3).float().repeat(1, 64, 1)
+    std, vol, s_avg, v_avg = O.diversity(tr2, sc2, va2, 20)
+    a, c, _, vl = M.measure_diversity(tr2.cuda(), sc2.cuda(), va2.cuda(), 20)
+    np.testing.assert_allclose(a, s_avg, rtol=1e-5)
+    np.testing.assert_allclose(c, v_avg, rtol=1e-5)
+    for i in range(3):
+        np.testing.assert_allclose(vl[i + 1], vol[:, i] * (va2[:, 0, i].numpy() != 0), rtol=1e-5, atol=1e-6)

@@ -138,3 +138,27 @@ def test_trajopt_loop(golden_dir):
     err = np.abs(rec["scores|%d" % (iters - 1)] - G["scores|%d" % (iters - 1)])
     assert np.percentile(err, 99) < 1e-4 * max(1.0, np.abs(G["scores|%d" % (iters - 1)]).max())
 
+
+
+def test_diversity_metrics(golden_dir):
+    """oracle diversity (masked std + scipy hull areas) and the device-agnostic metric functions of pstl_b200.metrics
+    against nusc_api.measure_diversity / measure_extra_diversity / compute_ade_fde of the reference"""
+    from make_golden import metric_inputs
+    from pstl_b200 import metrics as M
+    G = np.load(os.path.join(golden_dir, "metrics.npz"))
+    bs, m, nt = 5, 16, 20
+    b, trajs, scores, valids, u = metric_inputs(bs, m, nt, 2004)
+    np.testing.assert_allclose([checksum(trajs), checksum(scores), checksum(valids)], G["in_checksum"], rtol=1e-12)
+    std, vol, ma_std, ma_vol = O.diversity(trajs[..., :-1, :2].reshape(bs, m, 3, nt * 2), scores, valids, nt)
+    np.testing.assert_allclose(ma_std, G["ma_std"], rtol=1e-5)
+    np.testing.assert_allclose(ma_vol, G["ma_vol"], rtol=1e-6)
+    val = valids[:, 0, :].numpy() != 0
+    for i in range(3):
+        np.testing.assert_allclose(std[:, i] * val[:, i], G["std_list|%d" % (i + 1)], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(vol[:, i] * val[:, i], G["vol_list|%d" % (i + 1)], rtol=1e-6, atol=1e-9)
+    ex = M.measure_extra_diversity(trajs[..., :-1, :].reshape(bs, m, 3, nt * 4), scores, valids, nt,
+                                   u.reshape(bs, m, 3, nt * 2), -0.5, 0.5, -5.0, 5.0)
+    for k in ("ent_s", "ent_w", "ent_a", "ent_wa", "area"):
+        np.testing.assert_allclose(float(ex[k]), G["extra|" + k], rtol=1e-5)
+    ade, fde = M.compute_ade_fde(b["ego_traj"][..., :4], trajs[..., :-1, :4], valids)
+    np.testing.assert_allclose([float(ade), float(fde)], G["ade_fde"], rtol=1e-6)
