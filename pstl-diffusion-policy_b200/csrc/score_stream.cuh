@@ -113,18 +113,18 @@ PSTL_HD int pstl_stream_xcol(const PstlTerm& tm, bool grad) { return grad ? PSTL
 struct PstlStreamAcc {
   float am[PSTL_MAX_TERMS], as[PSTL_MAX_TERMS], g2[PSTL_MAX_TERMS];
   float top_m, top_s;
+  float rg_nei;  // 1 / g2 of the clearance term (negative), see the value-aware bound
 };
 
-template <bool GRAD, class Scene>
-PSTL_HD float pstl_stream_fwd(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose s, const float* u,
-                              const float* ego, int es, const float* p, float* tape, int tstride, PstlStreamAcc& A) {
-  const int T = c.T;
+#define PSTL_TAPE(col, t) tape[(size_t)((col) * T + (t)) * tstride]
+
+// The pass is split in three so a kernel can walk the horizon in chunks (scene tile re-staged per chunk):
+// init -> steps(t0, t1) ... -> finish.  pstl_stream_fwd below is the one-shot composition.
+PSTL_HD void pstl_stream_init(const PstlPlan& pl, const PstlEvalCfg& c, const float* p, PstlStreamAcc& A) {
   const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
-  const float back = 0.6931471805599453f / c.tau;  // ln2 / tau
   float (&am)[PSTL_MAX_TERMS] = A.am;
   float (&as)[PSTL_MAX_TERMS] = A.as;
   float (&g2)[PSTL_MAX_TERMS] = A.g2;
-#define PSTL_TAPE(col, t) tape[(size_t)((col) * T + (t)) * tstride]
 #pragma unroll
   for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
     am[k] = PSTL_LSE2_INIT; as[k] = 0.f; g2[k] = 0.f;
@@ -139,13 +139,26 @@ PSTL_HD float pstl_stream_fwd(const PstlPlan& pl, const Scene& sc, const PstlEva
     }
   }
 
-  float rg_nei = 0.f;  // 1 / g2 of the clearance term (negative), see the value-aware bound below
+  A.rg_nei = 0.f;
 #pragma unroll
   for (int k = 0; k < PSTL_MAX_TERMS; ++k)
-    if (k == pl.nei_term) rg_nei = 1.f / g2[k];
+    if (k == pl.nei_term) A.rg_nei = 1.f / g2[k];
+}
 
+// steps t0 <= t < t1 (t1 <= pl.need_pose); the accessor sc serves exactly those steps; s is the pose at t0 on entry and
+// at t1 on exit
+template <bool GRAD, class Scene>
+PSTL_HD void pstl_stream_steps(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose& s, const float* u,
+                               const float* ego, int es, const float* p, float* tape, int tstride, PstlStreamAcc& A,
+                               int t0, int t1) {
+  const int T = c.T;
+  const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
+  float (&am)[PSTL_MAX_TERMS] = A.am;
+  float (&as)[PSTL_MAX_TERMS] = A.as;
+  float (&g2)[PSTL_MAX_TERMS] = A.g2;
+  const float rg_nei = A.rg_nei;
 #pragma unroll 1
-  for (int t = 0; t < pl.need_pose; ++t) {
+  for (int t = t0; t < t1; ++t) {
     if (ego) {
       const float* e = ego + (size_t)t * es;
       s.x = e[0]; s.y = e[1]; s.th = e[2]; s.v = e[3];
@@ -265,7 +278,16 @@ PSTL_HD float pstl_stream_fwd(const PstlPlan& pl, const Scene& sc, const PstlEva
       s = pstl_unicycle_step(s, w, a, c.dt, cs, sn);
     }
   }
+}
 
+template <bool GRAD>
+PSTL_HD float pstl_stream_finish(const PstlPlan& pl, const PstlEvalCfg& c, const float* p, float* tape, int tstride,
+                                 PstlStreamAcc& A) {
+  const int T = c.T;
+  const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
+  const float back = 0.6931471805599453f / c.tau;  // ln2 / tau
+  float (&am)[PSTL_MAX_TERMS] = A.am;
+  float (&as)[PSTL_MAX_TERMS] = A.as;
   // terms with an inner suffix operator: y(t) = R2_{t' >= t} X(t') by one backward sweep, folded into R1
 #pragma unroll
   for (int k = 0; k < PSTL_MAX_TERMS; ++k) {
@@ -309,6 +331,14 @@ PSTL_HD float pstl_stream_fwd(const PstlPlan& pl, const Scene& sc, const PstlEva
   if (empty) return -INFINITY;
   if (!pl.listand) return single * back;
   return -((pstl_lg2(top_s) + top_m) * back);
+}
+
+template <bool GRAD, class Scene>
+PSTL_HD float pstl_stream_fwd(const PstlPlan& pl, const Scene& sc, const PstlEvalCfg& c, PstlPose s, const float* u,
+                              const float* ego, int es, const float* p, float* tape, int tstride, PstlStreamAcc& A) {
+  pstl_stream_init(pl, c, p, A);
+  pstl_stream_steps<GRAD>(pl, sc, c, s, u, ego, es, p, tape, tstride, A, 0, pl.need_pose);
+  return pstl_stream_finish<GRAD>(pl, c, p, tape, tstride, A);
 }
 
 template <class Scene>
@@ -448,25 +478,25 @@ PSTL_HD void pstl_stream_bwd(const PstlPlan& pl, const PstlEvalCfg& c, const flo
 // kernel
 // ---------------------------------------------------------------------------------------
 struct StreamSceneSmem {
-  const float4* nb;   // [T][K slots][PSTL_STREAM_NEI_F4], valid neighbours only, nearest (to the scene's ego) first
-  const float2* hdr;  // [T] (count, initial minimum)
+  const float4* nb;   // [TC][K slots][PSTL_STREAM_NEI_F4], valid neighbours only, nearest (to the scene's ego) first
+  const float2* hdr;  // [TC] (count, initial minimum)
   const float4* ln;   // [3][nseg] (x, y, theta, 0)
-  int K, T, nseg;
+  int K, t0, nseg;    // the tile holds steps t0 .. t0+TC-1 of the horizon
   __device__ __forceinline__ PstlF4 lane_pt(int l, int j) const {
     const float4 q = ln[l * nseg + j];
     return PstlF4{q.x, q.y, q.z, q.w};
   }
   __device__ __forceinline__ void nei_begin(int t, int& count, float& init) const {
-    const float2 h = hdr[t];
+    const float2 h = hdr[t - t0];
     count = __float_as_int(h.x);
     init = h.y;
   }
   __device__ __forceinline__ void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& rsum) const {
-    const float4 q = nb[(t * K + k) * PSTL_STREAM_NEI_F4 + 2];
+    const float4 q = nb[((t - t0) * K + k) * PSTL_STREAM_NEI_F4 + 2];
     valid = q.x; cx = q.y; cy = q.z; rsum = q.w;
   }
   __device__ __forceinline__ void nei(int k, int t, PstlNei& o) const {
-    const float4* q = nb + (t * K + k) * PSTL_STREAM_NEI_F4;
+    const float4* q = nb + ((t - t0) * K + k) * PSTL_STREAM_NEI_F4;
     const float4 a = q[0], b = q[1];
     o.cx[0] = a.x; o.cx[1] = a.y; o.cx[2] = a.z; o.cx[3] = a.w;
     o.cy[0] = b.x; o.cy[1] = b.y; o.cy[2] = b.z; o.cy[3] = b.w;
@@ -475,20 +505,21 @@ struct StreamSceneSmem {
   }
 };
 
-// shared-memory tile of one scene, in float4 units: neighbours | lanes | per-step headers (+ sort keys)
-__host__ __device__ __forceinline__ size_t stream_tile_f4(int K, int T, int nseg) {
-  return (size_t)K * T * PSTL_STREAM_NEI_F4 + (size_t)3 * nseg + (size_t)(T + 1) / 2 + (size_t)(K * T + 3) / 4;
+// shared-memory tile of TC steps of one scene, in float4 units: neighbours | lanes | per-step headers | sort keys
+__host__ __device__ __forceinline__ size_t stream_tile_f4(int K, int TC, int nseg) {
+  return (size_t)K * TC * PSTL_STREAM_NEI_F4 + (size_t)3 * nseg + (size_t)(TC + 1) / 2 + (size_t)(K * TC + 3) / 4;
 }
 
 // Block-cooperative staging.  Per step the valid neighbours are compacted and ordered nearest-first with
 // respect to the constant-velocity prediction of the block's first row, so the running minimum tightens early
 // and the exact cull rejects most of the rest (ordering and compaction never change the minimum itself).
-__device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4* tile) {
+// Stages steps [t0, t0 + tc) of the horizon (tc <= a.tc, the tile's capacity).
+__device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4* tile, int t0, int tc) {
   const PstlEvalCfg& c = a.cfg;
-  const int K = c.K, T = c.T;
-  float4* ln = tile + (size_t)K * T * PSTL_STREAM_NEI_F4;
+  const int K = c.K, T = c.T, TC = a.tc;
+  float4* ln = tile + (size_t)K * TC * PSTL_STREAM_NEI_F4;
   float2* hdr = reinterpret_cast<float2*>(ln + 3 * c.nseg);
-  float* keys = reinterpret_cast<float*>(ln + 3 * c.nseg + (T + 1) / 2);
+  float* keys = reinterpret_cast<float*>(ln + 3 * c.nseg + (TC + 1) / 2);
   const float* nb = a.neighbors + (size_t)scene * K * T * 7;
   // reference point of the ordering heuristic
   float rx = 0.f, ry = 0.f, rvx = 0.f, rvy = 0.f;
@@ -497,13 +528,13 @@ __device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4
     rx = s0[0]; ry = s0[1];
     rvx = s0[3] * cosf(s0[2]) * c.dt; rvy = s0[3] * sinf(s0[2]) * c.dt;
   }
-  for (int e = threadIdx.x; e < K * T; e += blockDim.x) {
-    const int k = e / T, t = e - k * T;
-    const float* p = nb + (size_t)e * 7;
+  for (int e = threadIdx.x; e < K * tc; e += blockDim.x) {
+    const int k = e / tc, tl = e - k * tc, t = t0 + tl;
+    const float* p = nb + ((size_t)k * T + t) * 7;
     float px = rx + rvx * (float)t, py = ry + rvy * (float)t;
     if (a.ego) { const float* q = a.ego + ((size_t)n0 * T + t) * a.ego_stride; px = q[0]; py = q[1]; }
     const float dx = p[1] - px, dy = p[2] - py;
-    keys[t * K + k] = (p[0] != 0.f) ? dx * dx + dy * dy : INFINITY;
+    keys[tl * K + k] = (p[0] != 0.f) ? dx * dx + dy * dy : INFINITY;
   }
   for (int e = threadIdx.x; e < 3 * c.nseg; e += blockDim.x) {
     const int l = e / c.nseg, j = e - l * c.nseg;
@@ -512,9 +543,9 @@ __device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4
   }
   __syncthreads();
   const float ego_half = c.ego_L / 2.f;
-  for (int e = threadIdx.x; e < K * T; e += blockDim.x) {
-    const int k = e / T, t = e - k * T;
-    const float* kt = keys + t * K;
+  for (int e = threadIdx.x; e < K * tc; e += blockDim.x) {
+    const int k = e / tc, tl = e - k * tc, t = t0 + tl;
+    const float* kt = keys + tl * K;
     const float key = kt[k];
     int rank = 0, n_valid = 0;
     for (int j = 0; j < K; ++j) {
@@ -522,12 +553,12 @@ __device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4
       n_valid += (kj != INFINITY) ? 1 : 0;
       rank += (kj < key || (kj == key && j < k)) ? 1 : 0;
     }
-    if (k == 0) hdr[t] = make_float2(__int_as_float(n_valid), n_valid < K ? 100.f : INFINITY);
+    if (k == 0) hdr[tl] = make_float2(__int_as_float(n_valid), n_valid < K ? 100.f : INFINITY);
     if (key == INFINITY) continue;  // valid == 0: clip(d)*0 + (1-0)*100, folded into the initial minimum
-    const float* p = nb + (size_t)e * 7;
+    const float* p = nb + ((size_t)k * T + t) * 7;
     PstlCircles cc;
     pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], cc);
-    float4* o = tile + (size_t)(t * K + rank) * PSTL_STREAM_NEI_F4;
+    float4* o = tile + (size_t)(tl * K + rank) * PSTL_STREAM_NEI_F4;
     o[0] = make_float4(cc.cx[0], cc.cx[1], cc.cx[2], cc.cx[3]);
     o[1] = make_float4(cc.cy[0], cc.cy[1], cc.cy[2], cc.cy[3]);
     o[2] = make_float4(p[0], p[1], p[2], ego_half + p[5] / 2.f + 1e-3f);
@@ -556,12 +587,19 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
     li = g * 96 + (w & 31) * 3 + (w >> 5);
   }
   const int n = n0 + li;
+  // the scene tile holds a.tc steps: the whole horizon when it fits (staged once), else the horizon is walked in
+  // chunks and the tile re-staged per chunk (long horizons / many neighbours, BASELINE config 5)
+  const int TC = SMEM_SCENE ? a.tc : T;
+  const bool chunked = SMEM_SCENE && TC < T;
   float4* tile = sm4;
   float* tape = reinterpret_cast<float*>(sm4);
+  int tstride = B;
   if (SMEM_SCENE) {
-    stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile);
-    tape = reinterpret_cast<float*>(sm4 + stream_tile_f4(c.K, T, c.nseg));
-    __syncthreads();
+    if (!chunked) {
+      stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile, 0, T);
+      __syncthreads();
+    }
+    tape = reinterpret_cast<float*>(sm4 + stream_tile_f4(c.K, TC, c.nseg));
   }
   tape += threadIdx.x;
   const bool live = n < a.N;
@@ -579,8 +617,9 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
   const float* stlp = a.stlp + (size_t)nn * 6;
   const float* ego = a.ego ? a.ego + (size_t)nn * T * a.ego_stride : nullptr;
   const int scene = nn / a.rows_per_scene;
-  const float4* tile_ln = tile + (size_t)c.K * T * PSTL_STREAM_NEI_F4;
-  StreamSceneSmem ss{tile, reinterpret_cast<const float2*>(tile_ln + 3 * c.nseg), tile_ln, c.K, T, c.nseg};
+  if (a.tape_global) { tape = a.ws + nn; tstride = a.N; }  // the X(t) columns do not fit next to the tile
+  const float4* tile_ln = tile + (size_t)c.K * TC * PSTL_STREAM_NEI_F4;
+  StreamSceneSmem ss{tile, reinterpret_cast<const float2*>(tile_ln + 3 * c.nseg), tile_ln, c.K, 0, c.nseg};
   PstlStreamSceneGlobal sg;
   sg.neib = a.neighbors + (size_t)scene * c.K * T * 7;
   for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
@@ -592,13 +631,36 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
   for (int cand = 0; cand < a.C; ++cand) {
     const float* u = a.controls ? a.controls + ((size_t)cand * a.N + nn) * T * 2 : nullptr;
     float sc = (m == 3) ? 1.0f : 0.0f;  // nusc_train.py:322 outlier score; unknown mode selects nothing (:150-151)
+    if (!chunked) {
 #pragma unroll 1
-    for (int mm = 0; mm < 3; ++mm) {
-      if (!__any_sync(0xffffffffu, m == mm)) continue;
-      if (m == mm) {
-        sc = SMEM_SCENE ? pstl_stream_eval(sp.p[mm], ss, c, s0, u, ego, a.ego_stride, stlp, tape, B)
-                        : pstl_stream_eval(sp.p[mm], sg, c, s0, u, ego, a.ego_stride, stlp, tape, B);
+      for (int mm = 0; mm < 3; ++mm) {
+        if (!__any_sync(0xffffffffu, m == mm)) continue;
+        if (m == mm) {
+          sc = SMEM_SCENE ? pstl_stream_eval(sp.p[mm], ss, c, s0, u, ego, a.ego_stride, stlp, tape, tstride)
+                          : pstl_stream_eval(sp.p[mm], sg, c, s0, u, ego, a.ego_stride, stlp, tape, tstride);
+        }
       }
+    } else {
+      PstlStreamAcc A;
+      PstlPose s = s0;
+      if (m < 3) pstl_stream_init(sp.p[m], c, stlp, A);
+#pragma unroll 1
+      for (int t0 = 0; t0 < T; t0 += TC) {
+        const int tc = (T - t0 < TC) ? T - t0 : TC;
+        __syncthreads();  // every thread is done with the previous chunk
+        stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile, t0, tc);
+        __syncthreads();
+        ss.t0 = t0;
+#pragma unroll 1
+        for (int mm = 0; mm < 3; ++mm) {
+          if (!__any_sync(0xffffffffu, m == mm)) continue;
+          if (m == mm) {
+            const int t1 = (t0 + tc < sp.p[mm].need_pose) ? t0 + tc : sp.p[mm].need_pose;
+            pstl_stream_steps<false>(sp.p[mm], ss, c, s, u, ego, a.ego_stride, stlp, tape, tstride, A, t0, t1);
+          }
+        }
+      }
+      if (m < 3) sc = pstl_stream_finish<false>(sp.p[m], c, stlp, tape, tstride, A);
     }
     if (live && a.scores_all) a.scores_all[(size_t)cand * a.N + n] = sc;
     if (cand == 0 || sc > best) { best = sc; bi = cand; }  // torch.max(dim=0): first maximum
@@ -639,9 +701,11 @@ k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     li = g * 96 + (w & 31) * 3 + (w >> 5);
   }
   const int n = n0 + li;
+  const int TC = SMEM_SCENE ? a.tc : T;
+  const bool chunked = SMEM_SCENE && TC < T;
   float4* tile = sm4;
-  if (SMEM_SCENE) {
-    stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile);
+  if (SMEM_SCENE && !chunked) {
+    stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile, 0, T);
     __syncthreads();
   }
   const bool live = n < a.N;
@@ -663,8 +727,8 @@ k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   float* ge = a.grad_ego ? a.grad_ego + (size_t)nn * T * 4 : nullptr;
   float* tape = a.ws + nn;
   const int scene = nn / a.rows_per_scene;
-  const float4* tile_ln = tile + (size_t)c.K * T * PSTL_STREAM_NEI_F4;
-  StreamSceneSmem ss{tile, reinterpret_cast<const float2*>(tile_ln + 3 * c.nseg), tile_ln, c.K, T, c.nseg};
+  const float4* tile_ln = tile + (size_t)c.K * TC * PSTL_STREAM_NEI_F4;
+  StreamSceneSmem ss{tile, reinterpret_cast<const float2*>(tile_ln + 3 * c.nseg), tile_ln, c.K, 0, c.nseg};
   PstlStreamSceneGlobal sg;
   sg.neib = a.neighbors + (size_t)scene * c.K * T * 7;
   for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
@@ -675,19 +739,43 @@ k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     if (gu) for (int i = 0; i < T * 2; ++i) gu[i] = 0.f;
     if (ge) for (int i = 0; i < T * 4; ++i) ge[i] = 0.f;
   }
+  PstlStreamAcc A;
+  float sc = 0.f;
+  if (!chunked) {
 #pragma unroll 1
-  for (int mm = 0; mm < 3; ++mm) {
-    if (!__any_sync(0xffffffffu, m == mm)) continue;
-    if (m == mm) {
-      PstlStreamAcc A;
-      const float sc = SMEM_SCENE ? pstl_stream_fwd<true>(sp.p[mm], ss, c, s0, u, ego, a.ego_stride, stlp, tape, a.N, A)
-                                  : pstl_stream_fwd<true>(sp.p[mm], sg, c, s0, u, ego, a.ego_stride, stlp, tape, a.N, A);
-      if (a.scores) a.scores[n] = sc;
-      float g;
-      if (a.grad_score) g = a.grad_score[n];
-      else g = (a.thres - sc > 0.f) ? -a.valid[n] * a.inv_norm : 0.f;  // guidance loss, nusc_train.py:616-619
-      pstl_stream_bwd(sp.p[mm], c, u, stlp, g, sc != -INFINITY, A, tape, a.N, gu, ge);
+    for (int mm = 0; mm < 3; ++mm) {
+      if (!__any_sync(0xffffffffu, m == mm)) continue;
+      if (m == mm)
+        sc = SMEM_SCENE ? pstl_stream_fwd<true>(sp.p[mm], ss, c, s0, u, ego, a.ego_stride, stlp, tape, a.N, A)
+                        : pstl_stream_fwd<true>(sp.p[mm], sg, c, s0, u, ego, a.ego_stride, stlp, tape, a.N, A);
     }
+  } else {
+    PstlPose s = s0;
+    if (m < 3) pstl_stream_init(sp.p[m], c, stlp, A);
+#pragma unroll 1
+    for (int t0 = 0; t0 < T; t0 += TC) {
+      const int tc = (T - t0 < TC) ? T - t0 : TC;
+      __syncthreads();
+      stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile, t0, tc);
+      __syncthreads();
+      ss.t0 = t0;
+#pragma unroll 1
+      for (int mm = 0; mm < 3; ++mm) {
+        if (!__any_sync(0xffffffffu, m == mm)) continue;
+        if (m == mm) {
+          const int t1 = (t0 + tc < sp.p[mm].need_pose) ? t0 + tc : sp.p[mm].need_pose;
+          pstl_stream_steps<true>(sp.p[mm], ss, c, s, u, ego, a.ego_stride, stlp, tape, a.N, A, t0, t1);
+        }
+      }
+    }
+    if (m < 3) sc = pstl_stream_finish<true>(sp.p[m], c, stlp, tape, a.N, A);
+  }
+  if (m < 3) {  // reverse sweep: scene-independent
+    if (a.scores) a.scores[n] = sc;
+    float g;
+    if (a.grad_score) g = a.grad_score[n];
+    else g = (a.thres - sc > 0.f) ? -a.valid[n] * a.inv_norm : 0.f;  // guidance loss, nusc_train.py:616-619
+    pstl_stream_bwd(sp.p[m], c, u, stlp, g, sc != -INFINITY, A, tape, a.N, gu, ge);
   }
 }
 #endif  // __CUDACC__

@@ -238,6 +238,8 @@ struct ScoreArgs {
   float *scores, *grad_controls, *grad_ego;
   float* ws;
   int smem_tape, F;
+  int tc;           // streaming scorer: steps of the horizon held by the shared-memory scene tile
+  int tape_global;  // streaming scorer: X(t) columns in the workspace (stride N) instead of shared memory
 };
 
 __device__ __forceinline__ size_t scene_tile_floats(const PstlEvalCfg& c) {
@@ -428,29 +430,45 @@ static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaSt
     sp.p[k] = progs[k]->plan;
     n_tapes = progs[k]->plan.n_tapes > n_tapes ? progs[k]->plan.n_tapes : n_tapes;
   }
-  const size_t tile_bytes = stream_tile_f4(c.K, c.T, c.nseg) * sizeof(float4);
-  const size_t budget = 100 * 1024;
+  // scene tile: as many steps of the horizon as fit in ~48 KB (all of them at the pipeline's shape)
+  const size_t budget = 100 * 1024, tile_budget = 48 * 1024;
+  int tc = c.T;
+  while (tc > 1 && stream_tile_f4(c.K, tc, c.nseg) * sizeof(float4) > tile_budget) tc = (tc + 1) / 2;
+  const size_t tile_bytes = stream_tile_f4(c.K, tc, c.nseg) * sizeof(float4);
   int block = 0;
-  bool smem_scene = false;
-  if (a.rows_per_scene % 32 == 0 && tile_bytes <= budget / 2) {  // one scene per block, staged in shared memory
+  bool smem_scene = false, tape_global = false;
+  const size_t tape_row = (size_t)n_tapes * c.T * sizeof(float);
+  if (a.rows_per_scene % 32 == 0 && tile_bytes <= tile_budget && (tc == c.T || tc >= 4)) {
+    // one scene per block, staged in shared memory (whole horizon, or chunk by chunk)
     static const int cands[] = {192, 96, 128, 64, 32};
+    int first = 0;  // largest block that divides the scene's rows
     for (int b : cands)
-      if (a.rows_per_scene % b == 0 && tile_bytes + (size_t)b * n_tapes * c.T * sizeof(float) <= budget) {
-        block = b;
-        smem_scene = true;
-        break;
-      }
+      if (!first && a.rows_per_scene % b == 0) first = b;
+    if (tile_bytes + (size_t)first * tape_row <= budget) {
+      block = first;
+      smem_scene = true;
+    } else if (a.ws) {  // long horizon: keep the block large, the X(t) columns go to the workspace (coalesced)
+      block = first;
+      smem_scene = true;
+      tape_global = true;
+    } else {
+      for (int b : cands)
+        if (a.rows_per_scene % b == 0 && tile_bytes + (size_t)b * tape_row <= budget) { block = b; smem_scene = true; break; }
+    }
   }
   if (!block) {
     static const int cands[] = {128, 64, 32};
     for (int b : cands)
-      if ((size_t)b * n_tapes * c.T * sizeof(float) <= budget / 2) {
+      if ((size_t)b * tape_row <= budget / 2) {
         block = b;
         break;
       }
+    if (!block && a.ws) { block = 128; tape_global = true; }
   }
   if (!block) return PSTL_OK;
-  const size_t smem = (smem_scene ? tile_bytes : 0) + (size_t)block * n_tapes * c.T * sizeof(float);
+  a.tc = smem_scene ? tc : c.T;
+  a.tape_global = tape_global ? 1 : 0;
+  const size_t smem = (smem_scene ? tile_bytes : 0) + (tape_global ? 0 : (size_t)block * tape_row);
   const int grid = pstl_ceil_div(a.N, block);
   const char* mb = getenv("PSTL_STREAM_MINB");
   if (smem_scene && !(mb && atoi(mb) == 5)) {
@@ -485,15 +503,18 @@ static int launch_score_stream_bwd(ScoreArgs& a, pstl_program_t const* progs, cu
   if (!stream_bwd_ws_floats(progs, a.N, c.T)) return PSTL_OK;
   StreamPlans sp;
   for (int k = 0; k < 3; ++k) sp.p[k] = progs[k]->plan;
-  const size_t tile_bytes = stream_tile_f4(c.K, c.T, c.nseg) * sizeof(float4);
-  const size_t budget = 100 * 1024;
+  const size_t budget = 100 * 1024, tile_budget = 48 * 1024;
+  int tc = c.T;
+  while (tc > 1 && stream_tile_f4(c.K, tc, c.nseg) * sizeof(float4) > tile_budget) tc = (tc + 1) / 2;
+  const size_t tile_bytes = stream_tile_f4(c.K, tc, c.nseg) * sizeof(float4);
   int block = 128;
   bool smem_scene = false;
-  if (a.rows_per_scene % 32 == 0 && tile_bytes <= budget) {
+  if (a.rows_per_scene % 32 == 0 && tile_bytes <= tile_budget && (tc == c.T || tc >= 4)) {
     static const int cands[] = {192, 96, 128, 64, 32};
     for (int b : cands)
       if (a.rows_per_scene % b == 0) { block = b; smem_scene = true; break; }
   }
+  a.tc = smem_scene ? tc : c.T;
   const int grid = pstl_ceil_div(a.N, block);
   if (smem_scene) {
     PSTL_CUDA(cudaFuncSetAttribute(k_score_stream_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
@@ -557,7 +578,12 @@ extern "C" size_t pstl_score_workspace_bytes(pstl_program_t const* progs, int N,
                           : max3(progs[0]->h.val_floats, progs[1]->h.val_floats, progs[2]->h.val_floats);
   TapePlan t = plan_tape(F, 96 * 1024, 32);
   const size_t interp = t.smem_tape ? 0 : (size_t)F * N * sizeof(float);
-  const size_t stream = with_grad ? stream_bwd_ws_floats(progs, N, T) * sizeof(float) : 0;
+  size_t stream = with_grad ? stream_bwd_ws_floats(progs, N, T) * sizeof(float) : 0;
+  if (!with_grad && stream_bwd_ws_floats(progs, N, T)) {  // forward: X(t) columns when they do not fit in shared memory
+    int n_tapes = 0;
+    for (int k = 0; k < 3; ++k) n_tapes = progs[k]->plan.n_tapes > n_tapes ? progs[k]->plan.n_tapes : n_tapes;
+    stream = (size_t)n_tapes * T * N * sizeof(float);
+  }
   return interp > stream ? interp : stream;
 }
 

@@ -55,6 +55,30 @@ def dense(n, T, K):
           % (n, T, K, ms, n / ms * 1e3, n * by / ms / 1e6, by))
 
 
+def sweep(T, K, scenes=512):
+    """config 5 shape: horizon T, K neighbours; scene-indexed pack (scenes x 192 rows) and dense per-row layout"""
+    args = NT.default_args(nt=T)
+    S = 64
+    b = {k: v.cuda() for k, v in synthetic.make_scene_batch(scenes, nt=T, n_neighbors=K, n_randoms=S, seed=11).items()}
+    nb = NT.LazyBatch({k: b[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+                                         "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp")})
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    pack = NT.augment_batch_data(nb, None, args, n_randoms=S)["_pstl_pack"]
+    progs = NT._fused_programs(NT.build_stl_cache(args), T)
+    g = torch.Generator().manual_seed(1)
+    u = ((torch.rand(pack.N, T, 2, generator=g) * 2 - 1) * torch.tensor([0.05, 2.0])).cuda()
+    ms = timeit(lambda: NT.score_pack(pack, u, args, progs), reps=3, warm=1)
+    print("sweep T=%d K=%d scene-indexed: %d trajectories  %.3f ms  %.3g traj/s" % (T, K, pack.N, ms, pack.N / ms * 1e3))
+    n = min(pack.N, int(6e9 // (16 * T + 28 * K * T + 600)))
+    x, idx, mask = synthetic.make_dense_stl_input(n, nt=T, n_neighbors=K, seed=7)
+    xc = {k: v.cuda() for k, v in x.items()}
+    stls = NT.build_stl_cache(args)
+    ms = timeit(lambda: NT.compute_stl_dense(xc, stls, idx.cuda(), mask.cuda(), args), reps=3, warm=1)
+    by = 16 * T + 28 * K * T + 36 * 15 + 24 + 8 + 4
+    print("sweep T=%d K=%d dense rows   : %d trajectories  %.3f ms  %.3g traj/s  %.1f GB/s algorithmic (%d B/traj)"
+          % (T, K, n, ms, n / ms * 1e3, n * by / ms / 1e6, by))
+
+
 def trajopt(scenes, iters):
     """trajectory optimisation (nusc_train.py:1303-1325): iterations/s on scenes x 64 x 3 stored control sequences"""
     args = NT.default_args()
@@ -70,7 +94,9 @@ def trajopt(scenes, iters):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "trajopt":
+    if sys.argv[1] == "sweep":
+        sweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 512)
+    elif sys.argv[1] == "trajopt":
         trajopt(int(sys.argv[2]) if len(sys.argv) > 2 else 256, int(sys.argv[3]) if len(sys.argv) > 3 else 100)
     elif sys.argv[1] == "guidance":
         guidance(int(sys.argv[2]) if len(sys.argv) > 2 else 256)

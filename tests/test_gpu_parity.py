@@ -649,3 +649,53 @@ def test_diversity_metrics_on_device(golden_dir):
     np.testing.assert_allclose(c, v_avg, rtol=1e-5)
     for i in range(3):
         np.testing.assert_allclose(vl[i + 1], vol[:, i] * (va2[:, 0, i].numpy() != 0), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("nt,knei,S_", [(50, 16, 32), (100, 32, 32), (200, 64, 64)])
+def test_config5_scene_indexed_long_horizon_vs_oracle(nt, knei, S_):
+    """BASELINE config 5 shapes on the scene-indexed path: the scene tile no longer holds the whole horizon, so the
+    kernel walks it in chunks (and parks the X(t) columns in the workspace at T = 200).  Forward scores and the
+    guidance-style gradient against the oracle on the replicated rows; chunked == interpreter kernels."""
+    bs = 2
+    args = NT.default_args(nt=nt, n_randoms=S_, sampling_size=S_)
+    bcpu = synthetic.make_scene_batch(bs, nt=nt, n_neighbors=knei, n_randoms=S_, seed=1100 + nt)
+    b = cuda(bcpu)
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    pack = NT.augment_batch_data(NT.LazyBatch(b), None, args, n_randoms=S_)["_pstl_pack"]
+    g = torch.Generator().manual_seed(nt)
+    u_cpu = (torch.rand(pack.N, nt, 2, generator=g) * 2 - 1) * torch.tensor([0.05, 1.0])
+    u = u_cpu.cuda()
+    progs = NT._fused_programs(NT.build_stl_cache(args), nt)
+    res = {}
+    try:
+        for kern in ("stream", "thread"):
+            os.environ["PSTL_SCORE_KERNEL"] = kern
+            res[kern] = NT.score_pack(pack, u, args, progs)["best_score"].clone()
+    finally:
+        os.environ.pop("PSTL_SCORE_KERNEL", None)
+    dense = O.densify(bcpu, S_, nt)
+    ref, _ = O.score_controls(dense, u_cpu, 0.5)
+    close(res["stream"], ref)
+    close(res["stream"], res["thread"], rtol=2e-6)
+    # reverse mode through the same chunked forward
+    L = native.lib()
+    pa = native.prog_array(progs)
+    sv, sp = pack.view(), NT._spec(args)
+    gs = torch.where(0.0005 - res["stream"] > 0, -pack.valid / pack.N, torch.zeros_like(pack.valid)).contiguous()
+    grads = {}
+    try:
+        for kern in ("stream", "thread"):
+            os.environ["PSTL_SCORE_KERNEL"] = kern
+            gu = torch.empty((pack.N, nt, 2), device="cuda")
+            ws = native.workspace(L.pstl_score_workspace_bytes(pa, pack.N, nt, 1), u.device, "t5")
+            native.check(L.pstl_score_fused_bwd(pa, native.C.byref(sv), native.C.byref(sp), native.fptr(pack.mode),
+                                                native.fptr(pack.state0), native.fptr(u), None, 0, native.fptr(pack.stlp),
+                                                pack.N, native.fptr(gs), None, native.fptr(gu), None, native.ptr(ws),
+                                                native.stream()), "pstl_score_fused_bwd")
+            grads[kern] = gu.clone()
+    finally:
+        os.environ.pop("PSTL_SCORE_KERNEL", None)
+    # the adjoint runs through nt Euler steps: rounding differences between the two kernels grow with the horizon
+    tol = 2e-4 * max(1.0, nt / 50.0)
+    np.testing.assert_allclose(grads["stream"].cpu().numpy(), grads["thread"].cpu().numpy(), rtol=tol,
+                               atol=tol * float(grads["thread"].abs().max()))
