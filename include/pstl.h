@@ -205,7 +205,8 @@ size_t pstl_denoiser_workspace_bytes(pstl_denoiser_t d, int N, int n_scenes, con
  * scene_feat (n_scenes,feat_dim); rows_per_scene as in pstl_scene_view; hl (N); stlp (N,6);
  * sched: HOST pointer, (3,steps) = beta, alpha, alpha_hat (get_diffusion_coeffs, nusc_train.py:528-537);
  * temb (steps,time_dim) device copy of the sinusoid table (pos_encoding, nusc_model.py:48-53);
- * x_init (N,2T): x_T; noise (steps-2,N,2T) injected z for i = steps-1..2, or NULL to draw
+ * x_init (N,2T): x_T, or NULL to draw it from the same Philox stream (step word `steps`);
+ * noise (steps-2,N,2T) injected z for i = steps-1..2, or NULL to draw
  * Philox normals (seed, offset); keep_last_k iterates are written, scaled by (w_max,a_max) and
  * clipped when clip != 0, to iterates_out (keep_last_k,N,T,2) in chronological order (last = x_0). */
 int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
@@ -265,6 +266,12 @@ int pstl_trajopt_step(pstl_program_t const* progs, const pstl_scene_view* scenes
  * trajs (n_scenes,m,3,2*nt) [x0,y0,x1,y1,...], scores / valids (n_scenes,m,3), m <= 128. */
 int pstl_diversity(const float* trajs, const float* scores, const float* valids, int n_scenes, int m, int nt,
                    float* std_out, float* vol_out, pstl_stream_t stream);
+
+/* acc and scene_acc of the sampling test (mask_mean, nusc_train.py:23-27, 336-343) for scores / valid (n_scenes*S*3) with
+ * rows n = (scene*S + sample)*3 + mode: out[0] = mean((score>0)*valid)/clip(mean(valid),1e-2); out[1] = the same for
+ * (max over the samples of a (scene, mode)) > 0 with the scene's lane validity.  partial: n_scenes*4 floats of scratch. */
+int pstl_accuracy(const float* scores, const float* valid, int n_scenes, int S, float* partial, float* out,
+                  pstl_stream_t stream);
 
 /* Three-layer ReLU MLP of the scene encoders in one launch (nusc_model.py:82-91, hidden width 256):
  * y (M,out) = W4 relu(W2 relu(W0 x + b0) + b2) + b4, weights (out_features, in_features) row-major as in nn.Linear.

@@ -106,3 +106,83 @@ extern "C" int pstl_diversity(const float* trajs, const float* scores, const flo
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
 }
+
+// --------------------------------------------------------------------------------------
+// acc / scene_acc of the sampling test (nusc_train.py:23-27, 336-343): mask_mean((score > 0), valid) over all chains
+// and mask_mean((max over the S samples of a (scene, mode)) > 0, valid of the scene's lanes).  Rows n = (b*S + r)*3 + m.
+// --------------------------------------------------------------------------------------
+__global__ void k_accuracy_partial(const float* __restrict__ scores, const float* __restrict__ valid, int S,
+                                   float* __restrict__ part /* (bs, 4): acc num, valid sum, scene num, lane-valid sum */) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ float s_num[3], s_val[3];
+  __shared__ int s_pos[3];
+  if (tid < 3) { s_num[tid] = 0.f; s_val[tid] = 0.f; s_pos[tid] = 0; }
+  __syncthreads();
+  for (int m = 0; m < 3; ++m) {
+    float num = 0.f, val = 0.f;
+    bool pos = false;  // max over the samples > 0  <=>  some sample > 0
+    for (int r = tid; r < S; r += blockDim.x) {
+      const size_t n = ((size_t)b * S + r) * 3 + m;
+      const float sc = scores[n], v = valid[n];
+      num += (sc > 0.f ? 1.f : 0.f) * v;
+      val += v;
+      pos = pos || sc > 0.f;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      num += __shfl_xor_sync(0xffffffffu, num, o);
+      val += __shfl_xor_sync(0xffffffffu, val, o);
+    }
+    const bool any_pos = __any_sync(0xffffffffu, pos);
+    if ((tid & 31) == 0) {  // counts are small integers (validity is 0/1): float atomics are exact and order-independent
+      atomicAdd(&s_num[m], num);
+      atomicAdd(&s_val[m], val);
+      if (any_pos) atomicOr(&s_pos[m], 1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float scene_num = 0.f, lane_val = 0.f;
+    for (int m = 0; m < 3; ++m) {
+      const bool pos = s_pos[m] != 0;
+      const float v0 = valid[((size_t)b * S) * 3 + m];
+      scene_num += (pos ? 1.f : 0.f) * v0;
+      lane_val += v0;
+    }
+    part[b * 4 + 0] = s_num[0] + s_num[1] + s_num[2];
+    part[b * 4 + 1] = s_val[0] + s_val[1] + s_val[2];
+    part[b * 4 + 2] = scene_num;
+    part[b * 4 + 3] = lane_val;
+  }
+}
+
+__global__ void k_accuracy_final(const float* __restrict__ part, int bs, int S, float* __restrict__ out) {
+  __shared__ float sh[4][32];
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = threadIdx.x; b < bs; b += blockDim.x)
+    for (int q = 0; q < 4; ++q) a[q] += part[b * 4 + q];
+  for (int q = 0; q < 4; ++q) {
+    for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = a[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < 4; ++q)
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t[q] += sh[q][w];
+    const float n_all = (float)bs * (float)S * 3.f, n_lane = (float)bs * 3.f;
+    out[0] = (t[0] / n_all) / fmaxf(t[1] / n_all, 1e-2f);    // mean(loss*mask) / clip(mean(mask), 1e-2)
+    out[1] = (t[2] / n_lane) / fmaxf(t[3] / n_lane, 1e-2f);
+  }
+}
+
+extern "C" int pstl_accuracy(const float* scores, const float* valid, int n_scenes, int S, float* partial, float* out,
+                             pstl_stream_t stream) {
+  PSTL_CHECK_ARG(scores && valid && partial && out && S >= 1, "bad argument");
+  if (n_scenes <= 0) return PSTL_OK;
+  k_accuracy_partial<<<n_scenes, 64, 0, (cudaStream_t)stream>>>(scores, valid, S, partial);
+  PSTL_LAUNCH_CHECK();
+  k_accuracy_final<<<1, 256, 0, (cudaStream_t)stream>>>(partial, n_scenes, S, out);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+

@@ -340,14 +340,21 @@ extern "C" int pstl_mlp3(const float* x, int M, int in_dim, const float* w0, con
 // small helper kernels
 // --------------------------------------------------------------------------------------
 // xin[n] = [x (T2) | hl | stlp(6) | 0]
+// draw != 0: x is not given and x_T ~ N(0,1) comes from the sampler's Philox stream at step word `draw_step`
+// (= steps, which no reverse step uses)
 __global__ void k_pack_xin(const float* __restrict__ x, int ldx_src, const float* __restrict__ hl,
-                           const float* __restrict__ stlp, float* __restrict__ xin, long long N, int T2) {
+                           const float* __restrict__ stlp, float* __restrict__ xin, long long N, int T2, int draw,
+                           unsigned long long seed, unsigned long long offset,
+                           const unsigned long long* __restrict__ offset_dev, int draw_step) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * PSTL_XIN_LD) return;
   const long long n = i / PSTL_XIN_LD;
   const int c = (int)(i - n * PSTL_XIN_LD);
   float v = 0.f;
-  if (c < T2) v = x ? x[n * ldx_src + c] : 0.f;
+  if (c < T2) {
+    if (draw) v = pstl_noise_at(seed, offset + (offset_dev ? *offset_dev : 0ull), draw_step, n, c);
+    else v = x ? x[n * ldx_src + c] : 0.f;
+  }
   else if (c == T2) v = hl[n];
   else if (c < T2 + 7) v = stlp[n * 6 + (c - T2 - 1)];
   xin[i] = v;
@@ -677,7 +684,7 @@ extern "C" int pstl_denoiser_eps(pstl_denoiser_t d, const float* scene_feat, int
                  d->w.feat_dim + T2, d->w.time_dim, w.ct, st);
   if (rc) return rc;
   const long long tot = (long long)N * PSTL_XIN_LD;
-  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x, T2, hl, stlp, w.xin, N, T2);
+  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x, T2, hl, stlp, w.xin, N, T2, 0, 0ull, 0ull, nullptr, 0);
   PSTL_LAUNCH_CHECK();
   rc = mlp_hidden(d, w, N, rows_per_scene, d->w1p, H, w.ct, d->w.p2_w, d->w.p2_b, st);
   if (rc) return rc;
@@ -694,7 +701,8 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
                                     float w_max, float a_max, int clip, int keep_last_k,
                                     const pstl_guidance_cfg* guidance, float* iterates_out, float* x_final,
                                     void* workspace, pstl_stream_t stream) {
-  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && sched && temb && x_init && workspace, "null argument");
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && sched && temb && workspace, "null argument");
+  PSTL_CHECK_ARG(x_init || !noise, "injected noise needs x_init");
   PSTL_CHECK_ARG(steps >= 2 && keep_last_k >= 0 && keep_last_k <= steps - 1, "bad steps / keep_last_k");
   PSTL_CHECK_ARG(rows_per_scene >= 1 && (long long)n_scenes * rows_per_scene >= N, "bad scene mapping");
   PSTL_CHECK_ARG(!keep_last_k || iterates_out, "iterates_out required");
@@ -709,7 +717,8 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
                  d->w.feat_dim + T2, d->w.time_dim, w.ct, st);
   if (rc) return rc;
   const long long tot = (long long)N * PSTL_XIN_LD;
-  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x_init, T2, hl, stlp, w.xin, N, T2);
+  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x_init, T2, hl, stlp, w.xin, N, T2, x_init ? 0 : 1, seed, offset,
+                                                          d->offset_dev, steps);
   PSTL_LAUNCH_CHECK();
   const float* hs = sched;  // host pointer by contract
   const float *beta = hs, *alpha = hs + steps, *abar = hs + 2 * steps;
@@ -820,7 +829,7 @@ extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_sce
     a.X = w.h2; a.ldx = MH; a.W = d->w.m4_w; a.ldw = MH; a.bias = d->w.m4_b; a.Y = w.g; a.ldy = T2; a.M = N; a.K = MH; a.Nout = T2;
     if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
     const long long tot = (long long)N * PSTL_XIN_LD;
-    k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(nullptr, 0, hl, stlp, w.xin, N, T2);
+    k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(nullptr, 0, hl, stlp, w.xin, N, T2, 0, 0ull, 0ull, nullptr, 0);
     PSTL_LAUNCH_CHECK();
     const long long gtot = (long long)(N / per) * T2;
     k_group_fuse<<<pstl_ceil_div(gtot, 256), 256, 0, st>>>(w.g, u0, w.xin, N, T2, n_randoms, per);

@@ -641,8 +641,8 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
     steps (eps-MLP, posterior update, noise, optional STL guidance) instead of ~100 launches per step.
 
     ``noise`` gives only shape/device, as upstream (:563).  Deterministic mode: ``args.inject_noise`` =
-    [x_T, z_1, ...] tensors (N,2nt) consumed in upstream's randn_like order; otherwise x_T is drawn with
-    torch and z by the kernel's Philox stream (``args.seed``)."""
+    [x_T, z_1, ...] tensors (N,2nt) consumed in upstream's randn_like order; otherwise x_T and z are drawn by the
+    kernels' Philox stream (``args.seed``)."""
     if mono or fastforward:
         raise NotImplementedError("mono / fastforward sampling is not on the hot path")
     _nv.require_cuda(noise, "noise")
@@ -668,7 +668,8 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
         x_T = _nv.f32(inj[0])
         z = torch.stack([_nv.f32(t) for t in inj[1:steps - 1]], 0).contiguous() if steps > 2 else None
     else:
-        x_T = torch.randn((n, T2), dtype=torch.float32, device=noise.device)
+        # x_T ~ N(0,1): drawn by the sampler from its own Philox stream (no separate randn launch / HBM round trip)
+        x_T = None
         z = None
     keep_all = bool(getattr(args, "refinement", False) or getattr(args, "keep_all_iterates", False))
     K = steps - 1 if keep_all else max(1, int(args.multi_cands or 1))
@@ -742,6 +743,17 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
 # open-loop sampling test (reference :890-1183; the timed region :957-1105)
 # ---------------------------------------------------------------------------------------
 
+def accuracy(scores, valid, bs, S):
+    """(acc, scene_acc) of the report line (reference :336-343): mask_mean of (score > 0) over the chains and of
+    (best sample of a (scene, mode) > 0) over the scenes' lanes — two small launches instead of a dozen tensor ops."""
+    _nv.require_cuda(scores, "scores")
+    part = torch.empty((bs, 4), dtype=torch.float32, device=scores.device)
+    out = torch.empty((2,), dtype=torch.float32, device=scores.device)
+    _nv.check(_nv.lib().pstl_accuracy(_nv.fptr(_nv.f32(scores.reshape(-1))), _nv.fptr(_nv.f32(valid.reshape(-1))), bs, S,
+                                      _nv.fptr(part), _nv.fptr(out), _nv.stream()), "pstl_accuracy")
+    return out[0], out[1]
+
+
 def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     """The timed region of run_sampling_test for the diffusion + RefineNet path:
     augment -> sampler -> best-of-K -> RefineNet (+n_rolls) -> final rollout + scores."""
@@ -782,9 +794,7 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
                 nn_controls = net.rect_forward(feature, highlevel_new, new_batch["stlp_dense"][:, 0], nn_controls, sc)
     r = score_pack(pack, nn_controls, args, progs, want=("best_score", "traj"))
     scores, nn_trajs = r["best_score"], r["traj"]
-    acc = mask_mean((scores > 0).float(), pack.valid)
-    sc_cube, m_cube = scores.reshape(-1, S, 3), pack.valid.reshape(-1, S, 3)
-    scene_acc = mask_mean((torch.max(sc_cube, dim=1)[0] > 0).float(), m_cube[:, 0, :])
+    acc, scene_acc = accuracy(scores, pack.valid, bs, S)
     out.update(controls=nn_controls, scores=scores, trajs=nn_trajs, acc=acc, scene_acc=scene_acc, pack=pack)
     return out
 
@@ -851,8 +861,7 @@ class CapturedPipeline:
     ``runner = CapturedPipeline(net, stls, coeffs, args, example_batch); out = runner(batch)``:
     ``batch`` tensors (host-pinned or device) are copied into the graph's static inputs, the graph is
     replayed, and ``out`` holds the graph's static output tensors (valid until the next call).
-    Noise: x_T comes from ``torch.randn`` under torch's graph-safe generator state; the z stream comes from
-    the sampler's Philox counter plus a device word that the graph bumps on every replay
+    Noise: x_T and the z stream come from the sampler's Philox counter plus a device word that the graph bumps on every replay
     (``pstl_denoiser_set_noise_counter``), so replays draw fresh normals as upstream's ``randn_like`` does.
     Not capturable: ``--guidance`` (its batch normaliser is read back on the host) and injected noise."""
 

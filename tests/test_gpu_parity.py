@@ -699,3 +699,50 @@ def test_config5_scene_indexed_long_horizon_vs_oracle(nt, knei, S_):
     tol = 2e-4 * max(1.0, nt / 50.0)
     np.testing.assert_allclose(grads["stream"].cpu().numpy(), grads["thread"].cpu().numpy(), rtol=tol,
                                atol=tol * float(grads["thread"].abs().max()))
+
+
+def test_accuracy_kernel_equals_mask_mean_expressions():
+    """pstl_accuracy == the reference's tensor expressions for acc / scene_acc (nusc_train.py:23-27, 336-343)"""
+    g = torch.Generator().manual_seed(12)
+    for bs, S_ in ((7, 16), (64, 64), (3, 1)):
+        sc = (torch.randn(bs * S_ * 3, generator=g)).cuda()
+        sc[::7] = 0.0
+        valid = (torch.rand(bs, 1, 3, generator=g) > 0.3).float().repeat(1, S_, 1).reshape(-1).cuda()
+        if bs == 3:
+            valid[:] = 0.0  # clip(mean(mask), 1e-2) branch
+        acc, scene_acc = NT.accuracy(sc, valid, bs, S_)
+        ref_acc = NT.mask_mean((sc > 0).float(), valid)
+        cube, mc = sc.reshape(-1, S_, 3), valid.reshape(-1, S_, 3)
+        ref_scene = NT.mask_mean((torch.max(cube, dim=1)[0] > 0).float(), mc[:, 0, :])
+        close(acc, ref_acc, rtol=1e-6)
+        close(scene_acc, ref_scene, rtol=1e-6)
+
+
+def test_sampler_draws_unit_normal_x_T():
+    """without injected noise the sampler draws x_T itself (Philox step word = steps): with one reverse step of a
+    zero-weight net the output is a deterministic affine image of x_T, so its moments identify N(0,1)"""
+    S_ = 64
+    args = NT.default_args(n_randoms=S_, sampling_size=S_, diffusion_steps=2, multi_cands=1, precision="fp32")
+    net = Net(args)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.zero_()
+    net = net.cuda()
+    b = cuda(synthetic.make_scene_batch(16, n_randoms=S_, seed=3))
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    nb = NT.augment_batch_data(NT.LazyBatch(b), None, args, n_randoms=S_)
+    N = 16 * S_ * 3
+    co = NT.get_diffusion_coeffs(args)
+    noise = torch.empty((N, 40), device="cuda")
+    args.diffusion_clip = False
+    r1 = NT.diffusion_rollout(noise, net, nb, nb["highlevel_dense"], None, args, co, n_randoms=S_)
+    r2 = NT.diffusion_rollout(noise, net, nb, nb["highlevel_dense"], None, args, co, n_randoms=S_)
+    x1 = (r1[0] if isinstance(r1, tuple) else r1).reshape(N, 20, 2) / torch.tensor([0.5, 5.0], device="cuda")
+    x2 = (r2[0] if isinstance(r2, tuple) else r2).reshape(N, 20, 2) / torch.tensor([0.5, 5.0], device="cuda")
+    beta, alpha, abar = [t.double() for t in co]
+    # eps = 0 + x (residual) ; x_0 = (x_T - c1 x_T) / sqrt(alpha_1), no noise at i = 1
+    k = float((1 - (1 - alpha[1]) / torch.sqrt(1 - abar[1])) / torch.sqrt(alpha[1]))
+    z = x1 / k
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+    assert abs((z ** 4).mean().item() - 3.0) < 0.1
+    assert (x1 - x2).abs().max().item() > 1e-3  # a fresh draw per call
