@@ -897,6 +897,7 @@ class CapturedPipeline:
     def prefetch(self, batch):
         """Start copying the NEXT batch (pinned host or device tensors) into the staging inputs on a separate stream;
         the copy overlaps whatever the main stream is running.  The next ``runner()`` call consumes it."""
+        self._check(batch)
         self._copy_stream.wait_event(self._staging_free)
         with torch.cuda.stream(self._copy_stream):
             for k, t in self.staging.items():
@@ -923,11 +924,19 @@ class CapturedPipeline:
             self._staging_free.record(cur)
             self._have_prefetch = False
         else:
+            self._check(batch)
             for k, t in self.static_in.items():
                 if batch[k] is not t:
                     t.copy_(batch[k], non_blocking=True)
         self.graph.replay()
         return self.out
+
+    def _check(self, batch):
+        """a captured graph has static shapes: refuse a batch of another shape instead of broadcasting it silently"""
+        for k, t in self.static_in.items():
+            if k not in batch or tuple(batch[k].shape) != tuple(t.shape):
+                raise ValueError("CapturedPipeline was captured for %s%s, got %s" %
+                                 (k, tuple(t.shape), tuple(batch[k].shape) if k in batch else "nothing"))
 
 
 def run_sampling_test(stls_cac, data_loader, net, coeffs, args, result_queue=None, thread_nusc=None):

@@ -562,6 +562,8 @@ def test_captured_pipeline_prefetch_matches_direct_call():
     assert torch.equal(NT.score_pack(pack, out["controls"], args, progs)["best_score"], out["scores"])
     with pytest.raises(ValueError):
         runner()
+    with pytest.raises(ValueError):  # static shapes
+        runner(cuda(synthetic.make_scene_batch(5, n_randoms=S_, seed=53)))
 
 
 @pytest.mark.parametrize("m,in_dim", [(1, 6), (37, 7), (3072, 45), (8192, 7)])
