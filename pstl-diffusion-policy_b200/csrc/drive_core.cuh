@@ -71,7 +71,7 @@ PSTL_HD float pstl_pair_clearance(const PstlCircles& e, float ec, float es, cons
 #pragma unroll
     for (int j = 0; j < PSTL_NL; ++j) {
       const float dx = e.cx[i] - n.cx[j], dy = e.cy[i] - n.cy[j];
-      const float d2 = dx * dx + dy * dy;
+      const float d2 = fmaf(dx, dx, dy * dy);  // one rounding less than the unfused sum; used by every kernel alike
       if (d2 < best) { best = d2; bi = i; bj = j; }
     }
   const float mind = sqrtf(best);  // sqrt is monotone: min of norms == norm at the min square

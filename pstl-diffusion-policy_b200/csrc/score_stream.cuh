@@ -84,7 +84,7 @@ struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
 // Exact cull (see pstl_cull_neighbour): rsum = L_ego/2 + L_nei/2 + margin
 PSTL_HD bool pstl_cull_neighbour_r(float dx, float dy, float rsum, float best) {
   const float R = fminf(best, 20.f) + rsum;
-  return R > 0.f && (dx * dx + dy * dy) >= R * R;
+  return R > 0.f && fmaf(dx, dx, dy * dy) >= R * R;
 }
 
 // value of a typed leaf (include/pstl.h, PSTL_OP_PRED): (sb*base + sp*stlp[pid]) / den
@@ -139,10 +139,7 @@ PSTL_HD void pstl_stream_init(const PstlPlan& pl, const PstlEvalCfg& c, const fl
     }
   }
 
-  A.rg_nei = 0.f;
-#pragma unroll
-  for (int k = 0; k < PSTL_MAX_TERMS; ++k)
-    if (k == pl.nei_term) A.rg_nei = 1.f / g2[k];
+  A.rg_nei = (pl.nei_term == 0) ? 1.f / g2[0] : 0.f;
 }
 
 // steps t0 <= t < t1 (t1 <= pl.need_pose); the accessor sc serves exactly those steps; s is the pose at t0 on entry and
@@ -175,13 +172,13 @@ PSTL_HD void pstl_stream_steps(const PstlPlan& pl, const Scene& sc, const PstlEv
       const int l = pl.lane;
       PstlF4 q = sc.lane_pt(l, 0);
       float dx = s.x - q.x, dy = s.y - q.y;
-      float prev = pstl_sqrt_search(dx * dx + dy * dy);
+      float prev = pstl_sqrt_search(fmaf(dx, dx, dy * dy));
       float bestv = INFINITY;
       int bi = 0;
       for (int j = 1; j < c.nseg; ++j) {
         q = sc.lane_pt(l, j);
         dx = s.x - q.x; dy = s.y - q.y;
-        const float dj = pstl_sqrt_search(dx * dx + dy * dy);
+        const float dj = pstl_sqrt_search(fmaf(dx, dx, dy * dy));
         const float sum = prev + dj;
         if (sum < bestv) { bestv = sum; bi = j - 1; }
         prev = dj;
@@ -198,9 +195,8 @@ PSTL_HD void pstl_stream_steps(const PstlPlan& pl, const Scene& sc, const PstlEv
       // 2^-36 to a sum >= 1 — nothing in fp32 — so neighbours that cannot come closer than thr are skipped.
       float thr = 20.f;
 #pragma unroll
-      for (int k = 0; k < PSTL_MAX_TERMS; ++k)
-        if (k == pl.nei_term) thr = fminf(thr, (am[k] - 36.f) * rg_nei);
-      if (pl.nei_term < 0) thr = 20.f;
+      for (int k = 0; k < 2; ++k)  // pstl_make_plan keeps the clearance term in slot 0 (the two-slot scan only steers ptxas
+        if (k == pl.nei_term) thr = fminf(thr, (am[k] - 36.f) * rg_nei);  // away from a spilling allocation)
       int cnt;
       float best, bg0 = 0.f, bg1 = 0.f, bg2 = 0.f;  // partials of the minimal term (first minimum, as torch.min)
       sc.nei_begin(t, cnt, best);
@@ -211,7 +207,7 @@ PSTL_HD void pstl_stream_steps(const PstlPlan& pl, const Scene& sc, const PstlEv
         sc.nei_meta(k, t, valid, ncx, ncy, rsum);
         const float dx = s.x - ncx, dy = s.y - ncy;
         const float R = thr + rsum;
-        const bool far = (valid == 1.f) && (R > 0.f) && (dx * dx + dy * dy >= R * R);
+        const bool far = (valid == 1.f) && (R > 0.f) && (fmaf(dx, dx, dy * dy) >= R * R);
         if (valid == 0.f || far) {  // 100, or a clipped clearance >= thr (== 20 when thr == 20): zero gradient
           const float ph = (valid == 0.f) ? 100.f : thr;
           if (ph < best) { best = ph; bg0 = bg1 = bg2 = 0.f; }

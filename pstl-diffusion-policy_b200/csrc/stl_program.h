@@ -165,8 +165,8 @@ struct PstlPlan {
   int lane;       // lane (0 curr, 1 left, 2 right) the distance / heading leaves refer to, -1: none
   int n_tapes;
   int need_pose, need_lane, need_nei;  // leading steps for which the pose / lane search / clearance are read
-  int nei_term;   // >= 0: the clearance signal feeds exactly this term and it is  Always_[lo,hi) (nei - q)/den
-                  // (soft-min, positive sign, no And/Or, no inner operator); -1 otherwise
+  int nei_term;   // 0: the clearance signal feeds exactly term 0 and it is  Always_[lo,hi) (nei - q)/den
+                  // (soft-min, positive sign, no And/Or, no inner operator; pstl_make_plan moves it to slot 0); -1 otherwise
   PstlTerm terms[PSTL_MAX_TERMS];
 };
 
@@ -255,5 +255,11 @@ static inline void pstl_make_plan(const PstlProgView& P, PstlPlan* pl) {
     }
   }
   pl->nei_term = (uses == 1) ? idx : -1;
+  if (pl->nei_term > 0) {  // keep it in slot 0 (ListAnd is symmetric): the scorer reads its accumulator at a fixed index
+    const PstlTerm t0 = pl->terms[0];
+    pl->terms[0] = pl->terms[pl->nei_term];
+    pl->terms[pl->nei_term] = t0;
+    pl->nei_term = 0;
+  }
   pl->valid = 1;
 }

@@ -156,7 +156,7 @@ def test_plan_recognition():
     assert [i["lane"] for i in infos] == [0, 1, 2]
     assert [i["n_tapes"] for i in infos] == [0, 2, 2]
     assert [i["n_terms"] for i in infos] == [6, 5, 5]
-    assert all(i["nei_term"] == i["n_terms"] - 1 and i["need_pose"] == nt for i in infos)
+    assert all(i["nei_term"] == 0 and i["need_pose"] == nt for i in infos)  # moved to slot 0 by pstl_make_plan
     L = _typed_leaves(nt)
     A, E = S.Always, S.Eventually
     assert _plan_info(hs, A(0, 7, L["vmin"]), nt) == dict(valid=1, n_terms=1, listand=0, lane=-1, n_tapes=0, need_pose=7,
