@@ -341,23 +341,40 @@ extern "C" int pstl_mlp3(const float* x, int M, int in_dim, const float* w0, con
 // --------------------------------------------------------------------------------------
 // xin[n] = [x (T2) | hl | stlp(6) | 0]
 // draw != 0: x is not given and x_T ~ N(0,1) comes from the sampler's Philox stream at step word `draw_step`
-// (= steps, which no reverse step uses)
+// (= steps, which no reverse step uses).  One thread per group of four columns: one Philox call yields the four
+// normals of a group (same counter layout as pstl_noise_at), and the row is written with 16-byte stores.
 __global__ void k_pack_xin(const float* __restrict__ x, int ldx_src, const float* __restrict__ hl,
                            const float* __restrict__ stlp, float* __restrict__ xin, long long N, int T2, int draw,
                            unsigned long long seed, unsigned long long offset,
                            const unsigned long long* __restrict__ offset_dev, int draw_step) {
+  constexpr int Q = PSTL_XIN_LD / 4;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * PSTL_XIN_LD) return;
-  const long long n = i / PSTL_XIN_LD;
-  const int c = (int)(i - n * PSTL_XIN_LD);
-  float v = 0.f;
-  if (c < T2) {
-    if (draw) v = pstl_noise_at(seed, offset + (offset_dev ? *offset_dev : 0ull), draw_step, n, c);
-    else v = x ? x[n * ldx_src + c] : 0.f;
+  if (i >= N * Q) return;
+  const long long n = i / Q;
+  const int c0 = (int)(i - n * Q) * 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (draw && c0 + 3 < T2) {
+    const unsigned long long off = offset + (offset_dev ? *offset_dev : 0ull);
+    const uint4 ctr = make_uint4((unsigned)(n & 0xffffffff), (unsigned)(n >> 32), (unsigned)(c0 >> 2),
+                                 (unsigned)draw_step + (unsigned)off);
+    const uint4 r = pstl_philox(ctr, make_uint2((unsigned)(seed & 0xffffffff), (unsigned)(seed >> 32)));
+    pstl_box_muller(r.x, r.y, v[0], v[1]);
+    pstl_box_muller(r.z, r.w, v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c0 + e;
+      if (c < T2) {
+        if (draw) v[e] = pstl_noise_at(seed, offset + (offset_dev ? *offset_dev : 0ull), draw_step, n, c);
+        else v[e] = x ? x[n * ldx_src + c] : 0.f;
+      } else if (c == T2) {
+        v[e] = hl[n];
+      } else if (c < T2 + 7) {
+        v[e] = stlp[n * 6 + (c - T2 - 1)];
+      }
+    }
   }
-  else if (c == T2) v = hl[n];
-  else if (c < T2 + 7) v = stlp[n * 6 + (c - T2 - 1)];
-  xin[i] = v;
+  *reinterpret_cast<float4*>(xin + n * PSTL_XIN_LD + c0) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // RefineNet shard pooling (nusc_model.py:186-200): rows n=(b*R+r)*3+m; max over the `per` samples of a shard
@@ -683,7 +700,7 @@ extern "C" int pstl_denoiser_eps(pstl_denoiser_t d, const float* scene_feat, int
   int rc = hoist(d->w.p0_w, in1, d->w.p0_b, H, scene_feat, n_scenes, d->w.feat_dim, w.cscene, temb_row, 1,
                  d->w.feat_dim + T2, d->w.time_dim, w.ct, st);
   if (rc) return rc;
-  const long long tot = (long long)N * PSTL_XIN_LD;
+  const long long tot = (long long)N * (PSTL_XIN_LD / 4);
   k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x, T2, hl, stlp, w.xin, N, T2, 0, 0ull, 0ull, nullptr, 0);
   PSTL_LAUNCH_CHECK();
   rc = mlp_hidden(d, w, N, rows_per_scene, d->w1p, H, w.ct, d->w.p2_w, d->w.p2_b, st);
@@ -716,7 +733,7 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
   int rc = hoist(d->w.p0_w, in1, d->w.p0_b, H, scene_feat, n_scenes, d->w.feat_dim, w.cscene, temb, steps,
                  d->w.feat_dim + T2, d->w.time_dim, w.ct, st);
   if (rc) return rc;
-  const long long tot = (long long)N * PSTL_XIN_LD;
+  const long long tot = (long long)N * (PSTL_XIN_LD / 4);
   k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x_init, T2, hl, stlp, w.xin, N, T2, x_init ? 0 : 1, seed, offset,
                                                           d->offset_dev, steps);
   PSTL_LAUNCH_CHECK();
@@ -828,7 +845,7 @@ extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_sce
     lin_defaults(a);
     a.X = w.h2; a.ldx = MH; a.W = d->w.m4_w; a.ldw = MH; a.bias = d->w.m4_b; a.Y = w.g; a.ldy = T2; a.M = N; a.K = MH; a.Nout = T2;
     if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
-    const long long tot = (long long)N * PSTL_XIN_LD;
+    const long long tot = (long long)N * (PSTL_XIN_LD / 4);
     k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(nullptr, 0, hl, stlp, w.xin, N, T2, 0, 0ull, 0ull, nullptr, 0);
     PSTL_LAUNCH_CHECK();
     const long long gtot = (long long)(N / per) * T2;
