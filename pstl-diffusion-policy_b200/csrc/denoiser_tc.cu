@@ -43,7 +43,8 @@ constexpr int kWeightBytes = kOffW3 + 4 * kN3 * 128;
 constexpr int kOffB2 = kWeightBytes;              // [256 x 16] bf16, K-major no-swizzle: (hi,lo) of b2 in every class pair
 constexpr int kOffB3 = kOffB2 + 256 * 16 * 2;
 constexpr int kOffBar = kOffB3 + 64 * 4;
-constexpr int kSmemBytes = kOffBar + 128;
+constexpr int kOffIt = kOffBar + 128;             // [128 x 40] fp32: one kept iterate of the tile, bulk-stored to HBM
+constexpr int kSmemBytes = kOffIt + kTileM * 40 * 4;
 static_assert(kWeightBytes == 188416, "weight image size");
 static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
 
@@ -464,13 +465,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       float x[20];
       const float* xr = a.xin + rrow * PSTL_XIN_LD;
 #pragma unroll
-      for (int j = 0; j < 20; ++j) x[j] = xr[c0 + j];
+      for (int j = 0; j < 20; j += 4) {  // 16-byte loads: the rows are 192 B apart, scalar loads cost a sector each
+        const float4 q = *reinterpret_cast<const float4*>(xr + c0 + j);
+        x[j] = q.x; x[j + 1] = q.y; x[j + 2] = q.z; x[j + 3] = q.w;
+      }
       // the layer-1 operand lives in TMEM too (columns kColX..+32): bf16 pairs of [x | hl stlp 0 | class one-hots]
       // constant columns 40..47: hl, stlp(6), 0 ; 48..63: ones at this row's scene class.  X shares its columns
       // with H2, so the whole operand is rewritten every step (the half-1 warps carry the constants).
       uint32_t pc[12];
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) pc[j / 2] = pack_bf16(xr[40 + j], xr[41 + j]);
+      for (int j = 0; j < 8; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(xr + 40 + j);
+        pc[j / 2] = pack_bf16(q.x, q.y);
+        pc[j / 2 + 1] = pack_bf16(q.z, q.w);
+      }
 #pragma unroll
       for (int c = 0; c < kMaxClasses; ++c) pc[4 + c] = (c == cls) ? 0x3F803F80u : 0u;
       auto store_x = [&]() {
@@ -606,16 +614,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           x[j] = mu + sb * zn[j];
         }
         const int kidx = a.keep - i;
-        if (a.iterates && kidx >= 0 && live) {
-          float* o = a.iterates + ((size_t)kidx * a.N + row) * 40 + c0;
+        if (a.iterates && kidx >= 0) {
+          // kept iterate: the tile's 128 x 40 block is contiguous in HBM, so it is assembled in shared memory and
+          // leaves as ONE bulk copy (per-thread 8-byte stores cost a 32-byte sector each: 1,800 cycles per step)
+          float* stg = reinterpret_cast<float*>(smem + kOffIt);
+          if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          float* o = stg + row_in_tile * 40 + c0;
 #pragma unroll
-          for (int j = 0; j < 20; j += 2) {
-            float w = x[j] * a.w_max, ac = x[j + 1] * a.a_max;
-            if (a.clip) {
-              w = fminf(fmaxf(w, -a.w_max), a.w_max);
-              ac = fminf(fmaxf(ac, -a.a_max), a.a_max);
+          for (int j = 0; j < 20; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lim = (e & 1) ? a.a_max : a.w_max;
+              v[e] = x[j + e] * lim;
+              if (a.clip) v[e] = fminf(fmaxf(v[e], -lim), lim);
             }
-            *reinterpret_cast<float2*>(o + j) = make_float2(w, ac);
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (warp == 0 && lane == 0) {
+            const long long r0 = (long long)tile * kTileM;
+            const int rows = (int)(((long long)a.N - r0 < kTileM) ? (long long)a.N - r0 : kTileM);
+            float* dst = a.iterates + ((size_t)kidx * a.N + r0) * 40;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stg)),
+                         "r"(rows * 160)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
         if (s + 1 < n_steps) {
@@ -630,9 +656,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
       if (live && !a.refine && !a.mu_out) {
         float* xw = a.xin + row * PSTL_XIN_LD;
 #pragma unroll
-        for (int j = 0; j < 20; ++j) xw[c0 + j] = x[j];
+        for (int j = 0; j < 20; j += 4) *reinterpret_cast<float4*>(xw + c0 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
       }
     }
+    if (warp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // kept iterates have landed
   }
   tc_fence_before();
   __syncthreads();
