@@ -572,6 +572,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           }
         }
         // ---- layer 3: eps, posterior mean, noise, next x ----
+        // x' = c2 (x - c1 (D3 + b3 + x)) + sb z = [c2 (1 - c1) x - c2 c1 b3 + sb z] - c2 c1 D3: the bracket is ready
+        // before D3 is, so one multiply-add per column is left after the wait
+        const float c1 = a.c1[i], c2 = a.c2[i], sb = a.sb[i];
+        const float kx = c2 * (1.f - c1), kd = c2 * c1;
+        float pre[20];
+        if (!a.refine && !a.mu_out) {
+#pragma unroll
+          for (int j = 0; j < 20; ++j) pre[j] = kx * x[j] - kd * b3s[c0 + j] + sb * zn[j];
+        }
         mbar_spin(bar_d3, ph);
         if (STAMP) a.dbg[13] = clock64();
         tc_fence_after();
@@ -597,7 +606,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           }
           continue;
         }
-        const float c1 = a.c1[i], c2 = a.c2[i], sb = a.sb[i];
         if (a.mu_out) {  // guided step: the mean goes to the guidance kernels, which add the noise afterwards
           float* mo = a.mu_out + rrow * 40 + c0;
 #pragma unroll
@@ -608,10 +616,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
           continue;
         }
 #pragma unroll
-        for (int j = 0; j < 20; ++j) {
-          const float eps = __uint_as_float(r[j]) + b3s[c0 + j] + x[j];
-          const float mu = c2 * (x[j] - c1 * eps);
-          x[j] = mu + sb * zn[j];
+        for (int j = 0; j < 20; ++j) x[j] = fmaf(-kd, __uint_as_float(r[j]), pre[j]);
+        // the next layer-1 operand first: the kept-iterate traffic below then runs in the shadow of the next step
+        if (s + 1 < n_steps) {
+          store_x();
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x);
+          if (STAMP) a.dbg[14] = clock64();
         }
         const int kidx = a.keep - i;
         if (a.iterates && kidx >= 0) {
@@ -643,14 +656,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-        }
-        if (s + 1 < n_steps) {
-          store_x();
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_x);
-          if (STAMP) a.dbg[14] = clock64();
         }
       }
       if (live && !a.refine && !a.mu_out) {
