@@ -49,6 +49,15 @@ def gather_scores(scores_local, best_idx_local=None, group=None, equal_sizes=Fal
         return scores_local, best_idx_local
     world = dist.get_world_size(group)
     if equal_sizes and scores_local.is_cuda:
+        n = scores_local.numel()
+        if best_idx_local is not None and best_idx_local.dtype == torch.int32 and scores_local.dtype == torch.float32:
+            # ONE collective: the int32 indices travel as raw bits behind the scores
+            send = torch.cat([scores_local.reshape(-1), best_idx_local.reshape(-1).view(torch.float32)])
+            out = torch.empty(world * 2 * n, dtype=torch.float32, device=send.device)
+            dist.all_gather_into_tensor(out, send, group=group)
+            out = out.reshape(world, 2, n)
+            return out[:, 0].reshape(-1), out[:, 1].contiguous().view(torch.int32).reshape(-1)
+
         def gather_eq(t):
             out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t.reshape(-1).contiguous(), group=group)
