@@ -66,6 +66,7 @@ struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
     const float* p = ln[l] + j * 3;
     return PstlF4{p[0], p[1], p[2], 0.f};
   }
+  PSTL_HD PstlF4 lane_xy(int l, int j) const { return lane_pt(l, j); }  // (x, y) for the segment search
   PSTL_HD void nei_begin(int, int& count, float& init) const { count = K; init = INFINITY; }
   PSTL_HD void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& rsum) const {
     const float* p = neib + ((size_t)k * T + t) * 7;
@@ -170,13 +171,13 @@ PSTL_HD void pstl_stream_steps(const PstlPlan& pl, const Scene& sc, const PstlEv
     if (t < pl.need_lane) {
       // nusc_api.py:693-712: closest segment = first arg-min of d_j + d_{j+1}
       const int l = pl.lane;
-      PstlF4 q = sc.lane_pt(l, 0);
+      PstlF4 q = sc.lane_xy(l, 0);
       float dx = s.x - q.x, dy = s.y - q.y;
       float prev = pstl_sqrt_search(fmaf(dx, dx, dy * dy));
       float bestv = INFINITY;
       int bi = 0;
       for (int j = 1; j < c.nseg; ++j) {
-        q = sc.lane_pt(l, j);
+        q = sc.lane_xy(l, j);
         dx = s.x - q.x; dy = s.y - q.y;
         const float dj = pstl_sqrt_search(fmaf(dx, dx, dy * dy));
         const float sum = prev + dj;
@@ -482,6 +483,7 @@ struct StreamSceneSmem {
     const float4 q = ln[l * nseg + j];
     return PstlF4{q.x, q.y, q.z, q.w};
   }
+  __device__ __forceinline__ PstlF4 lane_xy(int l, int j) const { return lane_pt(l, j); }
   __device__ __forceinline__ void nei_begin(int t, int& count, float& init) const {
     const float2 h = hdr[t - t0];
     count = __float_as_int(h.x);
@@ -566,6 +568,31 @@ struct StreamPlans {
   PstlPlan p[3];
 };
 
+// Dense per-row inputs come with arbitrary modes: a block sorts its rows by mode (stable counting sort, one thread —
+// ~1k cycles against ~100k of scoring) so that most warps evaluate ONE plan instead of serialising three.
+__device__ __forceinline__ int stream_sort_rows_by_mode(const float* __restrict__ mode, int n0, int N, int* s_perm) {
+  __shared__ unsigned char s_cls[256];
+  {
+    int v = 4;
+    if (n0 + (int)threadIdx.x < N) {
+      const float md = mode[n0 + threadIdx.x];
+      v = (md == 0.f) ? 0 : (md == 1.f) ? 1 : (md == 2.f) ? 2 : 3;
+    }
+    s_cls[threadIdx.x] = (unsigned char)v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int B = blockDim.x;
+    int cnt[5] = {0, 0, 0, 0, 0};
+    for (int r = 0; r < B; ++r) ++cnt[s_cls[r]];
+    int off[5], acc = 0;
+    for (int v = 0; v < 5; ++v) { off[v] = acc; acc += cnt[v]; }
+    for (int r = 0; r < B; ++r) s_perm[off[s_cls[r]]++] = r;
+  }
+  __syncthreads();
+  return s_perm[threadIdx.x];
+}
+
 #define PSTL_STREAM_BLOCK_MAX 192
 
 template <bool SMEM_SCENE, int MINB>
@@ -577,8 +604,11 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
   const int n0 = blockIdx.x * B;
   // rows of the pipeline cycle through the three formulas (n % 3): deal them to warps so that a warp
   // evaluates ONE plan (a divergence optimisation only; every thread still reads its own mode)
+  __shared__ int s_perm[PSTL_STREAM_BLOCK_MAX];
   int li = threadIdx.x;
-  if (B % 96 == 0) {
+  if (!SMEM_SCENE) {
+    li = stream_sort_rows_by_mode(a.mode, n0, a.N, s_perm);
+  } else if (B % 96 == 0) {
     const int g = li / 96, w = li - g * 96;
     li = g * 96 + (w & 31) * 3 + (w >> 5);
   }
@@ -691,8 +721,11 @@ k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   const PstlEvalCfg c = a.cfg;
   const int B = blockDim.x, T = c.T;
   const int n0 = blockIdx.x * B;
+  __shared__ int s_perm[PSTL_STREAM_BLOCK_MAX];
   int li = threadIdx.x;
-  if (B % 96 == 0) {
+  if (!SMEM_SCENE) {
+    li = stream_sort_rows_by_mode(a.mode, n0, a.N, s_perm);
+  } else if (B % 96 == 0) {
     const int g = li / 96, w = li - g * 96;
     li = g * 96 + (w & 31) * 3 + (w >> 5);
   }
