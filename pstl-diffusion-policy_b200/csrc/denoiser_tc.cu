@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
   } else if (warp == kEpiWarps) {
     // ================= MMA issuer: the whole warp walks the protocol, one elected lane issues =================
     mbar_wait(bar_w, 0);
-    const uint32_t idh = make_idesc(kTileM, kH / 2), id3 = make_idesc(kTileM, kN3);
+    const uint32_t idh = make_idesc(kTileM, kH / 2), id256 = make_idesc(kTileM, kH), id3 = make_idesc(kTileM, kN3);
     const uint64_t dW1 = make_desc(sbase + kOffW1);
     // Biases ride on the tensor pipe.  The X tile carries, in columns 48..63, a pair of ones at the row's
     // scene class; W1' columns 48..63 carry (hi, lo) bf16 halves of c_scene[scene0+class] + c_t[step], rewritten
@@ -408,14 +408,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         if (elect_one()) {
           // the bias of half 1 goes first: it is the last reader of X, which E2 (after d2[0]) overwrites
           mma_ts(tmem + kColD + 128, tmem + kColX + 24, dB2 + (uint64_t)256, idh, 0);
+          // K-steps 8..15 (the half of H1 that just arrived) go out at full width, N = 256: both column halves in one
+          // issue (149 cycles against 2 x 84); column half 0 is then complete
 #pragma unroll
           for (int k = 8; k < 16; ++k) {
             const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)((k & 3) * 2);
-            mma_ts(tmem + kColD, tmem + kColH1 + k * 8, dB, idh, 1);
+            mma_ts(tmem + kColD, tmem + kColH1 + k * 8, dB, id256, 1);
           }
           tc_commit(bar_d2);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
+          for (int k = 0; k < 8; ++k) {
             const uint64_t dB = make_desc(sbase + kOffW2 + (k >> 2) * (256 * 128)) + (uint64_t)(1024 + (k & 3) * 2);
             mma_ts(tmem + kColD + 128, tmem + kColH1 + k * 8, dB, idh, 1);
           }
