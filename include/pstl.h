@@ -267,6 +267,36 @@ int pstl_trajopt_step(pstl_program_t const* progs, const pstl_scene_view* scenes
 int pstl_diversity(const float* trajs, const float* scores, const float* valids, int n_scenes, int m, int nt,
                    float* std_out, float* vol_out, pstl_stream_t stream);
 
+/* RefineNet training losses, value and gradient (compute_policy_loss, nusc_train.py:411 loss_stl, :439-466 the
+ * --diverse_loss branch, :468-478 the plain branch).  Rows n = (scene*S + sample)*3 + mode as everywhere.
+ *   loss_stl = stl_weight * mask_mean(relu(stl_nn_thres - scores), valid)
+ *   diverse_loss:  groups of G = S/n_shards samples of one (scene, mode) (reshape/permute of :443, G <= 32);
+ *                  sim = exp(-diversity_scale * ||s_i - s_j||) on controls / [w_max, a_max];
+ *                  q = exp(score)[score>0]  (diverse_detach: [score>0], no gradient);
+ *                  loss_diversity = -diversity_weight * mean_g tr(I - (Q sim Q + I)^-1);
+ *                  loss_reg = mask_mean((rect - nn)^2, score >= 0)   (reported unweighted, as upstream);
+ *                  loss = loss_stl + rect_reg_loss * loss_reg + loss_diversity
+ *   otherwise:     loss_reg = rect_reg_loss * (mean(((rect-nn)[...,0]/w_max)^2) + mean(((rect-nn)[...,1]/a_max)^2));
+ *                  extra_loss_reg = extra_rect_reg * (mean(relu((rect[...,0]/w_max)^2 - 1)) + the same for a_max);
+ *                  loss = loss_stl + loss_reg + extra_loss_reg
+ * losses[PSTL_LOSS_N]: see the enum.  d_rect (N, 2*nt) / d_scores (N) receive d loss / d rect_controls (with scores
+ * held fixed) and d loss / d scores — chain d_scores through pstl_score_fused_bwd for the full gradient; both NULL for
+ * the value only.  nn_controls is a constant (upstream detaches it).  Sums are reduced in a fixed order in fp64. */
+typedef struct {
+  int n_scenes, S, nt, n_shards;
+  int diverse_loss, diverse_detach;
+  float w_max, a_max;
+  float stl_nn_thres, stl_weight;
+  float diversity_scale, diversity_weight;
+  float rect_reg_loss, extra_rect_reg;
+} pstl_loss_cfg;
+enum { PSTL_LOSS_TOTAL = 0, PSTL_LOSS_STL = 1, PSTL_LOSS_REG = 2, PSTL_LOSS_DIVERSITY = 3, PSTL_LOSS_EXTRA_REG = 4,
+       PSTL_LOSS_MEAN_VALID = 5, PSTL_LOSS_MEAN_NONNEG = 6, PSTL_LOSS_N = 8 };
+size_t pstl_refine_losses_workspace_bytes(const pstl_loss_cfg* cfg);
+int pstl_refine_losses(const pstl_loss_cfg* cfg, const float* rect_controls, const float* nn_controls,
+                       const float* scores, const float* valid, float* losses, float* d_rect, float* d_scores,
+                       void* workspace, pstl_stream_t stream);
+
 /* acc and scene_acc of the sampling test (mask_mean, nusc_train.py:23-27, 336-343) for scores / valid (n_scenes*S*3) with
  * rows n = (scene*S + sample)*3 + mode: out[0] = mean((score>0)*valid)/clip(mean(valid),1e-2); out[1] = the same for
  * (max over the samples of a (scene, mode)) > 0 with the scene's lane validity.  partial: n_scenes*4 floats of scratch. */

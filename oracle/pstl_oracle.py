@@ -492,3 +492,44 @@ def diversity(trajs, scores, valids, nt):
     n = max(int(val.sum()), 1)
     return std, vol, float((std * val).sum() / n), float((vol * val).sum() / n)
 
+
+
+def refine_losses(rect, nn, scores, valid, n_scenes, S, nt, n_shards=4, diverse_loss=True, diverse_detach=False,
+                  w_max=0.5, a_max=5.0, stl_nn_thres=0.0005, stl_weight=1.0, diversity_scale=1.0,
+                  diversity_weight=1.0, rect_reg_loss=0.0, extra_rect_reg=0.0):
+    """The RefineNet training losses of compute_policy_loss (nusc_train.py:411 loss_stl; :439-466 --diverse_loss:
+    DPP diversity over groups of S/n_shards samples + masked regulariser; :468-478 the plain branch), as differentiable
+    torch expressions of rect (N,nt,2) and scores (N,), rows n = (scene*S + sample)*3 + mode.  nn is a constant.
+    Returns a dict with loss, loss_stl, loss_reg, loss_diversity, extra_loss_reg."""
+    N = n_scenes * S * 3
+    rect = rect.reshape(N, nt, 2)
+    nn = nn.reshape(N, nt, 2).detach()
+    lim = torch.tensor([w_max, a_max], dtype=rect.dtype)
+    out = {}
+    out["loss_stl"] = mask_mean(torch.relu(stl_nn_thres - scores), valid) * stl_weight
+    zero = out["loss_stl"] * 0
+    if diverse_loss:
+        G = S // n_shards
+        # (scene, sample, mode) -> (scene, mode, shard) groups of G consecutive samples
+        u = (rect / lim).reshape(n_scenes, S, 3, nt * 2).transpose(1, 2).reshape(n_scenes * 3 * n_shards, G, nt * 2)
+        qual = scores.reshape(n_scenes, S, 3).transpose(1, 2).reshape(n_scenes * 3 * n_shards, G)
+        gap = (u.unsqueeze(2) - u.unsqueeze(1)).norm(dim=-1)
+        kern = torch.exp(-diversity_scale * gap)
+        pos = (qual > 0).to(rect.dtype)
+        q = pos.detach() if diverse_detach else torch.exp(qual) * pos
+        L = q.unsqueeze(2) * kern * q.unsqueeze(1)
+        eye = torch.eye(G, dtype=rect.dtype).unsqueeze(0)
+        div = (eye - torch.linalg.inv(L + eye)).diagonal(dim1=1, dim2=2).sum(1)
+        out["loss_diversity"] = -div.mean() * diversity_weight
+        keep = (scores.reshape(N, 1, 1) >= 0).to(rect.dtype)
+        out["loss_reg"] = ((rect - nn) ** 2 * keep).mean() / torch.clip(keep.mean(), 1e-2)
+        out["extra_loss_reg"] = zero
+        out["loss"] = out["loss_stl"] + out["loss_reg"] * rect_reg_loss + out["loss_diversity"]
+    else:
+        d = (rect - nn) / lim
+        out["loss_reg"] = ((d[..., 0] ** 2).mean() + (d[..., 1] ** 2).mean()) * rect_reg_loss
+        v = (rect / lim) ** 2 - 1
+        out["extra_loss_reg"] = (torch.relu(v[..., 0]).mean() + torch.relu(v[..., 1]).mean()) * extra_rect_reg
+        out["loss_diversity"] = zero
+        out["loss"] = out["loss_stl"] + out["loss_reg"] + out["extra_loss_reg"]
+    return out

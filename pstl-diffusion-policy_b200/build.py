@@ -23,6 +23,7 @@ UNITS = {
     "mlp_fp32.cu": [],
     "denoiser_tc.cu": [],
     "metrics.cu": [],
+    "losses.cu": [],
 }
 
 

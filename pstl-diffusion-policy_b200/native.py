@@ -24,6 +24,7 @@ EXPORTS = [
     "pstl_denoiser_create", "pstl_denoiser_destroy", "pstl_denoiser_workspace_bytes", "pstl_denoiser_sample",
     "pstl_denoiser_eps", "pstl_denoiser_set_noise_counter", "pstl_launch_count", "pstl_refine", "pstl_rollout", "pstl_rollout_bwd", "pstl_predicates", "pstl_linear", "pstl_encoder_inputs",
     "pstl_encoder_pool", "pstl_mlp3", "pstl_mlp3_batch", "pstl_trajopt_step", "pstl_diversity", "pstl_accuracy",
+    "pstl_refine_losses_workspace_bytes", "pstl_refine_losses",
 ]
 
 
@@ -60,6 +61,15 @@ class Mlp3Problem(C.Structure):
                [(f, C.c_int) for f in ("M", "in_dim", "hidden", "out_dim")]
 
 
+class LossCfg(C.Structure):
+    _fields_ = [(f, C.c_int) for f in ("n_scenes", "S", "nt", "n_shards", "diverse_loss", "diverse_detach")] + \
+               [(f, C.c_float) for f in ("w_max", "a_max", "stl_nn_thres", "stl_weight", "diversity_scale",
+                                         "diversity_weight", "rect_reg_loss", "extra_rect_reg")]
+
+
+LOSS_KEYS = ("loss", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg")
+
+
 class GuidanceCfg(C.Structure):
     _fields_ = [("valid", C.c_void_p), ("state0", C.c_void_p), ("progs", C.POINTER(C.c_void_p)),
                 ("scenes", C.POINTER(SceneView)), ("sp", C.POINTER(SpecParams)), ("before", C.c_int),
@@ -84,7 +94,8 @@ def lib():
         raise PstlNativeError("cannot load %s: %s" % (LIB_PATH, e))
     L.pstl_last_error.restype = C.c_char_p
     L.pstl_launch_count.restype = C.c_ulonglong
-    for name in ("pstl_stl_workspace_bytes", "pstl_score_workspace_bytes", "pstl_denoiser_workspace_bytes"):
+    for name in ("pstl_stl_workspace_bytes", "pstl_score_workspace_bytes", "pstl_denoiser_workspace_bytes",
+                 "pstl_refine_losses_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
     _lib = L
     return L

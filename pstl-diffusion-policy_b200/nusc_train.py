@@ -563,6 +563,118 @@ def compute_stl_dense(stl_input, stls_cac, stl_idx, mask, args, debug=False, tj_
 
 
 # ---------------------------------------------------------------------------------------
+# training losses of the RefineNet step (reference :370-478, diffusion + rect_head branch)
+# ---------------------------------------------------------------------------------------
+
+class _RefineLosses(torch.autograd.Function):
+    """(loss, terms) = pstl_refine_losses(rect_controls, scores); the kernel returns d loss / d rect_controls and
+    d loss / d scores with the value, backward scales them by the incoming gradient of ``loss``.  ``terms``
+    (loss_stl, loss_reg, loss_diversity, extra_loss_reg, ...) are reported values, not differentiable."""
+
+    @staticmethod
+    def forward(ctx, rect, scores, nn_controls, valid, cfg):
+        _nv.require_cuda(rect, "rect_controls")
+        r, n = _nv.f32(rect.reshape(rect.shape[0], -1)), _nv.f32(nn_controls.reshape(rect.shape[0], -1))
+        sc, vl = _nv.f32(scores.reshape(-1)), _nv.f32(valid.reshape(-1))
+        assert r.shape[0] == cfg.n_scenes * cfg.S * 3 == sc.shape[0] == vl.shape[0] and r.shape[1] == 2 * cfg.nt
+        L = _nv.lib()
+        losses = torch.empty((8,), dtype=torch.float32, device=rect.device)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_rect = torch.empty_like(r) if need else None
+        d_sc = torch.empty_like(sc) if need else None
+        ws = _nv.workspace(L.pstl_refine_losses_workspace_bytes(_nv.C.byref(cfg)), rect.device, "losses")
+        _nv.check(L.pstl_refine_losses(_nv.C.byref(cfg), _nv.fptr(r), _nv.fptr(n), _nv.fptr(sc), _nv.fptr(vl),
+                                       _nv.fptr(losses), _nv.fptr(d_rect), _nv.fptr(d_sc), _nv.ptr(ws), _nv.stream()),
+                  "pstl_refine_losses")
+        ctx.grads = (d_rect, d_sc, rect.shape, scores.shape)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g, _g_terms):
+        d_rect, d_sc, rs, ss = ctx.grads
+        return ((g * d_rect).reshape(rs) if ctx.needs_input_grad[0] else None,
+                (g * d_sc).reshape(ss) if ctx.needs_input_grad[1] else None, None, None, None)
+
+
+def loss_cfg(args, bs, S=None):
+    """pstl_loss_cfg from the parsed flags."""
+    return _nv.LossCfg(n_scenes=bs, S=S or args.n_randoms, nt=args.nt, n_shards=args.n_shards,
+                       diverse_loss=int(bool(args.diverse_loss)), diverse_detach=int(bool(args.diverse_detach)),
+                       w_max=args.mul_w_max, a_max=args.mul_a_max, stl_nn_thres=args.stl_nn_thres,
+                       stl_weight=args.stl_weight, diversity_scale=args.diversity_scale,
+                       diversity_weight=args.diversity_weight, rect_reg_loss=args.rect_reg_loss,
+                       extra_rect_reg=(args.extra_rect_reg or 0.0))
+
+
+def evaluate_all_scores(scores, gt_labels, valid_mask, n_randoms):
+    """reference :347-368: the per-scene score vectors grouped by in-label / out-of-label lane."""
+    names = ("curr", "left", "right")
+    keys = ["in_label_scores", "out_label_scores"] + ["%s_label_%s_scores" % (io, n) for io in ("in", "out") for n in names]
+    res = {k: [] for k in keys}
+    bs = gt_labels.shape[0]
+    # one device->host copy of the small label / validity tables and one unbind for the (scene, mode) score vectors
+    rows = scores.detach().reshape(bs, n_randoms, 3).permute(0, 2, 1).reshape(bs * 3, n_randoms).unbind(0)
+    vm = valid_mask.reshape(bs, n_randoms, 3)[:, 0].tolist()
+    lab = gt_labels.reshape(bs, -1)[:, 0].tolist()
+    for i in range(bs):
+        if lab[i] < 3:
+            for j in range(3):
+                if vm[i][j] > 0:
+                    io = "in" if lab[i] == j else "out"
+                    res["%s_label_scores" % io].append(rows[i * 3 + j])
+                    res["%s_label_%s_scores" % (io, names[j])].append(rows[i * 3 + j])
+    return res
+
+
+def compute_policy_loss(batch_cuda, nn_stlp, stls_cac, nn_trajs, rect_trajs, dense_trajs, args, diffusion_extras=None,
+                        vae_extras=None, dbgs_extras=None, bc_extras=None, nn_controls_adj=None,
+                        nn_controls_list_adj=None, opt_controls=None):
+    """The loss of one --diffusion training step (reference :370-478; the vae / bc / single-sample branches are not
+    built).  Scores of the trajectories that are trained (rect_trajs with --rect_head) come from the fused scoring
+    kernel; with --rect_head every loss term and its gradient w.r.t. rect_controls and the scores come from ONE native
+    call (pstl_refine_losses) instead of the ~40 autograd nodes upstream records.  Returns (rd, all_scores)."""
+    if diffusion_extras is None or vae_extras is not None or bc_extras is not None:
+        raise NotImplementedError("compute_policy_loss: only the diffusion branch is built")
+    _check_supported(args)
+    bs = batch_cuda["ego_traj"].shape[0]
+    S = args.n_randoms
+    self_trajs = rect_trajs if args.rect_head else nn_trajs
+    noised_a, est_cmds_a, highlevel_dense, dense_scores, dense_valids, epi, raw_noise, nn_controls, steps, rect_controls = \
+        diffusion_extras
+    rd = {"avg_speed": torch.mean(self_trajs[..., :-1, 3]), "avg_speed_gt": torch.mean(batch_cuda["ego_traj"][..., 3])}
+    stl_input = pre_prepare_stl_cache(batch_cuda, dense_trajs=self_trajs[:, :-1])
+    valid_mask = batch_cuda["valids_dense"].reshape(-1)
+    _, scores, acc = compute_stl_dense(stl_input, stls_cac, batch_cuda["highlevel_dense"], valid_mask, args)
+    stl_input_gt = {"ego_traj": batch_cuda["ego_traj"], "neighbors": batch_cuda["neighbor_trajs_aug"],
+                    "stlp": batch_cuda["stlp"]}
+    for k in ("currlane_wpts", "leftlane_wpts", "rightlane_wpts"):
+        stl_input_gt[k] = batch_cuda[k]
+    gt_hl = batch_cuda["gt_high_level"]
+    _, scores_gt, acc_gt = compute_stl_dense(stl_input_gt, stls_cac, gt_hl, (gt_hl[:, 0] != 3).float(), args)
+    all_scores = evaluate_all_scores(scores, gt_hl, valid_mask, S)
+    rd.update(acc=acc, acc_gt=acc_gt, scores=scores, scores_all=scores, scores_gt=scores_gt, scores_gt_all=scores_gt)
+    if getattr(args, "stl_bc_mask", False):
+        m = (dense_scores * dense_valids > 0).float().reshape(bs * S * 3, 1)
+        rd["loss_diffusion"] = mask_mean(torch.square(raw_noise - est_cmds_a), m)
+    else:
+        rd["loss_diffusion"] = torch.mean(torch.square(raw_noise - est_cmds_a))
+    if args.rect_head:
+        loss, terms = _RefineLosses.apply(rect_controls, scores, nn_controls.detach(), valid_mask, loss_cfg(args, bs, S))
+        rd["loss"], rd["loss_stl"], rd["loss_reg"] = loss, terms[1], terms[2]
+        rd["loss_coll"] = terms[1] * 0
+        if args.diverse_loss:
+            rd["loss_diversity"] = terms[3]
+        else:
+            rd["extra_loss_reg"] = terms[4]
+    else:
+        rd["loss_stl"] = mask_mean(torch.relu(args.stl_nn_thres - scores), valid_mask) * args.stl_weight
+        rd["loss_coll"] = rd["loss_stl"] * 0
+        rd["loss"] = rd["loss_stl"] + rd["loss_diffusion"] + rd["loss_coll"]
+    return rd, all_scores
+
+
+# ---------------------------------------------------------------------------------------
 # sampler (reference :528-655)
 # ---------------------------------------------------------------------------------------
 

@@ -2,6 +2,7 @@
    python tests/bench_configs.py guidance [scenes]     # config 3 shape: K=10, guidance last 10 steps, n_rolls 3
    python tests/bench_configs.py dense [n] [T] [Knei]  # config 1/5 shape: compute_stl_dense on dense rows
    python tests/bench_configs.py trajopt [scenes] [iters]  # trajectory-optimisation iterations
+   python tests/bench_configs.py losses [scenes]       # RefineNet training losses, value + gradient (§8(f) item 4)
 """
 import os
 import sys
@@ -93,8 +94,60 @@ def trajopt(scenes, iters):
           % (scenes, n, iters, ms, ms / iters, n * iters / ms * 1e3))
 
 
+def losses(scenes):
+    """compute_policy_loss of the --rect_head --diverse_loss step (nusc_train.py:370-478): rollout -> scores -> loss
+    terms and the gradient w.r.t. rect_controls, against the CPU oracle's autograd on a slice"""
+    from oracle import pstl_oracle as O
+    args = NT.default_args(stl_weight=0.5, rect_reg_loss=0.1)
+    S = args.n_randoms
+    b = {k: v.cuda() for k, v in synthetic.make_scene_batch(scenes, seed=5).items()}
+    nb = NT.LazyBatch(dict(b))
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    nb = NT.augment_batch_data(nb, b["pre_stlp"].reshape(scenes, S, 3, 6)[:, 0, 0], args)
+    stls = NT.build_stl_cache(args)
+    N = scenes * S * 3
+    states = b["ego_traj"][:, 0, :4].unsqueeze(1).repeat(1, S * 3, 1).reshape(N, 4)
+    nn = nb["params"].reshape(N, args.nt, 2).contiguous()
+    rect = (nn + 0.02 * torch.randn_like(nn)).requires_grad_()
+    zeros = torch.zeros(N, args.nt * 2, device="cuda")
+    nn_trajs = NT.generate_trajs(states, nn, args.dt)
+
+    def step():
+        rect.grad = None
+        rt = NT.generate_trajs(states, rect, args.dt)
+        ex = (None, zeros, nb["highlevel_dense"], zeros[:, 0], nb["valids_dense"].reshape(-1), 0, zeros, nn, None, rect)
+        rd, _ = NT.compute_policy_loss(nb, None, stls, nn_trajs, rt, None, args, diffusion_extras=ex)
+        rd["loss"].backward()
+        return rd
+
+    ms = timeit(step, reps=5, warm=2)
+    cfg = NT.loss_cfg(args, scenes, S)
+    sc, vl = step()["scores"].detach(), nb["valids_dense"].reshape(-1).float().contiguous()
+    r2, n2 = rect.detach().reshape(N, -1).contiguous(), nn.reshape(N, -1).contiguous()
+    out, dr, ds = torch.empty(8, device="cuda"), torch.empty_like(r2), torch.empty_like(sc)
+    L, C = NT._nv.lib(), NT._nv.C
+    ws = torch.empty(L.pstl_refine_losses_workspace_bytes(C.byref(cfg)), dtype=torch.uint8, device="cuda")
+    fp, st = NT._nv.fptr, NT._nv.stream()
+    k_ms = timeit(lambda: L.pstl_refine_losses(C.byref(cfg), fp(r2), fp(n2), fp(sc), fp(vl), fp(out), fp(dr), fp(ds),
+                                               NT._nv.ptr(ws), st), reps=20, warm=3)
+    sub = min(scenes, 64)
+    n_sub = sub * S * 3
+    rc, scc = r2[:n_sub].cpu().reshape(n_sub, args.nt, 2).requires_grad_(), sc[:n_sub].cpu().requires_grad_()
+    t0 = time.time()
+    o = O.refine_losses(rc, n2[:n_sub].cpu(), scc, vl[:n_sub].cpu(), n_scenes=sub, S=S, nt=args.nt, n_shards=args.n_shards,
+                        stl_weight=0.5, rect_reg_loss=0.1, stl_nn_thres=args.stl_nn_thres)
+    torch.autograd.grad(o["loss"], [rc, scc])
+    cpu_ms = (time.time() - t0) * 1e3 * scenes / sub
+    print("losses: scenes=%d rows=%d groups=%d  training-step loss fwd+bwd (rollout, scorer, loss kernel) %.3f ms; "
+          "pstl_refine_losses alone %.3f ms (%.3g groups/s); oracle autograd (loss terms only, %d threads, scaled from "
+          "%d scenes) %.1f ms" % (scenes, N, scenes * 3 * args.n_shards, ms, k_ms, scenes * 3 * args.n_shards / k_ms * 1e3,
+                                  torch.get_num_threads(), sub, cpu_ms))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "sweep":
+    if sys.argv[1] == "losses":
+        losses(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
+    elif sys.argv[1] == "sweep":
         sweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 512)
     elif sys.argv[1] == "trajopt":
         trajopt(int(sys.argv[2]) if len(sys.argv) > 2 else 256, int(sys.argv[3]) if len(sys.argv) > 3 else 100)

@@ -225,6 +225,100 @@ def gen_trajopt(iters=15, bs=2, S=16, seed=2003):
     print("trajopt:", len(out), "arrays; loss", out["loss|0"], "->", out["loss|%d" % (iters - 1)])
 
 
+TRAIN_FLAGS = ["-e", "e7_ours", "--diffusion", "--load_stlp", "--rect_head", "--flex", "--multi_cands", "5",
+               "--skip_nusc_load"]  # README "Ours" training command minus the loss switches varied below
+LOSS_VARIANTS = {
+    "ours": ["--stl_weight", "0.0", "--diverse_loss"],
+    "weighted": ["--stl_weight", "0.7", "--diverse_loss", "--rect_reg_loss", "0.3", "--diversity_scale", "0.8",
+                 "--diversity_weight", "1.5", "--stl_nn_thres", "0.05"],
+    "detach": ["--stl_weight", "0.5", "--diverse_loss", "--diverse_detach", "--rect_reg_loss", "0.2", "--n_shards", "2"],
+    "plain": ["--stl_weight", "0.5", "--rect_reg_loss", "0.4", "--extra_rect_reg", "0.6"],
+}
+
+
+def gen_losses(bs=3, S=16, seed=2005, warm_iters=120):
+    """compute_policy_loss (nusc_train.py:370-478) of the --rect_head training step on one synthetic batch, for the
+    README flags and three variants: the loss terms, the scores it derived, d loss / d rect_controls (total, through
+    the STL scores), the same with the trajectories detached (the direct part) and d loss / d scores.  The controls
+    come out of a short run of the reference's own traj-opt so that a fair share of the rows satisfies its formula."""
+    out = {}
+    T, args = ref_shim.load(TRAJOPT_FLAGS + ["--n_randoms", str(S), "--trajopt_lr", "0.03"])
+    nt = args.nt
+    batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=seed)
+    out["in_checksum"] = np.array([checksum(batch[k]) for k in sorted(batch)])
+    N = bs * S * 3
+
+    def prepare(T, args):
+        b = {k: v.clone() for k, v in batch.items()}
+        b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+        gt_stlp = b["pre_stlp"].reshape(bs, S, 3, 6)[:, 0, 0]
+        b = T.augment_batch_data(b, gt_stlp, args)
+        st = b["ego_traj"][:, 0, :4]
+        return b, st.unsqueeze(1).unsqueeze(1).repeat(1, S, 3, 1)
+
+    real_md = T.napi.measure_diversity
+    z = torch.zeros(())
+    T.napi.measure_diversity = lambda *a, **k: (z, z, [np.zeros(1)], [np.zeros(1)])
+    try:
+        b, dense_states = prepare(T, args)
+        stls = T.build_stl_cache(args)
+        params = b["params"].clone().requires_grad_()
+        opt = torch.optim.Adam([params], lr=args.trajopt_lr)
+        for ii in range(warm_iters):
+            trajs = T.generate_trajs(dense_states, params, args.dt)
+            res = T.compute_trajopt_loss_lite(params, trajs, stls, T.pre_prepare_stl_cache(b), ii, warm_iters)
+            opt.zero_grad()
+            res[0].backward()
+            opt.step()
+        nn_controls = params.detach().reshape(N, nt, 2).clone()
+        g = torch.Generator().manual_seed(seed)
+        lim = torch.tensor([args.mul_w_max, args.mul_a_max])
+        rect0 = nn_controls + 0.05 * lim * torch.randn(N, nt, 2, generator=g)
+        rect0[::7] *= 1.6  # some rows leave the control box
+        out["nn_controls"] = nn_controls.numpy()
+        out["rect_controls"] = rect0.numpy()
+        for tag, extra in LOSS_VARIANTS.items():
+            T, args = ref_shim.load(TRAIN_FLAGS + extra + ["--n_randoms", str(S)])
+            b, dense_states = prepare(T, args)
+            flat_states = dense_states.reshape(N, 4)
+            stls = T.build_stl_cache(args)
+            nn_trajs = T.generate_trajs(flat_states, nn_controls, args.dt)
+            zeros = torch.zeros(N, nt * 2)
+
+            def run(detach_trajs):
+                rect = rect0.clone().requires_grad_()
+                rect_trajs = T.generate_trajs(flat_states, rect, args.dt)
+                if detach_trajs:
+                    rect_trajs = rect_trajs.detach()
+                extras = (None, zeros, b["highlevel_dense"], torch.zeros(N), b["valids_dense"].reshape(-1), 0, zeros,
+                          nn_controls, None, rect)
+                rd, _ = T.compute_policy_loss(b, None, stls, nn_trajs, rect_trajs, None, args, diffusion_extras=extras)
+                return rect, rd
+
+            rect, rd = run(False)
+            gs = [rect] + ([rd["scores"]] if rd["scores"].requires_grad else [])
+            grads = torch.autograd.grad(rd["loss"], gs, allow_unused=True)
+            out[tag + "|scores"] = rd["scores"].detach().numpy()
+            out[tag + "|losses"] = np.array([float(rd[k].detach()) if k in rd else np.nan for k in
+                                             ("loss", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg")])
+            out[tag + "|grad_total"] = grads[0].numpy()
+            out[tag + "|grad_scores"] = (grads[1] if len(grads) > 1 and grads[1] is not None else torch.zeros(N)).numpy()
+            rect, rd = run(True)
+            (gd,) = torch.autograd.grad(rd["loss"], [rect], allow_unused=True)
+            out[tag + "|grad_direct"] = (gd if gd is not None else torch.zeros_like(rect)).numpy()
+            out[tag + "|hyper"] = np.array([args.stl_nn_thres, args.stl_weight, args.diversity_scale,
+                                            args.diversity_weight, args.rect_reg_loss, args.extra_rect_reg or 0.0,
+                                            args.n_shards, int(args.diverse_loss), int(args.diverse_detach),
+                                            args.mul_w_max, args.mul_a_max])
+            print("losses[%s]:" % tag, out[tag + "|losses"], "accepted %.2f" % float((rd["scores"] > 0).float().mean()))
+    finally:
+        T.napi.measure_diversity = real_md
+    out["valid"] = b["valids_dense"].reshape(-1).numpy()
+    out["shape"] = np.array([bs, S, nt])
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
+    print("losses:", len(out), "arrays")
+
+
 def metric_inputs(bs=5, m=16, nt=20, seed=2004):
     """trajectories / scores / validity for the diversity metrics: rollouts of the synthetic parameter bank, a random
     accept pattern that includes a lane with nothing accepted, one with two samples and one with collinear samples"""
@@ -278,6 +372,7 @@ def main():
     gen_pipeline()
     gen_trajopt()
     gen_metrics()
+    gen_losses()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -791,3 +791,131 @@ def test_full_size_pipeline_properties(name, scenes, flags, over):
         assert torch.equal(out["controls"][sat], out["best_controls"][sat])
     acc_ref = NT.mask_mean((out["scores"] > 0).float(), pack.valid)
     close(out["acc"], acc_ref, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# §8(f)4: RefineNet training losses (compute_policy_loss, nusc_train.py:370-478)
+# ------------------------------------------------------------------------------------------
+LOSS_TAGS = ("ours", "weighted", "detach", "plain")
+
+
+def _loss_cfg(kw):
+    return native.LossCfg(n_scenes=kw["n_scenes"], S=kw["S"], nt=kw["nt"], n_shards=kw["n_shards"],
+                          diverse_loss=int(kw["diverse_loss"]), diverse_detach=int(kw["diverse_detach"]),
+                          w_max=kw["w_max"], a_max=kw["a_max"], stl_nn_thres=kw["stl_nn_thres"],
+                          stl_weight=kw["stl_weight"], diversity_scale=kw["diversity_scale"],
+                          diversity_weight=kw["diversity_weight"], rect_reg_loss=kw["rect_reg_loss"],
+                          extra_rect_reg=kw["extra_rect_reg"])
+
+
+def _refine_losses_native(cfg, rect, nn, scores, valid, grads=True):
+    L = native.lib()
+    C = native.C
+    N = cfg.n_scenes * cfg.S * 3
+    r, n = rect.reshape(N, -1).contiguous(), nn.reshape(N, -1).contiguous()
+    losses = torch.full((8,), float("nan"), device="cuda")
+    d_rect = torch.full_like(r, float("nan")) if grads else None
+    d_sc = torch.full((N,), float("nan"), device="cuda") if grads else None
+    ws = torch.empty(L.pstl_refine_losses_workspace_bytes(C.byref(cfg)), dtype=torch.uint8, device="cuda")
+    rc = L.pstl_refine_losses(C.byref(cfg), native.fptr(r), native.fptr(n), native.fptr(scores), native.fptr(valid),
+                              native.fptr(losses), native.fptr(d_rect), native.fptr(d_sc), native.ptr(ws), native.stream())
+    return rc, losses, d_rect, d_sc
+
+
+@pytest.mark.parametrize("tag", LOSS_TAGS)
+def test_refine_losses_golden(golden_dir, tag):
+    """pstl_refine_losses through the C-ABI against the reference's compute_policy_loss (tests/golden/losses.npz):
+    loss terms, d loss / d rect_controls at fixed scores, d loss / d scores"""
+    from test_oracle_golden import loss_kwargs, LOSS_KEYS
+    G = np.load(os.path.join(golden_dir, "losses.npz"))
+    kw = loss_kwargs(G, tag)
+    rect, nn = torch.from_numpy(G["rect_controls"]).cuda(), torch.from_numpy(G["nn_controls"]).cuda()
+    scores, valid = torch.from_numpy(G[tag + "|scores"]).cuda(), torch.from_numpy(G["valid"]).cuda()
+    rc, losses, d_rect, d_sc = _refine_losses_native(_loss_cfg(kw), rect, nn, scores, valid)
+    assert rc == 0, native.lib().pstl_last_error()
+    for i, k in enumerate(LOSS_KEYS):
+        if np.isfinite(G[tag + "|losses"][i]):
+            np.testing.assert_allclose(losses[i].item(), G[tag + "|losses"][i], rtol=2e-5, atol=1e-7, err_msg=k)
+    close(d_rect.reshape(rect.shape), G[tag + "|grad_direct"], rtol=2e-5, what="d_rect")
+    close(d_sc, G[tag + "|grad_scores"], rtol=2e-5, what="d_scores")
+    rc, l2, _, _ = _refine_losses_native(_loss_cfg(kw), rect, nn, scores, valid, grads=False)
+    assert rc == 0 and torch.equal(l2[:5], losses[:5])  # value-only call: same reduction, same bits
+
+
+@pytest.mark.parametrize("tag", LOSS_TAGS)
+def test_policy_loss_golden(golden_dir, tag):
+    """nusc_train.compute_policy_loss (rollout -> fused scorer -> loss kernel, and back) against the reference's
+    training-step loss and its total gradient w.r.t. rect_controls"""
+    from test_oracle_golden import loss_kwargs, LOSS_KEYS
+    G = np.load(os.path.join(golden_dir, "losses.npz"))
+    kw = loss_kwargs(G, tag)
+    bs, S_, nt = kw["n_scenes"], kw["S"], kw["nt"]
+    args = NT.default_args(n_randoms=S_, sampling_size=S_, n_shards=kw["n_shards"], diverse_loss=kw["diverse_loss"],
+                           diverse_detach=kw["diverse_detach"], stl_nn_thres=kw["stl_nn_thres"],
+                           stl_weight=kw["stl_weight"], diversity_scale=kw["diversity_scale"],
+                           diversity_weight=kw["diversity_weight"], rect_reg_loss=kw["rect_reg_loss"],
+                           extra_rect_reg=kw["extra_rect_reg"])
+    b = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=2005))
+    nb = NT.LazyBatch(dict(b))
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    gt_stlp = b["pre_stlp"].reshape(bs, S_, 3, 6)[:, 0, 0]
+    nb = NT.augment_batch_data(nb, gt_stlp, args)
+    stls = NT.build_stl_cache(args)
+    N = bs * S_ * 3
+    states = b["ego_traj"][:, 0, :4].unsqueeze(1).repeat(1, S_ * 3, 1).reshape(N, 4)
+    nn = torch.from_numpy(G["nn_controls"]).cuda()
+    rect = torch.from_numpy(G["rect_controls"]).cuda().requires_grad_()
+    nn_trajs = NT.generate_trajs(states, nn, args.dt)
+    rect_trajs = NT.generate_trajs(states, rect, args.dt)
+    zeros = torch.zeros(N, nt * 2, device="cuda")
+    extras = (None, zeros, nb["highlevel_dense"], torch.zeros(N, device="cuda"), nb["valids_dense"].reshape(-1), 0, zeros,
+              nn, None, rect)
+    rd, all_scores = NT.compute_policy_loss(nb, None, stls, nn_trajs, rect_trajs, None, args, diffusion_extras=extras)
+    close(rd["scores"], G[tag + "|scores"], what="scores")
+    for i, k in enumerate(LOSS_KEYS):
+        if np.isfinite(G[tag + "|losses"][i]):
+            np.testing.assert_allclose(float(rd[k].detach()), G[tag + "|losses"][i], rtol=5e-5, atol=2e-6, err_msg=k)
+    rd["loss"].backward()
+    close(rect.grad, G[tag + "|grad_total"], rtol=1e-4, what="grad_total")
+    assert set(all_scores) >= {"in_label_scores", "out_label_scores"}
+
+
+@pytest.mark.parametrize("bs,S_,n_shards,nt,diverse,detach", [(4, 64, 4, 20, 1, 0), (3, 64, 2, 20, 1, 0), (5, 8, 4, 12, 1, 1),
+                                                                (2, 32, 32, 20, 1, 0), (4, 64, 4, 20, 0, 0)])
+def test_refine_losses_oracle(bs, S_, n_shards, nt, diverse, detach):
+    """group sizes 1..32, other horizons: the loss kernel against the oracle's autograd on seeded inputs"""
+    g = torch.Generator().manual_seed(bs * 1000 + S_)
+    N = bs * S_ * 3
+    lim = torch.tensor([0.5, 5.0])
+    nn = (torch.rand(N, nt, 2, generator=g) * 2 - 1) * lim
+    rect = nn + 0.2 * lim * torch.randn(N, nt, 2, generator=g)
+    idx = torch.arange(0, N - 3, 33)
+    rect[idx + 3] = rect[idx]  # rows n and n+3 are consecutive samples of one (scene, mode): zero distances in a group
+    scores = torch.randn(N, generator=g) * 0.4
+    scores[::13] = 0.0
+    valid = (torch.rand(N, generator=g) > 0.2).float()
+    kw = dict(n_scenes=bs, S=S_, nt=nt, n_shards=n_shards, diverse_loss=bool(diverse), diverse_detach=bool(detach),
+              w_max=0.5, a_max=5.0, stl_nn_thres=0.05, stl_weight=0.6, diversity_scale=0.7, diversity_weight=1.3,
+              rect_reg_loss=0.25, extra_rect_reg=0.35)
+    r0, s0 = rect.clone().requires_grad_(), scores.clone().requires_grad_()
+    out = O.refine_losses(r0, nn, s0, valid, **kw)
+    g_rect, g_sc = torch.autograd.grad(out["loss"], [r0, s0], allow_unused=True)
+    rc, losses, d_rect, d_sc = _refine_losses_native(_loss_cfg(kw), rect.cuda(), nn.cuda(), scores.cuda(), valid.cuda())
+    assert rc == 0, native.lib().pstl_last_error()
+    for i, k in enumerate(("loss", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg")):
+        np.testing.assert_allclose(losses[i].item(), float(out[k].detach()), rtol=2e-5, atol=1e-7, err_msg=k)
+    close(d_rect.reshape(rect.shape), g_rect, rtol=5e-5, what="d_rect")
+    close(d_sc, g_sc if g_sc is not None else torch.zeros(N), rtol=5e-5, what="d_scores")
+
+
+def test_refine_losses_errors():
+    kw = dict(n_scenes=2, S=66, nt=20, n_shards=4, diverse_loss=True, diverse_detach=False, w_max=0.5, a_max=5.0,
+              stl_nn_thres=0.0, stl_weight=1.0, diversity_scale=1.0, diversity_weight=1.0, rect_reg_loss=0.0,
+              extra_rect_reg=0.0)
+    N = 2 * 66 * 3
+    z = torch.zeros(N, 40, device="cuda")
+    rc, *_ = _refine_losses_native(_loss_cfg(kw), z, z, z[:, 0].contiguous(), z[:, 0].contiguous())
+    assert rc != 0 and b"n_shards" in native.lib().pstl_last_error()
+    kw.update(S=66, n_shards=1)
+    rc, *_ = _refine_losses_native(_loss_cfg(kw), z, z, z[:, 0].contiguous(), z[:, 0].contiguous())
+    assert rc != 0 and b"at most 32" in native.lib().pstl_last_error()

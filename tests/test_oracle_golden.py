@@ -162,3 +162,32 @@ def test_diversity_metrics(golden_dir):
         np.testing.assert_allclose(float(ex[k]), G["extra|" + k], rtol=1e-5)
     ade, fde = M.compute_ade_fde(b["ego_traj"][..., :4], trajs[..., :-1, :4], valids)
     np.testing.assert_allclose([float(ade), float(fde)], G["ade_fde"], rtol=1e-6)
+
+
+LOSS_TAGS = ("ours", "weighted", "detach", "plain")
+LOSS_KEYS = ("loss", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg")
+
+
+def loss_kwargs(G, tag):
+    thres, stl_w, dscale, dweight, reg_w, extra_w, n_shards, diverse, detach, w_max, a_max = [float(v) for v in G[tag + "|hyper"]]
+    bs, S_, nt = [int(v) for v in G["shape"]]
+    return dict(n_scenes=bs, S=S_, nt=nt, n_shards=int(n_shards), diverse_loss=bool(diverse), diverse_detach=bool(detach),
+                w_max=w_max, a_max=a_max, stl_nn_thres=thres, stl_weight=stl_w, diversity_scale=dscale,
+                diversity_weight=dweight, rect_reg_loss=reg_w, extra_rect_reg=extra_w)
+
+
+@pytest.mark.parametrize("tag", LOSS_TAGS)
+def test_refine_losses(golden_dir, tag):
+    """oracle refine_losses == the reference's compute_policy_loss (nusc_train.py:370-478, --rect_head training step):
+    loss terms, d loss / d rect_controls with the scores held fixed, and d loss / d scores"""
+    G = np.load(os.path.join(golden_dir, "losses.npz"))
+    kw = loss_kwargs(G, tag)
+    rect = torch.from_numpy(G["rect_controls"]).requires_grad_()
+    scores = torch.from_numpy(G[tag + "|scores"]).requires_grad_()
+    out = O.refine_losses(rect, torch.from_numpy(G["nn_controls"]), scores, torch.from_numpy(G["valid"]), **kw)
+    for i, k in enumerate(LOSS_KEYS):
+        if np.isfinite(G[tag + "|losses"][i]):
+            np.testing.assert_allclose(float(out[k].detach()), G[tag + "|losses"][i], rtol=2e-5, atol=1e-7, err_msg=k)
+    g_rect, g_sc = torch.autograd.grad(out["loss"], [rect, scores], allow_unused=True)
+    close(g_rect.numpy(), G[tag + "|grad_direct"], rtol=2e-5)
+    close((g_sc if g_sc is not None else torch.zeros_like(scores)).numpy(), G[tag + "|grad_scores"], rtol=2e-5)
