@@ -267,6 +267,21 @@ int pstl_trajopt_step(pstl_program_t const* progs, const pstl_scene_view* scenes
 int pstl_diversity(const float* trajs, const float* scores, const float* valids, int n_scenes, int m, int nt,
                    float* std_out, float* vol_out, pstl_stream_t stream);
 
+/* RefineNet backward for the --rect_head training step (autograd over Net.rect_forward, nusc_model.py:182-235; the
+ * optimiser upstream holds net.rect_net.parameters() only, nusc_train.py:1228-1233): from d_out = d loss / d rect_controls
+ * (N, 2*nt) to the gradients of rect_net.{0,2,4}.{weight,bias} in the reference's own shapes (row-major (out, in):
+ * g_r0_w (H, feat+7+2*nt), g_r2_w (H, H), g_r4_w (2*nt, H)).  Same row / scene arguments as pstl_refine.  The call is
+ * stateless: it recomputes the fp32 activations in its workspace (whatever the handle's precision), so it pairs with a
+ * forward made on a PSTL_PRECISION_FP32 handle.  Reductions over the rows run as split-K tiles summed in a fixed
+ * order: results are deterministic.  merge_net and the scene encoders receive no gradient (not in upstream's optimiser
+ * without --joint). */
+size_t pstl_refine_backward_workspace_bytes(pstl_denoiser_t d, int N, int n_scenes);
+int pstl_refine_backward(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene, const float* hl,
+                         const float* stlp, const float* u0, const float* scores, int N, int n_randoms, int n_shards,
+                         float w_max, float a_max, int clip_rect, const float* d_out, float* g_r0_w, float* g_r0_b,
+                         float* g_r2_w, float* g_r2_b, float* g_r4_w, float* g_r4_b, void* workspace,
+                         pstl_stream_t stream);
+
 /* RefineNet training losses, value and gradient (compute_policy_loss, nusc_train.py:411 loss_stl, :439-466 the
  * --diverse_loss branch, :468-478 the plain branch).  Rows n = (scene*S + sample)*3 + mode as everywhere.
  *   loss_stl = stl_weight * mask_mean(relu(stl_nn_thres - scores), valid)

@@ -533,3 +533,32 @@ def refine_losses(rect, nn, scores, valid, n_scenes, S, nt, n_shards=4, diverse_
         out["loss_diversity"] = zero
         out["loss"] = out["loss_stl"] + out["loss_reg"] + out["extra_loss_reg"]
     return out
+
+
+def refine_train_step(W, b, feat_scene, nn_controls, dt, tau=100.0, **loss_kw):
+    """One --rect_head training step up to the gradients (nusc_train.py:1402-1405 rect_forward on the detached
+    controls and their scores, :1420-1427 rollout + compute_policy_loss, :1523-1525 backward; the optimiser holds
+    rect_net only, :1228-1233), pSTL parameters per chain (training layout, :742).  W: state_dict-keyed tensors; the six
+    rect_net tensors are made leaves.  Returns rect, grad_rect, losses, prev_scores and grads {key: tensor}."""
+    S, nt = loss_kw["S"], loss_kw["nt"]
+    bs = b["currlane_wpts"].shape[0]
+    m = S * 3
+    N = bs * m
+    dense = densify(b, S, nt)
+    dense["stlp"] = b["pre_stlp"].reshape(N, 1, 6)
+    keys = ["rect_net.%d.%s" % (li, k) for li in (0, 2, 4) for k in ("weight", "bias")]
+    W = dict(W)
+    for k in keys:
+        W[k] = W[k].detach().clone().requires_grad_()
+    nn_controls = nn_controls.reshape(N, nt, 2).detach()
+    with torch.no_grad():
+        prev_scores, _ = score_controls(dense, nn_controls, dt, tau)
+    feat = feat_scene.unsqueeze(1).repeat(1, m, 1).reshape(N, -1)
+    rect = refine(W, feat, dense["mode"].reshape(N, 1), dense["stlp"].reshape(N, 6), nn_controls, prev_scores,
+                  n_randoms=S, n_shards=loss_kw["n_shards"], nt=nt, w_max=loss_kw["w_max"], a_max=loss_kw["a_max"])
+    rect.retain_grad()
+    scores, _ = score_controls(dense, rect, dt, tau)
+    out = refine_losses(rect, nn_controls, scores, dense["dense_valids"].reshape(-1), **loss_kw)
+    out["loss"].backward()
+    return {"rect": rect.detach(), "grad_rect": rect.grad, "losses": out, "prev_scores": prev_scores,
+            "grads": {k: W[k].grad for k in keys}, "W": W}

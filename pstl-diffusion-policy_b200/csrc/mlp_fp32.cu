@@ -807,19 +807,9 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
   return PSTL_OK;
 }
 
-extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
-                           const float* hl, const float* stlp, const float* u0, const float* scores, int N,
-                           int n_randoms, int n_shards, float w_max, float a_max, int clip_rect, float* out,
-                           void* workspace, pstl_stream_t stream) {
-  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && u0 && scores && out && workspace, "null argument");
-  PSTL_CHECK_ARG(d->w.r0_w && d->w.m0_w && d->r1p, "handle was created without rect_net / merge_net weights");
-  PSTL_CHECK_ARG(n_shards > 0 && n_randoms % n_shards == 0 && N % (3 * n_randoms) == 0,
-                 "rows must be (scene, n_randoms, 3 modes) with n_shards | n_randoms");
-  if (N <= 0) return PSTL_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  DenoiserWs w;
-  size_t total;
-  carve(d, N, n_scenes, 1, nullptr, workspace, &w, &total);
+// RefineNet input stage: hoisted scene term of rect_net.0, merge_net + shard max-pool + fuse -> packed rows w.xin
+static int refine_inputs(pstl_denoiser_t d, const DenoiserWs& w, const float* scene_feat, int n_scenes, const float* hl,
+                         const float* stlp, const float* u0, int N, int n_randoms, int n_shards, cudaStream_t st) {
   const int H = d->w.rect_hidden, T2 = d->T2, MH = d->w.merge_hidden;
   const int inr = d->w.feat_dim + 7 + T2;
   int rc = hoist(d->w.r0_w, inr, d->w.r0_b, H, scene_feat, n_scenes, d->w.feat_dim, w.cscene, nullptr, 0, 0, 0, nullptr, st);
@@ -852,6 +842,26 @@ extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_sce
     k_group_fuse<<<pstl_ceil_div(gtot, 256), 256, 0, st>>>(w.g, u0, w.xin, N, T2, n_randoms, per);
     PSTL_LAUNCH_CHECK();
   }
+  return PSTL_OK;
+}
+
+extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                           const float* hl, const float* stlp, const float* u0, const float* scores, int N,
+                           int n_randoms, int n_shards, float w_max, float a_max, int clip_rect, float* out,
+                           void* workspace, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && u0 && scores && out && workspace, "null argument");
+  PSTL_CHECK_ARG(d->w.r0_w && d->w.m0_w && d->r1p, "handle was created without rect_net / merge_net weights");
+  PSTL_CHECK_ARG(n_shards > 0 && n_randoms % n_shards == 0 && N % (3 * n_randoms) == 0,
+                 "rows must be (scene, n_randoms, 3 modes) with n_shards | n_randoms");
+  if (N <= 0) return PSTL_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DenoiserWs w;
+  size_t total;
+  carve(d, N, n_scenes, 1, nullptr, workspace, &w, &total);
+  const int H = d->w.rect_hidden, T2 = d->T2;
+  int rc = refine_inputs(d, w, scene_feat, n_scenes, hl, stlp, u0, N, n_randoms, n_shards, st);
+  if (rc) return rc;
+  LinArgs a;
   if (d->precision == PSTL_PRECISION_BF16 && pstl_tc_has_refine(d) && (128 + rows_per_scene - 1) / rows_per_scene + 1 <= 8)
     return pstl_tc_refine(d, w.cscene, rows_per_scene, w.xin, N, u0, scores, w_max, a_max, clip_rect, out, st);
   rc = mlp_hidden(d, w, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st);
@@ -860,4 +870,277 @@ extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_sce
   a.X = w.h2; a.ldx = H; a.W = d->w.r4_w; a.ldw = H; a.bias = d->w.r4_b; a.Y = out; a.ldy = T2; a.M = N; a.K = H; a.Nout = T2;
   a.u0 = u0; a.scores = scores; a.w_max = w_max; a.a_max = a_max; a.clip = clip_rect;
   return launch_linear<EPI_REFINE>(a, st);
+}
+
+// --------------------------------------------------------------------------------------
+// RefineNet backward (the --rect_head training step; upstream: autograd over Net.rect_forward, nusc_model.py:182-235,
+// with Adam over net.rect_net.parameters() only, nusc_train.py:1228-1233): given d loss / d rect_controls, the
+// gradients of rect_net's three weight matrices and biases.  Activations are recomputed (stateless call); the weight
+// gradients dW = dY^T . X are reductions over the N rows, computed as split-K tiles with a fixed-order second pass
+// (deterministic); the 224 scene-feature columns of rect_net.0 reduce per scene first (dh1 summed over a scene's
+// rows, then a (n_scenes)-deep product) — the same hoisting the forward uses.
+// --------------------------------------------------------------------------------------
+
+// d out / d y of the interval head (nusc_model.py:212-232): y -> tanh -> rescale to the headroom -> [score<0] -> clip
+__global__ void __launch_bounds__(256) k_refine_dy(float* __restrict__ y, const float* __restrict__ u0,
+                                                   const float* __restrict__ scores, const float* __restrict__ d_out,
+                                                   long long total, int T2, float w_max, float a_max, int clip) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const long long r = e / T2;
+  const int c = (int)(e - r * T2);
+  float g = 0.f;
+  if (scores[r] < 0.f) {
+    const float lim = (c & 1) ? a_max : w_max, init = u0[e];
+    const float rr = tanhf(y[e]);
+    const float dm = (rr >= 0.f) ? (lim - init) : (init - (-lim));
+    const float o = init + rr * dm;
+    const bool outside = clip && (o < -lim || o > lim);
+    if (!outside) g = d_out[e] * dm * (1.f - rr * rr);
+  }
+  y[e] = g;
+}
+
+__global__ void __launch_bounds__(256) k_relu_mask(float* __restrict__ g, const float* __restrict__ h, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 gv = reinterpret_cast<float4*>(g)[i];
+  const float4 hv = reinterpret_cast<const float4*>(h)[i];
+  gv.x = hv.x > 0.f ? gv.x : 0.f; gv.y = hv.y > 0.f ? gv.y : 0.f;
+  gv.z = hv.z > 0.f ? gv.z : 0.f; gv.w = hv.w > 0.f ? gv.w : 0.f;
+  reinterpret_cast<float4*>(g)[i] = gv;
+}
+
+__global__ void __launch_bounds__(256) k_transpose(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  Wt[(size_t)c * rows + r] = W[i];
+}
+
+// partial C[z] (Mo x No) = A[r0:r1]^T . B[r0:r1]; A (R, lda >= Mo), B (R, ldb >= No); 64 x 64 tile, 4 x 4 per thread
+#define WG_T 64
+#define WG_K 16
+__global__ void __launch_bounds__(256) k_wgrad(const float* __restrict__ A, int lda, int Mo, const float* __restrict__ B,
+                                               int ldb, int No, long long R, int rows_per_split, float* __restrict__ part) {
+  __shared__ __align__(16) float As[WG_K][WG_T + 4], Bs[WG_K][WG_T + 4];
+  const int tm = blockIdx.x * WG_T, tn = blockIdx.y * WG_T, tid = threadIdx.x;
+  const long long r0 = (long long)blockIdx.z * rows_per_split;
+  const long long r1 = (r0 + rows_per_split < R) ? r0 + rows_per_split : R;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;  // this thread's slab element: row lr, columns lc..lc+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  auto fetch = [&](const float* __restrict__ P, int ld, int ncols, int c0, long long row) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < r1) {
+      const float* q = P + row * ld + c0;
+      if (c0 + 3 < ncols && (ld & 3) == 0) v = *reinterpret_cast<const float4*>(q);
+      else {
+        if (c0 < ncols) v.x = q[0];
+        if (c0 + 1 < ncols) v.y = q[1];
+        if (c0 + 2 < ncols) v.z = q[2];
+        if (c0 + 3 < ncols) v.w = q[3];
+      }
+    }
+    return v;
+  };
+  float4 na = fetch(A, lda, Mo, tm + lc, r0 + lr), nb = fetch(B, ldb, No, tn + lc, r0 + lr);
+  for (long long r = r0; r < r1; r += WG_K) {
+    *reinterpret_cast<float4*>(&As[lr][lc]) = na;
+    *reinterpret_cast<float4*>(&Bs[lr][lc]) = nb;
+    __syncthreads();
+    if (r + WG_K < r1) {  // next slab in flight while this one is multiplied
+      na = fetch(A, lda, Mo, tm + lc, r + WG_K + lr);
+      nb = fetch(B, ldb, No, tn + lc, r + WG_K + lr);
+    }
+#pragma unroll
+    for (int k = 0; k < WG_K; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = part + (size_t)blockIdx.z * Mo * No;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = tm + ty * 4 + i;
+    if (m >= Mo) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = tn + tx * 4 + j;
+      if (n < No) out[(size_t)m * No + n] = acc[i][j];
+    }
+  }
+}
+
+// column sums of A (R, lda) over a row range: part[z][m]
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int lda, int Mo, long long R,
+                                                int rows_per_split, float* __restrict__ part) {
+  const int m = threadIdx.x;
+  if (m >= Mo) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_split;
+  const long long r1 = (r0 + rows_per_split < R) ? r0 + rows_per_split : R;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += A[r * lda + m];
+  part[(size_t)blockIdx.x * Mo + m] = s;
+}
+
+// out[m * ldo + map(n)] = sum over the splits in order; xin_map: packed-row column order -> rect_net.0 column order
+__global__ void __launch_bounds__(256) k_split_reduce(const float* __restrict__ part, int splits, int Mo, int No,
+                                                      float* __restrict__ out, int ldo, int col0, int xin_T2, int xin_kin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Mo * No) return;
+  const int m = i / No, n = i - m * No;
+  int col = col0 + n;
+  if (xin_T2 > 0) {  // packed row = [fused (T2) | hl | stlp6 | pad]; weight columns = [.. | hl | stlp6 | fused (T2)]
+    if (n >= xin_kin) return;
+    col = col0 + (n < xin_T2 ? 7 + n : n - xin_T2);
+  }
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * Mo * No + i];
+  out[(size_t)m * ldo + col] = s;
+}
+
+// sum of a scene's rows: out[scene][h]
+__global__ void __launch_bounds__(256) k_scene_sum(const float* __restrict__ g, int H, int rows_per_scene, float* __restrict__ out) {
+  const int h = threadIdx.x;
+  if (h >= H) return;
+  const float* p = g + (size_t)blockIdx.x * rows_per_scene * H + h;
+  float s = 0.f;
+  for (int r = 0; r < rows_per_scene; ++r) s += p[(size_t)r * H];
+  out[(size_t)blockIdx.x * H + h] = s;
+}
+
+namespace {
+struct RefineBwdWs {
+  DenoiserWs base;
+  float *dh, *w4t, *w2t, *sdh, *part;
+  size_t part_floats;
+};
+
+const size_t kWgradPartFloats = (size_t)4 << 20;  // 16 MB of split-K partials
+
+void carve_bwd(pstl_denoiser_t d, int N, int n_scenes, void* ws, RefineBwdWs* o, size_t* total) {
+  size_t base_bytes;
+  carve(d, N, n_scenes, 1, nullptr, ws, &o->base, &base_bytes);
+  const int H = d->w.rect_hidden;
+  float* p = ws ? (float*)((char*)ws + base_bytes) : nullptr;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* r = p ? p + off : nullptr; off += pstl_align_floats(n); return r; };
+  o->dh = take((size_t)N * H);
+  o->w4t = take((size_t)H * d->T2);
+  o->w2t = take((size_t)H * H);
+  o->sdh = take((size_t)n_scenes * H);
+  o->part = take(kWgradPartFloats);
+  o->part_floats = kWgradPartFloats;
+  *total = base_bytes + off * sizeof(float);
+}
+
+// C (Mo x No, written at out[m*ldo + col0 + n]) = A^T B over R rows
+int wgrad(const float* A, int lda, int Mo, const float* B, int ldb, int No, long long R, float* part, size_t part_floats,
+          float* out, int ldo, int col0, int xin_T2, int xin_kin, cudaStream_t st) {
+  const int tiles = pstl_ceil_div(Mo, WG_T) * pstl_ceil_div(No, WG_T);
+  long long splits = (148 * 4 + tiles - 1) / tiles;
+  const long long max_by_rows = (R + 255) / 256, max_by_ws = (long long)(part_floats / ((size_t)Mo * No));
+  if (splits > max_by_rows) splits = max_by_rows;
+  if (splits > max_by_ws) splits = max_by_ws;
+  if (splits < 1) splits = 1;
+  int rows_per_split = (int)((R + splits - 1) / splits);
+  rows_per_split = (rows_per_split + WG_K - 1) / WG_K * WG_K;
+  splits = (R + rows_per_split - 1) / rows_per_split;
+  dim3 grid(pstl_ceil_div(Mo, WG_T), pstl_ceil_div(No, WG_T), (unsigned)splits);
+  k_wgrad<<<grid, 256, 0, st>>>(A, lda, Mo, B, ldb, No, R, rows_per_split, part);
+  PSTL_LAUNCH_CHECK();
+  k_split_reduce<<<pstl_ceil_div(Mo * No, 256), 256, 0, st>>>(part, (int)splits, Mo, No, out, ldo, col0, xin_T2, xin_kin);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
+int colsum(const float* A, int lda, int Mo, long long R, float* part, float* out, cudaStream_t st) {
+  long long splits = (R + 255) / 256;
+  if (splits > 592) splits = 592;
+  const int rows_per_split = (int)((R + splits - 1) / splits);
+  splits = (R + rows_per_split - 1) / rows_per_split;
+  k_colsum<<<(unsigned)splits, 256, 0, st>>>(A, lda, Mo, R, rows_per_split, part);
+  PSTL_LAUNCH_CHECK();
+  k_split_reduce<<<pstl_ceil_div(Mo, 256), 256, 0, st>>>(part, (int)splits, 1, Mo, out, Mo, 0, 0, 0);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+}  // namespace
+
+extern "C" size_t pstl_refine_backward_workspace_bytes(pstl_denoiser_t d, int N, int n_scenes) {
+  if (!d) return 0;
+  RefineBwdWs w;
+  size_t total;
+  carve_bwd(d, N, n_scenes, nullptr, &w, &total);
+  return total;
+}
+
+extern "C" int pstl_refine_backward(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                                    const float* hl, const float* stlp, const float* u0, const float* scores, int N,
+                                    int n_randoms, int n_shards, float w_max, float a_max, int clip_rect,
+                                    const float* d_out, float* g_r0_w, float* g_r0_b, float* g_r2_w, float* g_r2_b,
+                                    float* g_r4_w, float* g_r4_b, void* workspace, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && u0 && scores && d_out && workspace, "null argument");
+  PSTL_CHECK_ARG(g_r0_w && g_r0_b && g_r2_w && g_r2_b && g_r4_w && g_r4_b, "null gradient output");
+  PSTL_CHECK_ARG(d->w.r0_w && d->w.m0_w && d->r1p, "handle was created without rect_net / merge_net weights");
+  PSTL_CHECK_ARG(n_shards > 0 && n_randoms % n_shards == 0 && N % (3 * n_randoms) == 0,
+                 "rows must be (scene, n_randoms, 3 modes) with n_shards | n_randoms");
+  PSTL_CHECK_ARG(N > 0 && (long long)n_scenes * rows_per_scene == N, "rows must be n_scenes * rows_per_scene");
+  cudaStream_t st = (cudaStream_t)stream;
+  RefineBwdWs w;
+  size_t total;
+  carve_bwd(d, N, n_scenes, workspace, &w, &total);
+  const DenoiserWs& b = w.base;
+  const int H = d->w.rect_hidden, T2 = d->T2, F = d->w.feat_dim, inr = F + 7 + T2;
+  PSTL_CHECK_ARG(H <= 256 && H % 4 == 0, "rect_net hidden width must be a multiple of 4, at most 256");
+  // forward, fp32, keeping the activations: xin, h1, h2 (post-ReLU) and y (pre-tanh)
+  int rc = refine_inputs(d, b, scene_feat, n_scenes, hl, stlp, u0, N, n_randoms, n_shards, st);
+  if (rc) return rc;
+  if ((rc = mlp_hidden(d, b, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st))) return rc;
+  LinArgs a;
+  lin_defaults(a);
+  a.X = b.h2; a.ldx = H; a.W = d->w.r4_w; a.ldw = H; a.bias = d->w.r4_b; a.Y = b.g; a.ldy = T2; a.M = N; a.K = H; a.Nout = T2;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  const long long tot = (long long)N * T2;
+  k_refine_dy<<<(unsigned)pstl_ceil_div(tot, 256), 256, 0, st>>>(b.g, u0, scores, d_out, tot, T2, w_max, a_max, clip_rect);
+  PSTL_LAUNCH_CHECK();
+  k_transpose<<<pstl_ceil_div(T2 * H, 256), 256, 0, st>>>(d->w.r4_w, T2, H, w.w4t);
+  PSTL_LAUNCH_CHECK();
+  k_transpose<<<pstl_ceil_div(H * H, 256), 256, 0, st>>>(d->w.r2_w, H, H, w.w2t);
+  PSTL_LAUNCH_CHECK();
+  // layer 4: dW4 (T2 x H) = dy^T h2, db4; dh2 = (dy W4) * [h2 > 0]
+  if ((rc = wgrad(b.g, T2, T2, b.h2, H, H, N, w.part, w.part_floats, g_r4_w, H, 0, 0, 0, st))) return rc;
+  if ((rc = colsum(b.g, T2, T2, N, w.part, g_r4_b, st))) return rc;
+  lin_defaults(a);
+  a.X = b.g; a.ldx = T2; a.W = w.w4t; a.ldw = T2; a.Y = w.dh; a.ldy = H; a.M = N; a.K = T2; a.Nout = H;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  const long long tot4 = (long long)N * H / 4;
+  k_relu_mask<<<(unsigned)pstl_ceil_div(tot4, 256), 256, 0, st>>>(w.dh, b.h2, tot4);
+  PSTL_LAUNCH_CHECK();
+  // layer 2: dW2 (H x H) = dh2^T h1, db2; dh1 = (dh2 W2) * [h1 > 0] (into h2's storage, which is dead now)
+  if ((rc = wgrad(w.dh, H, H, b.h1, H, H, N, w.part, w.part_floats, g_r2_w, H, 0, 0, 0, st))) return rc;
+  if ((rc = colsum(w.dh, H, H, N, w.part, g_r2_b, st))) return rc;
+  lin_defaults(a);
+  a.X = w.dh; a.ldx = H; a.W = w.w2t; a.ldw = H; a.Y = b.h2; a.ldy = H; a.M = N; a.K = H; a.Nout = H;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  k_relu_mask<<<(unsigned)pstl_ceil_div(tot4, 256), 256, 0, st>>>(b.h2, b.h1, tot4);
+  PSTL_LAUNCH_CHECK();
+  // layer 0: per-row columns [hl | stlp6 | fused] from the packed rows; the F scene-feature columns per scene
+  if ((rc = wgrad(b.h2, H, H, b.xin, PSTL_XIN_LD, PSTL_XIN_LD, N, w.part, w.part_floats, g_r0_w, inr, F, T2, d->kin, st)))
+    return rc;
+  k_scene_sum<<<n_scenes, 256, 0, st>>>(b.h2, H, rows_per_scene, w.sdh);
+  PSTL_LAUNCH_CHECK();
+  if ((rc = wgrad(w.sdh, H, H, scene_feat, F, F, n_scenes, w.part, w.part_floats, g_r0_w, inr, 0, 0, 0, st))) return rc;
+  return colsum(w.sdh, H, H, n_scenes, w.part, g_r0_b, st);
 }

@@ -24,7 +24,8 @@ EXPORTS = [
     "pstl_denoiser_create", "pstl_denoiser_destroy", "pstl_denoiser_workspace_bytes", "pstl_denoiser_sample",
     "pstl_denoiser_eps", "pstl_denoiser_set_noise_counter", "pstl_launch_count", "pstl_refine", "pstl_rollout", "pstl_rollout_bwd", "pstl_predicates", "pstl_linear", "pstl_encoder_inputs",
     "pstl_encoder_pool", "pstl_mlp3", "pstl_mlp3_batch", "pstl_trajopt_step", "pstl_diversity", "pstl_accuracy",
-    "pstl_refine_losses_workspace_bytes", "pstl_refine_losses",
+    "pstl_refine_losses_workspace_bytes", "pstl_refine_losses", "pstl_refine_backward_workspace_bytes",
+    "pstl_refine_backward",
 ]
 
 
@@ -95,7 +96,7 @@ def lib():
     L.pstl_last_error.restype = C.c_char_p
     L.pstl_launch_count.restype = C.c_ulonglong
     for name in ("pstl_stl_workspace_bytes", "pstl_score_workspace_bytes", "pstl_denoiser_workspace_bytes",
-                 "pstl_refine_losses_workspace_bytes"):
+                 "pstl_refine_losses_workspace_bytes", "pstl_refine_backward_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
     _lib = L
     return L

@@ -43,6 +43,44 @@ def normalize_xyth(state, base, valid=None, no_theta=False):
     return torch.stack([xr, yr, tr], dim=-1)
 
 
+class _RectForward(torch.autograd.Function):
+    """Net.rect_forward with gradients for rect_net's parameters: pstl_refine (fp32 handle) forward,
+    pstl_refine_backward for (weight, bias) of layers 0, 2, 4."""
+
+    @staticmethod
+    def forward(ctx, net, scene_feat, hl, stlp, u0, scores, *params):
+        a = net.args
+        n, bs = u0.shape[0], scene_feat.shape[0]
+        out = torch.empty((n, a.nt, 2), dtype=torch.float32, device=u0.device)
+        handle = net.native_handle("fp32")
+        L = _nv.lib()
+        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), u0.device, "denoiser")
+        _nv.check(L.pstl_refine(handle, _nv.fptr(scene_feat), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp), _nv.fptr(u0),
+                                _nv.fptr(scores), n, a.n_randoms, a.n_shards, _nv.C.c_float(a.mul_w_max),
+                                _nv.C.c_float(a.mul_a_max), int(bool(a.clip_rect)), _nv.fptr(out), _nv.ptr(ws),
+                                _nv.stream()), "pstl_refine")
+        ctx.net = net
+        ctx.save_for_backward(scene_feat, hl, stlp, u0, scores)
+        ctx.shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        net, a = ctx.net, ctx.net.args
+        scene_feat, hl, stlp, u0, scores = ctx.saved_tensors
+        n, bs = u0.shape[0], scene_feat.shape[0]
+        handle = net.native_handle("fp32")
+        L = _nv.lib()
+        grads = [torch.empty(s, dtype=torch.float32, device=u0.device) for s in ctx.shapes]
+        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), u0.device, "denoiser")
+        _nv.check(L.pstl_refine_backward(handle, _nv.fptr(scene_feat), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp),
+                                         _nv.fptr(u0), _nv.fptr(scores), n, a.n_randoms, a.n_shards,
+                                         _nv.C.c_float(a.mul_w_max), _nv.C.c_float(a.mul_a_max), int(bool(a.clip_rect)),
+                                         _nv.fptr(_nv.f32(g.reshape(n, a.nt * 2))), *[_nv.fptr(t) for t in grads],
+                                         _nv.ptr(ws), _nv.stream()), "pstl_refine_backward")
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
 class Net(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -271,6 +309,14 @@ class Net(nn.Module):
             scene_feat = feature.reshape(bs, -1, feature.shape[-1])[:, 0].contiguous()
         u0 = _nv.f32(init_controls.reshape(n, a.nt * 2))
         _nv.require_cuda(u0, "init_controls")
+        params = [p for li in (0, 2, 4) for p in (self.rect_net[li].weight, self.rect_net[li].bias)]
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
+            # training step (reference nusc_train.py:1228-1233: Adam over rect_net only): fp32 forward, native backward
+            if getattr(a, "joint", False):
+                raise NotImplementedError("--joint (gradients into merge_net / the encoders / the denoiser) is not built")
+            return _RectForward.apply(self, _nv.f32(scene_feat), _nv.f32(highlevel.reshape(n)).detach(),
+                                      _nv.f32(stlp_dense_feat.reshape(n, 6)).detach(), u0.detach(),
+                                      _nv.f32(scores.reshape(n)).detach(), *params)
         out = torch.empty((n, a.nt, 2), dtype=torch.float32, device=u0.device)
         handle = self.native_handle(getattr(a, "precision", "fp32"))
         L = _nv.lib()

@@ -866,6 +866,7 @@ def accuracy(scores, valid, bs, S):
     return out[0], out[1]
 
 
+@torch.no_grad()
 def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     """The timed region of run_sampling_test for the diffusion + RefineNet path:
     augment -> sampler -> best-of-K -> RefineNet (+n_rolls) -> final rollout + scores."""
@@ -909,6 +910,50 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     acc, scene_acc = accuracy(scores, pack.valid, bs, S)
     out.update(controls=nn_controls, scores=scores, trajs=nn_trajs, acc=acc, scene_acc=scene_acc, pack=pack)
     return out
+
+
+def train_step_rect(net, batch_cuda, stls_cac, coeffs, args, optimizer=None, gt_stlp=None):
+    """One training iteration of the --rect_head stage (reference nusc_train.py:1352-1427, 1523-1525; README "Ours"
+    training command): chains sampled with the frozen denoiser, best of the last ``multi_cands`` iterates,
+    ``rect_forward`` on the detached controls and scores, rollout, ``compute_policy_loss``, backward into rect_net and
+    the optimiser step (``torch.optim.Adam(net.rect_net.parameters())`` upstream).  pSTL parameters per chain from
+    ``pre_stlp`` (training layout); ``gt_stlp`` (bs, 6) only feeds the ground-truth scores of the report.  The
+    denoising loss upstream logs next to it (not part of this stage's ``loss``) is not evaluated.  Returns ``rd``."""
+    S = args.n_randoms
+    bs = batch_cuda["ego_traj"].shape[0]
+    N = bs * S * 3
+    nb = LazyBatch({k: batch_cuda[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+                                               "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp")
+                    if k in batch_cuda})
+    nb["neighbor_trajs_aug"] = batch_cuda["neighbors_traj"][..., :7]
+    if gt_stlp is None:
+        gt_stlp = batch_cuda["pre_stlp"].reshape(bs, -1, 3, 6)[:, 0, 0]
+    nb = augment_batch_data(nb, gt_stlp, args)
+    pack = nb["_pstl_pack"]
+    hl = nb["highlevel_dense"]
+    progs = _fused_programs(stls_cac, args.nt)
+    with torch.no_grad():
+        noise = torch.empty((N, args.nt * 2), device=hl.device)
+        res = diffusion_rollout(noise, net, nb, hl, None, args, coeffs, n_randoms=S, return_feature=True,
+                                scene_feature_only=True)
+        nn_controls, feature = res[0], res[1]
+        if args.multi_cands is not None:
+            r = score_pack(pack, res[2].stacked_last(args.multi_cands), args, progs, want=("best_score", "best_controls"))
+            nn_controls, prev_scores = r["best_controls"], r["best_score"]
+        else:
+            prev_scores = score_pack(pack, nn_controls, args, progs)["best_score"]
+        nn_trajs = generate_trajs(pack.state0, nn_controls, args.dt)
+    rect_controls = net.rect_forward(feature, hl, nb["stlp_dense"][:, 0], nn_controls.detach(), prev_scores.detach())
+    rect_trajs = generate_trajs(pack.state0, rect_controls, args.dt)
+    zeros = torch.zeros((N, args.nt * 2), device=hl.device)
+    extras = (None, zeros, hl, prev_scores, nb["valids_dense"].reshape(-1), 0, zeros, nn_controls, None, rect_controls)
+    rd, all_scores = compute_policy_loss(nb, None, stls_cac, nn_trajs, rect_trajs, None, args, diffusion_extras=extras)
+    rd["all_scores"] = all_scores
+    if optimizer is not None:
+        optimizer.zero_grad()
+        rd["loss"].backward()
+        optimizer.step()
+    return rd
 
 
 def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):

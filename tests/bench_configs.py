@@ -3,6 +3,7 @@
    python tests/bench_configs.py dense [n] [T] [Knei]  # config 1/5 shape: compute_stl_dense on dense rows
    python tests/bench_configs.py trajopt [scenes] [iters]  # trajectory-optimisation iterations
    python tests/bench_configs.py losses [scenes]       # RefineNet training losses, value + gradient (§8(f) item 4)
+   python tests/bench_configs.py train [scenes] [steps]  # full --rect_head training iterations (sampler .. Adam step)
 """
 import os
 import sys
@@ -144,8 +145,35 @@ def losses(scenes):
                                   torch.get_num_threads(), sub, cpu_ms))
 
 
+def train(scenes, steps):
+    """README "Ours" training stage (nusc_train.py:1352-1427, 1523-1525): iterations/s of sampler -> best-of-5 ->
+    RefineNet -> rollout -> scorer -> losses -> backward -> Adam over rect_net"""
+    args = NT.default_args(precision="bf16", stl_weight=0.5, rect_reg_loss=0.1)
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007))
+    net = net.cuda().train()
+    b = {k: v.cuda() for k, v in synthetic.make_scene_batch(scenes, seed=5).items()}
+    stls = NT.build_stl_cache(args)
+    coeffs = NT.get_diffusion_coeffs(args)
+    opt = torch.optim.Adam(net.rect_net.parameters(), lr=args.lr)
+    log = []
+
+    def it():
+        log.append(NT.train_step_rect(net, b, stls, coeffs, args, opt)["loss"].detach())
+
+    ms = timeit(it, reps=steps, warm=2)
+    n = scenes * args.n_randoms * 3
+    # the part after the sampler, on fixed controls
+    import time as _t
+    torch.cuda.synchronize()
+    print("train: scenes=%d chains=%d  %.2f ms per iteration (%.3g chains/s); loss %s"
+          % (scenes, n, ms, n / ms * 1e3, " ".join("%.4f" % float(v) for v in log[:2] + log[-2:])))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "losses":
+    if sys.argv[1] == "train":
+        train(int(sys.argv[2]) if len(sys.argv) > 2 else 1024, int(sys.argv[3]) if len(sys.argv) > 3 else 5)
+    elif sys.argv[1] == "losses":
         losses(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
     elif sys.argv[1] == "sweep":
         sweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 512)

@@ -319,6 +319,63 @@ def gen_losses(bs=3, S=16, seed=2005, warm_iters=120):
     print("losses:", len(out), "arrays")
 
 
+def gen_refine_step(bs=3, S=16, seed=2005):
+    """One --rect_head training step of the reference (nusc_train.py:1402-1405 rect_forward, :1420-1427 the loss,
+    :1523-1525 Adam over net.rect_net.parameters()) on the controls of losses.npz: RefineNet output, loss terms,
+    d loss / d rect_controls, the six rect_net gradients and the parameters after the step."""
+    Lz = np.load(os.path.join(HERE, "losses.npz"))
+    T, args = ref_shim.load(TRAIN_FLAGS + LOSS_VARIANTS["weighted"] + ["--n_randoms", str(S)])
+    import nusc_model
+    nt = args.nt
+    N = bs * S * 3
+    batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=seed)
+    b = {k: v.clone() for k, v in batch.items()}
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    b = T.augment_batch_data(b, b["pre_stlp"].reshape(bs, S, 3, 6)[:, 0, 0], args)
+    flat_states = b["ego_traj"][:, 0, :4].unsqueeze(1).repeat(1, S * 3, 1).reshape(N, 4)
+    stls = T.build_stl_cache(args)
+    net = nusc_model.Net(args)
+    net.load_state_dict(synthetic.make_weights(seed=1007, nt=nt), strict=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    feat_scene = 0.5 * torch.randn(bs, 224, generator=g)
+    feature = feat_scene.unsqueeze(1).repeat(1, S * 3, 1).reshape(N, 224)
+    nn_controls = torch.from_numpy(Lz["nn_controls"])
+    out = {"feat_scene": feat_scene.numpy()}
+    real_md = T.napi.measure_diversity
+    z = torch.zeros(())
+    T.napi.measure_diversity = lambda *a, **k: (z, z, [np.zeros(1)], [np.zeros(1)])
+    try:
+        prev_trajs = T.generate_trajs(flat_states, nn_controls, args.dt)
+        prev_in = T.pre_prepare_stl_cache(b, dense_trajs=prev_trajs[:, :-1])
+        _, prev_scores, _ = T.compute_stl_dense(prev_in, stls, b["highlevel_dense"], prev_in["dense_valids"].reshape(-1), args)
+        opt = torch.optim.Adam(net.rect_net.parameters(), lr=args.lr)
+        rect = net.rect_forward(feature, b["highlevel_dense"], b["stlp_dense"][:, 0], nn_controls.detach(), prev_scores.detach())
+        rect.retain_grad()
+        rect_trajs = T.generate_trajs(flat_states, rect, args.dt)
+        zeros = torch.zeros(N, nt * 2)
+        extras = (None, zeros, b["highlevel_dense"], torch.zeros(N), b["valids_dense"].reshape(-1), 0, zeros, nn_controls, None, rect)
+        rd, _ = T.compute_policy_loss(b, None, stls, prev_trajs, rect_trajs, None, args, diffusion_extras=extras)
+        opt.zero_grad()
+        rd["loss"].backward()
+        out["prev_scores"] = prev_scores.detach().numpy()
+        out["rect"] = rect.detach().numpy()
+        out["grad_rect"] = rect.grad.numpy()
+        out["losses"] = np.array([float(rd[k].detach()) for k in ("loss", "loss_stl", "loss_reg", "loss_diversity")])
+        for li in (0, 2, 4):
+            out["g_w%d" % li] = net.rect_net[li].weight.grad.numpy().copy()
+            out["g_b%d" % li] = net.rect_net[li].bias.grad.numpy().copy()
+        opt.step()
+        for li in (0, 2, 4):
+            out["w%d_after" % li] = net.rect_net[li].weight.detach().numpy().copy()
+            out["b%d_after" % li] = net.rect_net[li].bias.detach().numpy().copy()
+        out["lr"] = np.array(args.lr)
+    finally:
+        T.napi.measure_diversity = real_md
+    np.savez_compressed(os.path.join(HERE, "refine_step.npz"), **out)
+    print("refine_step:", len(out), "arrays; loss", out["losses"], "violating rows %.2f" % float((prev_scores < 0).float().mean()),
+          "|g_w0| %.3g |g_w2| %.3g |g_w4| %.3g" % tuple(float(np.abs(out["g_w%d" % li]).max()) for li in (0, 2, 4)))
+
+
 def metric_inputs(bs=5, m=16, nt=20, seed=2004):
     """trajectories / scores / validity for the diversity metrics: rollouts of the synthetic parameter bank, a random
     accept pattern that includes a lane with nothing accepted, one with two samples and one with collinear samples"""
@@ -373,6 +430,7 @@ def main():
     gen_trajopt()
     gen_metrics()
     gen_losses()
+    gen_refine_step()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -919,3 +919,112 @@ def test_refine_losses_errors():
     kw.update(S=66, n_shards=1)
     rc, *_ = _refine_losses_native(_loss_cfg(kw), z, z, z[:, 0].contiguous(), z[:, 0].contiguous())
     assert rc != 0 and b"at most 32" in native.lib().pstl_last_error()
+
+
+def _train_step_setup(bs, S_, nt, kw, seed, nn=None, feat_scene=None):
+    args = NT.default_args(n_randoms=S_, sampling_size=S_, n_shards=kw["n_shards"], diverse_loss=kw["diverse_loss"],
+                           diverse_detach=kw["diverse_detach"], stl_nn_thres=kw["stl_nn_thres"],
+                           stl_weight=kw["stl_weight"], diversity_scale=kw["diversity_scale"],
+                           diversity_weight=kw["diversity_weight"], rect_reg_loss=kw["rect_reg_loss"],
+                           extra_rect_reg=kw["extra_rect_reg"], precision="fp32")
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007, nt=nt))
+    net = net.cuda().train()
+    b = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=seed))
+    nb = NT.LazyBatch(dict(b))
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    nb = NT.augment_batch_data(nb, b["pre_stlp"].reshape(bs, S_, 3, 6)[:, 0, 0], args)
+    stls = NT.build_stl_cache(args)
+    N = bs * S_ * 3
+    states = b["ego_traj"][:, 0, :4].unsqueeze(1).repeat(1, S_ * 3, 1).reshape(N, 4)
+    nn = nb["params"].reshape(N, nt, 2).contiguous() if nn is None else nn
+    feature = feat_scene.unsqueeze(1).repeat(1, S_ * 3, 1).reshape(N, -1)
+
+    def step():
+        """rect_forward -> rollout -> compute_policy_loss (reference nusc_train.py:1402-1427)"""
+        with torch.no_grad():
+            prev_trajs = NT.generate_trajs(states, nn, args.dt)
+            prev_in = NT.pre_prepare_stl_cache(nb, dense_trajs=prev_trajs[:, :-1])
+            _, prev_scores, _ = NT.compute_stl_dense(prev_in, stls, nb["highlevel_dense"], nb["valids_dense"].reshape(-1), args)
+        rect = net.rect_forward(feature, nb["highlevel_dense"], nb["stlp_dense"][:, 0], nn.detach(), prev_scores.detach())
+        rect.retain_grad()
+        rect_trajs = NT.generate_trajs(states, rect, args.dt)
+        zeros = torch.zeros(N, nt * 2, device="cuda")
+        extras = (None, zeros, nb["highlevel_dense"], zeros[:, 0], nb["valids_dense"].reshape(-1), 0, zeros, nn, None, rect)
+        rd, _ = NT.compute_policy_loss(nb, None, stls, prev_trajs, rect_trajs, None, args, diffusion_extras=extras)
+        return prev_scores, rect, rd
+
+    return args, net, step
+
+
+def test_refine_train_step_golden(golden_dir):
+    """One --rect_head training step (rect_forward -> rollout -> scorer -> loss kernel -> reverse scorer -> rollout
+    adjoint -> pstl_refine_backward -> Adam over rect_net) against the reference's (tests/golden/refine_step.npz)"""
+    from test_oracle_golden import loss_kwargs
+    G = np.load(os.path.join(golden_dir, "refine_step.npz"))
+    Lz = np.load(os.path.join(golden_dir, "losses.npz"))
+    kw = loss_kwargs(Lz, "weighted")
+    args, net, step = _train_step_setup(kw["n_scenes"], kw["S"], kw["nt"], kw, 2005, torch.from_numpy(Lz["nn_controls"]).cuda(),
+                                        torch.from_numpy(G["feat_scene"]).cuda())
+    opt = torch.optim.Adam(net.rect_net.parameters(), lr=float(G["lr"]))
+    prev_scores, rect, rd = step()
+    close(prev_scores, G["prev_scores"], what="prev_scores")
+    close(rect, G["rect"], what="rect")
+    for i, k in enumerate(("loss", "loss_stl", "loss_reg", "loss_diversity")):
+        np.testing.assert_allclose(float(rd[k].detach()), G["losses"][i], rtol=5e-5, atol=2e-6, err_msg=k)
+    opt.zero_grad()
+    rd["loss"].backward()
+    close(rect.grad, G["grad_rect"], rtol=1e-4, what="grad_rect")
+    for li in (0, 2, 4):
+        close(net.rect_net[li].weight.grad, G["g_w%d" % li], rtol=1e-4, what="g_w%d" % li)
+        close(net.rect_net[li].bias.grad, G["g_b%d" % li], rtol=1e-4, what="g_b%d" % li)
+    assert net.merge_net[0].weight.grad is None and net.policy_net[0].weight.grad is None
+    opt.step()
+    for li in (0, 2, 4):
+        for p, key in ((net.rect_net[li].weight, "w%d_after"), (net.rect_net[li].bias, "b%d_after")):
+            err = np.abs(p.detach().cpu().numpy() - G[key % li])
+            assert np.percentile(err, 99) < 1e-6 and err.max() <= 2.001 * float(G["lr"]), (li, err.max())
+    # the handle follows the updated weights: a second step runs and moves the loss
+    _, _, rd2 = step()
+    assert torch.isfinite(rd2["loss"]) and float(rd2["loss"]) != float(rd["loss"])
+
+
+def test_refine_backward_oracle():
+    """pstl_refine_backward at 32 scenes x 64 samples (6,144 rows: split-K over several row ranges, per-scene
+    reduction of the feature columns) against the oracle's autograd"""
+    bs, S_, nt = 32, 64, 20
+    kw = dict(n_scenes=bs, S=S_, nt=nt, n_shards=4, diverse_loss=True, diverse_detach=False, w_max=0.5, a_max=5.0,
+              stl_nn_thres=0.05, stl_weight=0.6, diversity_scale=0.7, diversity_weight=1.3, rect_reg_loss=0.25,
+              extra_rect_reg=0.0)
+    g = torch.Generator().manual_seed(77)
+    feat_scene = 0.5 * torch.randn(bs, 224, generator=g)
+    args, net, step = _train_step_setup(bs, S_, nt, kw, 31, None, feat_scene.cuda())
+    b = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=31)
+    prev_scores, rect, rd = step()
+    rd["loss"].backward()
+    r = O.refine_train_step(synthetic.make_weights(1007, nt=nt), b, feat_scene, b["params"].reshape(-1, nt, 2), 0.5, **kw)
+    close(rect, r["rect"], what="rect")
+    np.testing.assert_allclose(float(rd["loss"].detach()), float(r["losses"]["loss"].detach()), rtol=1e-4, atol=1e-5)
+    for li in (0, 2, 4):
+        # sums over 6,144 rows in a different order than torch's GEMM: 1e-4 of the largest entry
+        close(net.rect_net[li].weight.grad, r["grads"]["rect_net.%d.weight" % li], rtol=2e-4, what="g_w%d" % li)
+        close(net.rect_net[li].bias.grad, r["grads"]["rect_net.%d.bias" % li], rtol=2e-4, what="g_b%d" % li)
+
+
+def test_train_step_rect_runs():
+    """nusc_train.train_step_rect: three iterations of the --rect_head stage; only rect_net moves, the loss stays
+    finite, and the bf16 sampler handle follows the new weights"""
+    args = NT.default_args(n_randoms=16, sampling_size=16, precision="bf16", stl_weight=0.5, rect_reg_loss=0.1)
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007))
+    net = net.cuda().train()
+    b = cuda(synthetic.make_scene_batch(8, n_randoms=16, seed=41))
+    stls, coeffs = NT.build_stl_cache(args), NT.get_diffusion_coeffs(args)
+    opt = torch.optim.Adam(net.rect_net.parameters(), lr=args.lr)
+    before = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    losses = [float(NT.train_step_rect(net, b, stls, coeffs, args, opt)["loss"].detach()) for _ in range(3)]
+    assert all(np.isfinite(losses)), losses
+    after = net.state_dict()
+    for k in before:
+        moved = not torch.equal(before[k], after[k])
+        assert moved == k.startswith("rect_net."), k

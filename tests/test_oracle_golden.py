@@ -191,3 +191,30 @@ def test_refine_losses(golden_dir, tag):
     g_rect, g_sc = torch.autograd.grad(out["loss"], [rect, scores], allow_unused=True)
     close(g_rect.numpy(), G[tag + "|grad_direct"], rtol=2e-5)
     close((g_sc if g_sc is not None else torch.zeros_like(scores)).numpy(), G[tag + "|grad_scores"], rtol=2e-5)
+
+
+def test_refine_train_step(golden_dir):
+    """oracle refine_train_step == one --rect_head training step of the reference (tests/golden/refine_step.npz):
+    RefineNet output, loss, d loss / d rect_controls, the six rect_net gradients, and the weights after Adam"""
+    G = np.load(os.path.join(golden_dir, "refine_step.npz"))
+    Lz = np.load(os.path.join(golden_dir, "losses.npz"))
+    kw = loss_kwargs(Lz, "weighted")
+    bs, S_, nt = kw["n_scenes"], kw["S"], kw["nt"]
+    b = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=2005)
+    W = synthetic.make_weights(seed=1007, nt=nt)
+    r = O.refine_train_step(W, b, torch.from_numpy(G["feat_scene"]), torch.from_numpy(Lz["nn_controls"]), 0.5, **kw)
+    close(r["prev_scores"].numpy(), G["prev_scores"])
+    close(r["rect"].numpy(), G["rect"])
+    for i, k in enumerate(("loss", "loss_stl", "loss_reg", "loss_diversity")):
+        np.testing.assert_allclose(float(r["losses"][k].detach()), G["losses"][i], rtol=5e-5, atol=1e-6, err_msg=k)
+    close(r["grad_rect"].numpy(), G["grad_rect"], rtol=1e-4)
+    for li in (0, 2, 4):
+        close(r["grads"]["rect_net.%d.weight" % li].numpy(), G["g_w%d" % li], rtol=1e-4)
+        close(r["grads"]["rect_net.%d.bias" % li].numpy(), G["g_b%d" % li], rtol=1e-4)
+    params = [r["W"]["rect_net.%d.%s" % (li, k)] for li in (0, 2, 4) for k in ("weight", "bias")]
+    torch.optim.Adam(params, lr=float(G["lr"])).step()
+    for li in (0, 2, 4):
+        # Adam's first step moves every weight by ~lr * sign(g): compare on the bulk, bound the rest by 2 lr
+        for k, key in (("weight", "w%d_after"), ("bias", "b%d_after")):
+            err = np.abs(r["W"]["rect_net.%d.%s" % (li, k)].detach().numpy() - G[key % li])
+            assert np.percentile(err, 99) < 1e-6 and err.max() <= 2.001 * float(G["lr"]), (li, k, err.max())
