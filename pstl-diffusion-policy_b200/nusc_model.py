@@ -310,7 +310,7 @@ class Net(nn.Module):
         u0 = _nv.f32(init_controls.reshape(n, a.nt * 2))
         _nv.require_cuda(u0, "init_controls")
         params = [p for li in (0, 2, 4) for p in (self.rect_net[li].weight, self.rect_net[li].bias)]
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             # training step (reference nusc_train.py:1228-1233: Adam over rect_net only): fp32 forward, native backward
             if getattr(a, "joint", False):
                 raise NotImplementedError("--joint (gradients into merge_net / the encoders / the denoiser) is not built")

@@ -163,11 +163,22 @@ def train(scenes, steps):
 
     ms = timeit(it, reps=steps, warm=2)
     n = scenes * args.n_randoms * 3
-    # the part after the sampler, on fixed controls
-    import time as _t
-    torch.cuda.synchronize()
     print("train: scenes=%d chains=%d  %.2f ms per iteration (%.3g chains/s); loss %s"
           % (scenes, n, ms, n / ms * 1e3, " ".join("%.4f" % float(v) for v in log[:2] + log[-2:])))
+    # the CPU oracle for the part after the sampler (RefineNet, rollout, scores, losses, backward), on a slice
+    from oracle import pstl_oracle as O
+    sub = min(scenes, 8)
+    bc = synthetic.make_scene_batch(sub, seed=5)
+    kw = dict(n_scenes=sub, S=args.n_randoms, nt=args.nt, n_shards=args.n_shards, diverse_loss=True, diverse_detach=False,
+              w_max=args.mul_w_max, a_max=args.mul_a_max, stl_nn_thres=args.stl_nn_thres, stl_weight=0.5,
+              diversity_scale=args.diversity_scale, diversity_weight=args.diversity_weight, rect_reg_loss=0.1,
+              extra_rect_reg=0.0)
+    t0 = time.time()
+    O.refine_train_step(synthetic.make_weights(1007), bc, torch.zeros(sub, 224), bc["params"].reshape(-1, args.nt, 2),
+                        args.dt, **kw)
+    cpu = time.time() - t0
+    print("train: oracle (torch CPU, %d threads) RefineNet + losses + backward on %d scenes: %.2f s -> %.1f s per %d-scene "
+          "iteration, without the sampler" % (torch.get_num_threads(), sub, cpu, cpu * scenes / sub, scenes))
 
 
 if __name__ == "__main__":
