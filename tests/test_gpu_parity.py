@@ -986,7 +986,7 @@ def test_refine_train_step_golden(golden_dir):
             assert np.percentile(err, 99) < 1e-6 and err.max() <= 2.001 * float(G["lr"]), (li, err.max())
     # the handle follows the updated weights: a second step runs and moves the loss
     _, _, rd2 = step()
-    assert torch.isfinite(rd2["loss"]) and float(rd2["loss"]) != float(rd["loss"])
+    assert torch.isfinite(rd2["loss"]) and float(rd2["loss"].detach()) != float(rd["loss"].detach())
 
 
 def test_refine_backward_oracle():
