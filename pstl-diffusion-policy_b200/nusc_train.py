@@ -10,6 +10,7 @@ Two calling styles are served by the same functions:
 Out of scope: training loop, losses, traj-opt, dataset, visualisation.
 """
 import argparse
+import os
 import math
 import time
 
@@ -1267,13 +1268,64 @@ def default_args(flags=None, **over):
     return args
 
 
+def save_model_freq_last(state_dict, model_dir, epi, save_freq, epochs):
+    """checkpoint cadence of the reference (utils.py:81-85): ``model_%05d.ckpt`` every ``save_freq`` epochs and at the
+    end, ``model_last.ckpt`` every 10 epochs and at the end; plain ``torch.save`` of the state_dict."""
+    os.makedirs(model_dir, exist_ok=True)
+    if epi % save_freq == 0 or epi == epochs - 1:
+        torch.save(state_dict, "%s/model_%05d.ckpt" % (model_dir, epi))
+    if epi % 10 == 0 or epi == epochs - 1:
+        torch.save(state_dict, "%s/model_last.ckpt" % (model_dir))
+
+
+def run_rect_training(stls_cac, train_loader, net, coeffs, args, model_dir=None, log=print):
+    """The epoch loop of the --rect_head stage (reference nusc_train.py:1228-1233 optimiser, :1245-1577 loop, train
+    mode only): ``args.epochs`` passes over ``train_loader`` (scene batches on the host or the device), one
+    ``train_step_rect`` per batch, the per-epoch means of the logged terms, checkpoints in upstream's layout when
+    ``model_dir`` is given.  Returns the list of per-epoch dicts."""
+    if not (args.rect_head and args.diffusion) or getattr(args, "joint", False):
+        raise NotImplementedError("only the --diffusion --rect_head stage (Adam over rect_net) is built")
+    optimizer = torch.optim.Adam(net.rect_net.parameters(), lr=args.lr)
+    keys = ("loss", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg", "acc", "avg_speed")
+    history = []
+    for epi in range(args.epochs):
+        sums = {}
+        nb = 0
+        for batch in train_loader:
+            batch_cuda = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            rd = train_step_rect(net, batch_cuda, stls_cac, coeffs, args, optimizer)
+            for k in keys:
+                if k in rd:
+                    sums[k] = sums.get(k, 0.0) + rd[k].detach()
+            nb += 1
+        means = {k: float(v) / max(nb, 1) for k, v in sums.items()}  # one device->host read per term and epoch
+        history.append(means)
+        if epi % max(int(getattr(args, "epi_print_freq", 1)), 1) == 0 or epi == args.epochs - 1:
+            log("[%05d/%05d] " % (epi, args.epochs) + " ".join("%s:%.4f" % (k, means[k]) for k in keys if k in means))
+        if model_dir is not None:
+            save_model_freq_last(net.state_dict(), model_dir, epi, args.save_freq, args.epochs)
+    return history
+
+
 def main(argv=None):
-    """``python -m pstl_b200.nusc_train ... --run_sampling_test --synthetic 32``"""
+    """``python -m pstl_b200.nusc_train ... --run_sampling_test --synthetic 32`` (open-loop test) or, without
+    ``--run_sampling_test`` and with ``--rect_head``, the RefineNet training stage on synthetic scene batches
+    (``--synthetic B`` scenes per batch, ``--epochs``, checkpoints under ``./exps_nusc/<exp_name>/models``)."""
     from . import synthetic
     from .nusc_model import Net
     args = generate_parser(argv)
     if not args.run_sampling_test:
-        raise SystemExit("only --run_sampling_test is built (training / traj-opt are out of scope)")
+        if not args.rect_head:
+            raise SystemExit("training: only the --rect_head stage is built (the denoiser stage / traj-opt CLI are not)")
+        torch.manual_seed(args.seed)
+        net = Net(args).cuda()
+        if args.net_pretrained_path is not None:
+            net.load_state_dict(torch.load(args.net_pretrained_path), strict=False)
+        bs = args.synthetic or args.batch_size
+        loader = [synthetic.make_scene_batch(bs, nt=args.nt, dt=args.dt, n_neighbors=args.n_neighbors, n_segs=args.n_segs,
+                                             n_randoms=args.n_randoms, seed=args.seed + i) for i in range(3)]
+        model_dir = os.path.join("exps_nusc", args.exp_name or "rect", "models")
+        return run_rect_training(build_stl_cache(args), loader, net, get_diffusion_coeffs(args), args, model_dir)
     torch.manual_seed(args.seed)
     stls_cac = build_stl_cache(args)
     net = Net(args).cuda()
