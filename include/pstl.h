@@ -267,6 +267,21 @@ int pstl_trajopt_step(pstl_program_t const* progs, const pstl_scene_view* scenes
 int pstl_diversity(const float* trajs, const float* scores, const float* valids, int n_scenes, int m, int nt,
                    float* std_out, float* vol_out, pstl_stream_t stream);
 
+/* Denoiser training step (diffusion_prep + net(...) + loss_diffusion, nusc_train.py:539-555, 1352-1356, 432-436).
+ * pstl_denoiser_eps_rows: eps = policy_net([feature, x, temb(t_row), hl, stlp]) + x with ONE TIMESTEP PER ROW;
+ * temb_rows (N, time_dim) is pos_encoding of each row's timestep (nusc_model.py:48-53).  fp32.
+ * pstl_denoiser_eps_backward: from d_eps (N, 2*nt) to the gradients of policy_net.{0,2,4}.{weight,bias} (reference
+ * shapes, row-major (out, in)) and, when d_scene_feat (n_scenes, feat_dim) is non-NULL, of the per-scene feature (the
+ * encoders' backward continues from there).  Stateless (activations are recomputed); deterministic reductions.
+ * Workspace: pstl_refine_backward_workspace_bytes for the backward, pstl_denoiser_workspace_bytes for the forward. */
+int pstl_denoiser_eps_rows(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene, const float* hl,
+                           const float* stlp, const float* x, int N, const float* temb_rows, float* eps_out,
+                           void* workspace, pstl_stream_t stream);
+int pstl_denoiser_eps_backward(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                               const float* hl, const float* stlp, const float* x, int N, const float* temb_rows,
+                               const float* d_eps, float* g_p0_w, float* g_p0_b, float* g_p2_w, float* g_p2_b,
+                               float* g_p4_w, float* g_p4_b, float* d_scene_feat, void* workspace, pstl_stream_t stream);
+
 /* RefineNet backward for the --rect_head training step (autograd over Net.rect_forward, nusc_model.py:182-235; the
  * optimiser upstream holds net.rect_net.parameters() only, nusc_train.py:1228-1233): from d_out = d loss / d rect_controls
  * (N, 2*nt) to the gradients of rect_net.{0,2,4}.{weight,bias} in the reference's own shapes (row-major (out, in):

@@ -562,3 +562,24 @@ def refine_train_step(W, b, feat_scene, nn_controls, dt, tau=100.0, **loss_kw):
     out["loss"].backward()
     return {"rect": rect.detach(), "grad_rect": rect.grad, "losses": out, "prev_scores": prev_scores,
             "grads": {k: W[k].grad for k in keys}, "W": W}
+
+
+def ddpm_train_step(W, b, noise, steps, noised, S, nt):
+    """One denoiser training step up to the gradients (README step 1): net(batch, timestep per row, noised commands)
+    (nusc_train.py:1352-1356, nusc_model.py:97-162) and loss_diffusion = mean((noise - eps)^2) (:436), every encoder /
+    policy_net tensor a leaf.  noise / steps / noised are diffusion_prep's outputs (:539-555).  pSTL per chain from
+    pre_stlp (training layout).  Returns eps, feature (bs,224), loss and grads {key: tensor}."""
+    bs = b["currlane_wpts"].shape[0]
+    m = S * 3
+    N = bs * m
+    keys = [k for k in W if k.startswith(("ego_encoder", "neighbor_encoder", "lane_encoder", "policy_net"))]
+    W = dict(W)
+    for k in keys:
+        W[k] = W[k].detach().clone().requires_grad_()
+    feat = encode_scene(W, b)
+    feat_dense = feat.unsqueeze(1).repeat(1, m, 1).reshape(N, -1)
+    mode = torch.tensor([0.0, 1.0, 2.0]).repeat(bs * S).reshape(N, 1)
+    eps = eps_model(W, feat_dense, noised, steps.reshape(N, 1), mode, b["pre_stlp"].reshape(N, 6))
+    loss = torch.mean((noise - eps) ** 2)
+    loss.backward()
+    return {"eps": eps.detach(), "feature": feat.detach(), "loss": loss.detach(), "grads": {k: W[k].grad for k in keys}, "W": W}

@@ -996,14 +996,15 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ A, int
 
 // out[m * ldo + map(n)] = sum over the splits in order; xin_map: packed-row column order -> rect_net.0 column order
 __global__ void __launch_bounds__(256) k_split_reduce(const float* __restrict__ part, int splits, int Mo, int No,
-                                                      float* __restrict__ out, int ldo, int col0, int xin_T2, int xin_kin) {
+                                                      float* __restrict__ out, int ldo, int col0, int xin_T2, int xin_kin,
+                                                      int col_tail) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Mo * No) return;
   const int m = i / No, n = i - m * No;
   int col = col0 + n;
-  if (xin_T2 > 0) {  // packed row = [fused (T2) | hl | stlp6 | pad]; weight columns = [.. | hl | stlp6 | fused (T2)]
+  if (xin_T2 > 0) {  // packed row = [x or fused (T2) | hl | stlp6 | pad]: the two blocks sit apart in the weight matrix
     if (n >= xin_kin) return;
-    col = col0 + (n < xin_T2 ? 7 + n : n - xin_T2);
+    col = n < xin_T2 ? col0 + n : col_tail + (n - xin_T2);
   }
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += part[(size_t)z * Mo * No + i];
@@ -1023,7 +1024,7 @@ __global__ void __launch_bounds__(256) k_scene_sum(const float* __restrict__ g, 
 namespace {
 struct RefineBwdWs {
   DenoiserWs base;
-  float *dh, *w4t, *w2t, *sdh, *part;
+  float *dh, *w4t, *w2t, *w0t, *sdh, *part;
   size_t part_floats;
 };
 
@@ -1032,13 +1033,14 @@ const size_t kWgradPartFloats = (size_t)4 << 20;  // 16 MB of split-K partials
 void carve_bwd(pstl_denoiser_t d, int N, int n_scenes, void* ws, RefineBwdWs* o, size_t* total) {
   size_t base_bytes;
   carve(d, N, n_scenes, 1, nullptr, ws, &o->base, &base_bytes);
-  const int H = d->w.rect_hidden;
+  const int H = d->w.hidden > d->w.rect_hidden ? d->w.hidden : d->w.rect_hidden;
   float* p = ws ? (float*)((char*)ws + base_bytes) : nullptr;
   size_t off = 0;
   auto take = [&](size_t n) { float* r = p ? p + off : nullptr; off += pstl_align_floats(n); return r; };
   o->dh = take((size_t)N * H);
   o->w4t = take((size_t)H * d->T2);
   o->w2t = take((size_t)H * H);
+  o->w0t = take((size_t)H * (d->w.feat_dim + d->T2 + d->w.time_dim + 7));
   o->sdh = take((size_t)n_scenes * H);
   o->part = take(kWgradPartFloats);
   o->part_floats = kWgradPartFloats;
@@ -1047,7 +1049,7 @@ void carve_bwd(pstl_denoiser_t d, int N, int n_scenes, void* ws, RefineBwdWs* o,
 
 // C (Mo x No, written at out[m*ldo + col0 + n]) = A^T B over R rows
 int wgrad(const float* A, int lda, int Mo, const float* B, int ldb, int No, long long R, float* part, size_t part_floats,
-          float* out, int ldo, int col0, int xin_T2, int xin_kin, cudaStream_t st) {
+          float* out, int ldo, int col0, int xin_T2, int xin_kin, int col_tail, cudaStream_t st) {
   const int tiles = pstl_ceil_div(Mo, WG_T) * pstl_ceil_div(No, WG_T);
   long long splits = (148 * 4 + tiles - 1) / tiles;
   const long long max_by_rows = (R + 255) / 256, max_by_ws = (long long)(part_floats / ((size_t)Mo * No));
@@ -1060,7 +1062,7 @@ int wgrad(const float* A, int lda, int Mo, const float* B, int ldb, int No, long
   dim3 grid(pstl_ceil_div(Mo, WG_T), pstl_ceil_div(No, WG_T), (unsigned)splits);
   k_wgrad<<<grid, 256, 0, st>>>(A, lda, Mo, B, ldb, No, R, rows_per_split, part);
   PSTL_LAUNCH_CHECK();
-  k_split_reduce<<<pstl_ceil_div(Mo * No, 256), 256, 0, st>>>(part, (int)splits, Mo, No, out, ldo, col0, xin_T2, xin_kin);
+  k_split_reduce<<<pstl_ceil_div(Mo * No, 256), 256, 0, st>>>(part, (int)splits, Mo, No, out, ldo, col0, xin_T2, xin_kin, col_tail);
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
 }
@@ -1072,8 +1074,70 @@ int colsum(const float* A, int lda, int Mo, long long R, float* part, float* out
   splits = (R + rows_per_split - 1) / rows_per_split;
   k_colsum<<<(unsigned)splits, 256, 0, st>>>(A, lda, Mo, R, rows_per_split, part);
   PSTL_LAUNCH_CHECK();
-  k_split_reduce<<<pstl_ceil_div(Mo, 256), 256, 0, st>>>(part, (int)splits, 1, Mo, out, Mo, 0, 0, 0);
+  k_split_reduce<<<pstl_ceil_div(Mo, 256), 256, 0, st>>>(part, (int)splits, 1, Mo, out, Mo, 0, 0, 0, 0);
   PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+}  // namespace
+
+namespace {
+// Backward of a hoisted three-layer ReLU MLP (RefineNet's rect_net, the denoiser's policy_net): dy (N, T2) ->
+// the six parameter gradients (+ the gradient of the per-scene feature).  Expects the forward activations in the
+// workspace: packed rows w.base.xin, h1, h2 (post-ReLU).  Layer-0 weight columns: [feature F | ...]; the packed-row
+// blocks [x (T2) | hl, stlp6] land at columns col_x / col_tail, the optional per-row time embedding at col_t.
+struct MlpBwd {
+  const float *W0, *W2, *W4;
+  int in0, H, col_x, col_tail;
+  const float* temb_rows;
+  int time_dim, col_t;
+  float *g_w0, *g_b0, *g_w2, *g_b2, *g_w4, *g_b4, *d_feat;
+};
+
+int mlp_backward(pstl_denoiser_t d, const RefineBwdWs& w, const float* dy, const float* scene_feat, int n_scenes,
+                 int rows_per_scene, int N, const MlpBwd& m, cudaStream_t st) {
+  const DenoiserWs& b = w.base;
+  const int H = m.H, T2 = d->T2, F = d->w.feat_dim;
+  int rc;
+  LinArgs a;
+  k_transpose<<<pstl_ceil_div(T2 * H, 256), 256, 0, st>>>(m.W4, T2, H, w.w4t);
+  PSTL_LAUNCH_CHECK();
+  k_transpose<<<pstl_ceil_div(H * H, 256), 256, 0, st>>>(m.W2, H, H, w.w2t);
+  PSTL_LAUNCH_CHECK();
+  // layer 4: dW4 (T2 x H) = dy^T h2, db4; dh2 = (dy W4) * [h2 > 0]
+  if ((rc = wgrad(dy, T2, T2, b.h2, H, H, N, w.part, w.part_floats, m.g_w4, H, 0, 0, 0, 0, st))) return rc;
+  if ((rc = colsum(dy, T2, T2, N, w.part, m.g_b4, st))) return rc;
+  lin_defaults(a);
+  a.X = dy; a.ldx = T2; a.W = w.w4t; a.ldw = T2; a.Y = w.dh; a.ldy = H; a.M = N; a.K = T2; a.Nout = H;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  const long long tot4 = (long long)N * H / 4;
+  k_relu_mask<<<(unsigned)pstl_ceil_div(tot4, 256), 256, 0, st>>>(w.dh, b.h2, tot4);
+  PSTL_LAUNCH_CHECK();
+  // layer 2: dW2 (H x H) = dh2^T h1, db2; dh1 = (dh2 W2) * [h1 > 0] (into h2's storage, which is dead now)
+  if ((rc = wgrad(w.dh, H, H, b.h1, H, H, N, w.part, w.part_floats, m.g_w2, H, 0, 0, 0, 0, st))) return rc;
+  if ((rc = colsum(w.dh, H, H, N, w.part, m.g_b2, st))) return rc;
+  lin_defaults(a);
+  a.X = w.dh; a.ldx = H; a.W = w.w2t; a.ldw = H; a.Y = b.h2; a.ldy = H; a.M = N; a.K = H; a.Nout = H;
+  if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  k_relu_mask<<<(unsigned)pstl_ceil_div(tot4, 256), 256, 0, st>>>(b.h2, b.h1, tot4);
+  PSTL_LAUNCH_CHECK();
+  // layer 0: the packed-row columns; the time-embedding columns; the F scene-feature columns per scene
+  if ((rc = wgrad(b.h2, H, H, b.xin, PSTL_XIN_LD, PSTL_XIN_LD, N, w.part, w.part_floats, m.g_w0, m.in0, m.col_x, T2, d->kin,
+                  m.col_tail, st)))
+    return rc;
+  if (m.temb_rows &&
+      (rc = wgrad(b.h2, H, H, m.temb_rows, m.time_dim, m.time_dim, N, w.part, w.part_floats, m.g_w0, m.in0, m.col_t, 0, 0, 0, st)))
+    return rc;
+  k_scene_sum<<<n_scenes, 256, 0, st>>>(b.h2, H, rows_per_scene, w.sdh);
+  PSTL_LAUNCH_CHECK();
+  if ((rc = wgrad(w.sdh, H, H, scene_feat, F, F, n_scenes, w.part, w.part_floats, m.g_w0, m.in0, 0, 0, 0, 0, st))) return rc;
+  if ((rc = colsum(w.sdh, H, H, n_scenes, w.part, m.g_b0, st))) return rc;
+  if (m.d_feat) {  // d loss / d scene feature = (sum of a scene's dh1 rows) . W0[:, :F]
+    k_transpose<<<pstl_ceil_div(H * m.in0, 256), 256, 0, st>>>(m.W0, H, m.in0, w.w0t);
+    PSTL_LAUNCH_CHECK();
+    lin_defaults(a);
+    a.X = w.sdh; a.ldx = H; a.W = w.w0t; a.ldw = H; a.Y = m.d_feat; a.ldy = F; a.M = n_scenes; a.K = H; a.Nout = F;
+    if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
+  }
   return PSTL_OK;
 }
 }  // namespace
@@ -1115,32 +1179,83 @@ extern "C" int pstl_refine_backward(pstl_denoiser_t d, const float* scene_feat, 
   const long long tot = (long long)N * T2;
   k_refine_dy<<<(unsigned)pstl_ceil_div(tot, 256), 256, 0, st>>>(b.g, u0, scores, d_out, tot, T2, w_max, a_max, clip_rect);
   PSTL_LAUNCH_CHECK();
-  k_transpose<<<pstl_ceil_div(T2 * H, 256), 256, 0, st>>>(d->w.r4_w, T2, H, w.w4t);
+  MlpBwd m{};
+  m.W0 = d->w.r0_w; m.W2 = d->w.r2_w; m.W4 = d->w.r4_w; m.in0 = inr; m.H = H;
+  m.col_x = F + 7; m.col_tail = F;
+  m.g_w0 = g_r0_w; m.g_b0 = g_r0_b; m.g_w2 = g_r2_w; m.g_b2 = g_r2_b; m.g_w4 = g_r4_w; m.g_b4 = g_r4_b;
+  return mlp_backward(d, w, b.g, scene_feat, n_scenes, rows_per_scene, N, m, st);
+}
+
+// --------------------------------------------------------------------------------------
+// Denoiser training step (reference nusc_train.py:539-555 diffusion_prep, :1352-1356 net(...), :432-436 loss_diffusion):
+// eps prediction with ONE TIMESTEP PER ROW (the sampler's entry takes one per call), and its backward into policy_net
+// and the scene feature (the encoders' own backward stays with autograd).  temb_rows (N, time_dim) is the sinusoidal
+// embedding of each row's timestep; its layer-0 term is a K = time_dim product added before the ReLU.
+// --------------------------------------------------------------------------------------
+static int eps_rows_activations(pstl_denoiser_t d, const DenoiserWs& w, const float* scene_feat, int n_scenes,
+                                int rows_per_scene, const float* hl, const float* stlp, const float* x, int N,
+                                const float* temb_rows, cudaStream_t st) {
+  const int H = d->w.hidden, T2 = d->T2, F = d->w.feat_dim, TD = d->w.time_dim;
+  const int in1 = F + T2 + TD + 7;
+  int rc = hoist(d->w.p0_w, in1, d->w.p0_b, H, scene_feat, n_scenes, F, w.cscene, nullptr, 0, 0, 0, nullptr, st);
+  if (rc) return rc;
+  const long long tot = (long long)N * (PSTL_XIN_LD / 4);
+  k_pack_xin<<<pstl_ceil_div(tot, 256), 256, 0, st>>>(x, T2, hl, stlp, w.xin, N, T2, 0, 0ull, 0ull, nullptr, 0);
   PSTL_LAUNCH_CHECK();
-  k_transpose<<<pstl_ceil_div(H * H, 256), 256, 0, st>>>(d->w.r2_w, H, H, w.w2t);
-  PSTL_LAUNCH_CHECK();
-  // layer 4: dW4 (T2 x H) = dy^T h2, db4; dh2 = (dy W4) * [h2 > 0]
-  if ((rc = wgrad(b.g, T2, T2, b.h2, H, H, N, w.part, w.part_floats, g_r4_w, H, 0, 0, 0, st))) return rc;
-  if ((rc = colsum(b.g, T2, T2, N, w.part, g_r4_b, st))) return rc;
-  lin_defaults(a);
-  a.X = b.g; a.ldx = T2; a.W = w.w4t; a.ldw = T2; a.Y = w.dh; a.ldy = H; a.M = N; a.K = T2; a.Nout = H;
+  LinArgs a;
+  lin_defaults(a);  // time term of layer 0 -> h2's storage (free until layer 2 writes it)
+  a.X = temb_rows; a.ldx = TD; a.W = d->w.p0_w + F + T2; a.ldw = in1; a.Y = w.h2; a.ldy = H; a.M = N; a.K = TD; a.Nout = H;
   if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
-  const long long tot4 = (long long)N * H / 4;
-  k_relu_mask<<<(unsigned)pstl_ceil_div(tot4, 256), 256, 0, st>>>(w.dh, b.h2, tot4);
-  PSTL_LAUNCH_CHECK();
-  // layer 2: dW2 (H x H) = dh2^T h1, db2; dh1 = (dh2 W2) * [h1 > 0] (into h2's storage, which is dead now)
-  if ((rc = wgrad(w.dh, H, H, b.h1, H, H, N, w.part, w.part_floats, g_r2_w, H, 0, 0, 0, st))) return rc;
-  if ((rc = colsum(w.dh, H, H, N, w.part, g_r2_b, st))) return rc;
   lin_defaults(a);
-  a.X = w.dh; a.ldx = H; a.W = w.w2t; a.ldw = H; a.Y = b.h2; a.ldy = H; a.M = N; a.K = H; a.Nout = H;
+  a.X = w.xin; a.ldx = PSTL_XIN_LD; a.W = d->w1p; a.ldw = d->kin; a.rowbias = w.cscene; a.rows_per_group = rows_per_scene;
+  a.ldrb = H; a.res = w.h2; a.ldres = H; a.Y = w.h1; a.ldy = H; a.M = N; a.K = d->kin; a.Nout = H; a.act = 1;
   if ((rc = launch_linear<EPI_PLAIN>(a, st))) return rc;
-  k_relu_mask<<<(unsigned)pstl_ceil_div(tot4, 256), 256, 0, st>>>(b.h2, b.h1, tot4);
-  PSTL_LAUNCH_CHECK();
-  // layer 0: per-row columns [hl | stlp6 | fused] from the packed rows; the F scene-feature columns per scene
-  if ((rc = wgrad(b.h2, H, H, b.xin, PSTL_XIN_LD, PSTL_XIN_LD, N, w.part, w.part_floats, g_r0_w, inr, F, T2, d->kin, st)))
-    return rc;
-  k_scene_sum<<<n_scenes, 256, 0, st>>>(b.h2, H, rows_per_scene, w.sdh);
-  PSTL_LAUNCH_CHECK();
-  if ((rc = wgrad(w.sdh, H, H, scene_feat, F, F, n_scenes, w.part, w.part_floats, g_r0_w, inr, 0, 0, 0, st))) return rc;
-  return colsum(w.sdh, H, H, n_scenes, w.part, g_r0_b, st);
+  lin_defaults(a);
+  a.X = w.h1; a.ldx = H; a.W = d->w.p2_w; a.ldw = H; a.bias = d->w.p2_b; a.Y = w.h2; a.ldy = H; a.M = N; a.K = H; a.Nout = H; a.act = 1;
+  return launch_linear<EPI_PLAIN>(a, st);
+}
+
+extern "C" int pstl_denoiser_eps_rows(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                                      const float* hl, const float* stlp, const float* x, int N, const float* temb_rows,
+                                      float* eps_out, void* workspace, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && x && temb_rows && eps_out && workspace, "null argument");
+  PSTL_CHECK_ARG(rows_per_scene >= 1 && (long long)n_scenes * rows_per_scene >= N, "bad scene mapping");
+  if (N <= 0) return PSTL_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DenoiserWs w;
+  size_t total;
+  carve(d, N, n_scenes, 1, nullptr, workspace, &w, &total);
+  int rc = eps_rows_activations(d, w, scene_feat, n_scenes, rows_per_scene, hl, stlp, x, N, temb_rows, st);
+  if (rc) return rc;
+  const int H = d->w.hidden, T2 = d->T2;
+  LinArgs a;
+  lin_defaults(a);  // eps = policy_net(...) + x (nusc_model.py:162)
+  a.X = w.h2; a.ldx = H; a.W = d->w.p4_w; a.ldw = H; a.bias = d->w.p4_b; a.res = x; a.ldres = T2; a.Y = eps_out; a.ldy = T2;
+  a.M = N; a.K = H; a.Nout = T2;
+  return launch_linear<EPI_PLAIN>(a, st);
+}
+
+extern "C" int pstl_denoiser_eps_backward(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
+                                          const float* hl, const float* stlp, const float* x, int N,
+                                          const float* temb_rows, const float* d_eps, float* g_p0_w, float* g_p0_b,
+                                          float* g_p2_w, float* g_p2_b, float* g_p4_w, float* g_p4_b, float* d_scene_feat,
+                                          void* workspace, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d && scene_feat && hl && stlp && x && temb_rows && d_eps && workspace, "null argument");
+  PSTL_CHECK_ARG(g_p0_w && g_p0_b && g_p2_w && g_p2_b && g_p4_w && g_p4_b, "null gradient output");
+  PSTL_CHECK_ARG(N > 0 && (long long)n_scenes * rows_per_scene == N, "rows must be n_scenes * rows_per_scene");
+  cudaStream_t st = (cudaStream_t)stream;
+  RefineBwdWs w;
+  size_t total;
+  carve_bwd(d, N, n_scenes, workspace, &w, &total);
+  const int H = d->w.hidden, T2 = d->T2, F = d->w.feat_dim, TD = d->w.time_dim;
+  PSTL_CHECK_ARG(H <= 256 && H % 4 == 0, "hidden width must be a multiple of 4, at most 256");
+  int rc = eps_rows_activations(d, w.base, scene_feat, n_scenes, rows_per_scene, hl, stlp, x, N, temb_rows, st);
+  if (rc) return rc;
+  MlpBwd m{};
+  m.W0 = d->w.p0_w; m.W2 = d->w.p2_w; m.W4 = d->w.p4_w; m.in0 = F + T2 + TD + 7; m.H = H;
+  m.col_x = F; m.col_tail = F + T2 + TD;
+  m.temb_rows = temb_rows; m.time_dim = TD; m.col_t = F + T2;
+  m.g_w0 = g_p0_w; m.g_b0 = g_p0_b; m.g_w2 = g_p2_w; m.g_b2 = g_p2_b; m.g_w4 = g_p4_w; m.g_b4 = g_p4_b;
+  m.d_feat = d_scene_feat;
+  return mlp_backward(d, w, d_eps, scene_feat, n_scenes, rows_per_scene, N, m, st);
 }

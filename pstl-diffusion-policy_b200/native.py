@@ -25,7 +25,7 @@ EXPORTS = [
     "pstl_denoiser_eps", "pstl_denoiser_set_noise_counter", "pstl_launch_count", "pstl_refine", "pstl_rollout", "pstl_rollout_bwd", "pstl_predicates", "pstl_linear", "pstl_encoder_inputs",
     "pstl_encoder_pool", "pstl_mlp3", "pstl_mlp3_batch", "pstl_trajopt_step", "pstl_diversity", "pstl_accuracy",
     "pstl_refine_losses_workspace_bytes", "pstl_refine_losses", "pstl_refine_backward_workspace_bytes",
-    "pstl_refine_backward",
+    "pstl_refine_backward", "pstl_denoiser_eps_rows", "pstl_denoiser_eps_backward",
 ]
 
 

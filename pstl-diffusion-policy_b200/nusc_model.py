@@ -81,6 +81,42 @@ class _RectForward(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(grads)
 
 
+class _EpsRows(torch.autograd.Function):
+    """Net.forward for training: eps with one timestep per row (pstl_denoiser_eps_rows) and its backward into
+    policy_net's parameters and the scene feature (pstl_denoiser_eps_backward)."""
+
+    @staticmethod
+    def forward(ctx, net, scene_feat, hl, stlp, x, temb_rows, *params):
+        n, bs = x.shape[0], scene_feat.shape[0]
+        handle = net.native_handle("fp32")
+        L = _nv.lib()
+        eps = torch.empty_like(x)
+        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), x.device, "denoiser")
+        sf = _nv.f32(scene_feat.detach())
+        _nv.check(L.pstl_denoiser_eps_rows(handle, _nv.fptr(sf), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp), _nv.fptr(x), n,
+                                           _nv.fptr(temb_rows), _nv.fptr(eps), _nv.ptr(ws), _nv.stream()),
+                  "pstl_denoiser_eps_rows")
+        ctx.net = net
+        ctx.save_for_backward(sf, hl, stlp, x, temb_rows)
+        ctx.shapes = [p.shape for p in params]
+        return eps
+
+    @staticmethod
+    def backward(ctx, g):
+        net = ctx.net
+        sf, hl, stlp, x, temb_rows = ctx.saved_tensors
+        n, bs = x.shape[0], sf.shape[0]
+        handle = net.native_handle("fp32")
+        L = _nv.lib()
+        grads = [torch.empty(s, dtype=torch.float32, device=x.device) for s in ctx.shapes]
+        d_feat = torch.empty_like(sf) if ctx.needs_input_grad[1] else None
+        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), x.device, "denoiser")
+        _nv.check(L.pstl_denoiser_eps_backward(handle, _nv.fptr(sf), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp), _nv.fptr(x), n,
+                                               _nv.fptr(temb_rows), _nv.fptr(_nv.f32(g)), *[_nv.fptr(t) for t in grads],
+                                               _nv.fptr(d_feat), _nv.ptr(ws), _nv.stream()), "pstl_denoiser_eps_backward")
+        return (None, d_feat, None, None, None, None) + tuple(grads)
+
+
 class Net(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -278,9 +314,22 @@ class Net(nn.Module):
         t = ext["timestep"]
         hl = _nv.f32(ext["highlevel"].reshape(n))
         stlp = _nv.f32(nn_input["stlp_dense"][:, 0])
+        params = [p for li in (0, 2, 4) for p in (self.policy_net[li].weight, self.policy_net[li].bias)]
+        if torch.is_grad_enabled() and (scene_feat.requires_grad or any(p.requires_grad for p in params)):
+            # training (reference nusc_train.py:1352-1356): one timestep per row, gradients into policy_net and,
+            # through the scene feature, into the encoders
+            temb_rows = self.pos_encoding(t.reshape(n, 1).to(x.device), self.time_dim).to(torch.float32).contiguous()
+            eps = _EpsRows.apply(self, scene_feat, hl.detach(), stlp.detach(), x.detach(), temb_rows, *params)
+            controls = eps.reshape(-1, self.args.nt, 2)
+            if get_feature:
+                k = scene_feat.shape[-1]
+                feature = scene_feat.reshape(bs, 1, k).expand(bs, n_rep, k).reshape(-1, k)
+                feature._pstl_scene_feat = scene_feat
+                return controls, feature
+            return controls
         t0 = int(t.reshape(-1)[0].item())
         if not bool((t == t0).all()):
-            raise NotImplementedError("native eps needs one timestep per call (the sampler's case)")
+            raise NotImplementedError("native eps without autograd needs one timestep per call (the sampler's case)")
         temb_row = self.pos_encoding(torch.tensor([[t0]], dtype=torch.long), self.time_dim).to(x.device).contiguous()
         handle = self.native_handle("fp32")
         eps = torch.empty_like(x)

@@ -913,6 +913,55 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     return out
 
 
+def diffusion_prep(dense_controls, n_randoms, coeffs=None, args=None, mono=False):
+    """reference :539-555: normalised commands, one timestep per row in [1, diffusion_steps), the forward-noised
+    commands.  Returns (noise, t (n,1), None, noised) like upstream."""
+    if mono:
+        raise NotImplementedError("mono (ground-truth-only) training is not built")
+    n = dense_controls.shape[0] * n_randoms * 3
+    cmd = dense_controls.reshape(n, args.nt, 2) / torch.tensor([args.mul_w_max, args.mul_a_max], device=dense_controls.device)
+    cmd = cmd.reshape(n, args.nt * 2)
+    noise = torch.normal(0, 1, (n, args.nt * 2), device=cmd.device)
+    beta, alpha, alpha_hat = coeffs
+    t = torch.randint(low=1, high=args.diffusion_steps, size=(n,), device=cmd.device)
+    ah = alpha_hat.to(cmd.device)[t]
+    return noise, t[:, None], None, torch.sqrt(ah)[:, None] * cmd + torch.sqrt(1 - ah)[:, None] * noise
+
+
+def train_step_ddpm(net, batch_cuda, coeffs, args, optimizer=None, gt_stlp=None, prep=None):
+    """One training iteration of the denoiser stage (README step 1; reference nusc_train.py:1352-1356, :436, :1523-1525):
+    ``diffusion_prep`` on the stored (traj-opt) controls, ``net(...)`` with one timestep per row, the eps-prediction
+    loss, backward (policy_net on the native kernels, the scene encoders through autograd from the per-scene feature
+    gradient) and the optimiser step (``Adam(net.parameters())`` upstream).  ``prep`` = (noise, t, noised) overrides the
+    draw.  With ``--stl_weight 0`` (the README command) this is the whole loss; the STL term of a sampled rollout that
+    upstream adds for a non-zero weight is not built.  Returns ``rd``."""
+    if float(args.stl_weight) != 0.0:
+        raise NotImplementedError("denoiser stage: only --stl_weight 0.0 (README step 1) is built")
+    S = args.n_randoms
+    bs = batch_cuda["ego_traj"].shape[0]
+    nb = LazyBatch({k: batch_cuda[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+                                               "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp", "params")
+                    if k in batch_cuda})
+    nb["neighbor_trajs_aug"] = batch_cuda["neighbors_traj"][..., :7]
+    if gt_stlp is None:
+        gt_stlp = batch_cuda["pre_stlp"].reshape(bs, -1, 3, 6)[:, 0, 0]
+    nb = augment_batch_data(nb, gt_stlp, args)
+    if prep is None:
+        noise, steps, _, noised = diffusion_prep(nb["params"], S, coeffs, args)
+    else:
+        noise, steps, noised = prep
+    est, feature = net(nb, ext={"timestep": steps, "highlevel": nb["highlevel_dense"], "noise": noised}, get_feature=True)
+    est = est.reshape(noise.shape)
+    rd = {"loss_diffusion": torch.mean(torch.square(noise - est)), "est_cmds_a": est, "feature": feature}
+    rd["loss_stl"] = rd["loss_diffusion"].detach() * 0
+    rd["loss"] = rd["loss_diffusion"]
+    if optimizer is not None:
+        optimizer.zero_grad()
+        rd["loss"].backward()
+        optimizer.step()
+    return rd
+
+
 def train_step_rect(net, batch_cuda, stls_cac, coeffs, args, optimizer=None, gt_stlp=None):
     """One training iteration of the --rect_head stage (reference nusc_train.py:1352-1427, 1523-1525; README "Ours"
     training command): chains sampled with the frozen denoiser, best of the last ``multi_cands`` iterates,

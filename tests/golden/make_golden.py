@@ -376,6 +376,51 @@ def gen_refine_step(bs=3, S=16, seed=2005):
           "|g_w0| %.3g |g_w2| %.3g |g_w4| %.3g" % tuple(float(np.abs(out["g_w%d" % li]).max()) for li in (0, 2, 4)))
 
 
+DDPM_FLAGS = ["-e", "e5_ddpm", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--skip_nusc_load"]  # README step 1
+
+
+def gen_ddpm_step(bs=3, S=16, seed=2006):
+    """One denoiser training step of the reference (README step 1; nusc_train.py:539-555 diffusion_prep, :1352-1356
+    net(...), :436 loss_diffusion, Adam over net.parameters()): the drawn noise / timesteps / noised commands, eps,
+    the loss, the gradients of policy_net (full) and of the encoders (first / last layers full, middle layer by its
+    norm and a 16 x 16 corner)."""
+    T, args = ref_shim.load(DDPM_FLAGS + ["--n_randoms", str(S)])
+    import nusc_model
+    nt = args.nt
+    N = bs * S * 3
+    batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=seed)
+    b = {k: v.clone() for k, v in batch.items()}
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    b = T.augment_batch_data(b, b["pre_stlp"].reshape(bs, S, 3, 6)[:, 0, 0], args)
+    net = nusc_model.Net(args)
+    sd = {k: v for k, v in synthetic.make_weights(seed=1007, nt=nt).items() if not k.startswith(("rect_net", "merge_net"))}
+    net.load_state_dict(sd, strict=True)
+    coeffs = T.get_diffusion_coeffs(args)
+    torch.manual_seed(seed)
+    noise, steps, _, noised = T.diffusion_prep(b["params"], n_randoms=S, coeffs=coeffs)
+    out = {"noise": noise.numpy(), "steps": steps.numpy(), "noised": noised.numpy()}
+    est, feature = net(b, ext={"timestep": steps, "highlevel": b["highlevel_dense"], "noise": noised}, get_feature=True)
+    est = est.reshape(N, nt * 2)
+    loss = torch.mean(torch.square(noise - est))
+    opt = torch.optim.Adam(net.parameters(), lr=args.lr)
+    opt.zero_grad()
+    loss.backward()
+    out["eps"] = est.detach().numpy()
+    out["feature_scene"] = feature.detach().reshape(bs, S * 3, -1)[:, 0].numpy()
+    out["loss"] = np.array(loss.item())
+    for name, p in net.named_parameters():
+        g = p.grad.numpy()
+        if name.startswith("policy_net") or ".2." not in name:
+            out["g|" + name] = g.copy()
+        else:
+            out["gn|" + name] = np.array(np.linalg.norm(g))
+            out["gc|" + name] = g[:16, :16].copy() if g.ndim == 2 else g[:16].copy()
+    np.savez_compressed(os.path.join(HERE, "ddpm_step.npz"), **out)
+    print("ddpm_step:", len(out), "arrays; loss %.5f" % loss.item(),
+          "|g policy.0| %.3g |g ego_encoder.0| %.3g" % (np.abs(out["g|policy_net.0.weight"]).max(),
+                                                         np.abs(out["g|ego_encoder.0.weight"]).max()))
+
+
 def metric_inputs(bs=5, m=16, nt=20, seed=2004):
     """trajectories / scores / validity for the diversity metrics: rollouts of the synthetic parameter bank, a random
     accept pattern that includes a lane with nothing accepted, one with two samples and one with collinear samples"""
@@ -431,6 +476,7 @@ def main():
     gen_metrics()
     gen_losses()
     gen_refine_step()
+    gen_ddpm_step()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -1052,3 +1052,59 @@ def test_rect_training_loop(tmp_path):
     for k, v in net2.state_dict().items():
         assert torch.equal(v.cpu(), net.state_dict()[k].cpu())
         assert torch.equal(v.cpu(), sd0[k]) != k.startswith("rect_net."), k
+
+
+def _ddpm_net(nt=20, **over):
+    args = NT.default_args(flags=["-e", "e5_ddpm", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--skip_nusc_load"],
+                           precision="fp32", **over)
+    net = Net(args)
+    sd = {k: v for k, v in synthetic.make_weights(1007, nt=nt).items() if not k.startswith(("rect_net", "merge_net"))}
+    net.load_state_dict(sd)
+    return args, net.cuda()
+
+
+def test_ddpm_train_step_golden(golden_dir):
+    """One denoiser training step (README step 1): eps with a timestep per row on pstl_denoiser_eps_rows, the loss, and
+    the gradients of policy_net (pstl_denoiser_eps_backward) and of the encoders (autograd from the native per-scene
+    feature gradient) against the reference's (tests/golden/ddpm_step.npz)"""
+    from test_oracle_golden import check_ddpm_grads
+    G = np.load(os.path.join(golden_dir, "ddpm_step.npz"))
+    bs, S_, nt = 3, 16, 20
+    args, net = _ddpm_net(nt, n_randoms=S_, sampling_size=S_)
+    b = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=2006))
+    prep = tuple(torch.from_numpy(G[k]).cuda() for k in ("noise", "steps", "noised"))
+    rd = NT.train_step_ddpm(net, b, NT.get_diffusion_coeffs(args), args, prep=prep)
+    close(rd["feature"]._pstl_scene_feat, G["feature_scene"], what="feature")
+    close(rd["est_cmds_a"], G["eps"], what="eps")
+    np.testing.assert_allclose(float(rd["loss"].detach()), float(G["loss"]), rtol=1e-5)
+    rd["loss"].backward()
+    check_ddpm_grads(G, {k: p.grad.cpu().numpy() for k, p in net.named_parameters()}, 1e-4)
+    # diffusion_prep: timesteps in [1, steps), the forward-noising identity
+    coeffs = NT.get_diffusion_coeffs(args)
+    noise, t, _, noised = NT.diffusion_prep(b["params"], S_, coeffs, args)
+    assert int(t.min()) >= 1 and int(t.max()) < args.diffusion_steps and t.shape == (bs * S_ * 3, 1)
+    ah = coeffs[2].cuda()[t[:, 0]][:, None]
+    cmd = (b["params"].reshape(-1, nt, 2) / torch.tensor([args.mul_w_max, args.mul_a_max], device="cuda")).reshape(-1, nt * 2)
+    close(noised, torch.sqrt(ah) * cmd + torch.sqrt(1 - ah) * noise)
+
+
+def test_ddpm_backward_oracle_and_training():
+    """pstl_denoiser_eps_backward at 32 scenes x 64 samples against the oracle's autograd; then a few Adam steps over
+    net.parameters() on a fixed draw lower the loss"""
+    bs, S_, nt = 32, 64, 20
+    args, net = _ddpm_net(nt, lr=1e-3)
+    coeffs = NT.get_diffusion_coeffs(args)
+    bc = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=33)
+    b = cuda(bc)
+    torch.manual_seed(5)
+    noise, t, _, noised = NT.diffusion_prep(b["params"], S_, coeffs, args)
+    rd = NT.train_step_ddpm(net, b, coeffs, args, prep=(noise, t, noised))
+    rd["loss"].backward()
+    r = O.ddpm_train_step(synthetic.make_weights(1007, nt=nt), bc, noise.cpu(), t.cpu(), noised.cpu(), S_, nt)
+    close(rd["est_cmds_a"], r["eps"], what="eps")
+    np.testing.assert_allclose(float(rd["loss"].detach()), float(r["loss"]), rtol=1e-5)
+    for k, p in net.named_parameters():
+        close(p.grad, r["grads"][k], rtol=2e-4, what=k)
+    opt = torch.optim.Adam(net.parameters(), lr=args.lr)
+    losses = [float(NT.train_step_ddpm(net, b, coeffs, args, opt, prep=(noise, t, noised))["loss"].detach()) for _ in range(5)]
+    assert losses[-1] < losses[0] and losses[0] == pytest.approx(float(rd["loss"].detach()), rel=1e-6), losses

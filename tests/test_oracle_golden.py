@@ -218,3 +218,35 @@ def test_refine_train_step(golden_dir):
         for k, key in (("weight", "w%d_after"), ("bias", "b%d_after")):
             err = np.abs(r["W"]["rect_net.%d.%s" % (li, k)].detach().numpy() - G[key % li])
             assert np.percentile(err, 99) < 1e-6 and err.max() <= 2.001 * float(G["lr"]), (li, k, err.max())
+
+
+def check_ddpm_grads(G, grads, rtol):
+    """policy_net and first/last encoder layers in full, the encoders' middle layer by norm and a corner"""
+    n = 0
+    for key in G.files:
+        kind, _, name = key.partition("|")
+        if kind == "g":
+            close(grads[name], G[key], rtol=rtol)
+        elif kind == "gn":
+            np.testing.assert_allclose(np.linalg.norm(np.asarray(grads[name], np.float64)), float(G[key]), rtol=10 * rtol)
+        elif kind == "gc":
+            g = np.asarray(grads[name])
+            close(g[:16, :16] if g.ndim == 2 else g[:16], G[key], rtol=rtol,
+                  atol=rtol * float(np.abs(g).max()))
+        else:
+            continue
+        n += 1
+    assert n == 30  # 24 tensors, the three middle encoder layers (weight, bias) counted twice
+
+
+def test_ddpm_train_step(golden_dir):
+    """oracle ddpm_train_step == one denoiser training step of the reference (tests/golden/ddpm_step.npz)"""
+    G = np.load(os.path.join(golden_dir, "ddpm_step.npz"))
+    bs, S_, nt = 3, 16, 20
+    b = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=2006)
+    r = O.ddpm_train_step(synthetic.make_weights(1007, nt=nt), b, torch.from_numpy(G["noise"]),
+                          torch.from_numpy(G["steps"]), torch.from_numpy(G["noised"]), S_, nt)
+    close(r["feature"].numpy(), G["feature_scene"])
+    close(r["eps"].numpy(), G["eps"])
+    np.testing.assert_allclose(float(r["loss"]), float(G["loss"]), rtol=1e-5)
+    check_ddpm_grads(G, {k: v.numpy() for k, v in r["grads"].items()}, 1e-4)
