@@ -1327,22 +1327,28 @@ def save_model_freq_last(state_dict, model_dir, epi, save_freq, epochs):
         torch.save(state_dict, "%s/model_last.ckpt" % (model_dir))
 
 
-def run_rect_training(stls_cac, train_loader, net, coeffs, args, model_dir=None, log=print):
-    """The epoch loop of the --rect_head stage (reference nusc_train.py:1228-1233 optimiser, :1245-1577 loop, train
-    mode only): ``args.epochs`` passes over ``train_loader`` (scene batches on the host or the device), one
-    ``train_step_rect`` per batch, the per-epoch means of the logged terms, checkpoints in upstream's layout when
+def run_training(stls_cac, train_loader, net, coeffs, args, model_dir=None, log=print):
+    """The epoch loop of the reference's two diffusion stages (nusc_train.py:1228-1235 optimiser, :1245-1577 loop, train
+    mode only): README step 1 (``--diffusion``: ``train_step_ddpm``, Adam over every parameter) or step 2
+    (``--rect_head``: ``train_step_rect``, Adam over rect_net).  ``args.epochs`` passes over ``train_loader`` (scene
+    batches on the host or the device), the per-epoch means of the logged terms, checkpoints in upstream's layout when
     ``model_dir`` is given.  Returns the list of per-epoch dicts."""
-    if not (args.rect_head and args.diffusion) or getattr(args, "joint", False):
-        raise NotImplementedError("only the --diffusion --rect_head stage (Adam over rect_net) is built")
-    optimizer = torch.optim.Adam(net.rect_net.parameters(), lr=args.lr)
-    keys = ("loss", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg", "acc", "avg_speed")
+    if not args.diffusion or getattr(args, "joint", False):
+        raise NotImplementedError("only the --diffusion stages (denoiser; --rect_head RefineNet) are built")
+    if args.rect_head:
+        optimizer = torch.optim.Adam(net.rect_net.parameters(), lr=args.lr)
+        step = lambda b: train_step_rect(net, b, stls_cac, coeffs, args, optimizer)
+    else:
+        optimizer = torch.optim.Adam(net.parameters(), lr=args.lr)
+        step = lambda b: train_step_ddpm(net, b, coeffs, args, optimizer)
+    keys = ("loss", "loss_diffusion", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg", "acc", "avg_speed")
     history = []
     for epi in range(args.epochs):
         sums = {}
         nb = 0
         for batch in train_loader:
             batch_cuda = {k: (v.cuda(non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
-            rd = train_step_rect(net, batch_cuda, stls_cac, coeffs, args, optimizer)
+            rd = step(batch_cuda)
             for k in keys:
                 if k in rd:
                     sums[k] = sums.get(k, 0.0) + rd[k].detach()
@@ -1356,16 +1362,21 @@ def run_rect_training(stls_cac, train_loader, net, coeffs, args, model_dir=None,
     return history
 
 
+run_rect_training = run_training
+
+
 def main(argv=None):
     """``python -m pstl_b200.nusc_train ... --run_sampling_test --synthetic 32`` (open-loop test) or, without
-    ``--run_sampling_test`` and with ``--rect_head``, the RefineNet training stage on synthetic scene batches
-    (``--synthetic B`` scenes per batch, ``--epochs``, checkpoints under ``./exps_nusc/<exp_name>/models``)."""
+    ``--run_sampling_test``, the README's training stages on synthetic scene batches: step 1 (``--diffusion``, the
+    denoiser) or step 2 (``--rect_head``, RefineNet); ``--synthetic B`` scenes per batch, ``--epochs``, checkpoints
+    under ``./exps_nusc/<exp_name>/models``."""
     from . import synthetic
     from .nusc_model import Net
     args = generate_parser(argv)
     if not args.run_sampling_test:
-        if not args.rect_head:
-            raise SystemExit("training: only the --rect_head stage is built (the denoiser stage / traj-opt CLI are not)")
+        if not args.diffusion or getattr(args, "trajopt_only", False):
+            raise SystemExit("training: the --diffusion stages are built (denoiser, --rect_head); see nusc_train.trajopt "
+                             "for the trajectory optimisation")
         torch.manual_seed(args.seed)
         net = Net(args).cuda()
         if args.net_pretrained_path is not None:
@@ -1374,7 +1385,7 @@ def main(argv=None):
         loader = [synthetic.make_scene_batch(bs, nt=args.nt, dt=args.dt, n_neighbors=args.n_neighbors, n_segs=args.n_segs,
                                              n_randoms=args.n_randoms, seed=args.seed + i) for i in range(3)]
         model_dir = os.path.join("exps_nusc", args.exp_name or "rect", "models")
-        return run_rect_training(build_stl_cache(args), loader, net, get_diffusion_coeffs(args), args, model_dir)
+        return run_training(build_stl_cache(args), loader, net, get_diffusion_coeffs(args), args, model_dir)
     torch.manual_seed(args.seed)
     stls_cac = build_stl_cache(args)
     net = Net(args).cuda()

@@ -4,6 +4,7 @@
    python tests/bench_configs.py trajopt [scenes] [iters]  # trajectory-optimisation iterations
    python tests/bench_configs.py losses [scenes]       # RefineNet training losses, value + gradient (§8(f) item 4)
    python tests/bench_configs.py train [scenes] [steps]  # full --rect_head training iterations (sampler .. Adam step)
+   python tests/bench_configs.py train_ddpm [scenes] [steps]  # denoiser training iterations (README step 1)
 """
 import os
 import sys
@@ -145,6 +146,32 @@ def losses(scenes):
                                   torch.get_num_threads(), sub, cpu_ms))
 
 
+def train_ddpm(scenes, steps):
+    """README step 1: denoiser training iterations (diffusion_prep -> eps with a timestep per row -> loss -> backward
+    into policy_net and the encoders -> Adam over all parameters)"""
+    args = NT.default_args(flags=["-e", "e5_ddpm", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--skip_nusc_load"])
+    net = Net(args)
+    net.load_state_dict({k: v for k, v in synthetic.make_weights(1007).items() if not k.startswith(("rect_net", "merge_net"))})
+    net = net.cuda()
+    b = {k: v.cuda() for k, v in synthetic.make_scene_batch(scenes, seed=5).items()}
+    coeffs = NT.get_diffusion_coeffs(args)
+    opt = torch.optim.Adam(net.parameters(), lr=args.lr)
+    log = []
+    ms = timeit(lambda: log.append(NT.train_step_ddpm(net, b, coeffs, args, opt)["loss"].detach()), reps=steps, warm=2)
+    n = scenes * args.n_randoms * 3
+    print("train_ddpm: scenes=%d rows=%d  %.2f ms per iteration (%.3g rows/s); loss %s"
+          % (scenes, n, ms, n / ms * 1e3, " ".join("%.4f" % float(v) for v in log[:2] + log[-2:])))
+    from oracle import pstl_oracle as O
+    sub = min(scenes, 16)
+    bc = synthetic.make_scene_batch(sub, seed=5)
+    noise, t, _, noised = NT.diffusion_prep(bc["params"], args.n_randoms, [c.cpu() for c in coeffs], args)
+    t0 = time.time()
+    O.ddpm_train_step(synthetic.make_weights(1007), bc, noise, t, noised, args.n_randoms, args.nt)
+    cpu = time.time() - t0
+    print("train_ddpm: oracle (torch CPU, %d threads) forward + backward on %d scenes: %.2f s -> %.1f s per %d-scene "
+          "iteration" % (torch.get_num_threads(), sub, cpu, cpu * scenes / sub, scenes))
+
+
 def train(scenes, steps):
     """README "Ours" training stage (nusc_train.py:1352-1427, 1523-1525): iterations/s of sampler -> best-of-5 ->
     RefineNet -> rollout -> scorer -> losses -> backward -> Adam over rect_net"""
@@ -182,7 +209,9 @@ def train(scenes, steps):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "train":
+    if sys.argv[1] == "train_ddpm":
+        train_ddpm(int(sys.argv[2]) if len(sys.argv) > 2 else 1024, int(sys.argv[3]) if len(sys.argv) > 3 else 5)
+    elif sys.argv[1] == "train":
         train(int(sys.argv[2]) if len(sys.argv) > 2 else 1024, int(sys.argv[3]) if len(sys.argv) > 3 else 5)
     elif sys.argv[1] == "losses":
         losses(int(sys.argv[2]) if len(sys.argv) > 2 else 1024)
