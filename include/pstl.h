@@ -273,29 +273,33 @@ int pstl_diversity(const float* trajs, const float* scores, const float* valids,
  * pstl_denoiser_eps_backward: from d_eps (N, 2*nt) to the gradients of policy_net.{0,2,4}.{weight,bias} (reference
  * shapes, row-major (out, in)) and, when d_scene_feat (n_scenes, feat_dim) is non-NULL, of the per-scene feature (the
  * encoders' backward continues from there).  Stateless (activations are recomputed); deterministic reductions.
- * Workspace: pstl_refine_backward_workspace_bytes for the backward, pstl_denoiser_workspace_bytes for the forward. */
+ * Workspace: pstl_refine_backward_workspace_bytes for the backward, pstl_denoiser_workspace_bytes for the forward.
+ * reuse_activations != 0 (both backward entries): the workspace is the very buffer the matching forward call
+ * (pstl_denoiser_eps_rows / pstl_refine on a PSTL_PRECISION_FP32 handle; sized for the backward) wrote, with the same
+ * arguments and weights, untouched since — the recompute is skipped. */
 int pstl_denoiser_eps_rows(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene, const float* hl,
                            const float* stlp, const float* x, int N, const float* temb_rows, float* eps_out,
                            void* workspace, pstl_stream_t stream);
 int pstl_denoiser_eps_backward(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene,
                                const float* hl, const float* stlp, const float* x, int N, const float* temb_rows,
                                const float* d_eps, float* g_p0_w, float* g_p0_b, float* g_p2_w, float* g_p2_b,
-                               float* g_p4_w, float* g_p4_b, float* d_scene_feat, void* workspace, pstl_stream_t stream);
+                               float* g_p4_w, float* g_p4_b, float* d_scene_feat, int reuse_activations, void* workspace,
+                               pstl_stream_t stream);
 
 /* RefineNet backward for the --rect_head training step (autograd over Net.rect_forward, nusc_model.py:182-235; the
  * optimiser upstream holds net.rect_net.parameters() only, nusc_train.py:1228-1233): from d_out = d loss / d rect_controls
  * (N, 2*nt) to the gradients of rect_net.{0,2,4}.{weight,bias} in the reference's own shapes (row-major (out, in):
  * g_r0_w (H, feat+7+2*nt), g_r2_w (H, H), g_r4_w (2*nt, H)).  Same row / scene arguments as pstl_refine.  The call is
- * stateless: it recomputes the fp32 activations in its workspace (whatever the handle's precision), so it pairs with a
- * forward made on a PSTL_PRECISION_FP32 handle.  Reductions over the rows run as split-K tiles summed in a fixed
+ * stateless unless reuse_activations is set (see pstl_denoiser_eps_backward): it recomputes the fp32 activations in its
+ * workspace (whatever the handle's precision), so it pairs with a forward made on a PSTL_PRECISION_FP32 handle.  Reductions over the rows run as split-K tiles summed in a fixed
  * order: results are deterministic.  merge_net and the scene encoders receive no gradient (not in upstream's optimiser
  * without --joint). */
 size_t pstl_refine_backward_workspace_bytes(pstl_denoiser_t d, int N, int n_scenes);
 int pstl_refine_backward(pstl_denoiser_t d, const float* scene_feat, int n_scenes, int rows_per_scene, const float* hl,
                          const float* stlp, const float* u0, const float* scores, int N, int n_randoms, int n_shards,
                          float w_max, float a_max, int clip_rect, const float* d_out, float* g_r0_w, float* g_r0_b,
-                         float* g_r2_w, float* g_r2_b, float* g_r4_w, float* g_r4_b, void* workspace,
-                         pstl_stream_t stream);
+                         float* g_r2_w, float* g_r2_b, float* g_r4_w, float* g_r4_b, int reuse_activations,
+                         void* workspace, pstl_stream_t stream);
 
 /* RefineNet training losses, value and gradient (compute_policy_loss, nusc_train.py:411 loss_stl, :439-466 the
  * --diverse_loss branch, :468-478 the plain branch).  Rows n = (scene*S + sample)*3 + mode as everywhere.

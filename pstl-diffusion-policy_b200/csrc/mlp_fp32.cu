@@ -1154,7 +1154,8 @@ extern "C" int pstl_refine_backward(pstl_denoiser_t d, const float* scene_feat, 
                                     const float* hl, const float* stlp, const float* u0, const float* scores, int N,
                                     int n_randoms, int n_shards, float w_max, float a_max, int clip_rect,
                                     const float* d_out, float* g_r0_w, float* g_r0_b, float* g_r2_w, float* g_r2_b,
-                                    float* g_r4_w, float* g_r4_b, void* workspace, pstl_stream_t stream) {
+                                    float* g_r4_w, float* g_r4_b, int reuse_activations, void* workspace,
+                                    pstl_stream_t stream) {
   PSTL_CHECK_ARG(d && scene_feat && hl && stlp && u0 && scores && d_out && workspace, "null argument");
   PSTL_CHECK_ARG(g_r0_w && g_r0_b && g_r2_w && g_r2_b && g_r4_w && g_r4_b, "null gradient output");
   PSTL_CHECK_ARG(d->w.r0_w && d->w.m0_w && d->r1p, "handle was created without rect_net / merge_net weights");
@@ -1168,10 +1169,13 @@ extern "C" int pstl_refine_backward(pstl_denoiser_t d, const float* scene_feat, 
   const DenoiserWs& b = w.base;
   const int H = d->w.rect_hidden, T2 = d->T2, F = d->w.feat_dim, inr = F + 7 + T2;
   PSTL_CHECK_ARG(H <= 256 && H % 4 == 0, "rect_net hidden width must be a multiple of 4, at most 256");
-  // forward, fp32, keeping the activations: xin, h1, h2 (post-ReLU) and y (pre-tanh)
-  int rc = refine_inputs(d, b, scene_feat, n_scenes, hl, stlp, u0, N, n_randoms, n_shards, st);
-  if (rc) return rc;
-  if ((rc = mlp_hidden(d, b, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st))) return rc;
+  // forward, fp32, keeping the activations: xin, h1, h2 (post-ReLU) and y (pre-tanh); with reuse_activations the
+  // first three are still in the workspace from the fp32 pstl_refine call and only y is rebuilt
+  int rc = PSTL_OK;
+  if (!reuse_activations) {
+    if ((rc = refine_inputs(d, b, scene_feat, n_scenes, hl, stlp, u0, N, n_randoms, n_shards, st))) return rc;
+    if ((rc = mlp_hidden(d, b, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st))) return rc;
+  }
   LinArgs a;
   lin_defaults(a);
   a.X = b.h2; a.ldx = H; a.W = d->w.r4_w; a.ldw = H; a.bias = d->w.r4_b; a.Y = b.g; a.ldy = T2; a.M = N; a.K = H; a.Nout = T2;
@@ -1239,7 +1243,7 @@ extern "C" int pstl_denoiser_eps_backward(pstl_denoiser_t d, const float* scene_
                                           const float* hl, const float* stlp, const float* x, int N,
                                           const float* temb_rows, const float* d_eps, float* g_p0_w, float* g_p0_b,
                                           float* g_p2_w, float* g_p2_b, float* g_p4_w, float* g_p4_b, float* d_scene_feat,
-                                          void* workspace, pstl_stream_t stream) {
+                                          int reuse_activations, void* workspace, pstl_stream_t stream) {
   PSTL_CHECK_ARG(d && scene_feat && hl && stlp && x && temb_rows && d_eps && workspace, "null argument");
   PSTL_CHECK_ARG(g_p0_w && g_p0_b && g_p2_w && g_p2_b && g_p4_w && g_p4_b, "null gradient output");
   PSTL_CHECK_ARG(N > 0 && (long long)n_scenes * rows_per_scene == N, "rows must be n_scenes * rows_per_scene");
@@ -1249,8 +1253,10 @@ extern "C" int pstl_denoiser_eps_backward(pstl_denoiser_t d, const float* scene_
   carve_bwd(d, N, n_scenes, workspace, &w, &total);
   const int H = d->w.hidden, T2 = d->T2, F = d->w.feat_dim, TD = d->w.time_dim;
   PSTL_CHECK_ARG(H <= 256 && H % 4 == 0, "hidden width must be a multiple of 4, at most 256");
-  int rc = eps_rows_activations(d, w.base, scene_feat, n_scenes, rows_per_scene, hl, stlp, x, N, temb_rows, st);
-  if (rc) return rc;
+  int rc = PSTL_OK;
+  if (!reuse_activations &&
+      (rc = eps_rows_activations(d, w.base, scene_feat, n_scenes, rows_per_scene, hl, stlp, x, N, temb_rows, st)))
+    return rc;
   MlpBwd m{};
   m.W0 = d->w.p0_w; m.W2 = d->w.p2_w; m.W4 = d->w.p4_w; m.in0 = F + T2 + TD + 7; m.H = H;
   m.col_x = F; m.col_tail = F + T2 + TD;

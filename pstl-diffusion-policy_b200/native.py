@@ -168,6 +168,20 @@ def workspace(nbytes, device, tag="default"):
     return buf
 
 
+_act_epoch = [0]
+
+
+def activation_workspace(nbytes, device):
+    """Scratch of a training forward whose activations the backward may reuse: returns (buffer, epoch); the epoch
+    moves on with every later training forward on this buffer (``activations_valid``)."""
+    _act_epoch[0] += 1
+    return workspace(nbytes, device, "train_act"), _act_epoch[0]
+
+
+def activations_valid(epoch):
+    return int(_act_epoch[0] == epoch)
+
+
 def make_scene_view(neighbors, lanes, rows_per_scene):
     """neighbors (n_scenes,K,T,7); lanes: 3 tensors (n_scenes,nseg,3)."""
     sv = SceneView()

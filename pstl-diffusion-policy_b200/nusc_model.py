@@ -54,7 +54,8 @@ class _RectForward(torch.autograd.Function):
         out = torch.empty((n, a.nt, 2), dtype=torch.float32, device=u0.device)
         handle = net.native_handle("fp32")
         L = _nv.lib()
-        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), u0.device, "denoiser")
+        ws, ctx.epoch = _nv.activation_workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), u0.device)
+        ctx.ws = ws
         _nv.check(L.pstl_refine(handle, _nv.fptr(scene_feat), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp), _nv.fptr(u0),
                                 _nv.fptr(scores), n, a.n_randoms, a.n_shards, _nv.C.c_float(a.mul_w_max),
                                 _nv.C.c_float(a.mul_a_max), int(bool(a.clip_rect)), _nv.fptr(out), _nv.ptr(ws),
@@ -72,12 +73,13 @@ class _RectForward(torch.autograd.Function):
         handle = net.native_handle("fp32")
         L = _nv.lib()
         grads = [torch.empty(s, dtype=torch.float32, device=u0.device) for s in ctx.shapes]
-        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), u0.device, "denoiser")
+        reuse = _nv.activations_valid(ctx.epoch)  # no other training forward has written the buffer since
+        ws = ctx.ws if reuse else _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), u0.device, "denoiser")
         _nv.check(L.pstl_refine_backward(handle, _nv.fptr(scene_feat), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp),
                                          _nv.fptr(u0), _nv.fptr(scores), n, a.n_randoms, a.n_shards,
                                          _nv.C.c_float(a.mul_w_max), _nv.C.c_float(a.mul_a_max), int(bool(a.clip_rect)),
                                          _nv.fptr(_nv.f32(g.reshape(n, a.nt * 2))), *[_nv.fptr(t) for t in grads],
-                                         _nv.ptr(ws), _nv.stream()), "pstl_refine_backward")
+                                         reuse, _nv.ptr(ws), _nv.stream()), "pstl_refine_backward")
         return (None, None, None, None, None, None) + tuple(grads)
 
 
@@ -91,7 +93,8 @@ class _EpsRows(torch.autograd.Function):
         handle = net.native_handle("fp32")
         L = _nv.lib()
         eps = torch.empty_like(x)
-        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), x.device, "denoiser")
+        ws, ctx.epoch = _nv.activation_workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), x.device)
+        ctx.ws = ws
         sf = _nv.f32(scene_feat.detach())
         _nv.check(L.pstl_denoiser_eps_rows(handle, _nv.fptr(sf), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp), _nv.fptr(x), n,
                                            _nv.fptr(temb_rows), _nv.fptr(eps), _nv.ptr(ws), _nv.stream()),
@@ -110,10 +113,12 @@ class _EpsRows(torch.autograd.Function):
         L = _nv.lib()
         grads = [torch.empty(s, dtype=torch.float32, device=x.device) for s in ctx.shapes]
         d_feat = torch.empty_like(sf) if ctx.needs_input_grad[1] else None
-        ws = _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), x.device, "denoiser")
+        reuse = _nv.activations_valid(ctx.epoch)  # no other training forward has written the buffer since
+        ws = ctx.ws if reuse else _nv.workspace(L.pstl_refine_backward_workspace_bytes(handle, n, bs), x.device, "denoiser")
         _nv.check(L.pstl_denoiser_eps_backward(handle, _nv.fptr(sf), bs, n // bs, _nv.fptr(hl), _nv.fptr(stlp), _nv.fptr(x), n,
                                                _nv.fptr(temb_rows), _nv.fptr(_nv.f32(g)), *[_nv.fptr(t) for t in grads],
-                                               _nv.fptr(d_feat), _nv.ptr(ws), _nv.stream()), "pstl_denoiser_eps_backward")
+                                               _nv.fptr(d_feat), reuse, _nv.ptr(ws), _nv.stream()),
+                  "pstl_denoiser_eps_backward")
         return (None, d_feat, None, None, None, None) + tuple(grads)
 
 

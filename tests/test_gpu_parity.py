@@ -1001,6 +1001,7 @@ def test_refine_backward_oracle():
     args, net, step = _train_step_setup(bs, S_, nt, kw, 31, None, feat_scene.cuda())
     b = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=31)
     prev_scores, rect, rd = step()
+    step()  # a later training forward takes over the activation buffer: this backward recomputes instead of reusing
     rd["loss"].backward()
     r = O.refine_train_step(synthetic.make_weights(1007, nt=nt), b, feat_scene, b["params"].reshape(-1, nt, 2), 0.5, **kw)
     close(rect, r["rect"], what="rect")
@@ -1099,6 +1100,7 @@ def test_ddpm_backward_oracle_and_training():
     torch.manual_seed(5)
     noise, t, _, noised = NT.diffusion_prep(b["params"], S_, coeffs, args)
     rd = NT.train_step_ddpm(net, b, coeffs, args, prep=(noise, t, noised))
+    NT.train_step_ddpm(net, b, coeffs, args)  # a later forward owns the activation buffer: the backward recomputes
     rd["loss"].backward()
     r = O.ddpm_train_step(synthetic.make_weights(1007, nt=nt), bc, noise.cpu(), t.cpu(), noised.cpu(), S_, nt)
     close(rd["est_cmds_a"], r["eps"], what="eps")
