@@ -7,7 +7,9 @@ Two calling styles are served by the same functions:
     ``ScenePack`` (compact scene tensors + per-row state/pSTL/mode), so the kernels index scenes
     instead of reading K-times-replicated copies; the dense tensors are only materialised if a
     caller actually reads them.
-Out of scope: training loop, losses, traj-opt, dataset, visualisation.
+Beyond the sampling test: ``trajopt`` (traj-opt data generation), ``compute_policy_loss``,
+``train_step_ddpm`` / ``train_step_rect`` / ``run_training`` (the README's two training stages).
+Out of scope: dataset / NuScenes access, pSTL calibration, visualisation, the VAE / BC baselines.
 """
 import argparse
 import os
