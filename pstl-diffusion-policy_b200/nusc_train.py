@@ -1050,6 +1050,56 @@ def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):
     return p.reshape(p0.shape), scores
 
 
+def save_trajopt_params(params, iter_i, traj_i, ti, args, save_stlp=None, model_dir=None):
+    """The traj-opt outputs in the reference's on-disk format (nusc_train.py:775-797): one ``.npy`` per scene sample,
+    ``params_<traj>_<ti>.npy`` ("final"), ``..._init.npy`` ("init"), ``..._iter<k>.npy`` (integer), ``scores_<traj>_<ti>.npy``
+    ("scores"), plus ``..._stlp.npy`` (n_randoms, 3, 1, 6) when ``save_stlp`` is given.  Nothing is written under --test."""
+    if getattr(args, "test", False):
+        return []
+    model_dir = model_dir or args.model_dir
+    os.makedirs(model_dir, exist_ok=True)
+    bs = params.shape[0]
+    arr = params.detach().cpu().numpy()
+    stlp = None
+    if save_stlp is not None:
+        stlp = save_stlp.detach().cpu().numpy().reshape(bs, args.n_randoms, 3, 1, save_stlp.shape[-1])
+    written = []
+    for i in range(bs):
+        key = (int(traj_i[i]), int(ti[i]))
+        if iter_i == "scores":
+            name = "scores_%05d_%04d.npy" % key
+        elif iter_i == "init":
+            name = "params_%05d_%04d_init.npy" % key
+        elif iter_i == "final":
+            name = "params_%05d_%04d.npy" % key
+        else:
+            name = "params_%05d_%04d_iter%05d.npy" % (key + (int(iter_i),))
+        np.save(os.path.join(model_dir, name), arr[i])
+        written.append(name)
+        if stlp is not None:
+            name = "params_%05d_%04d_stlp.npy" % key
+            np.save(os.path.join(model_dir, name), stlp[i])
+            written.append(name)
+    return written
+
+
+def load_trajopt_params(model_dir, traj_i, ti, load_stlp=True):
+    """What the reference's dataset reads back per sample (nusc_dataset.py:203-225): ``params`` / ``params_init``
+    (n_randoms, 3, nt, 2) and, with --load_stlp, ``pre_stlp`` (n_randoms, 3, 1, 6) and ``tj_scores_prior`` (n_randoms, 3),
+    stacked over the given (traj_i, ti) pairs."""
+    out = {"params": [], "params_init": []}
+    if load_stlp:
+        out.update(pre_stlp=[], tj_scores_prior=[])
+    for a, b in zip(traj_i, ti):
+        key = (int(a), int(b))
+        out["params"].append(np.load(os.path.join(model_dir, "params_%05d_%04d.npy" % key)))
+        out["params_init"].append(np.load(os.path.join(model_dir, "params_%05d_%04d_init.npy" % key)))
+        if load_stlp:
+            out["pre_stlp"].append(np.load(os.path.join(model_dir, "params_%05d_%04d_stlp.npy" % key)))
+            out["tj_scores_prior"].append(np.load(os.path.join(model_dir, "scores_%05d_%04d.npy" % key)))
+    return {k: torch.from_numpy(np.stack(v)).float() for k, v in out.items()}
+
+
 def closed_loop_pick(scores_all, ego_controls, ego_trajs):
     """candidate selection of the closed-loop simulator (reference nusc_sim.py:677-683): chains are rows
     ``n = sample*3 + mode`` of ONE scene; modes 1, 2 (lane changes) are masked to -1e4 and the global arg-max wins

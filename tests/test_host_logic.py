@@ -194,3 +194,32 @@ def test_closed_loop_pick_masks_lane_change_modes():
     assert int(idx) == int(torch.argmax(cube)) == 21 and float(best) == 9.0
     assert cu.shape == (1, 20, 2) and ct.shape == (1, 21, 4) and torch.equal(cu[0], u[21])
     assert sc[5 * 3 + 1] == 50.0  # input untouched
+
+
+def test_trajopt_params_files(tmp_path):
+    """save_trajopt_params / load_trajopt_params: the reference's per-sample .npy names and shapes
+    (nusc_train.py:775-797, nusc_dataset.py:203-225), nothing written under --test"""
+    from pstl_b200 import nusc_train as NT
+    args = NT.default_args(n_randoms=4)
+    args.test = False
+    bs, nt = 3, args.nt
+    g = torch.Generator().manual_seed(1)
+    params = torch.randn(bs, 4, 3, nt, 2, generator=g)
+    init = torch.randn(bs, 4, 3, nt, 2, generator=g)
+    scores = torch.randn(bs, 4, 3, generator=g)
+    stlp = torch.randn(bs * 4 * 3, 1, 6, generator=g)
+    traj_i, ti = torch.tensor([7, 7, 123]), torch.tensor([0, 15, 2])
+    d = str(tmp_path)
+    NT.save_trajopt_params(init, "init", traj_i, ti, args, model_dir=d)
+    NT.save_trajopt_params(params, 50, traj_i, ti, args, model_dir=d)
+    NT.save_trajopt_params(scores, "scores", traj_i, ti, args, model_dir=d)
+    names = NT.save_trajopt_params(params, "final", traj_i, ti, args, save_stlp=stlp, model_dir=d)
+    assert names[:2] == ["params_00007_0000.npy", "params_00007_0000_stlp.npy"]
+    assert "params_00123_0002_iter00050.npy" in os.listdir(d) and "scores_00007_0015.npy" in os.listdir(d)
+    back = NT.load_trajopt_params(d, traj_i, ti)
+    assert torch.equal(back["params"], params) and torch.equal(back["params_init"], init)
+    assert torch.equal(back["tj_scores_prior"], scores) and back["pre_stlp"].shape == (bs, 4, 3, 1, 6)
+    assert torch.equal(back["pre_stlp"].reshape(-1, 1, 6), stlp)
+    args.test = True
+    assert NT.save_trajopt_params(params, "final", traj_i, ti, args, model_dir=str(tmp_path / "none")) == []
+    assert not os.path.exists(tmp_path / "none")
