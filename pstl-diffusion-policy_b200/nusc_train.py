@@ -1433,9 +1433,16 @@ def main(argv=None):
         net = Net(args).cuda()
         if args.net_pretrained_path is not None:
             net.load_state_dict(torch.load(args.net_pretrained_path), strict=False)
-        bs = args.synthetic or args.batch_size
-        loader = [synthetic.make_scene_batch(bs, nt=args.nt, dt=args.dt, n_neighbors=args.n_neighbors, n_segs=args.n_segs,
-                                             n_randoms=args.n_randoms, seed=args.seed + i) for i in range(3)]
+        if args.synthetic is None and os.path.isfile(args.cache_path):
+            # real data, offline: --cache_path <cache.npz written by --collect_data>, traj-opt files under
+            # --params_load_path (a directory holding params_*.npy), optional split file in PSTL_SPLIT_FILE
+            from . import nusc_dataset
+            pdir = args.params_load_path if os.path.isdir(args.params_load_path or "") else None
+            loader = nusc_dataset.get_dataloader(args, args.cache_path, os.environ.get("PSTL_SPLIT_FILE"), pdir)
+        else:
+            bs = args.synthetic or args.batch_size
+            loader = [synthetic.make_scene_batch(bs, nt=args.nt, dt=args.dt, n_neighbors=args.n_neighbors, n_segs=args.n_segs,
+                                                 n_randoms=args.n_randoms, seed=args.seed + i) for i in range(3)]
         model_dir = os.path.join("exps_nusc", args.exp_name or "rect", "models")
         return run_training(build_stl_cache(args), loader, net, get_diffusion_coeffs(args), args, model_dir)
     torch.manual_seed(args.seed)

@@ -223,3 +223,81 @@ def test_trajopt_params_files(tmp_path):
     args.test = True
     assert NT.save_trajopt_params(params, "final", traj_i, ti, args, model_dir=str(tmp_path / "none")) == []
     assert not os.path.exists(tmp_path / "none")
+
+
+def test_offline_cache_round_trip(tmp_path):
+    """nusc_dataset: cache.npz in the reference's layout (data[traj_i][ti][key], meta_list) written from scene batches and
+    read back through the offline dataset + DataLoader, with the traj-opt files attached (nusc_train.py:153-208,
+    nusc_dataset.py:109-118, 203-240)"""
+    from pstl_b200 import nusc_train as NT, nusc_dataset as ND, synthetic
+    args = NT.default_args(n_randoms=4, batch_size=2, num_workers=0)
+    args.test = False
+    b = synthetic.make_scene_batch(3, n_randoms=4, seed=9)
+    b["traj_i"], b["ti"] = torch.tensor([5, 5, 9]), torch.tensor([1, 2, 1])
+    saved = ND.save_cache_data({k: v for k, v in b.items() if k not in ("pre_stlp", "tj_scores_prior", "params_init")}, {})
+    assert sorted(saved) == [5, 9] and sorted(saved[5]) == [1, 2] and "params" not in saved[5][1]
+    path = str(tmp_path / "cache.npz")
+    ND.write_cache(path, saved, [(5, ["t0", "t1", "t2"]), (9, ["u0", "u1"])])
+    data, meta = ND.read_cache(path)
+    assert np.array_equal(data[9][1]["ego_traj"], b["ego_traj"][2].numpy()) and meta[1][0] == 9
+    pdir = str(tmp_path / "models")
+    NT.save_trajopt_params(b["params_init"], "init", b["traj_i"], b["ti"], args, model_dir=pdir)
+    NT.save_trajopt_params(b["tj_scores_prior"], "scores", b["traj_i"], b["ti"], args, model_dir=pdir)
+    NT.save_trajopt_params(b["params"], "final", b["traj_i"], b["ti"], args, save_stlp=b["pre_stlp"].reshape(-1, 1, 6), model_dir=pdir)
+    split = tmp_path / "split.txt"
+    split.write_text("5 1 tok_a\n9 1 tok_b\n5 2 tok_c\n")
+    loader = ND.get_dataloader(args, path, str(split), pdir, shuffle=False)
+    batches = list(loader)
+    assert [x["traj_i"].tolist() for x in batches] == [[5, 9], [5]]
+    first = batches[0]
+    for k in ("ego_traj", "neighbors_traj", "currlane_wpts", "curr_id", "gt_high_level"):
+        assert torch.equal(first[k], b[k][[0, 2]].float()), k
+    assert torch.equal(first["params"], b["params"][[0, 2]]) and torch.equal(first["pre_stlp"], b["pre_stlp"][[0, 2]])
+    assert torch.equal(first["tj_scores_prior"], b["tj_scores_prior"][[0, 2]])
+    # no files: fresh initial controls in upstream's ranges
+    fresh = ND.CacheDataset(data, args)[0]
+    assert fresh["params"].shape == (4, 3, args.nt, 2) and float(fresh["params"][..., 0].abs().max()) <= 0.1 * args.mul_w_max
+
+
+@pytest.mark.ref
+def test_offline_cache_loads_in_reference_dataset(tmp_path, monkeypatch):
+    """a cache + traj-opt files written by this package load in the UNMODIFIED reference's MyDataset (--offline), sample
+    for sample equal to what nusc_dataset.CacheDataset returns; and the reference's save_cache_data output reads here"""
+    import ref_shim
+    from pstl_b200 import nusc_dataset as ND, synthetic
+    T, rargs = ref_shim.load(["-e", "e5_ddpm", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--n_randoms", "4",
+                              "--params_load_path", "e1"])
+    import nusc_dataset as RD
+    args = NT.default_args(n_randoms=4, batch_size=2, num_workers=0)
+    args.test = False
+    b = synthetic.make_scene_batch(3, n_randoms=4, seed=9)
+    b["traj_i"], b["ti"] = torch.tensor([5, 5, 9]), torch.tensor([1, 2, 1])
+    scene = {k: v for k, v in b.items() if k not in ("pre_stlp", "tj_scores_prior", "params_init")}
+    ours = ND.save_cache_data(scene, {})
+    theirs = T.save_cache_data(scene, {})
+    for t in theirs:
+        for k in theirs[t]:
+            assert sorted(theirs[t][k]) == sorted(ours[t][k])
+            for key in theirs[t][k]:
+                assert np.array_equal(theirs[t][k][key], ours[t][k][key]), key
+    # reference layout on disk: <root>/e5/ (exp_dir_full), <root>/e1/models/ (params_load_path)
+    root = tmp_path
+    (root / "e5").mkdir()
+    pdir = str(root / "e1" / "models")
+    NT.save_trajopt_params(b["params_init"], "init", b["traj_i"], b["ti"], args, model_dir=pdir)
+    NT.save_trajopt_params(b["tj_scores_prior"], "scores", b["traj_i"], b["ti"], args, model_dir=pdir)
+    NT.save_trajopt_params(b["params"], "final", b["traj_i"], b["ti"], args, save_stlp=b["pre_stlp"].reshape(-1, 1, 6), model_dir=pdir)
+    meta = [(5, ["t0", "t1", "t2"]), (9, ["u0", "u1"])]
+    rargs.offline, rargs.exp_dir_full, rargs.generate_split_on_the_fly, rargs.test = True, str(root / "e5"), True, False
+    rargs.train_ratio = 1.0
+    ds_ref = RD.MyDataset(None, None, meta, ours, "train", rargs)
+    ds_ref.indices = [(5, 1, "t1"), (5, 2, "t2"), (9, 1, "u1")]
+    ds = ND.CacheDataset(ours, args, ds_ref.indices, pdir)
+    for i in range(3):
+        r, o = ds_ref[i], ds[i]
+        assert set(r) == set(o), set(r) ^ set(o)
+        for k in r:
+            if isinstance(r[k], torch.Tensor):
+                assert r[k].dtype == o[k].dtype and torch.equal(r[k], o[k]), k
+            else:
+                assert r[k] == o[k], k
