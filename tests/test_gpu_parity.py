@@ -1123,3 +1123,28 @@ def test_ddpm_training_loop(tmp_path):
     assert len(hist) == 4 and all(np.isfinite(h["loss"]) for h in hist) and hist[-1]["loss"] < hist[0]["loss"], hist
     sd1 = torch.load(tmp_path / "m" / "model_last.ckpt")
     assert all(not torch.equal(sd0[k], sd1[k].cpu()) for k in sd0)
+
+
+def test_training_from_offline_cache(tmp_path):
+    """the denoiser stage fed by nusc_dataset (cache.npz + params files -> DataLoader -> run_training)"""
+    from pstl_b200 import nusc_dataset as ND
+    args, net = _ddpm_net(20, n_randoms=8, sampling_size=8, epochs=2, batch_size=4, num_workers=0, lr=1e-3)
+    args.test = False
+    b = synthetic.make_scene_batch(8, n_randoms=8, seed=71)
+    b["traj_i"], b["ti"] = torch.arange(8) // 2, torch.arange(8) % 2 + 1
+    saved = ND.save_cache_data({k: v for k, v in b.items() if k not in ("pre_stlp", "tj_scores_prior", "params_init")}, {})
+    ND.write_cache(str(tmp_path / "cache.npz"), saved, [(i, ["a", "b", "c"]) for i in range(4)])
+    pdir = str(tmp_path / "models")
+    NT.save_trajopt_params(b["params_init"], "init", b["traj_i"], b["ti"], args, model_dir=pdir)
+    NT.save_trajopt_params(b["tj_scores_prior"], "scores", b["traj_i"], b["ti"], args, model_dir=pdir)
+    NT.save_trajopt_params(b["params"], "final", b["traj_i"], b["ti"], args, save_stlp=b["pre_stlp"].reshape(-1, 1, 6), model_dir=pdir)
+    loader = ND.get_dataloader(args, str(tmp_path / "cache.npz"), None, pdir, shuffle=False)
+    torch.manual_seed(1)
+    hist = NT.run_training(None, loader, net, NT.get_diffusion_coeffs(args), args, log=lambda s: None)
+    assert len(hist) == 2 and all(np.isfinite(h["loss"]) for h in hist)
+    # same batches straight from memory give the same first-epoch loss
+    args2, net2 = _ddpm_net(20, n_randoms=8, sampling_size=8, epochs=1, lr=1e-3)
+    torch.manual_seed(1)
+    direct = [{k: v[i:i + 4] for k, v in b.items()} for i in (0, 4)]
+    h2 = NT.run_training(None, direct, net2, NT.get_diffusion_coeffs(args2), args2, log=lambda s: None)
+    assert hist[0]["loss"] == pytest.approx(h2[0]["loss"], rel=1e-6)
