@@ -1451,10 +1451,15 @@ def main(argv=None):
     if args.net_pretrained_path is not None:
         net.load_state_dict(torch.load(args.net_pretrained_path), strict=(not args.rect_head))
     coeffs = get_diffusion_coeffs(args)
-    bs = args.synthetic or args.batch_size
-    loader = [synthetic.make_scene_batch(bs, nt=args.nt, dt=args.dt, n_neighbors=args.n_neighbors,
-                                         n_segs=args.n_segs, n_randoms=args.n_randoms, seed=args.seed + i)
-              for i in range(min(args.n_trials + 1, 3))]
+    if args.synthetic is None and os.path.isfile(args.cache_path):  # offline real data, see the training branch
+        from . import nusc_dataset
+        pdir = args.params_load_path if os.path.isdir(args.params_load_path or "") else None
+        loader = nusc_dataset.get_dataloader(args, args.cache_path, os.environ.get("PSTL_SPLIT_FILE"), pdir, shuffle=False)
+    else:
+        bs = args.synthetic or args.batch_size
+        loader = [synthetic.make_scene_batch(bs, nt=args.nt, dt=args.dt, n_neighbors=args.n_neighbors,
+                                             n_segs=args.n_segs, n_randoms=args.n_randoms, seed=args.seed + i)
+                  for i in range(min(args.n_trials + 1, 3))]
     return run_sampling_test(stls_cac, loader, net, coeffs, args)
 
 
