@@ -15,6 +15,7 @@
 #ifndef PSTL_H_
 #define PSTL_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

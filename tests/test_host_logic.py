@@ -301,3 +301,16 @@ def test_offline_cache_loads_in_reference_dataset(tmp_path, monkeypatch):
                 assert r[k].dtype == o[k].dtype and torch.equal(r[k], o[k]), k
             else:
                 assert r[k] == o[k], k
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pstl.h is the drop-in boundary: it must compile as C99 on its own (no torch / C++ types)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "pstl.h"\nint main(void) { pstl_loss_cfg c; pstl_spec_params s; (void)c; (void)s; return PSTL_LOSS_N; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
