@@ -314,3 +314,29 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_c_program_links_the_library(tmp_path):
+    """a plain C consumer: compile against include/pstl.h, link libpstl_b200.so, call the entry points that need no GPU"""
+    import shutil
+    import subprocess
+    from pstl_b200 import native
+    if shutil.which("gcc") is None or not os.path.exists(native.LIB_PATH):
+        pytest.skip("no gcc or library not built")
+    src = tmp_path / "use.c"
+    src.write_text('#include <stdio.h>\n#include "pstl.h"\n'
+                   'int main(void) {\n'
+                   '  pstl_loss_cfg c = {0};\n'
+                   '  printf("%d|%zu|%d\\n", pstl_version(), pstl_refine_losses_workspace_bytes(&c),\n'
+                   '         pstl_refine_losses(&c, 0, 0, 0, 0, 0, 0, 0, 0, 0));\n'
+                   '  printf("%s\\n", pstl_last_error());\n  return 0;\n}\n')
+    libdir = os.path.dirname(native.LIB_PATH)
+    exe = tmp_path / "use"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir, "-lpstl_b200",
+                        "-Wl,-rpath," + libdir, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    first, second = out.stdout.strip().split("\n")[:2]
+    ver, ws, rc = first.split("|")
+    assert int(ver) > 0 and int(ws) == 64 and int(rc) != 0 and "null argument" in second
