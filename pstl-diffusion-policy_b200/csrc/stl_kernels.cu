@@ -441,9 +441,12 @@ static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaSt
   if (a.rows_per_scene % 32 == 0 && tile_bytes <= tile_budget && (tc == c.T || tc >= 4)) {
     // one scene per block, staged in shared memory (whole horizon, or chunk by chunk)
     static const int cands[] = {192, 96, 128, 64, 32};
-    int first = 0;  // largest block that divides the scene's rows
+    int first = 0;  // largest block that divides the scene's rows (PSTL_STREAM_BLOCK: upper bound, for experiments)
+    const char* fb = getenv("PSTL_STREAM_BLOCK");
+    const int cap = fb ? atoi(fb) : 1024;
     for (int b : cands)
-      if (!first && a.rows_per_scene % b == 0) first = b;
+      if (!first && b <= cap && a.rows_per_scene % b == 0) first = b;
+    if (!first) first = 32;
     if (tile_bytes + (size_t)first * tape_row <= budget) {
       block = first;
       smem_scene = true;
