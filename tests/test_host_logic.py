@@ -340,3 +340,63 @@ def test_c_program_links_the_library(tmp_path):
     first, second = out.stdout.strip().split("\n")[:2]
     ver, ws, rc = first.split("|")
     assert int(ver) > 0 and int(ws) == 64 and int(rc) != 0 and "null argument" in second
+
+
+@pytest.mark.ref
+def test_evaluate_all_scores_matches_reference():
+    """evaluate_all_scores (nusc_train.py:347-368): same keys, same score vectors in the same order"""
+    import ref_shim
+    T, rargs = ref_shim.load(ref_shim.OURS_FLAGS + ["--n_randoms", "8"])
+    g = torch.Generator().manual_seed(3)
+    bs, S_ = 6, 8
+    scores = torch.randn(bs * S_ * 3, generator=g)
+    labels = torch.tensor([[0.0], [1.0], [2.0], [3.0], [1.0], [0.0]])
+    valid = (torch.rand(bs, 1, 3, generator=g) > 0.3).float().repeat(1, S_, 1).reshape(-1)
+    ref = T.evaluate_all_scores(scores, labels, valid)
+    ours = NT.evaluate_all_scores(scores, labels, valid, S_)
+    assert set(ref) == set(ours)
+    for k in ref:
+        assert len(ref[k]) == len(ours[k]), k
+        for a, b in zip(ref[k], ours[k]):
+            assert torch.equal(a, b), k
+
+
+@pytest.mark.ref
+def test_diffusion_prep_matches_reference():
+    """diffusion_prep (nusc_train.py:539-555) draws from torch's global generator in upstream's order: same seed, same
+    noise, timesteps and noised commands"""
+    import ref_shim
+    T, rargs = ref_shim.load(["-e", "e5_ddpm", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--n_randoms", "4"])
+    args = NT.default_args(flags=["-e", "e5_ddpm", "--diffusion", "--stl_weight", "0.0", "--load_stlp"], n_randoms=4)
+    g = torch.Generator().manual_seed(8)
+    controls = torch.randn(5, 4, 3, args.nt, 2, generator=g)
+    coeffs = T.get_diffusion_coeffs(rargs)
+    torch.manual_seed(123)
+    r_noise, r_t, _, r_noised = T.diffusion_prep(controls, n_randoms=4, coeffs=coeffs)
+    torch.manual_seed(123)
+    noise, t, _, noised = NT.diffusion_prep(controls, 4, [c.cpu() for c in NT.get_diffusion_coeffs(args)], args)
+    assert torch.equal(t, r_t) and torch.equal(noise, r_noise)
+    np.testing.assert_allclose(noised.numpy(), r_noised.numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.ref
+def test_save_trajopt_params_matches_reference(tmp_path):
+    """save_trajopt_params writes the same files with the same contents as the reference's (nusc_train.py:775-797)"""
+    import ref_shim
+    T, rargs = ref_shim.load(["-e", "e1", "--diffusion", "--load_stlp", "--trajopt_only", "--n_randoms", "4"])
+    args = NT.default_args(n_randoms=4)
+    args.test = rargs.test = False
+    g = torch.Generator().manual_seed(2)
+    params = torch.randn(2, 4, 3, args.nt, 2, generator=g)
+    stlp = torch.randn(2 * 4 * 3, 1, 6, generator=g)
+    traj_i, ti = torch.tensor([3, 41]), torch.tensor([7, 0])
+    d_ref, d_our = tmp_path / "ref", tmp_path / "our"
+    d_ref.mkdir()
+    rargs.model_dir = str(d_ref)
+    for it, st in (("init", None), (12, None), ("scores", None), ("final", stlp)):
+        payload = params[..., 0, 0] if it == "scores" else params
+        T.save_trajopt_params(payload, it, traj_i, ti, rargs, save_stlp=st)
+        NT.save_trajopt_params(payload, it, traj_i, ti, args, save_stlp=st, model_dir=str(d_our))
+    assert sorted(os.listdir(d_ref)) == sorted(os.listdir(d_our)) and len(os.listdir(d_our)) == 10
+    for f in os.listdir(d_ref):
+        assert np.array_equal(np.load(d_ref / f), np.load(d_our / f)), f
