@@ -121,7 +121,8 @@ typedef struct {
   float ego_L, ego_W;
   float w_scale, a_scale; /* controls = in * scale (1 for physical controls, (w_max,a_max) for mu) */
   int clip_controls;      /* clip to +-scale after scaling (normalize_diff, nusc_train.py:647-655) */
-  int clip_dist;          /* --clip_dist: lane distance clipped to +-5 (nusc_api.py:732-733)       */
+  int clip_dist;          /* lane flag word: bit 0 --clip_dist, lane distance clipped to +-5 (nusc_api.py:732-733);
+                             bit 1 --inline, end-cap distances before / after the polyline (nusc_api.py:716-724)   */
   int hard;
 } pstl_spec_params;
 
@@ -155,7 +156,8 @@ int pstl_score_fused_bwd(pstl_program_t const* progs, const pstl_scene_view* sce
  * aliasing quirk that makes iter 0 a plain Adam step).  inv_norm = 1/(N_total*clip(mean(valid),1e-2)). */
 int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_view* scenes, const pstl_spec_params* sp,
                        const float* mode, const float* state0, const float* stlp, const float* valid, int N,
-                       float thres, float inv_norm, float lr, float beta_t, int iter,
+                       float thres, float inv_norm, const float* inv_norm_dev /* device word overriding inv_norm, or NULL */,
+                       float lr, float beta_t, int iter,
                        float* mu, float* adam_m, float* adam_v, float* mu_anchor,
                        void* workspace, pstl_stream_t stream);
 
@@ -164,6 +166,7 @@ int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_view* scene
  * diffusion_rollout + normalize_diff (nusc_train.py:557-655) and Net.rect_forward
  * (nusc_model.py:182-235).
  * ------------------------------------------------------------------------------------- */
+#define PSTL_MAX_STEPS 1024   /* most diffusion steps a sampler call takes (workspace's per-step table) */
 #define PSTL_PRECISION_FP32 0 /* SIMT fp32, 1e-5 parity mode                       */
 #define PSTL_PRECISION_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate (2e-2)     */
 
@@ -175,8 +178,12 @@ typedef struct {
   int hidden, rect_hidden, merge_hidden, feat_dim, time_dim, T;
 } pstl_weights;
 
+/* PSTL_ERR_UNSUPPORTED when 2*T+7 exceeds the packed input row (T <= 20). */
 int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_denoiser_t* out);
 int pstl_denoiser_destroy(pstl_denoiser_t d);
+/* The caller updated the weight tensors IN PLACE (an optimiser step on the same storage): re-derive the handle's own
+ * copies (hoisted first-layer blocks, bf16 operand images) on `stream`.  No allocation, no synchronisation. */
+int pstl_denoiser_refresh(pstl_denoiser_t d, pstl_stream_t stream);
 
 /* Philox offset word in DEVICE memory (or NULL to clear): the sampler adds *device_counter to the
  * `offset` argument of pstl_denoiser_sample when it draws noise.  A CUDA graph that captured the
@@ -190,11 +197,15 @@ typedef struct {
   pstl_program_t const* progs;
   const pstl_scene_view* scenes;
   const pstl_spec_params* sp; /* w_scale/a_scale = (w_max,a_max), clip_controls = 0          */
-  int before;            /* guide reverse steps i <= before                                   */
+  int before;            /* guide reverse steps i <= before (when step_mask is NULL)          */
+  const unsigned char* step_mask; /* HOST pointer, `steps` entries, or NULL: step_mask[i] != 0 guides reverse
+                            step i (--guidance_sets / --guidance_freq / --guidance_reverse, nusc_train.py:589-598) */
   int niters;
   float lr, thres;
   float inv_norm;        /* 1/(N_total*clip(mean(valid),1e-2)); N_total spans all shards if the
                             caller wants single-batch semantics across GPUs                   */
+  const float* inv_norm_dev; /* DEVICE word holding inv_norm, or NULL: read by the kernels at run time, so a CUDA
+                            graph that captured the sampler follows the batch's own lane-validity mean           */
 } pstl_guidance_cfg;
 
 /* Scratch the sampler needs for N chains (activations, Adam state, STL tape). */
@@ -241,8 +252,17 @@ int pstl_rollout_bwd(const float* traj, const float* grad_traj, int N, int T, fl
  * ego (N,T,>=3) with row stride ego_stride -> sig (N,7,T) = [d_curr, th_curr, d_left, th_left,
  * d_right, th_right, min_nei_d]; part (N,12,T) (may be NULL) = per lane (dd/dx, dd/dy, dth/dtheta),
  * then d min_nei_d/d(x, y, theta): what autograd needs to chain into ego. */
-int pstl_predicates(const pstl_scene_view* scenes, float ego_L, float ego_W, int clip_dist, const float* ego,
+int pstl_predicates(const pstl_scene_view* scenes, float ego_L, float ego_W, int clip_dist /* lane flag word */, const float* ego,
                     int ego_stride, int N, float* sig, float* part, pstl_stream_t stream);
+
+/* Car-to-car anchor distances for any (--refined_nL, --refined_nW) grid, and the extra signals --collision_loss adds to
+ * prep_stl_cache (dist_between_two_cars with full=True, utils.py:465-526; nusc_train.py:81-83, 142-148):
+ * min_dist (N,Knei,T) = min over the (nL*nW)^2 anchor pairs of the centre distance, rad_sum (N,Knei,T) = r_ego + r_nei;
+ * part (N,Knei,T,3) (may be NULL) = d min_dist / d (ego x, y, theta).  The callers compose
+ *   car_dist = min_dist - rad_sum,  min_nei_d = min_k(clip(car_dist,-5,20)*valid + (1-valid)*100),
+ *   min_centroid_d = min_dist*valid + (1-valid)*100   exactly as upstream.  nL*nW <= 64. */
+int pstl_car_distances(const pstl_scene_view* scenes, float ego_L, float ego_W, int nL, int nW, const float* ego,
+                       int ego_stride, int N, float* min_dist, float* rad_sum, float* part, pstl_stream_t stream);
 
 /* Plain fused linear layer used by the scene encoders (nusc_model.py:82-91):
  * y (M,Nout) = act(x (M,K) @ w(Nout,K)^T + b); act: 0 none, 1 relu. */

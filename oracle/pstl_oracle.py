@@ -137,53 +137,91 @@ def lane_distance(points, lane, clip=False, inline=False):
     return d0.reshape(n, t), ang.reshape(n, t)
 
 
-def _anchor_circles(x, y, th, L, W, nL=4):
-    """utils.py:465-497 with num_W=1: circle centres along the body axis and their radius."""
-    r = torch.minimum(torch.maximum(L / nL / 2, W / 1 / 2), W / 2)
+def _anchor_circles(x, y, th, L, W, nL=4, nW=1):
+    """utils.py:465-497: the nL x nW grid of circle centres (row-major over (length, width)) and their radius."""
+    r = torch.minimum(torch.maximum(L / nL / 2, W / nW / 2), W / 2)
     alpha = torch.linspace(0, 1, nL)
+    beta = torch.linspace(0, 1, nW)  # num_W=1: beta=[0] picks the y3+r end
     xs_ = (-L / 2 + r)[..., None] * (1 - alpha) + (L / 2 - r)[..., None] * alpha
-    ys_ = (-W / 2 + r)[..., None].expand_as(xs_)  # num_W=1: beta=[0] picks the y3+r end
+    ys_ = (-W / 2 + r)[..., None] * (1 - beta) + (W / 2 - r)[..., None] * beta
+    lead = list(x.shape)
+    xs_ = xs_[..., None].expand(lead + [nL, nW]).reshape(lead + [nL * nW])
+    ys_ = ys_[..., None, :].expand(lead + [nL, nW]).reshape(lead + [nL * nW])
     cx = xs_ * torch.cos(th[..., None]) - ys_ * torch.sin(th[..., None]) + x[..., None]
     cy = xs_ * torch.sin(th[..., None]) + ys_ * torch.cos(th[..., None]) + y[..., None]
     return torch.stack([cx, cy], dim=-1), r
 
 
-def neighbour_clearance(ego, nei, ego_L=4.084, ego_W=1.730, nL=4):
+def neighbour_clearance(ego, nei, ego_L=4.084, ego_W=1.730, nL=4, nW=1, full=False):
     """utils.py:499-526 + nusc_train.py:142-148.
-    ego (N,T,>=3); nei (N,K,T,7)=[valid,x,y,th,v,L,W] -> min_k clearance (N,T)."""
+    ego (N,T,>=3); nei (N,K,T,7)=[valid,x,y,th,v,L,W] -> min_k clearance (N,T); ``full`` (--collision_loss,
+    nusc_train.py:81-83) also returns min_centroid_d (N,K,T) and radius_sum (N,K,T)."""
     e = ego.unsqueeze(1)
     c1, r1 = _anchor_circles(e[..., 0], e[..., 1], e[..., 2], ego_L * torch.ones_like(e[..., 0]),
-                             ego_W * torch.ones_like(e[..., 0]), nL)
-    c2, r2 = _anchor_circles(nei[..., 1], nei[..., 2], nei[..., 3], nei[..., 5], nei[..., 6], nL)
+                             ego_W * torch.ones_like(e[..., 0]), nL, nW)
+    c2, r2 = _anchor_circles(nei[..., 1], nei[..., 2], nei[..., 3], nei[..., 5], nei[..., 6], nL, nW)
     d = torch.norm(c1[..., None, :] - c2[..., None, :, :], dim=-1)
-    d = d.reshape(list(d.shape[:-2]) + [nL * nL]).min(dim=-1)[0] - r1 - r2
+    md = d.reshape(list(d.shape[:-2]) + [(nL * nW) ** 2]).min(dim=-1)[0]
     ind = nei[..., 0]
-    return torch.min(torch.clip(d, -5, 20) * ind + (1 - ind) * 100, dim=1)[0]
+    clear = torch.min(torch.clip(md - r1 - r2, -5, 20) * ind + (1 - ind) * 100, dim=1)[0]
+    if full:
+        return clear, md * ind + (1 - ind) * 100, r1 + r2
+    return clear
 
 
-def predicates(x, ego_L=4.084, ego_W=1.730, clip_dist=False, inline=False, nL=4):
+def predicates(x, ego_L=4.084, ego_W=1.730, clip_dist=False, inline=False, nL=4, nW=1, collision=False):
     """nusc_train.py:74-93 — adds the lane and neighbour signals to the dense dict ``x``."""
     p = x["ego_traj"][..., 0:3]
     for k in ("curr", "left", "right"):
         x["x2%s_d" % k], x["x2%s_th" % k] = lane_distance(p, x["%slane_wpts" % k], clip_dist, inline)
-    x["min_nei_d"] = neighbour_clearance(x["ego_traj"], x["neighbors"], ego_L, ego_W, nL)
+    if collision:
+        x["min_nei_d"], x["min_centroid_d"], x["radius_sum"] = neighbour_clearance(x["ego_traj"], x["neighbors"], ego_L,
+                                                                                   ego_W, nL, nW, full=True)
+    else:
+        x["min_nei_d"] = neighbour_clearance(x["ego_traj"], x["neighbors"], ego_L, ego_W, nL, nW)
     return x
 
 
-def driving_spec(nt):
-    """nusc_train.py:95-140 (norm_stl=False): [stl_curr, stl_left, stl_right] as formula tuples."""
-    P = lambda i: (lambda x: x["stlp"][..., i])
+def collision_loss(x, weight):
+    """nusc_train.py:416-420 on the signals ``predicates(..., collision=True)`` added."""
+    coll = torch.relu(1 - x["min_centroid_d"] / torch.clip(x["radius_sum"], 1e-1))
+    return torch.mean(torch.clip(torch.sum(coll, dim=-1), max=1)) * weight
+
+
+def guidance_steps(steps, before=1000, sets=None, freq=None, reverse=False):
+    """nusc_train.py:589-598: the reverse steps i that run guidance."""
+    hit = []
+    for i in range(1, steps):
+        i_val = steps - 1 - i if reverse else i
+        if sets is not None:
+            on = i_val in sets
+        elif freq is not None:
+            on = i_val % freq == 0
+        else:
+            on = i <= before
+        if on:
+            hit.append(i)
+    return hit
+
+
+def driving_spec(nt, norm=False):
+    """nusc_train.py:95-140: [stl_curr, stl_left, stl_right] as formula tuples; ``norm`` = --norm_stl (:88-91,
+    98-113: margins divided by clip(vmax-vmin,.3), clip(5(dmax-dmin),.3), clip(dsafe,.3))."""
     G = lambda f: ("always", 0, nt, f)
-    v_lo = G(("ap", lambda x: x["ego_traj"][..., 3] - x["stlp"][..., 0]))
-    v_hi = G(("ap", lambda x: -x["ego_traj"][..., 3] + x["stlp"][..., 1]))
-    d_lo = G(("ap", lambda x: x["x2curr_d"] - x["stlp"][..., 2]))
-    d_hi = G(("ap", lambda x: -x["x2curr_d"] + x["stlp"][..., 3]))
+    one = lambda x: 1.0
+    vf = (lambda x: torch.clip(x["stlp"][..., 1] - x["stlp"][..., 0], 0.3)) if norm else one
+    df = (lambda x: torch.clip((x["stlp"][..., 3] - x["stlp"][..., 2]) * 5, 0.3)) if norm else one
+    sf = (lambda x: torch.clip(x["stlp"][..., 4], 0.3)) if norm else one
+    v_lo = G(("ap", lambda x: (x["ego_traj"][..., 3] - x["stlp"][..., 0]) / vf(x)))
+    v_hi = G(("ap", lambda x: (-x["ego_traj"][..., 3] + x["stlp"][..., 1]) / vf(x)))
+    d_lo = G(("ap", lambda x: (x["x2curr_d"] - x["stlp"][..., 2]) / df(x)))
+    d_hi = G(("ap", lambda x: (-x["x2curr_d"] + x["stlp"][..., 3]) / df(x)))
     th_c = G(("ap", lambda x: (x["stlp"][..., 5] - x["x2curr_th"]) / x["stlp"][..., 5]))
-    safe = G(("ap", lambda x: x["min_nei_d"] - x["stlp"][..., 4]))
+    safe = G(("ap", lambda x: (x["min_nei_d"] - x["stlp"][..., 4]) / sf(x)))
 
     def reach(side):
-        band = ("and", ("ap", lambda x: x["x2%s_d" % side] - x["stlp"][..., 2]),
-                ("ap", lambda x: -x["x2%s_d" % side] + x["stlp"][..., 3]))
+        band = ("and", ("ap", lambda x: (x["x2%s_d" % side] - x["stlp"][..., 2]) / df(x)),
+                ("ap", lambda x: (-x["x2%s_d" % side] + x["stlp"][..., 3]) / df(x)))
         rd = ("eventually", 0, nt // 2, G(band))
         rt = ("eventually", 0, nt // 2,
               G(("ap", lambda x: (x["stlp"][..., 5] - x["x2%s_th" % side]) / x["stlp"][..., 5])))
@@ -201,12 +239,12 @@ def mask_mean(v, m):
     return torch.mean(v * m) / torch.clip(torch.mean(m), 1e-2)
 
 
-def stl_scores(x, mode, tau=100.0, nt=None, **pred_kw):
+def stl_scores(x, mode, tau=100.0, nt=None, norm=False, **pred_kw):
     """nusc_train.py:318-323,150-151 — all three formulas, [:,0], arithmetic select (+outlier 1.0).
     ``x`` dense dict; ``mode`` (N,) float in {0,1,2,3}.  Returns scores (N,)."""
     x = predicates(x, **pred_kw)
     T = x["ego_traj"].shape[1] if nt is None else nt
-    per = [stl_eval(f, x, tau)[:, 0] for f in driving_spec(T)]
+    per = [stl_eval(f, x, tau)[:, 0] for f in driving_spec(T, norm)]
     per.append(per[-1].detach() * 0.0 + 1.0)
     return sum(per[k] * (mode == k).float() for k in range(4))
 
@@ -315,13 +353,15 @@ def guidance_update(mu, beta_t, dense, s0, mode, valid, lr, thres, nt, dt, tau=1
 def ddpm_sample(W, feat_dense, hl, stlp, x_T, noises, steps=100, nt=20, clip=True, guidance=None):
     """nusc_train.py:557-645 — reverse loop i=steps-1..1 with t==i.
     ``noises``: list of (N,2nt) tensors consumed in order for i>1 (injected z).
-    ``guidance``: None or dict(before, lr, thres, dense, s0, mode, valid, dt, tau, niters).
+    ``guidance``: None or dict(before | sets | freq [, reverse], lr, thres, dense, s0, mode, valid, dt, tau, niters).
     Returns list of steps (N,nt,2) control iterates x_T..x_0 (normalised as diff_full does)."""
     beta, alpha, abar = ddpm_schedule(steps)
     n = x_T.shape[0]
     x = x_T
     its = [x]
     zi = 0
+    guided = set() if guidance is None else set(guidance_steps(steps, guidance.get("before", 1000), guidance.get("sets"),
+                                                               guidance.get("freq"), guidance.get("reverse", False)))
     for i in reversed(range(1, steps)):
         t = torch.full((n, 1), i, dtype=torch.long)
         with torch.no_grad():
@@ -333,7 +373,7 @@ def ddpm_sample(W, feat_dense, hl, stlp, x_T, noises, steps=100, nt=20, clip=Tru
         else:
             z = torch.zeros_like(x)
         mu = 1 / torch.sqrt(a) * (x - ((1 - a) / (torch.sqrt(1 - ah))) * eps)
-        if guidance is not None and i <= guidance["before"]:
+        if i in guided:
             g = guidance
             mu = guidance_update(mu, b.item(), g["dense"], g["s0"], g["mode"], g["valid"], g["lr"], g["thres"],
                                  nt, g["dt"], g.get("tau", 100.0), g.get("niters", 1))
@@ -390,8 +430,33 @@ def score_controls(dense, u, dt, tau=100.0):
     return stl_scores(x, dense["mode"], tau), tr
 
 
+REFINEMENT_ITERATES = {8: [0, 50, 80, 85, 90, 95, 98]}  # nusc_train.py:1051-1054, K = 8
+
+
+def refinement(d, u, its, dt, tau=100.0, K=8, n_iters=50, thres=0.0005, lr=3e-1):
+    """--refinement, nusc_train.py:1034-1071: violating rows become a softmax-weighted mix of their controls and K-1
+    earlier iterates; the logits take 50 Adam steps on mask_mean(relu(5e-4 - score), valid)."""
+    N = u.shape[0]
+    lam = torch.ones(N, K, requires_grad=True)
+    opt = torch.optim.Adam([lam], lr=lr)
+    sc, _ = score_controls(d, u, dt, tau)
+    valid = d["dense_valids"].reshape(-1)
+    viol = ((sc <= 0) & (valid > 0)).float().reshape(N, 1, 1)
+    for _ in range(n_iters):
+        r = torch.softmax(lam, dim=-1)
+        comb = [its[idx].detach() * r[..., j + 1:j + 2, None] for j, idx in enumerate(REFINEMENT_ITERATES[K])]
+        oc = u.detach() * r[..., 0:1, None] + torch.sum(torch.stack(comb, dim=-1), dim=-1)
+        oc = u.detach() * (1 - viol) + viol * oc
+        s2, _ = score_controls(d, oc, dt, tau)
+        loss = mask_mean(torch.relu(thres - s2), valid)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    return oc.detach()
+
+
 def pipeline(W, b, x_T, noises, S=64, K=5, n_rolls=0, refinenet=True, steps=100, nt=20, dt=0.5, tau=100.0,
-             guidance=None, n_randoms=64, n_shards=4):
+             guidance=None, n_randoms=64, n_shards=4, refine_mix=False):
     """The timed region of run_sampling_test (nusc_train.py:957-1105) for the README
     "Ours" / "Ours+guidance" flag sets.  Returns dict of intermediates for parity checks."""
     bs = b["ego_traj"].shape[0]
@@ -419,7 +484,11 @@ def pipeline(W, b, x_T, noises, S=64, K=5, n_rolls=0, refinenet=True, steps=100,
             for _ in range(n_rolls):
                 sc, _ = score_controls(d, u, dt, tau)
                 u = refine(W, fd, hl, stlp, u, sc, n_randoms, n_shards, nt)
-    sc, tr = score_controls(d, u, dt, tau)
+    out["rect_controls"] = u
+    if refine_mix:
+        u = refinement(d, u, its, dt, tau)
+    with torch.no_grad():
+        sc, tr = score_controls(d, u, dt, tau)
     m = d["dense_valids"].reshape(-1)
     out.update(controls=u, scores=sc, trajs=tr, acc=mask_mean((sc > 0).float(), m))
     return out
@@ -564,9 +633,10 @@ def refine_train_step(W, b, feat_scene, nn_controls, dt, tau=100.0, **loss_kw):
             "grads": {k: W[k].grad for k in keys}, "W": W}
 
 
-def ddpm_train_step(W, b, noise, steps, noised, S, nt):
+def ddpm_train_step(W, b, noise, steps, noised, S, nt, stl_bc_mask=True):
     """One denoiser training step up to the gradients (README step 1): net(batch, timestep per row, noised commands)
-    (nusc_train.py:1352-1356, nusc_model.py:97-162) and loss_diffusion = mean((noise - eps)^2) (:436), every encoder /
+    (nusc_train.py:1352-1356, nusc_model.py:97-162) and loss_diffusion = mask_mean((noise - eps)^2, tj_scores_prior *
+    valids > 0) (:435-437; the plain mean without stl_bc_mask), every encoder /
     policy_net tensor a leaf.  noise / steps / noised are diffusion_prep's outputs (:539-555).  pSTL per chain from
     pre_stlp (training layout).  Returns eps, feature (bs,224), loss and grads {key: tensor}."""
     bs = b["currlane_wpts"].shape[0]
@@ -580,6 +650,11 @@ def ddpm_train_step(W, b, noise, steps, noised, S, nt):
     feat_dense = feat.unsqueeze(1).repeat(1, m, 1).reshape(N, -1)
     mode = torch.tensor([0.0, 1.0, 2.0]).repeat(bs * S).reshape(N, 1)
     eps = eps_model(W, feat_dense, noised, steps.reshape(N, 1), mode, b["pre_stlp"].reshape(N, 6))
-    loss = torch.mean((noise - eps) ** 2)
+    if stl_bc_mask:  # nusc_train.py:435-437: dense_scores = tj_scores_prior (:1282-1283), mask_mean (:23-27)
+        valids = torch.cat([b["curr_id"], b["left_id"], b["right_id"]], dim=-1).unsqueeze(1).repeat(1, S, 1).reshape(N, 1)
+        mk = (b["tj_scores_prior"].reshape(N, 1) * valids > 0).float()
+        loss = torch.mean((noise - eps) ** 2 * mk) / torch.clip(torch.mean(mk), 1e-2)
+    else:
+        loss = torch.mean((noise - eps) ** 2)
     loss.backward()
     return {"eps": eps.detach(), "feature": feat.detach(), "loss": loss.detach(), "grads": {k: W[k].grad for k in keys}, "W": W}

@@ -108,6 +108,72 @@ extern "C" int pstl_predicates(const pstl_scene_view* sv, float ego_L, float ego
   return PSTL_OK;
 }
 
+// Car-to-car distances for any (--refined_nL, --refined_nW) anchor grid and the extra signals of --collision_loss
+// (utils.py:465-526 with full=True; nusc_train.py:81-83, 142-148).  One thread per (row, neighbour, step):
+//   min_dist = min over the (nL*nW)^2 anchor pairs of the centre distance (first minimum, as torch.min)
+//   rad_sum  = r_ego + r_nei,  r = min(max(L/nL/2, W/nW/2), W/2)
+// part (N,K,T,3), optional: d min_dist / d (ego x, y, theta) through the arg-min pair (torch.norm's backward).
+#define PSTL_MAX_ANCHORS 64
+__device__ __forceinline__ void car_anchor(float x, float y, float c, float sn, float L, float W, int nL, int nW, int i,
+                                           float r, float& ax, float& ay, float& qx, float& qy) {
+  const int il = i / nW, iw = i - il * nW;
+  const float al = pstl_linspace01(il, nL), be = pstl_linspace01(iw, nW);
+  qx = (-L / 2.f + r) * (1.f - al) + (L / 2.f - r) * al;
+  qy = (-(W / 2.f) + r) * (1.f - be) + (W / 2.f - r) * be;
+  ax = qx * c - qy * sn + x;
+  ay = qx * sn + qy * c + y;
+}
+
+__global__ void k_car_distances(const float* __restrict__ nei, int K, int T, int rows_per_scene, float ego_L, float ego_W,
+                                int nL, int nW, const float* __restrict__ ego, int es, int N, float* __restrict__ min_dist,
+                                float* __restrict__ rad_sum, float* __restrict__ part) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * K * T) return;
+  const int t = (int)(i % T), k = (int)((i / T) % K), n = (int)(i / ((long long)T * K));
+  const float* e = ego + ((size_t)n * T + t) * es;
+  const float* p = nei + (((size_t)(n / rows_per_scene) * K + k) * T + t) * 7;
+  const float ec = cosf(e[2]), esn = sinf(e[2]), nc = cosf(p[3]), nsn = sinf(p[3]);
+  const float r1 = fminf(fmaxf(ego_L / (float)nL / 2.f, ego_W / (float)nW / 2.f), ego_W / 2.f);
+  const float r2 = fminf(fmaxf(p[5] / (float)nL / 2.f, p[6] / (float)nW / 2.f), p[6] / 2.f);
+  const int na = nL * nW;
+  float best = INFINITY, bdx = 0.f, bdy = 0.f, bqx = 0.f, bqy = 0.f;
+  for (int a = 0; a < na; ++a) {
+    float ax, ay, qx, qy;
+    car_anchor(e[0], e[1], ec, esn, ego_L, ego_W, nL, nW, a, r1, ax, ay, qx, qy);
+    for (int b = 0; b < na; ++b) {
+      float bx, by, ux, uy;
+      car_anchor(p[1], p[2], nc, nsn, p[5], p[6], nL, nW, b, r2, bx, by, ux, uy);
+      const float dx = ax - bx, dy = ay - by;
+      const float d2 = dx * dx + dy * dy;
+      if (d2 < best) { best = d2; bdx = dx; bdy = dy; bqx = qx; bqy = qy; }
+    }
+  }
+  const float md = sqrtf(best);
+  min_dist[i] = md;
+  rad_sum[i] = r1 + r2;
+  if (part) {
+    const float ux = bdx / md, uy = bdy / md;  // NaN when the anchors coincide, as torch.norm's backward
+    part[i * 3] = ux;
+    part[i * 3 + 1] = uy;
+    part[i * 3 + 2] = ux * (-bqx * esn - bqy * ec) + uy * (bqx * ec - bqy * esn);
+  }
+}
+
+extern "C" int pstl_car_distances(const pstl_scene_view* sv, float ego_L, float ego_W, int nL, int nW, const float* ego,
+                                  int ego_stride, int N, float* min_dist, float* rad_sum, float* part,
+                                  pstl_stream_t stream) {
+  PSTL_CHECK_ARG(sv && ego && min_dist && rad_sum && ego_stride >= 3, "bad argument");
+  PSTL_CHECK_ARG(nL >= 1 && nW >= 1 && nL * nW <= PSTL_MAX_ANCHORS, "bad anchor grid");
+  PSTL_CHECK_ARG(sv->rows_per_scene >= 1 && (long long)sv->n_scenes * sv->rows_per_scene >= N, "bad scene view");
+  if (N <= 0) return PSTL_OK;
+  const long long tot = (long long)N * sv->Knei * sv->T;
+  k_car_distances<<<pstl_ceil_div(tot, 128), 128, 0, (cudaStream_t)stream>>>(
+      sv->neighbors, sv->Knei, sv->T, sv->rows_per_scene, ego_L, ego_W, nL, nW, ego, ego_stride, N, min_dist, rad_sum,
+      part);
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
+}
+
 // --------------------------------------------------------------------------------------
 // scene-encoder glue (Net.encode_feat, reference nusc_model.py:55-95): the ego-frame transform of every
 // neighbour / lane point and the input layouts of the three encoder MLPs in ONE launch (upstream: ~90

@@ -677,6 +677,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 
 }  // namespace
 
+// (re)build the bf16 weight images from the handle's current fp32 weights: no allocation, no synchronisation
+int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st) {
+  TcState* s = (TcState*)d->tc;
+  PSTL_CHECK_ARG(s, "engine not created");
+  k_build_image<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image);
+  PSTL_LAUNCH_CHECK();
+  if (s->image_r) {
+    k_build_image<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_r);
+    PSTL_LAUNCH_CHECK();
+  }
+  return PSTL_OK;
+}
+
 int pstl_tc_create(pstl_denoiser* d) {
   if (d->w.hidden != kH || d->T2 != 40 || d->kin != 47) {
     pstl_set_error("PSTL_PRECISION_BF16 engine is built for hidden=256, nt=20 (got hidden=%d, nt=%d)", d->w.hidden, d->w.T);
@@ -698,14 +711,13 @@ int pstl_tc_create(pstl_denoiser* d) {
   PSTL_CUDA(cudaMemset(s->image, 0, kWeightBytes));
   PSTL_CUDA(cudaMalloc(&s->zeros, kH * sizeof(float)));
   PSTL_CUDA(cudaMemset(s->zeros, 0, kH * sizeof(float)));
-  k_build_image<<<(256 * 256 + 255) / 256, 256>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image);
-  PSTL_LAUNCH_CHECK();
   if (d->r1p && d->w.rect_hidden == kH) {
     PSTL_CUDA(cudaMalloc(&s->image_r, kWeightBytes));
     PSTL_CUDA(cudaMemset(s->image_r, 0, kWeightBytes));
-    k_build_image<<<(256 * 256 + 255) / 256, 256>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_r);
-    PSTL_LAUNCH_CHECK();
   }
+  d->tc = s;
+  int rc = pstl_tc_refresh(d, nullptr);
+  if (rc) return rc;
   PSTL_CUDA(cudaDeviceSynchronize());
   PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
   d->tc = s;

@@ -26,6 +26,8 @@ PSTL_HD float pstl_linspace01(int k, int n) {
   return (k < n / 2) ? step * (float)k : 1.0f - step * (float)(n - k - 1);
 }
 
+#define PSTL_LANE_CLIP 1    // bits of the lane flag word carried in pstl_spec_params.clip_dist
+#define PSTL_LANE_INLINE 2
 #define PSTL_NL 4  // --refined_nL (the only value built; checked on the host side)
 
 // utils.py:465-497 (num_W = 1): body-axis circle centres of a car and the common radius.
@@ -98,10 +100,13 @@ PSTL_HD float pstl_pair_clearance(const PstlCircles& e, float ec, float es, cons
   return term;
 }
 
-// Exact cull for a neighbour with valid == 1: every circle centre lies within L/2 - r of the car
-// centre, so  car_dist >= |C_ego - C_nei| - L_ego/2 - reach_nei  with reach = L_nei/2.  If that bound
-// (less a rounding margin) is not below min(best, 20) the neighbour cannot lower the running minimum
-// and its clipped term is exactly 20 when the bound exceeds 20.
+// Farthest a car's circles reach from its centre: centres at body offsets |q| <= |L/2 - r| with r = W/2
+// (utils.py:465-497), so reach = |L/2 - W/2| + W/2 = max(L/2, W - L/2) (L/2 for car-shaped boxes, L >= W).
+PSTL_HD float pstl_car_reach(float L, float W) { return fmaxf(L / 2.f, W - L / 2.f); }
+
+// Exact cull for a neighbour with valid == 1:  car_dist >= |C_ego - C_nei| - reach_ego - reach_nei
+// (pstl_car_reach).  If that bound (less a rounding margin) is not below min(best, 20) the neighbour cannot
+// lower the running minimum and its clipped term is exactly 20 when the bound exceeds 20.
 PSTL_HD bool pstl_cull_neighbour(float dx, float dy, float ego_half_len, float reach, float best) {
   const float R = fminf(best, 20.f) + ego_half_len + reach + 1e-3f;
   return R > 0.f && (dx * dx + dy * dy) >= R * R;
@@ -121,9 +126,12 @@ PSTL_HD float pstl_sqrt_search(float x) {
 
 // nusc_api.py:693-735, after the segment search: signed lateral distance (triangle area / base) and
 // heading error of pose p to the segment (x2,y2,th2)-(x3,y3).
+// flags: PSTL_LANE_CLIP (--clip_dist, :732-733) | PSTL_LANE_INLINE (--inline end-caps, :716-724: a pose behind the
+// first / ahead of the last segment takes the clamped point distance to that end, signed like the line distance);
+// at_first / at_last: the arg-min segment is the polyline's first / last one (min_idx == 0 / nseg-2).
 // part (3 floats or null): d dist/d px, d dist/d py, d ang/d pth.
 PSTL_HD void pstl_lane_finish(float px, float py, float pth, float x2, float y2, float th2, float x3, float y3,
-                              int clip_dist, float& dist, float& ang, float* part) {
+                              int flags, bool at_first, bool at_last, float& dist, float& ang, float* part) {
   const float area = px * (y2 - y3) + x2 * (y3 - py) + x3 * (py - y2);
   const float bx = x2 - x3, by = y2 - y3;
   const float base = sqrtf(bx * bx + by * by);
@@ -139,7 +147,24 @@ PSTL_HD void pstl_lane_finish(float px, float py, float pth, float x2, float y2,
     gdy = ok * (x3 - x2) / den;
     if (ok == 0.f && q >= 1e-3f) { gdx += ex / l2; gdy += ey / l2; }
   }
-  if (clip_dist) {
+  if (flags & PSTL_LANE_INLINE) {
+    const float fx = px - x3, fy = py - y3;
+    const float qb = fx * fx + fy * fy;
+    const float l2b = sqrtf(fmaxf(qb, 1e-3f));
+    const bool behind = at_first && (ex * (x3 - x2) + ey * (y3 - y2) <= 0.f);
+    const bool ahead = at_last && (fx * (x2 - x3) + fy * (y2 - y3) <= 0.f);
+    if (behind || ahead) {
+      const float sg = (d0 > 0.f) ? 1.f : (d0 < 0.f) ? -1.f : 0.f;  // torch.sign: no gradient
+      const float fb = behind ? 1.f : 0.f, fa = ahead ? 1.f : 0.f;
+      d0 = fb * l2 * sg + fa * l2b * sg;
+      if (part) {
+        gdx = 0.f; gdy = 0.f;
+        if (behind && q >= 1e-3f) { gdx += sg * (ex / l2); gdy += sg * (ey / l2); }
+        if (ahead && qb >= 1e-3f) { gdx += sg * (fx / l2b); gdy += sg * (fy / l2b); }
+      }
+    }
+  }
+  if (flags & PSTL_LANE_CLIP) {
     if (d0 < -5.f || d0 > 5.f) { gdx = 0.f; gdy = 0.f; }
     d0 = fminf(fmaxf(d0, -5.f), 5.f);
   }
@@ -156,7 +181,7 @@ PSTL_HD void pstl_lane_finish(float px, float py, float pth, float x2, float y2,
 // nusc_api.py:693-735: closest segment by arg-min of d_j + d_{j+1} (first minimum), then pstl_lane_finish.
 template <class LaneAcc>
 PSTL_HD void pstl_lane_pred(float px, float py, float pth, const LaneAcc& lane, int nseg, int clip_dist,
-                            float& dist, float& ang, float* part) {
+                            float& dist, float& ang, float* part) {  // clip_dist: PSTL_LANE_* flags
   float prev = 0.f;
   float bestv = INFINITY;
   int bi = 0;
@@ -170,7 +195,7 @@ PSTL_HD void pstl_lane_pred(float px, float py, float pth, const LaneAcc& lane, 
     prev = d;
   }
   pstl_lane_finish(px, py, pth, lane(bi, 0), lane(bi, 1), lane(bi, 2), lane(bi + 1, 0), lane(bi + 1, 1), clip_dist,
-                   dist, ang, part);
+                   bi == 0, bi == nseg - 2, dist, ang, part);
 }
 
 // decode helpers for PSTL_OP_PRED

@@ -16,7 +16,7 @@ struct PstlSceneGlobal {
   PSTL_HD float lane(int l, int j, int f) const { return ln[l][j * 3 + f]; }
   PSTL_HD void nei_meta(int k, int t, float& cx, float& cy, float& reach, float& valid) const {
     const float* p = neib + ((size_t)k * T + t) * 7;
-    valid = p[0]; cx = p[1]; cy = p[2]; reach = p[5] / 2.f;
+    valid = p[0]; cx = p[1]; cy = p[2]; reach = pstl_car_reach(p[5], p[6]);
   }
   PSTL_HD void nei(int k, int t, PstlNei& out) const {
     const float* p = neib + ((size_t)k * T + t) * 7;
@@ -102,7 +102,7 @@ PSTL_HD float pstl_eval_traj(const PstlProgView& P, const Scene& sc, const PstlE
                              int stride) {
   const int T = c.T;
   const int need_pose = pstl_need_pose(P);
-  const float ego_half = c.ego_L / 2.f;
+  const float ego_half = pstl_car_reach(c.ego_L, c.ego_W);
 #define VT(off) vt[(size_t)(off) * stride]
 #define PT(row, t) pt[(size_t)((row) * T + (t)) * stride]
   for (int t = 0; t < need_pose; ++t) {

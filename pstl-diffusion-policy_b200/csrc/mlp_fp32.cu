@@ -565,11 +565,50 @@ int pstl_tc_refine(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
                    const float* scores, float w_max, float a_max, int clip_rect, float* out, cudaStream_t st);
 bool pstl_tc_has_refine(pstl_denoiser* d);
 
+// the hoisted first-layer column blocks the per-step GEMMs read (copies of the caller's weights)
+static cudaError_t snapshot_first_layers(pstl_denoiser* d, cudaStream_t st) {
+  const pstl_weights* w = &d->w;
+  const int in1 = w->feat_dim + d->T2 + w->time_dim + 7;  // 303
+  const size_t f = sizeof(float);
+  // [x | hl | stlp] <- columns [feat : feat+T2], [feat+T2+time], [feat+T2+time+1 : +7]
+  cudaError_t e = cudaMemcpy2DAsync(d->w1p, d->kin * f, w->p0_w + w->feat_dim, in1 * f, d->T2 * f, w->hidden,
+                                    cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(d->w1p + d->T2, d->kin * f, w->p0_w + w->feat_dim + d->T2 + w->time_dim, in1 * f, 7 * f,
+                          w->hidden, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess && d->r1p) {
+    const int inr = w->feat_dim + 7 + d->T2;  // 271: [feat | hl | stlp | fused]
+    e = cudaMemcpy2DAsync(d->r1p, d->kin * f, w->r0_w + w->feat_dim + 7, inr * f, d->T2 * f, w->rect_hidden,
+                          cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(d->r1p + d->T2, d->kin * f, w->r0_w + w->feat_dim, inr * f, 7 * f, w->rect_hidden,
+                            cudaMemcpyDeviceToDevice, st);
+  }
+  return e;
+}
+
+int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st);  // denoiser_tc.cu
+
+extern "C" int pstl_denoiser_refresh(pstl_denoiser_t d, pstl_stream_t stream) {
+  PSTL_CHECK_ARG(d, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = snapshot_first_layers(d, st);
+  if (e != cudaSuccess) {
+    pstl_set_error("pstl_denoiser_refresh: %s", cudaGetErrorString(e));
+    return PSTL_ERR_CUDA;
+  }
+  return d->tc ? pstl_tc_refresh(d, st) : PSTL_OK;
+}
+
 extern "C" int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_denoiser_t* out) {
   PSTL_CHECK_ARG(w && out, "null argument");
   PSTL_CHECK_ARG(w->p0_w && w->p0_b && w->p2_w && w->p2_b && w->p4_w && w->p4_b, "policy_net weights required");
   PSTL_CHECK_ARG(w->T > 0 && w->hidden > 0 && w->feat_dim > 0 && w->time_dim > 0, "bad dims");
   PSTL_CHECK_ARG(precision == PSTL_PRECISION_FP32 || precision == PSTL_PRECISION_BF16, "bad precision");
+  if (2 * w->T + 7 > PSTL_XIN_LD) {  // the packed input row [x | hl | stlp] has a fixed leading dimension
+    pstl_set_error("pstl_denoiser_create: T = %d needs 2T+7 <= %d packed input columns", w->T, PSTL_XIN_LD);
+    return PSTL_ERR_UNSUPPORTED;
+  }
   pstl_denoiser* d = new pstl_denoiser();
   d->w = *w;
   d->precision = precision;
@@ -578,25 +617,10 @@ extern "C" int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_d
   d->w1p = d->r1p = nullptr;
   d->tc = nullptr;
   d->offset_dev = nullptr;
-  const int in1 = w->feat_dim + d->T2 + w->time_dim + 7;  // 303
   const size_t f = sizeof(float);
   cudaError_t e = cudaMalloc(&d->w1p, (size_t)w->hidden * d->kin * f);
-  // [x | hl | stlp] <- columns [feat : feat+T2], [feat+T2+time], [feat+T2+time+1 : +7]
-  if (e == cudaSuccess)
-    e = cudaMemcpy2D(d->w1p, d->kin * f, w->p0_w + w->feat_dim, in1 * f, d->T2 * f, w->hidden, cudaMemcpyDeviceToDevice);
-  if (e == cudaSuccess)
-    e = cudaMemcpy2D(d->w1p + d->T2, d->kin * f, w->p0_w + w->feat_dim + d->T2 + w->time_dim, in1 * f, 7 * f, w->hidden,
-                     cudaMemcpyDeviceToDevice);
-  if (e == cudaSuccess && w->r0_w) {
-    const int inr = w->feat_dim + 7 + d->T2;  // 271: [feat | hl | stlp | fused]
-    e = cudaMalloc(&d->r1p, (size_t)w->rect_hidden * d->kin * f);
-    if (e == cudaSuccess)
-      e = cudaMemcpy2D(d->r1p, d->kin * f, w->r0_w + w->feat_dim + 7, inr * f, d->T2 * f, w->rect_hidden,
-                       cudaMemcpyDeviceToDevice);
-    if (e == cudaSuccess)
-      e = cudaMemcpy2D(d->r1p + d->T2, d->kin * f, w->r0_w + w->feat_dim, inr * f, 7 * f, w->rect_hidden,
-                       cudaMemcpyDeviceToDevice);
-  }
+  if (e == cudaSuccess && w->r0_w) e = cudaMalloc(&d->r1p, (size_t)w->rect_hidden * d->kin * f);
+  if (e == cudaSuccess) e = snapshot_first_layers(d, nullptr);
   if (e != cudaSuccess) {
     pstl_set_error("pstl_denoiser_create: %s", cudaGetErrorString(e));
     pstl_denoiser_destroy(d);
@@ -655,7 +679,7 @@ extern "C" size_t pstl_denoiser_workspace_bytes(pstl_denoiser_t d, int N, int n_
   if (!d) return 0;
   DenoiserWs w;
   size_t total;
-  carve(d, N, n_scenes, 1024, g, nullptr, &w, &total);
+  carve(d, N, n_scenes, PSTL_MAX_STEPS, g, nullptr, &w, &total);
   return total;
 }
 
@@ -721,6 +745,7 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
   PSTL_CHECK_ARG(d && scene_feat && hl && stlp && sched && temb && workspace, "null argument");
   PSTL_CHECK_ARG(x_init || !noise, "injected noise needs x_init");
   PSTL_CHECK_ARG(steps >= 2 && keep_last_k >= 0 && keep_last_k <= steps - 1, "bad steps / keep_last_k");
+  PSTL_CHECK_ARG(steps <= PSTL_MAX_STEPS, "steps exceeds PSTL_MAX_STEPS (the workspace's per-step table)");
   PSTL_CHECK_ARG(rows_per_scene >= 1 && (long long)n_scenes * rows_per_scene >= N, "bad scene mapping");
   PSTL_CHECK_ARG(!keep_last_k || iterates_out, "iterates_out required");
   if (N <= 0) return PSTL_OK;
@@ -741,21 +766,24 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
   const float *beta = hs, *alpha = hs + steps, *abar = hs + 2 * steps;
   const size_t NT2 = (size_t)N * T2;
 
-  int tc_from = steps;  // reverse steps [tc_lo, steps-1] run on the tcgen05 engine when available
-  if (d->precision == PSTL_PRECISION_BF16) {
-    // guided steps (i <= before) need mu materialised: they run on the fp32 path below
-    const int lo = guidance ? (guidance->before + 1 > 1 ? guidance->before + 1 : 1) : 1;
-    if (lo <= steps - 1) {
+  // which reverse steps are guided (nusc_train.py:589-598): the caller's per-step mask, or i <= before
+  auto guided_at = [&](int i) {
+    return guidance && (guidance->step_mask ? guidance->step_mask[i] != 0 : i <= guidance->before);
+  };
+  const bool tc_guided = d->precision == PSTL_PRECISION_BF16;
+  for (int i = steps - 1; i >= 1; --i) {
+    const bool guided = guided_at(i);
+    if (tc_guided && !guided) {
+      // a maximal run of unguided steps [lo, i] is ONE launch of the tcgen05 engine; guided steps need mu
+      // materialised and go through the single-step path below
+      int lo = i;
+      while (lo - 1 >= 1 && !guided_at(lo - 1)) --lo;
       rc = pstl_tc_sample(d, w.cscene, rows_per_scene, w.ct, w.xin, N, sched, steps, noise, seed, offset, w_max, a_max,
-                          clip, keep_last_k, iterates_out, steps - 1, lo, nullptr, st);
-      if (rc) return rc;
-      tc_from = lo;
+                          clip, keep_last_k, iterates_out, i, lo, nullptr, st);
+      if (rc) break;
+      i = lo;
+      continue;
     }
-  }
-
-  const bool tc_guided = d->precision == PSTL_PRECISION_BF16 && tc_from < steps;  // engine usable for this shape
-  for (int i = tc_from - 1; i >= 1; --i) {
-    const bool guided = guidance && i <= guidance->before;
     if (!(guided && tc_guided)) {
       rc = mlp_hidden(d, w, N, rows_per_scene, d->w1p, H, w.ct + (size_t)i * H, d->w.p2_w, d->w.p2_b, st);
       if (rc) break;
@@ -790,7 +818,7 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
       if (e != cudaSuccess) { rc = PSTL_ERR_CUDA; pstl_set_error("memset: %s", cudaGetErrorString(e)); break; }
       for (int j = 0; j < guidance->niters && !rc; ++j)
         rc = pstl_guidance_step(guidance->progs, guidance->scenes, guidance->sp, hl, guidance->state0, stlp,
-                                guidance->valid, N, guidance->thres, guidance->inv_norm, guidance->lr, beta[i], j, w.g,
+                                guidance->valid, N, guidance->thres, guidance->inv_norm, guidance->inv_norm_dev, guidance->lr, beta[i], j, w.g,
                                 m, v, anchor, w.gws, stream);
       if (rc) break;
       k_finish_step<<<pstl_ceil_div((long long)NT2, 256), 256, 0, st>>>(w.g, w.xin, a.z, N, T2, a.sqrt_beta, noise_mode,

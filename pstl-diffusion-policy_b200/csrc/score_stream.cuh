@@ -55,7 +55,7 @@ struct PstlF4 {
 //   lane_pt(l, j)                         lane l point j as (x, y, theta, -)
 //   nei_begin(t, count, init)             neighbours to visit at step t and the initial running minimum
 //                                         (100 when a zero-valid neighbour was dropped from the list)
-//   nei_meta(slot, t, valid, cx, cy, rsum) car centre and  L_ego/2 + L_nei/2 + 1e-3  (cull radius less min(best,20))
+//   nei_meta(slot, t, valid, cx, cy, rsum) car centre and  reach_ego + reach_nei + 1e-3  (cull radius less min(best,20))
 //   nei(slot, t, out)                     circle centres, radius, valid
 struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
   const float* neib;            // (K,T,7)
@@ -70,7 +70,7 @@ struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
   PSTL_HD void nei_begin(int, int& count, float& init) const { count = K; init = INFINITY; }
   PSTL_HD void nei_meta(int k, int t, float& valid, float& cx, float& cy, float& rsum) const {
     const float* p = neib + ((size_t)k * T + t) * 7;
-    valid = p[0]; cx = p[1]; cy = p[2]; rsum = ego_half + p[5] / 2.f + 1e-3f;
+    valid = p[0]; cx = p[1]; cy = p[2]; rsum = ego_half + pstl_car_reach(p[5], p[6]) + 1e-3f;
   }
   PSTL_HD void nei(int k, int t, PstlNei& out) const {
     const float* p = neib + ((size_t)k * T + t) * 7;
@@ -82,7 +82,7 @@ struct PstlStreamSceneGlobal {  // raw tensors of this row's scene
   }
 };
 
-// Exact cull (see pstl_cull_neighbour): rsum = L_ego/2 + L_nei/2 + margin
+// Exact cull (see pstl_cull_neighbour): rsum = reach_ego + reach_nei + margin (pstl_car_reach)
 PSTL_HD bool pstl_cull_neighbour_r(float dx, float dy, float rsum, float best) {
   const float R = fminf(best, 20.f) + rsum;
   return R > 0.f && fmaf(dx, dx, dy * dy) >= R * R;
@@ -186,7 +186,8 @@ PSTL_HD void pstl_stream_steps(const PstlPlan& pl, const Scene& sc, const PstlEv
       }
       const PstlF4 p2 = sc.lane_pt(l, bi), p3 = sc.lane_pt(l, bi + 1);
       float part[3];
-      pstl_lane_finish(s.x, s.y, s.th, p2.x, p2.y, p2.z, p3.x, p3.y, c.clip_dist, d, th, GRAD ? part : nullptr);
+      pstl_lane_finish(s.x, s.y, s.th, p2.x, p2.y, p2.z, p3.x, p3.y, c.clip_dist, bi == 0, bi == c.nseg - 2, d, th,
+                       GRAD ? part : nullptr);
       if (GRAD) { PSTL_TAPE(6, t) = part[0]; PSTL_TAPE(7, t) = part[1]; PSTL_TAPE(8, t) = part[2]; }
     }
     if (t < pl.need_nei) {
@@ -540,7 +541,7 @@ __device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4
     ln[e] = make_float4(src[0], src[1], src[2], 0.f);
   }
   __syncthreads();
-  const float ego_half = c.ego_L / 2.f;
+  const float ego_half = pstl_car_reach(c.ego_L, c.ego_W);
   for (int e = threadIdx.x; e < K * tc; e += blockDim.x) {
     const int k = e / tc, tl = e - k * tc, t = t0 + tl;
     const float* kt = keys + tl * K;
@@ -559,7 +560,7 @@ __device__ void stream_stage_scene(const ScoreArgs& a, int scene, int n0, float4
     float4* o = tile + (size_t)(tl * K + rank) * PSTL_STREAM_NEI_F4;
     o[0] = make_float4(cc.cx[0], cc.cx[1], cc.cx[2], cc.cx[3]);
     o[1] = make_float4(cc.cy[0], cc.cy[1], cc.cy[2], cc.cy[3]);
-    o[2] = make_float4(p[0], p[1], p[2], ego_half + p[5] / 2.f + 1e-3f);
+    o[2] = make_float4(p[0], p[1], p[2], ego_half + pstl_car_reach(p[5], p[6]) + 1e-3f);
     o[3] = make_float4(cc.r, 0.f, 0.f, 0.f);
   }
 }
@@ -649,7 +650,7 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
   PstlStreamSceneGlobal sg;
   sg.neib = a.neighbors + (size_t)scene * c.K * T * 7;
   for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
-  sg.K = c.K; sg.T = T; sg.ego_half = c.ego_L / 2.f;
+  sg.K = c.K; sg.T = T; sg.ego_half = pstl_car_reach(c.ego_L, c.ego_W);
 
   float best = -INFINITY;
   int bi = 0;
@@ -761,7 +762,7 @@ k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   PstlStreamSceneGlobal sg;
   sg.neib = a.neighbors + (size_t)scene * c.K * T * 7;
   for (int l = 0; l < 3; ++l) sg.ln[l] = a.lanes[l] + (size_t)scene * c.nseg * 3;
-  sg.K = c.K; sg.T = T; sg.ego_half = c.ego_L / 2.f;
+  sg.K = c.K; sg.T = T; sg.ego_half = pstl_car_reach(c.ego_L, c.ego_W);
 
   if (live && m >= 3) {
     if (a.scores) a.scores[n] = (m == 3) ? 1.0f : 0.0f;
@@ -803,7 +804,7 @@ k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
     if (a.scores) a.scores[n] = sc;
     float g;
     if (a.grad_score) g = a.grad_score[n];
-    else g = (a.thres - sc > 0.f) ? -a.valid[n] * a.inv_norm : 0.f;  // guidance loss, nusc_train.py:616-619
+    else g = (a.thres - sc > 0.f) ? -a.valid[n] * (a.inv_norm_dev ? __ldg(a.inv_norm_dev) : a.inv_norm) : 0.f;  // guidance loss, nusc_train.py:616-619
     pstl_stream_bwd(sp.p[m], c, u, stlp, g, sc != -INFINITY, A, tape, a.N, gu, ge);
   }
 }

@@ -188,7 +188,7 @@ __device__ void stage_scene_soa(const ScoreArgs& a, int scene, float* tile) {
     float* o = tile + (size_t)k * PSTL_SOA_F * c.T + t;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { o[i * c.T] = cc.cx[i]; o[(4 + i) * c.T] = cc.cy[i]; }
-    o[8 * c.T] = cc.r; o[9 * c.T] = p[0]; o[10 * c.T] = p[1]; o[11 * c.T] = p[2]; o[12 * c.T] = p[5] / 2.f;
+    o[8 * c.T] = cc.r; o[9 * c.T] = p[0]; o[10 * c.T] = p[1]; o[11 * c.T] = p[2]; o[12 * c.T] = pstl_car_reach(p[5], p[6]);
   }
   for (int l = 0; l < 3; ++l) {
     const float* src = a.lanes[l] + (size_t)scene * c.nseg * 3;
@@ -221,7 +221,7 @@ __device__ __noinline__ void warp_predicates(const PstlProgView& P, const Scene&
   if (t < P.base_need[PSTL_SIG_NEI]) {
     PstlCircles e;
     pstl_car_circles(s.x, s.y, cs, sn, c.ego_L, c.ego_W, e);
-    const float ego_half = c.ego_L / 2.f;
+    const float ego_half = pstl_car_reach(c.ego_L, c.ego_W);
     float best = INFINITY;
     for (int k = 0; k < c.K; ++k) {
       float ncx, ncy, reach, valid;

@@ -235,6 +235,7 @@ struct ScoreArgs {
   // reverse mode
   const float *grad_score, *valid;
   float thres, inv_norm;
+  const float* inv_norm_dev;  // when set, the loss normaliser is read from device memory (graph-capturable guidance)
   float *scores, *grad_controls, *grad_ego;
   float* ws;
   int smem_tape, F;
@@ -259,7 +260,7 @@ __device__ void stage_scene(const ScoreArgs& a, int scene, float* tile) {
     pstl_car_circles(p[1], p[2], cosf(p[3]), sinf(p[3]), p[5], p[6], cc);
     float* o = circ + (size_t)e * W;
     for (int i = 0; i < PSTL_NL; ++i) { o[i] = cc.cx[i]; o[PSTL_NL + i] = cc.cy[i]; }
-    o[8] = cc.r; o[9] = p[0]; o[10] = p[1]; o[11] = p[2]; o[12] = p[5] / 2.f;
+    o[8] = cc.r; o[9] = p[0]; o[10] = p[1]; o[11] = p[2]; o[12] = pstl_car_reach(p[5], p[6]);
     o[13] = o[14] = o[15] = 0.f;
   }
   for (int l = 0; l < 3; ++l) {
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
     if (a.grad_score) {
       g = a.grad_score[n];
     } else {  // guidance loss (nusc_train.py:616-619): mean(relu(thres-score)*valid)/clip(mean(valid),1e-2)
-      g = (a.thres - sc > 0.f) ? -a.valid[n] * a.inv_norm : 0.f;
+      g = (a.thres - sc > 0.f) ? -a.valid[n] * (a.inv_norm_dev ? __ldg(a.inv_norm_dev) : a.inv_norm) : 0.f;
     }
     pstl_eval_traj_bwd<true>(P, c, u, stlp, g, vt, gt, pt, stride, gu, ge);
   }
@@ -709,9 +710,9 @@ __global__ void k_guidance_apply(const float* __restrict__ g, float* __restrict_
 
 extern "C" int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_view* scenes,
                                   const pstl_spec_params* sp, const float* mode, const float* state0,
-                                  const float* stlp, const float* valid, int N, float thres, float inv_norm, float lr,
-                                  float beta_t, int iter, float* mu, float* adam_m, float* adam_v, float* mu_anchor,
-                                  void* workspace, pstl_stream_t stream) {
+                                  const float* stlp, const float* valid, int N, float thres, float inv_norm,
+                                  const float* inv_norm_dev, float lr, float beta_t, int iter, float* mu, float* adam_m,
+                                  float* adam_v, float* mu_anchor, void* workspace, pstl_stream_t stream) {
   int rc = check_score_args(progs, scenes, sp, mode, stlp, N);
   if (rc) return rc;
   PSTL_CHECK_ARG(state0 && valid && mu && adam_m && adam_v && mu_anchor && workspace, "null argument");
@@ -723,7 +724,8 @@ extern "C" int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_
   ScoreArgs a;
   base_args(a, progs, scenes, sp);
   a.mode = mode; a.state0 = state0; a.controls = mu; a.stlp = stlp; a.N = N; a.C = 1;
-  a.valid = valid; a.thres = thres; a.inv_norm = inv_norm; a.grad_controls = grad; a.ws = tape;
+  a.valid = valid; a.thres = thres; a.inv_norm = inv_norm; a.inv_norm_dev = inv_norm_dev; a.grad_controls = grad;
+  a.ws = tape;
   int took = 0;
   rc = launch_score_stream_bwd(a, progs, (cudaStream_t)stream, &took);
   if (rc) return rc;

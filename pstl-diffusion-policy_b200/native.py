@@ -25,7 +25,8 @@ EXPORTS = [
     "pstl_denoiser_eps", "pstl_denoiser_set_noise_counter", "pstl_launch_count", "pstl_refine", "pstl_rollout", "pstl_rollout_bwd", "pstl_predicates", "pstl_linear", "pstl_encoder_inputs",
     "pstl_encoder_pool", "pstl_mlp3", "pstl_mlp3_batch", "pstl_trajopt_step", "pstl_diversity", "pstl_accuracy",
     "pstl_refine_losses_workspace_bytes", "pstl_refine_losses", "pstl_refine_backward_workspace_bytes",
-    "pstl_refine_backward", "pstl_denoiser_eps_rows", "pstl_denoiser_eps_backward",
+    "pstl_refine_backward", "pstl_denoiser_eps_rows", "pstl_denoiser_eps_backward", "pstl_car_distances",
+    "pstl_denoiser_refresh",
 ]
 
 
@@ -74,7 +75,8 @@ LOSS_KEYS = ("loss", "loss_stl", "loss_reg", "loss_diversity", "extra_loss_reg")
 class GuidanceCfg(C.Structure):
     _fields_ = [("valid", C.c_void_p), ("state0", C.c_void_p), ("progs", C.POINTER(C.c_void_p)),
                 ("scenes", C.POINTER(SceneView)), ("sp", C.POINTER(SpecParams)), ("before", C.c_int),
-                ("niters", C.c_int), ("lr", C.c_float), ("thres", C.c_float), ("inv_norm", C.c_float)]
+                ("step_mask", C.c_void_p), ("niters", C.c_int), ("lr", C.c_float), ("thres", C.c_float),
+                ("inv_norm", C.c_float), ("inv_norm_dev", C.c_void_p)]
 
 
 _lib = None

@@ -2,8 +2,8 @@
 (reference nusc_model.py:8-235): same constructor, sub-module names (so reference checkpoints
 load with ``load_state_dict``), ``forward`` / ``rect_forward`` signatures.
 
-The eps-MLP and RefineNet run in libpstl_b200.so; the per-scene encoders (O(bs) work, SURVEY.md
-§8(f) "next") stay PyTorch.  VAE / BC / init-hint variants are out of scope and raise.
+The eps-MLP, RefineNet and (without autograd) the per-scene encoders run in libpstl_b200.so; with autograd
+on the encoders are the plain nn.Sequential stacks.  VAE / BC / init-hint variants are out of scope and raise.
 """
 import torch
 import torch.nn as nn
@@ -141,42 +141,61 @@ class Net(nn.Module):
         latent_dim = args.nt * 2 + self.time_dim + 1 + stlp_dim
         self.policy_net = build_relu_nn(latent_dim + feat_dim * 7, args.nt * 2, args.hiddens)
         if args.rect_head:
-            if args.diverse_loss and not args.no_arch and args.diverse_fuse_type != "add":
-                raise NotImplementedError("only --diverse_fuse_type add is built")
+            extra_in_dim = 0
+            if args.diverse_loss and not args.no_arch and args.diverse_fuse_type == "cat":
+                extra_in_dim += args.nt * 2  # reference nusc_model.py:40-41: [init | pooled] side by side
             if args.diverse_loss:
                 self.merge_net = build_relu_nn(args.nt * 2, args.nt * 2, [32, 32])
-            self.rect_net = build_relu_nn(latent_dim - self.time_dim + feat_dim * 7, args.nt * 2, args.rect_hiddens)
+            self.rect_net = build_relu_nn(latent_dim - self.time_dim + feat_dim * 7 + extra_in_dim, args.nt * 2,
+                                          args.rect_hiddens)
         self._handles = {}
 
     # --- native handle -------------------------------------------------------------------
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
+    def invalidate_native(self):
+        """Call after editing parameters through ``p.data`` (which does not bump the version counter autograd keeps):
+        the next ``native_handle`` re-derives the library's weight copies."""
+        for prec, c in list(self._handles.items()):
+            self._handles[prec] = ((c[0][0], None), c[1], c[2], c[3])
+
     def native_handle(self, precision="fp32"):
-        """pstl_denoiser_t over this module's parameters (rebuilt if they were modified)."""
+        """pstl_denoiser_t over this module's parameters.  The handle points at the parameter storage; an in-place update
+        (optimiser step: same storage, new version) only refreshes the library's own copies — the hoisted first-layer
+        blocks and the bf16 operand images — on the current stream (``pstl_denoiser_refresh``: no allocation, no
+        synchronisation); parameters that moved to other storage rebuild the handle."""
         prec = {"fp32": _nv.PRECISION_FP32, "bf16": _nv.PRECISION_BF16}[precision]
-        key = (prec, self._weights_key())
+        ps = list(self.parameters())
+        ptrs, vers = tuple(p.data_ptr() for p in ps), tuple(p._version for p in ps)
         cached = self._handles.get(prec)
-        if cached is not None and cached[0] == key:
+        if cached is not None and cached[0] == (ptrs, vers):
+            return cached[1]
+        if cached is not None and cached[0][0] == ptrs and cached[3]:
+            _nv.check(_nv.lib().pstl_denoiser_refresh(cached[1], _nv.stream()), "pstl_denoiser_refresh")
+            self._handles[prec] = ((ptrs, vers), cached[1], cached[2], True)
             return cached[1]
         if len(self.args.hiddens) != 2 or len(getattr(self.args, "rect_hiddens", [0, 0])) != 2 or \
                 self.args.hiddens[0] != self.args.hiddens[1]:
             raise NotImplementedError("native denoiser needs two equal hidden layers")
         w = _nv.Weights()
         keep = []
+        in_place = [True]  # the handle reads the parameters' own storage (fp32, contiguous): refreshable
 
         def put(prefix, seq):
             for li in (0, 2, 4):
                 for kind in ("weight", "bias"):
                     t = getattr(seq[li], kind).detach()
                     _nv.require_cuda(t, "model parameters")
-                    t = t.to(torch.float32).contiguous()
+                    tc = t.to(torch.float32).contiguous()
+                    in_place[0] = in_place[0] and tc.data_ptr() == t.data_ptr()
+                    t = tc
                     keep.append(t)
                     setattr(w, "%s%d_%s" % (prefix, li, kind[0]), t.data_ptr())
 
         put("p", self.policy_net)
         w.merge_hidden = 32
-        if hasattr(self, "rect_net"):
+        if hasattr(self, "rect_net") and self._rect_native():
             put("r", self.rect_net)
             if hasattr(self, "merge_net"):
                 put("m", self.merge_net)
@@ -187,7 +206,7 @@ class Net(nn.Module):
         _nv.check(_nv.lib().pstl_denoiser_create(_nv.C.byref(w), prec, _nv.C.byref(h)), "pstl_denoiser_create")
         if cached is not None:
             _nv.lib().pstl_denoiser_destroy(cached[1])
-        self._handles[prec] = (key, h, keep)
+        self._handles[prec] = ((ptrs, vers), h, keep, in_place[0])
         return h
 
     def pos_encoding(self, t, channels):
@@ -352,10 +371,56 @@ class Net(nn.Module):
         return controls
 
     # --- RefineNet (reference nusc_model.py:182-235) --------------------------------------
+    def _rect_native(self):
+        """the fused RefineNet kernels (pstl_refine) cover the README configuration: --diverse_loss with the shard
+        max-pool added to the controls, tanh-interval head"""
+        a = self.args
+        return bool(a.diverse_loss and not a.no_arch and a.diverse_fuse_type == "add" and a.interval)
+
+    def _rect_forward_generic(self, feature, highlevel, stlp_dense_feat, init_controls, scores):
+        """The other RefineNet variants of the reference (nusc_model.py:182-235): --no_arch / no --diverse_loss (no shard
+        pooling), --diverse_fuse_type cat (pooled controls as extra inputs), no --interval (raw head).  Inference only:
+        the dense layers run on pstl_linear (``_mlp``), the pooling / head arithmetic are upstream's tensor expressions."""
+        a = self.args
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.rect_net.parameters()):
+            raise NotImplementedError("training is built for the README RefineNet configuration only "
+                                      "(--diverse_loss, --diverse_fuse_type add, --interval)")
+        n, T2 = init_controls.shape[0], a.nt * 2
+        sf = getattr(feature, "_pstl_scene_feat", None)
+        if sf is not None:  # per-scene rows from this package's sampler
+            feature = sf.reshape(sf.shape[0], 1, -1).expand(-1, n // sf.shape[0], -1).reshape(n, -1)
+        init_controls = init_controls.reshape(n, a.nt, 2)
+        if a.diverse_loss and not a.no_arch:
+            fused = self._mlp(self.merge_net, init_controls.reshape(n, T2))
+            bs, NS = n // 3 // a.n_randoms, a.n_shards
+            fused = fused.reshape(bs, a.n_randoms, 3, T2).permute(0, 2, 1, 3).reshape(bs, 3, NS, a.n_randoms // NS, T2)
+            fused = torch.max(fused, dim=3, keepdim=True)[0].repeat(1, 1, 1, a.n_randoms // NS, 1)
+            fused = fused.reshape(bs, 3, a.n_randoms, T2).permute(0, 2, 1, 3).reshape(n, a.nt, 2)
+            if a.diverse_fuse_type == "add":
+                fused = init_controls + fused
+                cols = [feature, highlevel, stlp_dense_feat, fused.reshape(n, T2)]
+            elif a.diverse_fuse_type == "cat":
+                cols = [feature, highlevel, stlp_dense_feat, init_controls.reshape(n, T2), fused.reshape(n, T2)]
+            else:
+                raise NotImplementedError("--diverse_fuse_type %s" % a.diverse_fuse_type)
+        else:
+            cols = [feature, highlevel, stlp_dense_feat, init_controls.reshape(n, T2)]
+        raw = self._mlp(self.rect_net, torch.cat([c.reshape(n, -1) for c in cols], dim=-1)).reshape(n, a.nt, 2)
+        if a.interval:
+            raw = torch.tanh(raw)
+            lim = torch.tensor([a.mul_w_max, a.mul_a_max], device=raw.device)
+            mk = (raw >= 0).float()
+            raw = (raw * (init_controls + lim)) * (1 - mk) + (raw * (lim - init_controls)) * mk
+        out = init_controls + raw * (scores < 0).float()[:, None, None]
+        if a.clip_rect:
+            out = torch.stack([torch.clip(out[..., 0], -a.mul_w_max, a.mul_w_max),
+                               torch.clip(out[..., 1], -a.mul_a_max, a.mul_a_max)], dim=-1)
+        return out
+
     def rect_forward(self, feature, highlevel, stlp_dense_feat, init_controls, scores, extras=None):
         a = self.args
-        if not (a.diverse_loss and not a.no_arch and a.interval):
-            raise NotImplementedError("native RefineNet is built for --diverse_loss --interval (implied by --rect_head)")
+        if not self._rect_native():
+            return self._rect_forward_generic(feature, highlevel, stlp_dense_feat, init_controls, scores)
         n = init_controls.shape[0]
         bs = int(n / 3 / a.n_randoms)
         scene_feat = getattr(feature, "_pstl_scene_feat", None)

@@ -230,16 +230,55 @@ def _fused_programs(stls_cac, T):
 
 def _spec(args, w_scale=1.0, a_scale=1.0, clip_controls=0):
     return _nv.make_spec(args.dt, args.smoothing_factor, args.ego_L, args.ego_W, w_scale, a_scale, clip_controls,
-                         int(bool(args.clip_dist)), 0)
+                         _lane_flags(args), 0)
 
 
-def _check_supported(args):
-    if getattr(args, "inline", False):
-        raise NotImplementedError("--inline lane end-caps are not implemented in the fused kernels")
-    if getattr(args, "collision_loss", None) is not None:
-        raise NotImplementedError("--collision_loss (TrafficSim baseline) is out of scope")
-    if int(getattr(args, "refined_nL", 4)) != 4 or int(getattr(args, "refined_nW", 1)) != 1:
-        raise NotImplementedError("only refined_nL=4, refined_nW=1 are built")
+def _lane_flags(args):
+    """lane flag word of the kernels: bit 0 --clip_dist, bit 1 --inline (reference nusc_api.py:716-724, 732-733)"""
+    return int(bool(args.clip_dist)) | (int(bool(getattr(args, "inline", False))) << 1)
+
+
+def _default_anchors(args):
+    """the fused scoring kernels hold the (refined_nL, refined_nW) = (4, 1) anchor grid of the reference's defaults in
+    registers; any other grid is served by prep_stl_cache (pstl_car_distances) + the generic formula kernels"""
+    return int(getattr(args, "refined_nL", 4)) == 4 and int(getattr(args, "refined_nW", 1)) == 1
+
+
+def _check_fused_supported(args, what):
+    if not _default_anchors(args):
+        raise NotImplementedError("%s runs on the fused kernels, which are built for --refined_nL 4 --refined_nW 1; "
+                                  "compute_stl_dense / prep_stl_cache take any anchor grid" % what)
+
+
+class _CarDistances(torch.autograd.Function):
+    """(min_dist, rad_sum) (N,K,T) of dist_between_two_cars(full=True) for any anchor grid (reference utils.py:465-526);
+    differentiable w.r.t. the ego poses."""
+
+    @staticmethod
+    def forward(ctx, ego, sv_holder, args):
+        nei, lanes, rps = sv_holder
+        N, T = ego.shape[0], ego.shape[1]
+        K = nei.shape[1]
+        e = _nv.f32(ego)
+        md = torch.empty((N, K, T), dtype=torch.float32, device=ego.device)
+        rs = torch.empty((N, K, T), dtype=torch.float32, device=ego.device)
+        part = torch.empty((N, K, T, 3), dtype=torch.float32, device=ego.device) if ctx.needs_input_grad[0] else None
+        sv = _nv.make_scene_view(nei, lanes, rps)
+        _nv.check(_nv.lib().pstl_car_distances(_nv.C.byref(sv), _nv.C.c_float(args.ego_L), _nv.C.c_float(args.ego_W),
+                                               int(args.refined_nL), int(args.refined_nW), _nv.fptr(e), e.shape[2], N,
+                                               _nv.fptr(md), _nv.fptr(rs), _nv.fptr(part), _nv.stream()),
+                  "pstl_car_distances")
+        ctx.part = part
+        ctx.width = ego.shape[2]
+        ctx.mark_non_differentiable(rs)
+        return md, rs
+
+    @staticmethod
+    def backward(ctx, g_md, _g_rs):
+        N, K, T, _ = ctx.part.shape
+        ge = torch.zeros((N, T, ctx.width), dtype=torch.float32, device=g_md.device)
+        ge[..., :3] = (g_md.unsqueeze(-1) * ctx.part).sum(dim=1)
+        return ge, None, None
 
 
 class _Predicates(torch.autograd.Function):
@@ -252,7 +291,7 @@ class _Predicates(torch.autograd.Function):
         part = torch.empty((N, 12, T), dtype=torch.float32, device=ego.device)
         sv = _nv.make_scene_view(nei, lanes, rps)
         _nv.check(_nv.lib().pstl_predicates(_nv.C.byref(sv), _nv.C.c_float(args.ego_L), _nv.C.c_float(args.ego_W),
-                                            int(bool(args.clip_dist)), _nv.fptr(e), e.shape[2], N, _nv.fptr(sig),
+                                            _lane_flags(args), _nv.fptr(e), e.shape[2], N, _nv.fptr(sig),
                                             _nv.fptr(part), _nv.stream()), "pstl_predicates")
         ctx.save_for_backward(part)
         ctx.width = ego.shape[2]
@@ -275,7 +314,6 @@ class _Predicates(torch.autograd.Function):
 
 def prep_stl_cache(x, args):
     """adds x2{curr,left,right}_{d,th} and min_nei_d to the dense dict (reference :74-93)."""
-    _check_supported(args)
     ego = x["ego_traj"]
     _nv.require_cuda(ego, "ego_traj")
     pack = x.get("_pstl_pack") if isinstance(x, dict) else None
@@ -290,6 +328,15 @@ def prep_stl_cache(x, args):
     for l, k in enumerate(("curr", "left", "right")):
         x["x2%s_d" % k], x["x2%s_th" % k] = sig[:, 2 * l], sig[:, 2 * l + 1]
     x["min_nei_d"] = sig[:, 6]
+    full = getattr(args, "collision_loss", None) is not None
+    if full or not _default_anchors(args):
+        # reference :81-86, 142-148 on the general anchor-grid kernel
+        md, rs = _CarDistances.apply(ego, holder, args)
+        nei = holder[0]
+        ind = nei[..., 0] if holder[2] == 1 else nei[..., 0][torch.arange(ego.shape[0], device=ego.device) // holder[2]]
+        x["min_nei_d"] = torch.min(torch.clip(md - rs, -5, 20) * ind + (1 - ind) * 100, dim=1)[0]
+        if full:
+            x["min_centroid_d"], x["radius_sum"] = md * ind + (1 - ind) * 100, rs
     if getattr(args, "norm_stl", False):
         x["v_factor"] = torch.clip((x["stlp"][..., I_VMAX] - x["stlp"][..., I_VMIN]), 0.3)
         x["d_factor"] = torch.clip((x["stlp"][..., I_DMAX] - x["stlp"][..., I_DMIN]) * 5, 0.3)
@@ -462,6 +509,7 @@ def score_pack(pack, controls, args, progs, scaled=True, want=("best_score",)):
     controls: (C,N,T,2) or (N,T,2) physical controls (``scaled``) or raw mu/x (then scaled+clipped
     per normalize_diff).  Returns dict with the requested outputs among
     scores_all (C,N), best_score (N), best_idx (N), best_controls (N,T,2), traj (N,T+1,4)."""
+    _check_fused_supported(args, "score_pack (the sampling pipeline)")
     c = controls if controls.dim() == 4 else controls.unsqueeze(0)
     c = _nv.f32(c)
     C_, N, T, _ = c.shape
@@ -497,13 +545,14 @@ def compute_stl_dense(stl_input, stls_cac, stl_idx, mask, args, debug=False, tj_
     Returns (scores_list, scores, acc[, scene_acc | stl_input]) like upstream.  With the typed
     spec of ``build_stl_cache`` this is ONE fused kernel (predicates + formula, only the row's own
     formula — the reference evaluates all three and multiplies by one-hot masks, equal whenever the
-    unused formulas are finite); custom AP lambdas fall back to predicates + generic interpreter."""
-    _check_supported(args)
+    unused formulas are finite); custom AP lambdas, other anchor grids (--refined_nL / --refined_nW) and
+    --collision_loss (whose extra signals the caller reads from stl_input) run predicates + generic interpreter."""
     ego = stl_input["ego_traj"]
     _nv.require_cuda(ego, "ego_traj")
     N, T = ego.shape[0], ego.shape[1]
     mode = _nv.f32(stl_idx[:, 0])
-    progs = _fused_programs(stls_cac, T)
+    fused_ok = _default_anchors(args) and getattr(args, "collision_loss", None) is None
+    progs = _fused_programs(stls_cac, T) if fused_ok else None
     pack = stl_input.get("_pstl_pack") if isinstance(stl_input, dict) else None
     if progs is not None:
         if pack is not None:
@@ -639,7 +688,6 @@ def compute_policy_loss(batch_cuda, nn_stlp, stls_cac, nn_trajs, rect_trajs, den
     call (pstl_refine_losses) instead of the ~40 autograd nodes upstream records.  Returns (rd, all_scores)."""
     if diffusion_extras is None or vae_extras is not None or bc_extras is not None:
         raise NotImplementedError("compute_policy_loss: only the diffusion branch is built")
-    _check_supported(args)
     bs = batch_cuda["ego_traj"].shape[0]
     S = args.n_randoms
     self_trajs = rect_trajs if args.rect_head else nn_trajs
@@ -662,17 +710,24 @@ def compute_policy_loss(batch_cuda, nn_stlp, stls_cac, nn_trajs, rect_trajs, den
         rd["loss_diffusion"] = mask_mean(torch.square(raw_noise - est_cmds_a), m)
     else:
         rd["loss_diffusion"] = torch.mean(torch.square(raw_noise - est_cmds_a))
+    loss_coll = None
+    if getattr(args, "collision_loss", None) is not None:
+        # TrafficSim-style collision term (reference :416-420) on the extra signals prep_stl_cache added to stl_input
+        coll_dist = torch.relu(1 - stl_input["min_centroid_d"] / torch.clip(stl_input["radius_sum"], 1e-1))
+        loss_coll = torch.mean(torch.clip(torch.sum(coll_dist, dim=-1), max=1)) * args.collision_loss
     if args.rect_head:
         loss, terms = _RefineLosses.apply(rect_controls, scores, nn_controls.detach(), valid_mask, loss_cfg(args, bs, S))
         rd["loss"], rd["loss_stl"], rd["loss_reg"] = loss, terms[1], terms[2]
-        rd["loss_coll"] = terms[1] * 0
+        rd["loss_coll"] = terms[1] * 0 if loss_coll is None else loss_coll
         if args.diverse_loss:
-            rd["loss_diversity"] = terms[3]
+            rd["loss_diversity"] = terms[3]  # upstream's --diverse_loss total leaves loss_coll out (:466)
         else:
             rd["extra_loss_reg"] = terms[4]
+            if loss_coll is not None:
+                rd["loss"] = rd["loss"] + loss_coll
     else:
         rd["loss_stl"] = mask_mean(torch.relu(args.stl_nn_thres - scores), valid_mask) * args.stl_weight
-        rd["loss_coll"] = rd["loss_stl"] * 0
+        rd["loss_coll"] = rd["loss_stl"] * 0 if loss_coll is None else loss_coll
         rd["loss"] = rd["loss_stl"] + rd["loss_diffusion"] + rd["loss_coll"]
     return rd, all_scores
 
@@ -708,8 +763,9 @@ class IterateList:
     """final_list of diffusion_rollout (reference :633-634): ``steps`` entries x_T..x_0, of which only
     the last ``K`` are stored (the reference keeps all 100 = 3.1 GB at 196,608 chains)."""
 
-    def __init__(self, steps, kept):
+    def __init__(self, steps, kept, first=None):
         self.steps, self.kept = steps, kept  # kept (K,N,T,2), chronological
+        self.first = first                   # normalised x_T (entry 0), when the caller kept it
 
     def __len__(self):
         return self.steps
@@ -717,6 +773,8 @@ class IterateList:
     def _one(self, i):
         if i < 0:
             i += self.steps
+        if i == 0 and self.first is not None:
+            return self.first
         j = i - (self.steps - self.kept.shape[0])
         if j < 0 or i >= self.steps:
             raise IndexError("iterate %d was not kept (only the last %d are; pass keep_all_iterates)"
@@ -749,6 +807,58 @@ def _host_schedule(beta, alpha, alpha_hat):
     return s
 
 
+def guidance_step(pack, mu, stls_cac, args, beta_t, it=0, state=None, maximize=False, n_total=None):
+    """ONE iteration of the guidance block of a reverse step on ``mu`` (N, nt, 2), in place (reference :605-626, the
+    body of ``for j in range(guidance_niters)``): rollout of ``mu * (w_max, a_max)`` -> STL scores -> loss
+    ``mask_mean(relu(thres - score), valid)`` -> Adam step (+ the |delta| clip to ``beta_t`` from the second iteration,
+    see the aliasing note in DESIGN.md).  ``state`` = (m, v, anchor) Adam moments / anchor, created zeroed when None
+    (pass it back for ``it`` >= 1).  Returns (mu, grad (N, nt, 2) of the loss w.r.t. mu, scores are not returned).
+    The sampler runs exactly this call inside ``pstl_denoiser_sample``; it is exposed for tests and custom loops."""
+    _check_fused_supported(args, "guidance_step")
+    N, T = pack.N, pack.T
+    mu = mu.reshape(N, T, 2)
+    _nv.require_cuda(mu, "mu")
+    if mu.dtype != torch.float32 or not mu.is_contiguous():
+        raise ValueError("mu must be contiguous float32 (it is updated in place)")
+    progs = _fused_programs(stls_cac, T)
+    if progs is None:
+        raise NotImplementedError("guidance needs the typed spec of build_stl_cache")
+    L = _nv.lib()
+    pa = _nv.prog_array(progs)
+    sv, sp = pack.view(), _spec(args, args.mul_w_max, args.mul_a_max, 0)
+    if state is None:
+        state = tuple(torch.zeros_like(mu) for _ in range(3))
+    ws = _nv.workspace(N * T * 2 * 4 + L.pstl_score_workspace_bytes(pa, N, T, 1), mu.device, "guidance")
+    n_total = float(N if n_total is None else n_total)
+    inv_norm = 1.0 / (n_total * max(float(pack.valid.mean().item()), 1e-2))
+    thres = 100.0 if maximize else args.stl_nn_thres
+    _nv.check(L.pstl_guidance_step(pa, _nv.C.byref(sv), _nv.C.byref(sp), _nv.fptr(pack.mode), _nv.fptr(pack.state0),
+                                   _nv.fptr(pack.stlp), _nv.fptr(pack.valid), N, _nv.C.c_float(thres),
+                                   _nv.C.c_float(inv_norm), None, _nv.C.c_float(args.guidance_lr),
+                                   _nv.C.c_float(beta_t), int(it), _nv.fptr(mu), _nv.fptr(state[0]), _nv.fptr(state[1]),
+                                   _nv.fptr(state[2]), _nv.ptr(ws), _nv.stream()), "pstl_guidance_step")
+    grad = ws[:N * T * 2 * 4].view(torch.float32).reshape(N, T, 2).clone()
+    return mu, grad, state
+
+
+def guidance_step_mask(args):
+    """which reverse steps i (index into a ``diffusion_steps``-long uint8 array) run STL guidance — the trigger chain
+    of reference :589-598: ``i_val in guidance_sets``, else ``i_val % guidance_freq == 0``, else ``i <= guidance_before``
+    with ``i_val = diffusion_steps-1-i`` under --guidance_reverse (the last rule reads ``i`` itself, as upstream)."""
+    steps = args.diffusion_steps
+    mask = np.zeros(steps, dtype=np.uint8)
+    for i in range(1, steps):
+        i_val = steps - 1 - i if args.guidance_reverse else i
+        if args.guidance_sets is not None:
+            hit = i_val in args.guidance_sets
+        elif args.guidance_freq is not None:
+            hit = i_val % args.guidance_freq == 0
+        else:
+            hit = i <= args.guidance_before
+        mask[i] = 1 if hit else 0
+    return mask
+
+
 def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, coeffs=None, fastforward=False,
                       n_randoms=None, return_feature=False, mono=False, tmp_stlp=None, guidance_extras=None,
                       maximize=False, scene_feature_only=False):
@@ -758,8 +868,6 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
     ``noise`` gives only shape/device, as upstream (:563).  Deterministic mode: ``args.inject_noise`` =
     [x_T, z_1, ...] tensors (N,2nt) consumed in upstream's randn_like order; otherwise x_T and z are drawn by the
     kernels' Philox stream (``args.seed``)."""
-    if mono or fastforward:
-        raise NotImplementedError("mono / fastforward sampling is not on the hot path")
     _nv.require_cuda(noise, "noise")
     n = noise.shape[0]
     nt, T2, steps = args.nt, args.nt * 2, args.diffusion_steps
@@ -768,6 +876,17 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
     bs = batch_cuda["ego_traj"].shape[0]
     if n_randoms is None:
         n_randoms = args.n_randoms
+    if fastforward:
+        # reference :567: the reverse loop is skipped, the "sample" is the initial noise x_T (a training-time switch
+        # that keeps the call's return shape while saving the sampling cost on epochs that are not visualised)
+        inj = getattr(args, "inject_noise", None)
+        x_T = _nv.f32(inj[0]) if inj is not None else torch.randn((n, T2), device=noise.device)
+        final = normalize_diff(x_T, n, nt, args.mul_w_max, args.mul_a_max, args.diffusion_clip)
+        dense_feature = feature
+        if args.diff_full:
+            fl = IterateList(1, final.unsqueeze(0))
+            return (final, dense_feature, fl) if return_feature else (final, fl)
+        return (final, dense_feature) if return_feature else final
     scene_feat = getattr(feature, "_pstl_scene_feat", None) if feature is not None else None
     if scene_feat is None:
         if feature is not None:
@@ -776,8 +895,17 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
             with torch.no_grad():
                 scene_feat = net.encode_feat(batch_cuda)
     rows_per_scene = n // bs
-    hl = _nv.f32(highlevel_dense.reshape(n))
-    stlp = _nv.f32(batch_cuda["stlp_dense"].reshape(n, 6))
+    if mono:
+        # --gt_data_training layout (reference :570-572, nusc_model.py:124-128): one row per (scene, sample); the scene's
+        # high-level mode (bs,1) and ground-truth pSTL parameters tmp_stlp (bs,6) are shared by its n // bs rows
+        if feature is None or tmp_stlp is None:
+            raise ValueError("mono sampling takes prev_feature (bs, k) and tmp_stlp (bs, 6), as upstream")
+        hl = _nv.f32(highlevel_dense.reshape(bs, 1).expand(bs, rows_per_scene).reshape(n))
+        stlp = _nv.f32(tmp_stlp.reshape(bs, 1, 6).expand(bs, rows_per_scene, 6).reshape(n, 6))
+        scene_feat = _nv.f32(feature.reshape(bs, -1))
+    else:
+        hl = _nv.f32(highlevel_dense.reshape(n))
+        stlp = _nv.f32(batch_cuda["stlp_dense"].reshape(n, 6))
     inj = getattr(args, "inject_noise", None)
     if inj is not None:
         x_T = _nv.f32(inj[0])
@@ -789,14 +917,15 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
     keep_all = bool(getattr(args, "refinement", False) or getattr(args, "keep_all_iterates", False))
     K = steps - 1 if keep_all else max(1, int(args.multi_cands or 1))
     K = min(K, steps - 1)
+    if keep_all and x_T is None:
+        x_T = torch.randn((n, T2), device=noise.device)  # entry 0 of final_list (x_T itself) must be readable
     iterates = torch.empty((K, n, nt, 2), dtype=torch.float32, device=noise.device)
     handle = net.native_handle(getattr(args, "precision", "fp32"))
     L = _nv.lib()
     gcfg = None
     keepalive = []
     if args.guidance:
-        if args.guidance_sets is not None or args.guidance_freq is not None or args.guidance_reverse:
-            raise NotImplementedError("only the `i <= guidance_before` trigger (README flags) is built")
+        _check_fused_supported(args, "--guidance")
         new_batch, states_flat_new, stls_cac = guidance_extras
         pack = new_batch.get("_pstl_pack")
         if pack is None:
@@ -809,17 +938,28 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
         sp = _spec(args, args.mul_w_max, args.mul_a_max, 0)
         pa = _nv.prog_array(progs)
         n_total = float(getattr(args, "guidance_n_total", n))
-        mean_valid = float(getattr(args, "guidance_mean_valid", valid.mean().item()))
         gcfg = _nv.GuidanceCfg()
+        mv = getattr(args, "guidance_mean_valid", None)
+        if mv is None:
+            # the loss normaliser 1 / (N clip(mean(valid), 1e-2)) (reference :23-27, 616-619) stays on the device: no host
+            # read-back in the middle of the batch, and a captured graph follows each batch's own validity mean
+            inv_dev = (1.0 / (n_total * torch.clip(valid.mean().double(), 1e-2))).float().reshape(1)
+            gcfg.inv_norm_dev = inv_dev.data_ptr()
+            gcfg.inv_norm = 0.0
+            keepalive.append(inv_dev)
+        else:
+            gcfg.inv_norm = 1.0 / (n_total * max(float(mv), 1e-2))
         s0 = _nv.f32(states_flat_new)
         keepalive.append(s0)
         gcfg.valid, gcfg.state0 = valid.data_ptr(), s0.data_ptr()
         gcfg.progs = _nv.C.cast(pa, _nv.C.POINTER(_nv.C.c_void_p))
         gcfg.scenes, gcfg.sp = _nv.C.pointer(sv), _nv.C.pointer(sp)
         gcfg.before, gcfg.niters = int(min(args.guidance_before, steps - 1)), int(args.guidance_niters)
+        step_mask = guidance_step_mask(args)
+        gcfg.step_mask = step_mask.ctypes.data
+        keepalive.append(step_mask)
         gcfg.lr = args.guidance_lr
         gcfg.thres = 100.0 if maximize else args.stl_nn_thres
-        gcfg.inv_norm = 1.0 / (n_total * max(mean_valid, 1e-2))
         keepalive += [pack, sv, sp, pa, progs, states_flat_new]
     ws_bytes = L.pstl_denoiser_workspace_bytes(handle, n, bs, _nv.C.byref(gcfg) if gcfg is not None else None)
     ws = _nv.workspace(ws_bytes, noise.device, "denoiser")
@@ -849,7 +989,8 @@ def diffusion_rollout(noise, net, batch_cuda, highlevel_dense, feature, args, co
             dense_feature = scene_feat.reshape(bs, 1, k).expand(bs, rows_per_scene, k).reshape(-1, k)
         dense_feature._pstl_scene_feat = scene_feat
     if args.diff_full:
-        final_list = IterateList(steps, iterates)
+        first = normalize_diff(x_T, n, nt, args.mul_w_max, args.mul_a_max, args.diffusion_clip) if keep_all else None
+        final_list = IterateList(steps, iterates, first)
         return (diffused_result, dense_feature, final_list) if return_feature else (diffused_result, final_list)
     return (diffused_result, dense_feature) if return_feature else diffused_result
 
@@ -893,7 +1034,7 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     else:
         nn_controls, feature = res
         nn_list = None
-    out = {"final_iterate": nn_controls}
+    out = {"final_iterate": nn_controls, "iterates": nn_list}
     if args.rect_head and not args.not_use_rect:
         if args.multi_cands is not None:
             cand = nn_list.stacked_last(args.multi_cands)  # (K,N,T,2) physical controls
@@ -908,11 +1049,76 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
             for _ in range(args.n_rolls):
                 sc = score_pack(pack, nn_controls, args, progs)["best_score"]
                 nn_controls = net.rect_forward(feature, highlevel_new, new_batch["stlp_dense"][:, 0], nn_controls, sc)
+        if getattr(args, "refinement", False):
+            nn_controls = refine_by_mixing(pack, nn_controls, nn_list, stls_cac, args)
+            out["refinement"] = True
     r = score_pack(pack, nn_controls, args, progs, want=("best_score", "traj"))
     scores, nn_trajs = r["best_score"], r["traj"]
     acc, scene_acc = accuracy(scores, pack.valid, bs, S)
     out.update(controls=nn_controls, scores=scores, trajs=nn_trajs, acc=acc, scene_acc=scene_acc, pack=pack)
     return out
+
+
+REFINEMENT_ITERATES = {2: [0], 3: [80, 95], 4: [80, 90, 95], 6: [0, 50, 80, 90, 95], 8: [0, 50, 80, 85, 90, 95, 98],
+                       10: [0, 50, 80, 85, 90, 95, 96, 97, 98],
+                       20: [0, 10, 30, 50, 60, 70, 75, 80, 85, 90, 91, 92, 93, 94, 95, 96, 97, 98, 99]}
+
+
+def refine_by_mixing(pack, nn_controls, nn_controls_list, stls_cac, args, K=8, n_iters=50, stl_thres=0.0005, lr=3e-1):
+    """--refinement (reference nusc_train.py:1034-1071): rows whose final controls still violate the spec are replaced
+    by a convex mix of those controls and K-1 earlier iterates of their own chain (REFINEMENT_ITERATES[K] indexes
+    final_list); the softmax logits of the mix take ``n_iters`` Adam steps on mask_mean(relu(stl_thres - score), valid).
+    Upstream's constants (K=8, 50 iterations, lr 0.3) are the defaults.  Every iteration is the fused reverse-mode
+    scorer (score + d score / d controls in one launch) plus a handful of tensor ops on the (N, K) logits."""
+    mix = MixingProblem(pack, nn_controls, nn_controls_list, stls_cac, args, K, stl_thres)
+    optim = None
+    with torch.enable_grad():
+        lamdas = torch.ones(pack.N, K, device=nn_controls.device, requires_grad=True)
+        optimizer = torch.optim.Adam([lamdas], lr=lr)
+        for _ in range(n_iters):
+            optim, _ = mix.backward_into(lamdas)
+            optimizer.step()
+    return optim.detach().reshape(pack.N, pack.T, 2)
+
+
+class MixingProblem:
+    """The objective of --refinement for one batch: ``backward_into(lamdas)`` evaluates the mixed controls of the current
+    logits, their scores and the gradient of mask_mean(relu(stl_thres - score), valid) w.r.t. the logits (left in
+    ``lamdas.grad``) — what one iteration of the reference's loop computes before ``optimizer.step()``."""
+
+    def __init__(self, pack, nn_controls, nn_controls_list, stls_cac, args, K=8, stl_thres=0.0005):
+        N, T = pack.N, pack.T
+        self.pack, self.args, self.stl_thres = pack, args, stl_thres
+        self.progs = _fused_programs(stls_cac, T)
+        base = torch.stack([nn_controls.detach()] + [nn_controls_list[i].detach() for i in REFINEMENT_ITERATES[K]], dim=1)
+        self.base = base.reshape(N, K, T * 2)                                 # (N, K, 2T) physical controls
+        self.scores0 = score_pack(pack, nn_controls, args, self.progs)["best_score"]
+        self.violated = ((self.scores0 <= 0) & (pack.valid > 0)).float().reshape(N, 1)
+        self.keep = nn_controls.detach().reshape(N, T * 2) * (1 - self.violated)
+        L = _nv.lib()
+        self.pa = _nv.prog_array(self.progs)
+        self.sv, self.sp = pack.view(), _spec(args)
+        self.ws = _nv.workspace(L.pstl_score_workspace_bytes(self.pa, N, T, 1), base.device, "score")
+        # d loss / d score = -valid / (N clip(mean(valid), 1e-2)) on the rows where stl_thres - score > 0 (relu'), else 0;
+        # the reverse-mode scorer is linear in it, so it runs with the first factor and its rows are masked afterwards
+        self.g_s = (-pack.valid / (N * torch.clip(pack.valid.mean(), 1e-2))).contiguous()
+        self.scores = torch.empty((N,), dtype=torch.float32, device=base.device)
+        self.g_u = torch.empty((N, T, 2), dtype=torch.float32, device=base.device)
+
+    def backward_into(self, lamdas):
+        pack, N, T = self.pack, self.pack.N, self.pack.T
+        ratios = torch.softmax(lamdas, dim=-1)
+        optim = self.keep + self.violated * torch.einsum("nk,nkd->nd", ratios, self.base)
+        oc = optim.detach().reshape(N, T, 2).contiguous()
+        _nv.check(_nv.lib().pstl_score_fused_bwd(self.pa, _nv.C.byref(self.sv), _nv.C.byref(self.sp), _nv.fptr(pack.mode),
+                                                 _nv.fptr(pack.state0), _nv.fptr(oc), None, 0, _nv.fptr(pack.stlp), N,
+                                                 _nv.fptr(self.g_s), _nv.fptr(self.scores), _nv.fptr(self.g_u), None,
+                                                 _nv.ptr(self.ws), _nv.stream()), "pstl_score_fused_bwd")
+        active = (self.stl_thres - self.scores > 0).float().reshape(N, 1)
+        if lamdas.grad is not None:
+            lamdas.grad = None
+        optim.backward(self.g_u.reshape(N, T * 2) * active)
+        return optim, self.scores
 
 
 def diffusion_prep(dense_controls, n_randoms, coeffs=None, args=None, mono=False):
@@ -935,14 +1141,17 @@ def train_step_ddpm(net, batch_cuda, coeffs, args, optimizer=None, gt_stlp=None,
     ``diffusion_prep`` on the stored (traj-opt) controls, ``net(...)`` with one timestep per row, the eps-prediction
     loss, backward (policy_net on the native kernels, the scene encoders through autograd from the per-scene feature
     gradient) and the optimiser step (``Adam(net.parameters())`` upstream).  ``prep`` = (noise, t, noised) overrides the
-    draw.  With ``--stl_weight 0`` (the README command) this is the whole loss; the STL term of a sampled rollout that
-    upstream adds for a non-zero weight is not built.  Returns ``rd``."""
+    draw.  The loss is upstream's: ``mask_mean(square(noise - est), tj_scores_prior * valids_dense > 0)`` under
+    ``stl_bc_mask`` (forced by the parser), the plain mean otherwise.  With ``--stl_weight 0`` (the README command) this
+    is the whole loss; the STL term of a sampled rollout that upstream adds for a non-zero weight is not built.
+    Returns ``rd``."""
     if float(args.stl_weight) != 0.0:
         raise NotImplementedError("denoiser stage: only --stl_weight 0.0 (README step 1) is built")
     S = args.n_randoms
     bs = batch_cuda["ego_traj"].shape[0]
     nb = LazyBatch({k: batch_cuda[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
-                                               "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp", "params")
+                                               "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp", "params",
+                                               "tj_scores_prior")
                     if k in batch_cuda})
     nb["neighbor_trajs_aug"] = batch_cuda["neighbors_traj"][..., :7]
     if gt_stlp is None:
@@ -954,7 +1163,17 @@ def train_step_ddpm(net, batch_cuda, coeffs, args, optimizer=None, gt_stlp=None,
         noise, steps, noised = prep
     est, feature = net(nb, ext={"timestep": steps, "highlevel": nb["highlevel_dense"], "noise": noised}, get_feature=True)
     est = est.reshape(noise.shape)
-    rd = {"loss_diffusion": torch.mean(torch.square(noise - est)), "est_cmds_a": est, "feature": feature}
+    if getattr(args, "stl_bc_mask", False):
+        # reference :435-437 with dense_scores = tj_scores_prior (:1282-1283): rows of non-existent lanes and traj-opt
+        # samples that violate the spec carry no denoising loss (the parser forces stl_bc_mask, :1781)
+        if "tj_scores_prior" not in nb:
+            raise KeyError("train_step_ddpm with stl_bc_mask needs batch['tj_scores_prior'] (bs, n_randoms, 3)")
+        n = bs * S * 3
+        m = (nb["tj_scores_prior"].reshape(n, 1) * nb["valids_dense"].reshape(n, 1) > 0).float()
+        loss_diffusion = mask_mean(torch.square(noise - est), m)
+    else:
+        loss_diffusion = torch.mean(torch.square(noise - est))
+    rd = {"loss_diffusion": loss_diffusion, "est_cmds_a": est, "feature": feature}
     rd["loss_stl"] = rd["loss_diffusion"].detach() * 0
     rd["loss"] = rd["loss_diffusion"]
     if optimizer is not None:
@@ -1017,6 +1236,7 @@ def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):
     fused rollout + STL reverse-mode kernel and the regulariser + Adam update (upstream: ~600 autograd launches).
     Returns (optimised params, same shape; scores (N,) of the iterate BEFORE the last step, as upstream logs them).
     ``record(ii, scores)`` is called after every iteration when given (forces no sync by itself)."""
+    _check_fused_supported(args, "trajopt")
     iters = int(args.traj_opt_iters if iters is None else iters)
     p0 = batch_cuda["params"] if params is None else params
     _nv.require_cuda(p0, "params")
@@ -1122,14 +1342,15 @@ class CapturedPipeline:
     replayed, and ``out`` holds the graph's static output tensors (valid until the next call).
     Noise: x_T and the z stream come from the sampler's Philox counter plus a device word that the graph bumps on every replay
     (``pstl_denoiser_set_noise_counter``), so replays draw fresh normals as upstream's ``randn_like`` does.
-    Not capturable: ``--guidance`` (its batch normaliser is read back on the host) and injected noise."""
+    ``--guidance`` is captured too: its batch normaliser lives in a device word (``pstl_guidance_cfg.inv_norm_dev``).
+    Not capturable: injected noise (the test mode) and ``--refinement`` (a host-driven optimiser loop)."""
 
     KEYS = ("ego_traj", "neighbors", "neighbors_traj", "currlane_wpts", "leftlane_wpts", "rightlane_wpts", "curr_id",
             "left_id", "right_id", "gt_high_level", "pre_stlp")
 
     def __init__(self, net, stls_cac, coeffs, args, example_batch, warmup=2):
-        if args.guidance or getattr(args, "inject_noise", None) is not None:
-            raise NotImplementedError("CapturedPipeline: --guidance / injected noise run on the eager path")
+        if getattr(args, "inject_noise", None) is not None or getattr(args, "refinement", False):
+            raise NotImplementedError("CapturedPipeline: injected noise / --refinement run on the eager path")
         self.net, self.stls, self.coeffs, self.args = net, stls_cac, coeffs, args
         dev = next(net.parameters()).device
         _nv.require_cuda(next(net.parameters()), "model parameters")
@@ -1145,6 +1366,8 @@ class CapturedPipeline:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._body()
+        self._weights_key = net._weights_key()
+        self._handle_value = net.native_handle(getattr(args, "precision", "fp32")).value
         # double buffering of the inputs: `prefetch` fills a staging copy on its own stream while a replay runs
         self.staging = {k: torch.empty_like(t) for k, t in self.static_in.items()}
         self._copy_stream = torch.cuda.Stream(device=dev)
@@ -1187,6 +1410,12 @@ class CapturedPipeline:
             for k, t in self.static_in.items():
                 if batch[k] is not t:
                     t.copy_(batch[k], non_blocking=True)
+        if self.net._weights_key() != self._weights_key:
+            # in-place parameter updates: the handle re-derives its weight copies in place on this stream, ahead of the
+            # replay; parameters that moved to other storage rebuilt the handle the graph baked in
+            if self.net.native_handle(getattr(self.args, "precision", "fp32")).value != self._handle_value:
+                raise RuntimeError("CapturedPipeline: the model's parameters moved since the capture; build a new runner")
+            self._weights_key = self.net._weights_key()
         self.graph.replay()
         return self.out
 

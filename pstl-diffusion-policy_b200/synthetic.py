@@ -118,9 +118,14 @@ def make_scene_batch(bs, nt=20, dt=0.5, n_neighbors=8, n_segs=15, n_randoms=64, 
     }
 
 
-def make_dense_stl_input(n, nt=20, dt=0.5, n_neighbors=8, n_segs=15, seed=1008):
+def make_dense_stl_input(n, nt=20, dt=0.5, n_neighbors=8, n_segs=15, seed=1008, endcaps=False, overlap=False):
     """Config-1/5 shape: ``n`` pre-rolled trajectories with per-row (dense) scene tensors,
     exactly what the reference's compute_stl_dense consumes (nusc_train.py:318-345).
+    ``endcaps``: a third of the rows start 20 m behind the first lane point and a third 85 m further along
+    the lane (so they run off its far end) — the cases the --inline end-cap distances exist for.
+
+    ``overlap``: every fifth row gets neighbour 0 riding 1.2 m ahead / 0.6 m beside the ego (overlapping boxes: the
+    negative clearances and the --collision_loss term are exercised).
 
     Returns (stl_input dict, stl_idx (n,1), mask (n,)).
     """
@@ -130,6 +135,12 @@ def make_dense_stl_input(n, nt=20, dt=0.5, n_neighbors=8, n_segs=15, seed=1008):
     m = 192
     rep = lambda x: x.unsqueeze(1).repeat((1, m) + (1,) * (x.dim() - 1)).reshape((-1,) + x.shape[1:])[:n]
     s0 = rep(b["ego_traj"][:, 0, :4])
+    if endcaps:
+        grp = (torch.arange(n) // 3) % 3
+        shift = torch.where(grp == 1, torch.tensor(-20.0), torch.where(grp == 2, torch.tensor(85.0), torch.tensor(0.0)))
+        s0 = s0.clone()
+        s0[:, 0] = s0[:, 0] + shift * torch.cos(s0[:, 2])
+        s0[:, 1] = s0[:, 1] + shift * torch.sin(s0[:, 2])
     w = _u(g, -0.05, 0.05, n, nt)
     a = _u(g, -5.0, 5.0, n, nt) * 0.2
     st = s0
@@ -143,9 +154,15 @@ def make_dense_stl_input(n, nt=20, dt=0.5, n_neighbors=8, n_segs=15, seed=1008):
     valids = torch.cat([b["curr_id"], b["left_id"], b["right_id"]], -1)  # (bs,3)
     mask = valids[:, None, :].repeat(1, 64, 1).reshape(-1)[:n]
     idx = torch.tensor([0.0, 1.0, 2.0]).repeat(bs * 64)[:n].reshape(n, 1)
+    nei = rep(b["neighbors_traj"]).contiguous()
+    if overlap:
+        rows = torch.arange(n) % 5 == 0
+        c, sn = torch.cos(ego[rows, :, 2]), torch.sin(ego[rows, :, 2])
+        nei[rows, 0] = torch.stack([torch.ones_like(c), ego[rows, :, 0] + 1.2 * c - 0.6 * sn, ego[rows, :, 1] + 1.2 * sn + 0.6 * c,
+                                    ego[rows, :, 2] + 0.05, ego[rows, :, 3], torch.full_like(c, 4.5), torch.full_like(c, 1.9)], -1)
     stl_input = {
         "ego_traj": ego,
-        "neighbors": rep(b["neighbors_traj"]).contiguous(),
+        "neighbors": nei,
         "currlane_wpts": rep(b["currlane_wpts"]).contiguous(),
         "leftlane_wpts": rep(b["leftlane_wpts"]).contiguous(),
         "rightlane_wpts": rep(b["rightlane_wpts"]).contiguous(),
@@ -155,7 +172,7 @@ def make_dense_stl_input(n, nt=20, dt=0.5, n_neighbors=8, n_segs=15, seed=1008):
     return stl_input, idx, mask
 
 
-def make_weights(seed=1007, nt=20, n_segs=15, hidden=256, rect_hidden=256):
+def make_weights(seed=1007, nt=20, n_segs=15, hidden=256, rect_hidden=256, rect_extra_in=0):
     """Random-init weights with the reference ``Net`` state_dict keys/shapes:
     {ego,neighbor,lane}_encoder, policy_net (303->256->256->2nt), merge_net (2nt->32->32->2nt),
     rect_net (271->256->256->2nt).  U(-1/sqrt(fan_in), 1/sqrt(fan_in)) like nn.Linear's default,
@@ -175,7 +192,8 @@ def make_weights(seed=1007, nt=20, n_segs=15, hidden=256, rect_hidden=256):
     mlp("lane_encoder", [n_segs * 3, hidden, hidden, 32])
     mlp("policy_net", [224 + out + 32 + 1 + 6, hidden, hidden, out])
     mlp("merge_net", [out, 32, 32, out])
-    mlp("rect_net", [224 + 1 + 6 + out, rect_hidden, rect_hidden, out])
+    # rect_extra_in = 2*nt for --diverse_fuse_type cat (drawn last: the other tensors do not depend on it)
+    mlp("rect_net", [224 + 1 + 6 + out + rect_extra_in, rect_hidden, rect_hidden, out])
     return sd
 
 

@@ -118,6 +118,31 @@ def run_pipeline(flags, tag, bs, S, seed, out):
     real_randn_like = torch.randn_like
     torch.randn_like = lambda t, **k: next(it).to(t.dtype)
     real_roll, real_stl, real_rect = T.diffusion_rollout, T.compute_stl_dense, net.rect_forward
+    real_gen = T.generate_trajs
+    cap["us"] = []
+
+    def gen(s_, us_, dt_):
+        cap["us"].append(us_.detach().clone())
+        if len(cap["us"]) > 2:
+            del cap["us"][0]
+        return real_gen(s_, us_, dt_)
+
+    T.generate_trajs = gen
+    # guided reverse steps: what every fresh Adam of nusc_train.py:607 saw and did (mu before, gradient, mu after)
+    real_adam = torch.optim.Adam
+    cap["gsteps"] = []
+
+    class RecordingAdam(real_adam):
+        def step(self, *a, **k):
+            p = self.param_groups[0]["params"][0]
+            rec = [p.detach().clone(), p.grad.detach().clone()]
+            r = super().step(*a, **k)
+            rec.append(p.detach().clone())
+            cap["gsteps"].append(rec)
+            return r
+
+    if args.guidance or getattr(args, "refinement", False):
+        torch.optim.Adam = RecordingAdam
 
     def roll(*a, **k):
         r = real_roll(*a, **k)
@@ -154,6 +179,8 @@ def run_pipeline(flags, tag, bs, S, seed, out):
     finally:
         torch.randn_like = real_randn_like
         T.diffusion_rollout, T.compute_stl_dense = real_roll, real_stl
+        T.generate_trajs = real_gen
+        torch.optim.Adam = real_adam
         T.napi.measure_diversity, T.napi.measure_extra_diversity = real_md, real_ex
     final, feature, its = cap["rollout"]
     K = args.multi_cands
@@ -163,13 +190,32 @@ def run_pipeline(flags, tag, bs, S, seed, out):
     out[tag + "|final_iterate"] = final.detach().numpy()
     out[tag + "|iter_mid"] = its[50].detach().numpy()
     # stl calls in order: [0]=traj-opt reference rows, [guidance calls...], best-of-K, n_rolls..., final
-    n_guid = len(cap["stl"]) - 1 - 1 - (args.n_rolls or 0) - 1
+    n_ref = 51 if getattr(args, "refinement", False) else 0  # --refinement: one scoring + 50 optimisation iterations
+    n_guid = len(cap["stl"]) - 1 - 1 - (args.n_rolls or 0) - 1 - n_ref
     out[tag + "|n_guidance_calls"] = np.array(n_guid)
     out[tag + "|tj_scores"] = cap["stl"][0].numpy()
     out[tag + "|cand_scores"] = cap["stl"][1 + n_guid].reshape(K, N).numpy()
     out[tag + "|rect_first"] = cap["rect"][0].numpy()
     out[tag + "|controls"] = cap["rect"][-1].numpy()
+    out[tag + "|final_controls"] = cap["us"][-1].numpy()  # what the last generate_trajs rolled out (differs under --refinement)
     out[tag + "|scores"] = cap["stl"][-1].numpy()
+    if args.guidance and args.guidance_niters == 1:
+        assert len(cap["gsteps"]) == n_guid
+        out[tag + "|gstep_mu_in"] = torch.stack([r[0] for r in cap["gsteps"]]).reshape(n_guid, N, -1).numpy()
+        out[tag + "|gstep_grad"] = torch.stack([r[1] for r in cap["gsteps"]]).reshape(n_guid, N, -1).numpy()
+        out[tag + "|gstep_mu_out"] = torch.stack([r[2] for r in cap["gsteps"]]).reshape(n_guid, N, -1).numpy()
+        out[tag + "|gstep_scores"] = torch.stack(cap["stl"][1:1 + n_guid]).numpy()
+    if getattr(args, "refinement", False):
+        # the mixing logits of --refinement (nusc_train.py:1034-1071) at a few of the 50 Adam iterations: value going in,
+        # gradient, value coming out, and the scores of that iteration's mixed controls
+        assert len(cap["gsteps"]) == 50
+        its_kept = [0, 1, 2, 10, 25, 49]
+        out[tag + "|mix_iters"] = np.array(its_kept)
+        out[tag + "|mix_lam_in"] = torch.stack([cap["gsteps"][j][0] for j in its_kept]).numpy()
+        out[tag + "|mix_grad"] = torch.stack([cap["gsteps"][j][1] for j in its_kept]).numpy()
+        out[tag + "|mix_lam_out"] = torch.stack([cap["gsteps"][j][2] for j in its_kept]).numpy()
+        out[tag + "|mix_scores"] = torch.stack([cap["stl"][-51 + j] for j in its_kept]).numpy()
+        out[tag + "|mix_scores0"] = cap["stl"][-52].numpy()
     print(tag, "N=%d stl_calls=%d rect_calls=%d guidance_calls=%d" % (N, len(cap["stl"]), len(cap["rect"]), n_guid))
 
 
@@ -401,7 +447,15 @@ def gen_ddpm_step(bs=3, S=16, seed=2006):
     out = {"noise": noise.numpy(), "steps": steps.numpy(), "noised": noised.numpy()}
     est, feature = net(b, ext={"timestep": steps, "highlevel": b["highlevel_dense"], "noise": noised}, get_feature=True)
     est = est.reshape(N, nt * 2)
-    loss = torch.mean(torch.square(noise - est))
+    # the reference's own loss of this stage (nusc_train.py:435-437 with dense_scores = tj_scores_prior, :1282-1283;
+    # the parser forces stl_bc_mask, :1781)
+    assert args.stl_bc_mask
+    dense_scores = b["tj_scores_prior"].reshape(bs * S, 3)
+    dense_valids = b["valids_dense"]
+    stl_acc_mask = (dense_scores * dense_valids > 0).float().reshape(bs * S * 3, 1, 1)
+    loss = T.mask_mean(torch.square(noise - est), stl_acc_mask.squeeze(-1))
+    out["loss_unmasked"] = np.array(torch.mean(torch.square(noise - est)).item())
+    out["mask"] = stl_acc_mask.reshape(-1).numpy()
     opt = torch.optim.Adam(net.parameters(), lr=args.lr)
     opt.zero_grad()
     loss.backward()
@@ -466,17 +520,150 @@ def gen_metrics(bs=5, m=16, nt=20, seed=2004):
     print("metrics:", {k: (v.tolist() if v.size < 4 else v.shape) for k, v in out.items()})
 
 
+def gen2_flags(n=96, nt=20, knei=8, seed=1010):
+    """compute_stl_dense / prep_stl_cache of the reference under the flags that change the predicate math
+    (SURVEY 8(b)): --inline (lane end-caps, rows placed before / beyond the polylines), --clip_dist, --norm_stl,
+    --refined_nL / --refined_nW (anchor grid), --collision_loss (extra signals + the loss term of nusc_train.py:416-420)."""
+    T, args = ref_shim.load(ref_shim.OURS_FLAGS)
+    out = {}
+    variants = {"inline": dict(inline=True), "inline_clip": dict(inline=True, clip_dist=True), "norm": dict(norm_stl=True),
+                "nl3w2": dict(refined_nL=3, refined_nW=2), "nl6": dict(refined_nL=6), "coll": dict(collision_loss=1.0)}
+    base = {k: getattr(args, k) for k in ("inline", "clip_dist", "norm_stl", "refined_nL", "refined_nW", "collision_loss")}
+    for tag, over in variants.items():
+        for k, v in base.items():
+            setattr(args, k, v)
+        for k, v in over.items():
+            setattr(args, k, v)
+        stls = T.build_stl_cache(args)
+        x, idx, mask = synthetic.make_dense_stl_input(n, nt=nt, n_neighbors=knei, seed=seed, endcaps=True, overlap=True)
+        out[tag + "|in_checksum"] = np.array([checksum(x[k]) for k in sorted(x)])
+        x["ego_traj"] = x["ego_traj"].clone().requires_grad_()
+        scores_list, scores, acc, xo = T.compute_stl_dense(x, stls, idx, mask, args, debug=True)
+        for k in ("x2curr_d", "x2left_d", "x2right_d", "min_nei_d"):
+            out[tag + "|" + k] = xo[k].detach().numpy()
+        out[tag + "|scores"] = scores.detach().numpy()
+        loss = T.mask_mean(torch.relu(args.stl_nn_thres - scores), mask)
+        if args.collision_loss is not None:
+            out[tag + "|min_centroid_d"] = xo["min_centroid_d"].detach().numpy()
+            out[tag + "|radius_sum"] = xo["radius_sum"].detach().numpy()
+            coll_dist = torch.nn.ReLU()(1 - xo["min_centroid_d"] / torch.clip(xo["radius_sum"], 1e-1))
+            coll = torch.mean(torch.clip(torch.sum(coll_dist, dim=-1), max=1)) * args.collision_loss
+            out[tag + "|loss_coll"] = np.array(coll.item())
+            loss = loss + coll
+        (g,) = torch.autograd.grad(loss, [x["ego_traj"]])
+        out[tag + "|grad_ego"] = g.numpy()
+        if tag == "inline":  # how many poses actually sit on an end-cap
+            out[tag + "|n_endcap"] = np.array(int((xo["x2curr_d"].detach() != T.napi.compute_t2l_dist(
+                x["ego_traj"].detach()[..., :3], x["currlane_wpts"], False, with_angle=True, inline=False)[0]).sum()))
+    for k, v in base.items():
+        setattr(args, k, v)
+    # get_neighbor_trajs (nusc_train.py:51-60)
+    b = synthetic.make_scene_batch(3, nt=nt, n_randoms=4, seed=seed + 1)
+    out["nei|short"] = T.get_neighbor_trajs(b["neighbors"], nt, args.dt).numpy()
+    out["nei|full"] = T.get_neighbor_trajs(b["neighbors"], nt, args.dt, full=True).numpy()
+    # the closed-loop pick (nusc_sim.py:677-683), executed from the reference's own source lines
+    import textwrap
+    src = open(os.path.join(ref_shim.REF_DIR, "nusc_sim.py")).read().split("\n")[676:683]
+    assert "scores_all.reshape(n//3, 3)" in src[0] and "sim_traj = ego_trajs[total_idx]" in src[-1], src
+    g = torch.Generator().manual_seed(seed + 2)
+    n_rows = 192
+    env = {"torch": torch, "time": __import__("time"), "n": n_rows, "scores_all": torch.randn(n_rows, generator=g),
+           "ego_controls": torch.randn(n_rows, nt, 2, generator=g), "ego_trajs": torch.randn(n_rows, nt + 1, 4, generator=g)}
+    env["scores_all"][30] = env["scores_all"][60] = env["scores_all"].max() + 1.0  # a tie between two mode-0 rows
+    out["pick|scores"] = env["scores_all"].clone().numpy()
+    out["pick|controls"], out["pick|trajs"] = env["ego_controls"].numpy(), env["ego_trajs"].numpy()
+    exec(textwrap.dedent("\n".join(src)), env)
+    out["pick|idx"] = np.array(int(env["total_idx"]))
+    out["pick|highest"] = np.array(float(env["highest_score"]))
+    out["pick|ctrl"], out["pick|traj"] = env["sim_ctrl"].numpy(), env["sim_traj"].numpy()
+    np.savez_compressed(os.path.join(HERE, "flags.npz"), **out)
+    print("flags:", len(out), "arrays; end-cap poses", int(out["inline|n_endcap"]), "loss_coll", float(out["coll|loss_coll"]))
+
+
+def gen2_sampler_modes():
+    """The sampler's other trigger / call modes, from the reference's own run_sampling_test / diffusion_rollout:
+    --guidance_freq, --guidance_sets with --guidance_reverse (nusc_train.py:589-598), --refinement (:1034-1071), and a
+    mono rollout under --gt_data_training (:570-572)."""
+    out = {}
+    gflags = [f for f in ref_shim.GUIDE_FLAGS]
+    run_pipeline(gflags + ["--guidance_freq", "7"], "freq", bs=1, S=16, seed=2011, out=out)
+    run_pipeline(gflags + ["--guidance_sets", "3", "40", "41", "--guidance_reverse"], "sets", bs=1, S=16, seed=2012, out=out)
+    run_pipeline(ref_shim.OURS_FLAGS + ["--refinement"], "refine", bs=2, S=16, seed=2013, out=out)
+    for k in [k for k in out if k.split("|")[1] in ("feature", "iter_mid", "tj_scores", "rect_first")]:
+        del out[k]
+    # mono
+    S, bs, seed = 16, 2, 2014
+    T, args = ref_shim.load(ref_shim.OURS_FLAGS + ["--n_randoms", str(S), "--gt_data_training"])
+    import nusc_model
+    nt = args.nt
+    batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=seed)
+    net = nusc_model.Net(args)
+    net.load_state_dict(synthetic.make_weights(seed=1007, nt=nt), strict=True)
+    n = bs * S
+    stream = synthetic.noise_stream(seed + 77, n, nt * 2, args.diffusion_steps - 1)
+    it = iter(stream)
+    real = torch.randn_like
+    torch.randn_like = lambda t, **k: next(it).to(t.dtype)
+    try:
+        with torch.no_grad():
+            feature = net.encode_feat(batch)
+            gt_stlp = batch["pre_stlp"].reshape(bs, S, 3, 6)[:, 0, 0]
+            hl = batch["gt_high_level"]
+            res = T.diffusion_rollout(torch.zeros(n, nt * 2), net, batch, hl, feature, args, T.get_diffusion_coeffs(args),
+                                      mono=True, tmp_stlp=gt_stlp)
+    finally:
+        torch.randn_like = real
+    out["mono|final"] = res[0].numpy()
+    out["mono|iter_mid"] = res[1][50].numpy()
+    np.savez_compressed(os.path.join(HERE, "sampler_modes.npz"), **out)
+    print("sampler_modes:", sorted(out))
+
+
+def gen2_rect_variants(bs=2, S=16, seed=2015):
+    """Net.rect_forward of the reference for the RefineNet variants (nusc_model.py:182-235): --diverse_fuse_type cat,
+    --no_arch, no --diverse_loss."""
+    out = {}
+    base = ["-e", "x", "--diffusion", "--stl_weight", "0.0", "--load_stlp", "--rect_head", "--flex", "--skip_nusc_load",
+            "--n_randoms", str(S)]
+    for tag, extra, ex_in in (("cat", ["--diverse_loss", "--diverse_fuse_type", "cat"], 40),
+                              ("noarch", ["--diverse_loss", "--no_arch"], 0), ("plain", [], 0), ("clip", ["--diverse_loss", "--clip_rect"], 0)):
+        T, args = ref_shim.load(base + extra)
+        import nusc_model
+        nt = args.nt
+        net = nusc_model.Net(args)
+        sd = synthetic.make_weights(seed=1007, nt=nt, rect_extra_in=ex_in)
+        if not args.diverse_loss:
+            sd = {k: v for k, v in sd.items() if not k.startswith("merge_net")}
+        net.load_state_dict(sd, strict=True)
+        n = bs * S * 3
+        g = torch.Generator().manual_seed(seed)
+        batch = synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=seed)
+        with torch.no_grad():
+            feat = net.encode_feat(batch).reshape(bs, 1, -1).repeat(1, S * 3, 1).reshape(n, -1)
+            hl = torch.tensor([0.0, 1.0, 2.0]).repeat(bs * S).reshape(n, 1)
+            stlp = batch["pre_stlp"].reshape(n, 6)
+            u0 = torch.stack([(torch.rand(n, nt, generator=g) - 0.5) * 0.8, (torch.rand(n, nt, generator=g) - 0.5) * 8], -1)
+            sc = torch.randn(n, generator=g)
+            out[tag + "|out"] = net.rect_forward(feat, hl, stlp, u0, sc).numpy()
+        out[tag + "|u0"], out[tag + "|scores"] = u0.numpy(), sc.numpy()
+    np.savez_compressed(os.path.join(HERE, "rect_variants.npz"), **out)
+    print("rect_variants:", sorted(out))
+
+
 def main():
+    """``python tests/golden/make_golden.py [name ...]``: all fixtures, or only the named generators."""
     torch.set_num_threads(8)
     T, args = ref_shim.load(ref_shim.OURS_FLAGS)
-    gen_stl_kats()
-    gen_dense(T, args)
-    gen_pipeline()
-    gen_trajopt()
-    gen_metrics()
-    gen_losses()
-    gen_refine_step()
-    gen_ddpm_step()
+    gens = [("stl_kats", gen_stl_kats), ("dense", lambda: gen_dense(T, args)), ("pipeline", gen_pipeline),
+            ("trajopt", gen_trajopt), ("metrics", gen_metrics), ("losses", gen_losses), ("refine_step", gen_refine_step),
+            ("ddpm_step", gen_ddpm_step)]
+    gens += [(k[5:], v) for k, v in sorted(globals().items()) if k.startswith("gen2_")]
+    want = sys.argv[1:]
+    unknown = [w for w in want if w not in dict(gens)]
+    assert not unknown, "unknown generators %s; have %s" % (unknown, [g[0] for g in gens])
+    for name, fn in gens:
+        if not want or name in want:
+            fn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -97,7 +97,7 @@ extern "C" int hs_score_stream(const pstl_op* const* ops3, const int* n_ops3, in
     const int scene = n / rows_per_scene;
     sg.neib = neighbors + (size_t)scene * K * T * 7;
     for (int l = 0; l < 3; ++l) sg.ln[l] = ln[l] + (size_t)scene * nseg * 3;
-    sg.K = K; sg.T = T; sg.ego_half = c.ego_L / 2.f;
+    sg.K = K; sg.T = T; sg.ego_half = pstl_car_reach(c.ego_L, c.ego_W);
     PstlPose s0{0, 0, 0, 0};
     if (state0) s0 = PstlPose{state0[n * 4], state0[n * 4 + 1], state0[n * 4 + 2], state0[n * 4 + 3]};
     const float* u = controls ? controls + (size_t)n * T * 2 : nullptr;
@@ -151,7 +151,7 @@ extern "C" int hs_score_stream_grad(const pstl_op* const* ops3, const int* n_ops
     const int scene = n / rows_per_scene;
     sg.neib = neighbors + (size_t)scene * K * T * 7;
     for (int l = 0; l < 3; ++l) sg.ln[l] = ln[l] + (size_t)scene * nseg * 3;
-    sg.K = K; sg.T = T; sg.ego_half = c.ego_L / 2.f;
+    sg.K = K; sg.T = T; sg.ego_half = pstl_car_reach(c.ego_L, c.ego_W);
     PstlPose s0{0, 0, 0, 0};
     if (state0) s0 = PstlPose{state0[n * 4], state0[n * 4 + 1], state0[n * 4 + 2], state0[n * 4 + 3]};
     const float* u = controls ? controls + (size_t)n * T * 2 : nullptr;
