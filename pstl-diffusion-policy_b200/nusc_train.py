@@ -1227,7 +1227,7 @@ def train_step_rect(net, batch_cuda, stls_cac, coeffs, args, optimizer=None, gt_
     return rd
 
 
-def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):
+def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None, state=None):
     """Trajectory optimisation of the stored control parameters (reference nusc_train.py:287-316, 1303-1325):
     ``iters`` (default ``args.traj_opt_iters``) Adam steps, lr ``args.trajopt_lr``, on
     ``mean(relu(stl_trajopt_thres - score) * valid) / clip(mean(valid), 1e-3) + reg_loss * (mean relu(w^2 - w_max^2) + ...)``.
@@ -1235,7 +1235,8 @@ def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):
     ``params`` defaults to ``batch_cuda["params"]`` (bs, n_randoms, 3, nt, 2).  Every iteration is two launches: the
     fused rollout + STL reverse-mode kernel and the regulariser + Adam update (upstream: ~600 autograd launches).
     Returns (optimised params, same shape; scores (N,) of the iterate BEFORE the last step, as upstream logs them).
-    ``record(ii, scores)`` is called after every iteration when given (forces no sync by itself)."""
+    ``record(ii, scores)`` is called after every iteration when given (forces no sync by itself).
+    ``state`` = (adam_m, adam_v, first_iteration) resumes a run (Adam moments (N, nt, 2), updated in place)."""
     _check_fused_supported(args, "trajopt")
     iters = int(args.traj_opt_iters if iters is None else iters)
     p0 = batch_cuda["params"] if params is None else params
@@ -1250,7 +1251,11 @@ def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):
     if progs is None:
         raise NotImplementedError("trajopt needs the typed spec of build_stl_cache")
     p = _nv.f32(p0.reshape(N, nt, 2)).clone()
-    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    it0 = 0
+    if state is None:
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+    else:
+        m, v, it0 = _nv.f32(state[0].reshape(N, nt, 2)), _nv.f32(state[1].reshape(N, nt, 2)), int(state[2])
     scores = torch.empty((N,), dtype=torch.float32, device=p.device)
     L = _nv.lib()
     pa = _nv.prog_array(progs)
@@ -1258,7 +1263,7 @@ def trajopt(batch_cuda, stls_cac, args, iters=None, params=None, record=None):
     ws = _nv.workspace(N * nt * 2 * 4 + L.pstl_score_workspace_bytes(pa, N, nt, 1), p.device, "trajopt")
     # one scalar per call, computed on the device side of the host API (valid is a batch constant)
     inv_norm = 1.0 / (N * max(float(pack.valid.mean().item()), 1e-3))
-    for ii in range(iters):
+    for ii in range(it0, it0 + iters):
         _nv.check(L.pstl_trajopt_step(pa, _nv.C.byref(sv), _nv.C.byref(sp), _nv.fptr(pack.mode), _nv.fptr(pack.state0),
                                       _nv.fptr(pack.stlp), _nv.fptr(pack.valid), N, _nv.C.c_float(args.stl_trajopt_thres),
                                       _nv.C.c_float(inv_norm), _nv.C.c_float(args.reg_loss), _nv.C.c_float(args.mul_w_max),

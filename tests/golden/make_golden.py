@@ -261,7 +261,16 @@ def gen_trajopt(iters=15, bs=2, S=16, seed=2003):
             loss.backward()
             if ii == 0:
                 out["grad|0"] = params.grad.detach().reshape(-1, nt, 2).numpy().copy()
+            if ii in (4, 9):  # one mid-run iteration in full, for the teacher-forced check of a single step
+                st = opt.state[params]
+                out["tf%d|params_in" % ii] = params.detach().reshape(-1, nt, 2).numpy().copy()
+                out["tf%d|m" % ii] = st["exp_avg"].reshape(-1, nt, 2).numpy().copy()
+                out["tf%d|v" % ii] = st["exp_avg_sq"].reshape(-1, nt, 2).numpy().copy()
+                out["tf%d|grad" % ii] = params.grad.detach().reshape(-1, nt, 2).numpy().copy()
+                out["tf%d|scores" % ii] = dense_scores.detach().reshape(-1).numpy().copy()
             opt.step()
+            if ii in (4, 9):
+                out["tf%d|params_out" % ii] = params.detach().reshape(-1, nt, 2).numpy().copy()
             if ii in (0, 4, iters - 1):
                 out["params|%d" % ii] = params.detach().reshape(-1, nt, 2).numpy().copy()
     finally:

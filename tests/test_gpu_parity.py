@@ -265,16 +265,20 @@ def test_pipeline_ours_golden(golden_dir):
 
 
 def test_pipeline_guidance_golden(golden_dir):
+    """Free-running "Ours+guidance" against the reference's run.  Each guided step on its own reproduces the reference's
+    update to < 1e-6 (tests/test_gpu_flags.py::test_guided_steps_golden, teacher-forced, no exemptions); run freely, a row
+    that crosses relu'(thres - score) or an arg-min on a 1e-7 input difference takes another lr-sized step, which the
+    later guided steps and the three RefineNet rolls carry on.  Bound: 1e-5 on the median row, lr * (guided steps) on
+    every row's iterate, and a max on the scores."""
     G = np.load(os.path.join(golden_dir, "pipeline.npz"))
     out, net, batch, args = _run_pipeline(NT.GUIDANCE_FLAGS, 2002)
-    # guidance moves mu by lr*g/(|g|+1e-8): rows whose gradient is ~1e-8 amplify fp32 rounding, so the
-    # bound is stated on the bulk (99th percentile) plus a loose max
     a, b = out["final_iterate"].cpu().numpy(), G["guide|final_iterate"]
-    err = np.abs(a - b) / max(1.0, np.abs(b).max())
-    assert np.percentile(err, 99) < 1e-5 and err.max() < 5e-3, (np.percentile(err, 99), err.max())
+    err = (np.abs(a - b) / np.array([0.5, 5.0])).reshape(a.shape[0], -1).max(axis=1)  # normalised units, per row
+    assert np.median(err) < 1e-5 and np.percentile(err, 90) < 1e-5 and err.max() < args.guidance_lr * 10, \
+        (np.median(err), np.percentile(err, 90), err.max())
     a, b = out["scores"].cpu().numpy(), G["guide|scores"]
     err = np.abs(a - b) / max(1.0, np.abs(b).max())
-    assert np.percentile(err, 97) < 1e-5, np.percentile(err, 97)
+    assert np.percentile(err, 90) < 1e-5 and err.max() < 0.05, (np.percentile(err, 90), err.max())
 
 
 def test_net_forward_eps_vs_oracle():
@@ -613,12 +617,29 @@ def test_trajopt_golden(golden_dir):
         snap["params|%d" % (k - 1)] = p.reshape(-1, nt, 2).clone()
     close(snap["scores|0"], G["scores|0"])
     close(snap["params|0"], G["params|0"])
+    # Teacher-forced single steps mid-run (iterations 4 and 9): the reference's own parameters and Adam moments going in,
+    # our scores and updated parameters against the reference's — 1e-5, except the entries whose reference gradient is
+    # within rounding of Adam's eps-scale (0 < |g| < 1e-6: the step lr * m_hat / (sqrt(v_hat) + 1e-8) hinges on it),
+    # which are counted and bounded by lr
+    for ii in (4, 9):
+        tf = {k: torch.from_numpy(G["tf%d|%s" % (ii, k)]).cuda() for k in ("params_in", "m", "v", "grad", "scores", "params_out")}
+        p, sc = NT.trajopt(nb, stls, args, iters=1, params=tf["params_in"].reshape(b["params"].shape),
+                           state=(tf["m"].clone(), tf["v"].clone(), ii))
+        close(sc, tf["scores"], what="teacher-forced scores, iteration %d" % ii)
+        err = (p.reshape(-1, nt, 2) - tf["params_out"]).abs()
+        g = tf["grad"].abs()
+        soft = (g > 0) & (g < 1e-6)
+        assert float(soft.float().mean()) < 0.15, float(soft.float().mean())
+        assert float(err[~soft].max()) < 1e-5, (ii, float(err[~soft].max()))
+        assert float(err.max()) <= 2 * lr
+    # the free-running loop: a rounding-level difference in one of those entries moves it by up to lr per iteration,
+    # so the run is bounded on the median entry (1e-5) and on every entry (lr * iterations), with a max bound on scores
     for ii in (4, iters - 1):
-        err = (snap["params|%d" % ii].cpu().numpy() - G["params|%d" % ii])
-        err = np.abs(err)
-        assert np.percentile(err, 99) < 1e-5 and err.max() < 2 * lr * (ii + 1), (ii, np.percentile(err, 99), err.max())
+        err = np.abs(snap["params|%d" % ii].cpu().numpy() - G["params|%d" % ii])
+        assert np.median(err) < 1e-6 and np.percentile(err, 99) < 1e-5 and err.max() < 2 * lr * (ii + 1), (ii, err.max())
     err = np.abs(snap["scores|%d" % (iters - 1)].cpu().numpy() - G["scores|%d" % (iters - 1)])
     assert np.percentile(err, 99) < 1e-4 * max(1.0, np.abs(G["scores|%d" % (iters - 1)]).max())
+    assert err.max() < 0.5, err.max()  # a row that moved by lr * iterations in a few controls
 
 
 def test_diversity_metrics_on_device(golden_dir):
