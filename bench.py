@@ -8,6 +8,12 @@ that went through all of it.  Scenes shard across GPUs (weak scaling: 1,024 scen
 
   python bench.py --gpus N --steps K --warmup W          # our CUDA path
   python bench.py --impl reference ...                   # CPU reference arm (oracle port on host cores)
+
+The JSON line also carries an ``extra`` block with short runs of the other BASELINE configs (same process, after the
+headline): config 1 (4,096 dense rows through compute_stl_dense), config 3 (Ours+guidance, 4,096 scenes, K=10, n_rolls 3,
+captured graph), config 5 (four corner cells of the robustness sweep, dense per-row layout and scene-indexed) at N=1,
+and config 4 (8,192 scenes per GPU, K=10) when launched on 8 GPUs; each with its time, algorithmic bytes or flops,
+fraction of the measured peak and a CPU-port figure on a bounded sample.  --no-extras skips them.
 """
 import argparse
 import json
@@ -38,6 +44,7 @@ def parse():
     p.add_argument("--cpu-scenes", type=int, default=32, help="scenes per CPU-baseline batch")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
+    p.add_argument("--no-extras", action="store_true", help="skip the short runs of BASELINE configs 1/3/4/5")
     return p.parse_args()
 
 
@@ -53,12 +60,16 @@ def measured_traffic(chains):
 
 
 def peaks():
+    """(bf16 TFLOP/s, HBM GB/s, source).  The tensor peak is the BURST figure: the sampler runs ~3 ms bursts at full
+    clocks inside a step that is mostly other kernels (clocks line: 1965 MHz, no power cap), which is the regime the
+    burst number was measured in; the sustained figure (power-capped after seconds of back-to-back GEMMs) would flatter
+    the fraction."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             d = json.load(f)
-        return d["bf16_tflops_sustained"], d["hbm_gbs"], "measured"
+        return d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json: bf16 burst, HBM copy)"
     except Exception:
-        return 1400.0, 6650.0, "fallback"
+        return 1668.8, 6551.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -133,6 +144,183 @@ def oracle_batch_time(scenes, reps, seed=4000):
     return scenes * S * 3, times
 
 
+# ------------------------------------------------------------------------------------------------------------
+# the other BASELINE configs, short runs for the ``extra`` block
+# ------------------------------------------------------------------------------------------------------------
+def _timeit(fn, reps=3, warm=1, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def dense_bytes(T, K, nseg=15):
+    """algorithmic bytes per trajectory of the dense drop-in API: ego 16T, neighbours 28 K T, three lanes
+    36 nseg, pSTL 24, mode + valid 8, score 4"""
+    return 16 * T + 28 * K * T + 36 * nseg + 24 + 8 + 4
+
+
+def _dense_rows_on_device(n, T, K, dev, seed, scenes=256):
+    """``n`` dense per-row inputs of compute_stl_dense built ON the device from a small synthetic scene batch (every row
+    owns its copy of the scene tensors, as the reference's layout has it; rows of one scene differ in trajectory / pSTL)"""
+    from pstl_b200 import synthetic
+    from pstl_b200 import nusc_train as NT
+    S = 64
+    b = synthetic.make_scene_batch(scenes, nt=T, n_neighbors=K, n_randoms=S, seed=seed)
+    sc = torch.arange(n, device=dev) % scenes
+    g = torch.Generator(device=dev).manual_seed(seed)
+    s0 = b["ego_traj"][:, 0, :4].to(dev)[sc]
+    u = (torch.rand((n, T, 2), device=dev, generator=g) * 2 - 1) * torch.tensor([0.05, 1.0], device=dev)
+    ego = NT.generate_trajs(s0, u, 0.5)[:, :-1].contiguous()
+    x = {"ego_traj": ego, "neighbors": b["neighbors_traj"].to(dev)[sc].contiguous(),
+         "stlp": b["pre_stlp"].reshape(scenes, S * 3, 1, 6).to(dev)[sc, torch.arange(n, device=dev) % (S * 3)].contiguous()}
+    for k in ("curr", "left", "right"):
+        x["%slane_wpts" % k] = b["%slane_wpts" % k].to(dev)[sc].contiguous()
+    valids = torch.cat([b["curr_id"], b["left_id"], b["right_id"]], -1).to(dev)
+    idx = (torch.arange(n, device=dev) % 3).float().reshape(n, 1)
+    mask = valids[sc, torch.arange(n, device=dev) % 3].contiguous()
+    return x, idx, mask
+
+
+def _cpu_dense_rate(n, T, K, seed):
+    """oracle port of compute_stl_dense on ``n`` dense rows, all host threads: trajectories/s"""
+    from pstl_b200 import synthetic
+    from oracle import pstl_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, idx, _ = synthetic.make_dense_stl_input(n, nt=T, n_neighbors=K, seed=seed)
+    with torch.no_grad():
+        O.stl_scores(dict(x), idx[:, 0], 100.0)
+        t0 = time.perf_counter()
+        O.stl_scores(dict(x), idx[:, 0], 100.0)
+        return n / (time.perf_counter() - t0)
+
+
+def extra_dense(n, T, K, dev, hbm_peak, seed, cpu_rows, flush=None, tag="dense"):
+    from pstl_b200 import nusc_train as NT
+    args = NT.default_args(nt=T)
+    stls = NT.build_stl_cache(args)
+    x, idx, mask = _dense_rows_on_device(n, T, K, dev, seed)
+    ms = _timeit(lambda: NT.compute_stl_dense(x, stls, idx, mask, args), reps=3, warm=1, flush=flush)
+    by = dense_bytes(T, K)
+    gbs = n * by / ms / 1e6
+    out = {"layout": "dense per-row tensors (the reference's compute_stl_dense inputs)", "rows": n, "T": T, "Knei": K,
+           "ms": ms, "traj_per_s": n / ms * 1e3, "algorithmic_bytes_per_traj": by, "GBps": gbs, "frac_hbm": gbs / hbm_peak,
+           "l2": "flushed between reps" if flush is not None else "inputs %.1f GB > L2" % (n * by / 1e9)}
+    if cpu_rows:
+        out["cpu_port_traj_per_s"] = _cpu_dense_rate(cpu_rows, T, K, seed)
+        out["cpu_sample"] = "%d rows, oracle stl_scores, %d threads" % (cpu_rows, torch.get_num_threads())
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_scene_indexed(T, K, dev, seed, scenes=5209, base=256):
+    """config 5, scene-indexed layout: ``scenes`` x 192 trajectories, scene tensors stored once per scene"""
+    from pstl_b200 import synthetic
+    from pstl_b200 import nusc_train as NT
+    S = 64
+    args = NT.default_args(nt=T)
+    b = synthetic.make_scene_batch(base, nt=T, n_neighbors=K, n_randoms=S, seed=seed)
+    sel = torch.arange(scenes) % base
+    b = {k: v[sel].to(dev) for k, v in b.items() if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == base}
+    nb = NT.LazyBatch({k: b[k] for k in ("ego_traj", "neighbors", "currlane_wpts", "leftlane_wpts", "rightlane_wpts",
+                                         "curr_id", "left_id", "right_id", "gt_high_level", "pre_stlp")})
+    nb["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    pack = NT.augment_batch_data(nb, None, args, n_randoms=S)["_pstl_pack"]
+    progs = NT._fused_programs(NT.build_stl_cache(args), T)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    u = (torch.rand((pack.N, T, 2), device=dev, generator=g) * 2 - 1) * torch.tensor([0.05, 2.0], device=dev)
+    ms = _timeit(lambda: NT.score_pack(pack, u, args, progs), reps=3, warm=1)
+    out = {"layout": "scene-indexed (scene tensors once per scene, 192 rows each)", "rows": pack.N, "T": T, "Knei": K,
+           "ms": ms, "traj_per_s": pack.N / ms * 1e3, "bound": "fp32 ALU / SFU (HBM traffic collapses; no HBM fraction quoted)"}
+    del pack, b, nb, u
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_pipeline(flags, scenes, dev, W, what, cpu_scenes, cpu_kw, reps=3):
+    """a pipeline config under one captured CUDA graph: ms per batch, chains/s, CPU port on a bounded sample"""
+    from pstl_b200 import synthetic
+    from pstl_b200 import nusc_train as NT
+    from pstl_b200.nusc_model import Net
+    from oracle import pstl_oracle as O
+    S, nt = 64, 20
+    args = NT.default_args(flags, precision="bf16")
+    net = Net(args)
+    net.load_state_dict(W)
+    net = net.to(dev)
+    stls, co = NT.build_stl_cache(args), NT.get_diffusion_coeffs(args)
+    b = {k: v.to(dev) for k, v in synthetic.make_scene_batch(scenes, nt=nt, n_randoms=S, seed=3003).items()}
+    runner = NT.CapturedPipeline(net, stls, co, args, b)
+    ms = _timeit(lambda: runner(b), reps=reps, warm=1)
+    n = scenes * S * 3
+    acc = float(runner(b)["acc"])
+    out = {"workload": what, "scenes": scenes, "chains": n, "multi_cands": args.multi_cands, "n_rolls": args.n_rolls,
+           "guidance": bool(args.guidance), "ms": ms, "chains_per_s": n / ms * 1e3, "acc": acc,
+           "launch": "CUDA graph replay (NT.CapturedPipeline)", "l2": "inputs + state > L2"}
+    if cpu_scenes:
+        torch.set_num_threads(os.cpu_count() or 1)
+        bc = synthetic.make_scene_batch(cpu_scenes, nt=nt, n_randoms=S, seed=3004)
+        nc = cpu_scenes * S * 3
+        g = torch.Generator().manual_seed(1)
+        t0 = time.perf_counter()
+        O.pipeline(W, bc, torch.randn(nc, nt * 2, generator=g), [torch.randn(nc, nt * 2, generator=g) for _ in range(98)],
+                   S=S, n_randoms=S, **cpu_kw)
+        out["cpu_port_chains_per_s"] = nc / (time.perf_counter() - t0)
+        out["cpu_sample"] = "%d scenes (%d chains), oracle pipeline, %d threads, one batch" % (cpu_scenes, nc, torch.get_num_threads())
+    del runner, net
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_extras(a, world, rank, dev, net, W):
+    import torch.distributed as dist
+    from pstl_b200 import nusc_train as NT
+    _, hbm_peak, _ = peaks()
+    ex = {}
+    if world == 1:
+        flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        ex["config1"] = extra_dense(4096, 20, 8, dev, hbm_peak, 1008, cpu_rows=4096, flush=flush)
+        ex["config1_at_262144_rows"] = extra_dense(262144, 20, 8, dev, hbm_peak, 1008, cpu_rows=0)
+        del flush
+        ex["config3"] = extra_pipeline(NT.GUIDANCE_FLAGS, 4096, dev, W,
+                                       "config3: Ours+guidance (last 10 reverse steps, 1 iteration, lr 0.01), K=10, n_rolls 3",
+                                       cpu_scenes=8, cpu_kw=dict(K=10, n_rolls=3, guidance=dict(before=10, lr=0.01, thres=0.0005, niters=1)))
+        cells = []
+        for T, K, cpu_rows in ((20, 8, 2048), (50, 16, 512), (100, 32, 128), (200, 64, 32)):
+            by = dense_bytes(T, K)
+            n = int(min(1000128, 6e9 // by))
+            d = extra_dense(n, T, K, dev, hbm_peak, 1100 + T, cpu_rows=cpu_rows)
+            d["ms_per_1M_rows"] = d["ms"] * 1000128 / n
+            s = extra_scene_indexed(T, K, dev, 1200 + T)
+            s["cpu_port_traj_per_s"] = d["cpu_port_traj_per_s"]
+            cells.append({"T": T, "Knei": K, "dense": d, "scene_indexed": s})
+        ex["config5"] = cells
+    if world == 8 or (world > 1 and os.environ.get("PSTL_BENCH_CONFIG4")):
+        flags = [f for f in NT.OURS_FLAGS]
+        flags[flags.index("--multi_cands") + 1] = "10"
+        c4 = extra_pipeline(flags, 8192, dev, W, "config4: RefineNet flex head + diverse-loss sampling, K=10, "
+                            "8,192 scenes per GPU (65,536 over 8 GPUs)", cpu_scenes=0, cpu_kw={})
+        t = torch.tensor([c4["ms"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c4["ms"] = float(t[0])
+        c4["n_gpus"], c4["chains_all_gpus"] = world, c4["chains"] * world
+        c4["chains_per_s"] = c4["chains_all_gpus"] / c4["ms"] * 1e3
+        c4["note"] = "max over ranks of the per-rank device time; scene-sharded, no data-path collective"
+        ex["config4"] = c4
+    return ex
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -171,11 +359,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at every debug level
-        if "PSTL_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["PSTL_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL's log (communicator ranks, transports) goes to stderr; stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     native.lib()  # fail loudly if the CUDA library is missing
 
@@ -211,7 +397,10 @@ def main():
     resident = [{k: hb[k].to(dev) for k in need} for hb in host]
     host_scores = torch.empty(N, dtype=torch.float32).pin_memory()
     host_idx = torch.empty(N, dtype=torch.int32).pin_memory()
-    d2h_bytes = N * 8
+    host_plan = torch.empty((a.scenes, nt, 2), dtype=torch.float32).pin_memory()
+    host_pick = torch.empty(a.scenes, dtype=torch.int64).pin_memory()
+    d2h_bytes = N * 8 + a.scenes * (nt * 2 * 4 + 8)
+    gather = sharding.AsyncScoreGather(N, dev)
     flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -231,12 +420,19 @@ def main():
                 b = {k: b[k].to(dev, non_blocking=True) for k in need}
             out = NT.sample_and_score(net, b, stls, coeffs, args)
         if world > 1:
-            sharding.gather_scores(out["scores"], out["best_idx"], equal_sizes=True)
+            gather.submit(out["scores"], out["best_idx"])  # side stream: runs under the next step's kernels
         if e2e:
-            host_scores.copy_(out["scores"], non_blocking=True)
-            host_idx.copy_(out["best_idx"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            d2h(out)
         return out
+
+    def d2h(out):
+        """the step's result on the host: per-chain scores and selected-iterate index, per-scene chosen chain and its
+        control sequence (the plan a caller executes)"""
+        host_scores.copy_(out["scores"], non_blocking=True)
+        host_idx.copy_(out["best_idx"], non_blocking=True)
+        host_plan.copy_(out["scene_plan"], non_blocking=True)
+        host_pick.copy_(out["scene_pick"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     # roofline numerator's time: CUDA events immediately around the native sampler call
     # (pstl_denoiser_sample = hoist GEMMs + input pack + the persistent tcgen05 kernel)
@@ -260,6 +456,8 @@ def main():
     launches = int(L.pstl_launch_count() - c0)
 
     def barrier():
+        if world > 1:
+            gather.result()  # the last step's gather belongs to the step
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -278,10 +476,13 @@ def main():
     for i in range(a.steps):
         flush.zero_()  # L2 flush between timed iterations (inputs < L2)
         step(i, False)
+    if world > 1:
+        gather.result()  # current stream waits for the last gather: it is inside the timed region
     e1.record()
     barrier()
     clk.mark(w0, time.time())
     dev_ms = e0.elapsed_time(e1)
+    gather_us = gather.last_us()
     if runner is not None:
         # CUDA events cannot be read back from inside a replayed graph: the dominant kernel is timed by the same
         # events around the same native call over a second pass of the same K steps, launched eagerly
@@ -303,10 +504,8 @@ def main():
         if not last:
             runner.prefetch(host[(i + 1) % n_host])
         if world > 1:
-            sharding.gather_scores(out["scores"], out["best_idx"], equal_sizes=True)
-        host_scores.copy_(out["scores"], non_blocking=True)
-        host_idx.copy_(out["best_idx"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            gather.submit(out["scores"], out["best_idx"])
+        d2h(out)
         return out
 
     step(0, True)
@@ -320,10 +519,19 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clk.mark(time.time() - e2e_ms / 1e3, time.time())
-    tm = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    tm = torch.tensor([dev_ms, e2e_ms, gather_us or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = tm.tolist()
+    dev_ms, e2e_ms, gather_us = tm.tolist()
+    extra = {}
+    if not a.no_extras:
+        # release the headline's graph / buffers before the other configs allocate theirs
+        del runner, flush
+        torch.cuda.empty_cache()
+        try:
+            extra = run_extras(a, world, rank, dev, net, W)
+        except Exception as e:  # the headline number stands on its own
+            extra = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -341,18 +549,25 @@ def main():
                                    "%d scenes x 64 samples x 3 modes = %d chains per GPU per step" % (a.scenes, N),
                        "scenes_per_gpu": a.scenes, "chains_per_gpu": N, "multi_cands": K, "precision": precision,
                        "noise": "in-kernel Philox", "l2": "flushed between timed steps (160 MB write)",
-                       "launch": "eager" if runner is None else "CUDA graph replay of sample_and_score (NT.CapturedPipeline)",
-                       "parallelism": "scene-sharded x%d, NCCL all-gather of scores" % world},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                       "launch": "eager" if a.eager else "CUDA graph replay of sample_and_score (NT.CapturedPipeline)",
+                       "parallelism": "scene-sharded x%d, NCCL all-gather of scores + selected indices on a side stream "
+                                      "(overlaps the next step; the last one is inside the timed region)" % world},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "h2d": "scene batch (ego, neighbours + tracks, 3 lanes, ids, pSTL parameters) from pinned host memory",
+                    "d2h": "per chain: final score + selected-iterate index; per scene: chosen chain and its 20x2 control "
+                           "sequence (the refined controls of all chains, 31 MB, stay on the device)"},
+            "gather_us": gather_us if world > 1 else None,
             "gpu_launches": launches * a.steps,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": measured_traffic(N) if precision == "bf16" else None,
                          "kernel": "denoiser reverse loop (%s)" % precision,
                          "note": "minimal hoisted FLOP count 17.39 MFLOP/chain / sampler time %.3f ms (CUDA events around "
-                                 "pstl_denoiser_sample, %s); peak = %s bf16 sustained"
-                                 % (sampler_ms, "timed region" if runner is None else "eager pass of the same K steps after "
+                                 "pstl_denoiser_sample, %s); peak = %s"
+                                 % (sampler_ms, "timed region" if a.eager else "eager pass of the same K steps after "
                                     "the graph-replay region", src)}}
+    if extra:
+        line["extra"] = extra
     if not a.no_cpu_baseline:
         n, times = oracle_batch_time(a.cpu_scenes, 3)
         best = min(times[1:]) if len(times) > 1 else times[0]

@@ -1055,7 +1055,11 @@ def sample_and_score(net, batch_cuda, stls_cac, coeffs, args):
     r = score_pack(pack, nn_controls, args, progs, want=("best_score", "traj"))
     scores, nn_trajs = r["best_score"], r["traj"]
     acc, scene_acc = accuracy(scores, pack.valid, bs, S)
-    out.update(controls=nn_controls, scores=scores, trajs=nn_trajs, acc=acc, scene_acc=scene_acc, pack=pack)
+    # the plan a caller would execute per scene: the best-scoring chain over its samples and valid lane modes
+    pick = torch.where(pack.valid > 0, scores, torch.full_like(scores, -1e4)).reshape(bs, S * 3).argmax(dim=1)
+    rows = pick + torch.arange(bs, device=pick.device) * (S * 3)
+    out.update(controls=nn_controls, scores=scores, trajs=nn_trajs, acc=acc, scene_acc=scene_acc, pack=pack,
+               scene_pick=rows, scene_plan=nn_controls.reshape(N, args.nt, 2)[rows])
     return out
 
 

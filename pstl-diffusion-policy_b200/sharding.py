@@ -80,6 +80,61 @@ def gather_scores(scores_local, best_idx_local=None, group=None, equal_sizes=Fal
     return gather(scores_local), (gather(best_idx_local) if best_idx_local is not None else None)
 
 
+class AsyncScoreGather:
+    """The per-batch all-gather of scores / selected indices taken OFF the compute stream (the only
+    collective of the path).  ``submit`` snapshots the two per-chain tensors into a send buffer on a side stream (the
+    compute stream only waits for that device-to-device copy, a few microseconds, before the next batch may overwrite
+    them) and issues ONE ``all_gather_into_tensor`` there; the collective then runs under the next batch's kernels.
+    ``result()`` makes the caller's stream wait for the latest gather and returns (scores_all, best_idx_all) in rank
+    order.  ``last_us()`` is the device time of the latest collective on this rank (CUDA events on the side stream).
+    Equal shard sizes (weak scaling); on CPU tensors / without a process group it degrades to ``gather_scores``."""
+
+    def __init__(self, n_local, device, group=None):
+        self.group, self.n = group, int(n_local)
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and \
+            torch.device(device).type == "cuda"
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._fallback = None
+        if not self.on:
+            return
+        self.stream = torch.cuda.Stream(device=device)
+        self.send = torch.empty(2 * self.n, dtype=torch.float32, device=device)
+        self.recv = torch.empty(self.world * 2 * self.n, dtype=torch.float32, device=device)
+        self.copied, self.done = torch.cuda.Event(), torch.cuda.Event()
+        self.t0, self.t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self._timed = False
+
+    def submit(self, scores_local, best_idx_local):
+        if not self.on:
+            self._fallback = gather_scores(scores_local, best_idx_local, self.group, equal_sizes=True)
+            return
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)  # the batch that produced the scores
+        with torch.cuda.stream(self.stream):
+            self.send[:self.n].copy_(scores_local.reshape(-1), non_blocking=True)
+            self.send[self.n:].view(torch.int32).copy_(best_idx_local.reshape(-1), non_blocking=True)
+            self.copied.record(self.stream)
+            self.t0.record(self.stream)
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+            self.t1.record(self.stream)
+            self.done.record(self.stream)
+            self._timed = True
+        cur.wait_event(self.copied)  # the next batch may overwrite scores / best_idx once they are snapshotted
+
+    def result(self):
+        if not self.on:
+            return self._fallback
+        torch.cuda.current_stream().wait_event(self.done)
+        out = self.recv.reshape(self.world, 2, self.n)
+        return out[:, 0].reshape(-1), out[:, 1].contiguous().view(torch.int32).reshape(-1)
+
+    def last_us(self):
+        if not (self.on and self._timed):
+            return None
+        self.t1.synchronize()
+        return 1e3 * self.t0.elapsed_time(self.t1)
+
+
 def reduce_metrics(partials, group=None):
     """sum a small dict of scalar partial sums over ranks (acc numerators/denominators etc.)"""
     keys = sorted(partials)
