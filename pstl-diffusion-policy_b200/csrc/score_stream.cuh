@@ -278,12 +278,12 @@ PSTL_HD void pstl_stream_steps(const PstlPlan& pl, const Scene& sc, const PstlEv
   }
 }
 
+PSTL_HD float pstl_stream_top(const PstlPlan& pl, const PstlEvalCfg& c, const float* p, PstlStreamAcc& A);
+
 template <bool GRAD>
 PSTL_HD float pstl_stream_finish(const PstlPlan& pl, const PstlEvalCfg& c, const float* p, float* tape, int tstride,
                                  PstlStreamAcc& A) {
   const int T = c.T;
-  const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
-  const float back = 0.6931471805599453f / c.tau;  // ln2 / tau
   float (&am)[PSTL_MAX_TERMS] = A.am;
   float (&as)[PSTL_MAX_TERMS] = A.as;
   // terms with an inner suffix operator: y(t) = R2_{t' >= t} X(t') by one backward sweep, folded into R1
@@ -307,7 +307,16 @@ PSTL_HD float pstl_stream_finish(const PstlPlan& pl, const PstlEvalCfg& c, const
     }
   }
 
-  // top level (stl_d_lib.py:97-112): ListAnd = soft-min over the terms; empty window -> -inf (:7-8,16-17)
+  return pstl_stream_top(pl, c, p, A);
+}
+
+// top level (stl_d_lib.py:97-112) from the per-term accumulators: ListAnd = soft-min over the terms;
+// empty window -> -inf (:7-8,16-17)
+PSTL_HD float pstl_stream_top(const PstlPlan& pl, const PstlEvalCfg& c, const float* p, PstlStreamAcc& A) {
+  const float k2 = c.tau * 1.4426950408889634f;   // tau * log2(e)
+  const float back = 0.6931471805599453f / c.tau;  // ln2 / tau
+  float (&am)[PSTL_MAX_TERMS] = A.am;
+  float (&as)[PSTL_MAX_TERMS] = A.as;
   float top_m = PSTL_LSE2_INIT, top_s = 0.f, single = 0.f;
   bool empty = false;
 #pragma unroll

@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(256) k_score(ScoreArgs a) {
 
 #include "score_warp.cuh"
 #include "score_stream.cuh"
+#include "score_dense.cuh"
 
 // PSTL_SCORE_KERNEL=stream|warp|thread pins the forward scoring kernel (tests compare the three)
 static bool score_kernel_forced(const char* name) {
@@ -412,6 +413,59 @@ static int launch_score_warp(ScoreArgs& a, pstl_program_t const* progs, cudaStre
     k_score_warp<true><<<grid, 256, tile_bytes + stack_bytes, st>>>(a, wp);
   } else {
     k_score_warp<false><<<grid, 256, stack_bytes, st>>>(a, wp);
+  }
+  PSTL_LAUNCH_CHECK();
+  *took = 1;
+  return PSTL_OK;
+}
+
+// forward scoring of the reference's dense per-row layout on the time-parallel kernel (score_dense.cuh);
+// sets *took when it owned the launch
+static int launch_score_dense_tp(ScoreArgs& a, pstl_program_t const* progs, cudaStream_t st, int* took) {
+  *took = 0;
+  const PstlEvalCfg& c = a.cfg;
+  const bool forced = score_kernel_forced("dense");
+  if (c.hard || score_kernel_forced("warp") || score_kernel_forced("thread") || score_kernel_forced("stream")) return PSTL_OK;
+  if (a.rows_per_scene != 1 || !a.ego || a.controls || a.C != 1 || a.traj_out || a.best_controls) return PSTL_OK;
+  if (c.T > PSTL_DENSE_MAX_THREADS || c.T < 1 || c.K < 1) return PSTL_OK;
+  if (((size_t)c.K * c.T) % 4 != 0 || ((uintptr_t)a.neighbors & 15) != 0) return PSTL_OK;  // 16-byte bulk copies
+  if (a.ego_stride == 4 && ((uintptr_t)a.ego & 15) != 0) return PSTL_OK;
+  if (!forced && a.N < 1024) return PSTL_OK;  // tiny calls stay on the thread-per-row kernel (one wave either way)
+  StreamPlans sp;
+  for (int k = 0; k < 3; ++k) {
+    if (!progs[k]->plan.valid) return PSTL_OK;
+    sp.p[k] = progs[k]->plan;
+  }
+  DenseTpCfg d;
+  const char* er = getenv("PSTL_DENSE_ROWS");
+  int R = er ? atoi(er) : (c.T <= 21 ? 12 : 8);  // measured at T=20, K=8: 12 rows (240 threads) 2.39 ms per 1M rows, 8 rows 2.50
+  if (R < 1) R = 1;
+  if (R > PSTL_DENSE_MAX_THREADS / c.T) R = PSTL_DENSE_MAX_THREADS / c.T;
+  if (R > 32) R = 32;
+  const char* eb = getenv("PSTL_DENSE_CHUNK_KB");
+  const size_t chunk_budget = (size_t)(eb ? atoi(eb) : 32) * 1024;
+  int KC = 0;
+  for (int kc = c.K; kc >= 1; --kc)
+    if ((size_t)R * kc * c.T * 28 <= chunk_budget && ((size_t)kc * c.T * 7) % 4 == 0) { KC = kc; break; }
+  if (!eb && (size_t)R * c.K * c.T * 28 <= 64 * 1024) KC = c.K;  // the whole block in one go when it is small enough
+  if (!KC) return PSTL_OK;
+  const char* enb = getenv("PSTL_DENSE_NBUF");
+  d.R = R; d.KC = KC; d.nbuf = (KC < c.K) ? ((enb && atoi(enb) == 1) ? 1 : 2) : 1; d.chunk_floats = KC * c.T * 7;
+  const size_t smem = dtp_smem_layout(d, c.T, c.nseg).total * sizeof(float);
+  if (smem > 160 * 1024 || c.nseg * 3 > 64 || R * c.T > 65535) return PSTL_OK;
+  int threads = ((R * c.T + 31) / 32) * 32;
+  if (threads < 64) threads = 64;  // the lane staging deals 64 threads per row
+  if (threads < ((R * PSTL_MAX_TERMS + 31) & ~31)) threads = (R * PSTL_MAX_TERMS + 31) & ~31;
+  const int per = c.nseg * 3;
+  d.bulk_small = (a.ego_stride == 4 && (R * per) % 4 == 0 && R % 4 == 0 && ((uintptr_t)a.ego & 15) == 0 &&
+                  ((uintptr_t)a.lanes[0] & 15) == 0 && ((uintptr_t)a.lanes[1] & 15) == 0 && ((uintptr_t)a.lanes[2] & 15) == 0 &&
+                  ((uintptr_t)a.stlp & 15) == 0 && ((uintptr_t)a.mode & 15) == 0) ? 1 : 0;
+  if (c.T == 20 && c.nseg == 15) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_dense_tp<20, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    k_score_dense_tp<20, 15><<<pstl_ceil_div(a.N, R), threads, smem, st>>>(a, sp, d);
+  } else {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_dense_tp<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    k_score_dense_tp<0, 0><<<pstl_ceil_div(a.N, R), threads, smem, st>>>(a, sp, d);
   }
   PSTL_LAUNCH_CHECK();
   *took = 1;
@@ -643,6 +697,8 @@ extern "C" int pstl_score_fused(pstl_program_t const* progs, const pstl_scene_vi
   a.scores_all = scores_all; a.best_score = best_score; a.best_idx = best_idx;
   a.best_controls = best_controls; a.traj_out = traj_out; a.ws = (float*)workspace;
   int took = 0;
+  rc = launch_score_dense_tp(a, progs, (cudaStream_t)stream, &took);
+  if (rc || took) return rc;
   rc = launch_score_stream(a, progs, (cudaStream_t)stream, &took);
   if (rc || took) return rc;
   rc = launch_score_warp(a, progs, (cudaStream_t)stream, &took);
