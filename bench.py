@@ -360,8 +360,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL's log (communicator ranks, transports) goes to stderr; stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout: set both explicitly)
+        os.environ["NCCL_DEBUG"] = os.environ.get("PSTL_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("PSTL_NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     native.lib()  # fail loudly if the CUDA library is missing
 

@@ -47,14 +47,18 @@ def _digest():
 
 def build(force=False, verbose=False):
     stamp = os.path.join(HERE, "build", "stamp")
-    dig = _digest()
+    units = dict(UNITS)
+    if os.environ.get("PSTL_BUILD_TC_DEBUG"):
+        # developer build: clock64 timeline stamps inside k_denoiser_tc (tests/tc_timeline.py); never shipped
+        units["denoiser_tc.cu"] = units["denoiser_tc.cu"] + ["-DPSTL_TC_DEBUG"]
+    dig = _digest() + ("+tcdebug" if os.environ.get("PSTL_BUILD_TC_DEBUG") else "")
     if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
         return OUT
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
-    for unit, extra in UNITS.items():
+    for unit, extra in units.items():
         obj = os.path.join(HERE, "build", unit.replace(".cu", ".o"))
         cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, unit), "-o", obj]
         procs.append((unit, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -49,8 +49,15 @@ static_assert(kWeightBytes == 188416, "weight image size");
 static_assert(kSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
 
 constexpr uint32_t kColD = 0, kColH1 = 256, kColH2 = 384, kColD3 = 256, kColX = 384;  // X: 32 columns = 64 bf16 of layer-1 input
+// Timeline instrumentation (clock64 stamps of one tile-step) exists only in builds made with -DPSTL_TC_DEBUG
+// (tests/tc_timeline.py builds its own copy); the product library carries none of it.
+#ifdef PSTL_TC_DEBUG
 #define MSTAMP (a.dbg && blockIdx.x == 0 && it == 2 && lane == 0)
 #define STAMP (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0)
+#else
+#define MSTAMP false
+#define STAMP false
+#endif
 
 struct TcState {
   uint8_t* image;    // device: swizzled bf16 weight image of policy_net (kWeightBytes)
@@ -264,7 +271,6 @@ struct TcArgs {
   const unsigned long long* offset_dev;  // optional device word added to offset (graph replays draw fresh noise)
   // RefineNet pass (Net.rect_forward, reference nusc_model.py:209-233): one "step", no x update
   int refine;
-  int exp_skip_bias;    // timing experiment only (PSTL_TC_EXP=skipbias): results are wrong
   const float* u0;      // (N, 40) controls being refined
   const float* scores;  // (N)
   float* out;           // (N, 40)
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int s = 0; s < n_steps; ++s, ++it) {
         if (it > 0) mbar_wait(bar_d1 + 8, (it - 1) & 1);
-        if (!a.exp_skip_bias || s == 0) write_bias_cols(tile, a.first_step - s);
+        write_bias_cols(tile, a.first_step - s);
         if (lane == 0) mbar_arrive(bar_b);
       }
     }
@@ -759,9 +765,10 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   const int n_tiles = (N + kTileM - 1) / kTileM;
   const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
   long long* dbg = nullptr;
+#ifdef PSTL_TC_DEBUG
   if (getenv("PSTL_TC_DEBUG")) { cudaMalloc(&dbg, 32 * sizeof(long long)); cudaMemset(dbg, 0, 32 * sizeof(long long)); }
+#endif
   a.dbg = dbg;
-  a.exp_skip_bias = getenv("PSTL_TC_EXP") != nullptr;
   k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
   if (dbg) {
     cudaStreamSynchronize(st);

@@ -1,4 +1,6 @@
-"""PSTL_TC_DEBUG=1 python tests/tc_timeline.py — print the clock64 timeline of one tile-step of k_denoiser_tc"""
+"""Print the clock64 timeline of one tile-step of k_denoiser_tc.  Needs a developer build of the library:
+    PSTL_BUILD_TC_DEBUG=1 python pstl-diffusion-policy_b200/build.py --force && python tests/tc_timeline.py
+(the product build compiles the instrumentation out; rebuild without the variable afterwards)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

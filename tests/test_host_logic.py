@@ -162,6 +162,12 @@ def _worker(rank, world, port, q):
     valid = (torch.arange(lo * 12, hi * 12) % 3 != 1).float()
     n_tot, mean_v = sharding.guidance_normaliser(valid)
     ok = ok and n_tot == 60 and abs(mean_v - 2.0 / 3.0) < 1e-6
+    # the side-stream gather degrades to the blocking collective on CPU tensors (equal shard sizes)
+    g = sharding.AsyncScoreGather(12, "cpu")
+    g.submit(torch.arange(12).float() + 100 * rank, torch.arange(12).int() + 7 * rank)
+    ga, gi = g.result()
+    ok = ok and torch.equal(ga, torch.cat([torch.arange(12).float() + 100 * r for r in range(world)]))
+    ok = ok and torch.equal(gi, torch.cat([torch.arange(12).int() + 7 * r for r in range(world)])) and g.last_us() is None
     red = sharding.reduce_metrics({"num": torch.tensor(float(rank + 1)), "den": torch.tensor(2.0)})
     ok = ok and red == {"den": 2.0 * world, "num": world * (world + 1) / 2}
     q.put((rank, bool(ok)))
