@@ -185,6 +185,12 @@ int pstl_denoiser_destroy(pstl_denoiser_t d);
  * copies (hoisted first-layer blocks, bf16 operand images) on `stream`.  No allocation, no synchronisation. */
 int pstl_denoiser_refresh(pstl_denoiser_t d, pstl_stream_t stream);
 
+/* Which tcgen05 engine PSTL_PRECISION_BF16 launches: 0 = automatic (default: the CTA-pair engine, two 256-row tiles
+ * in flight per SM pair, once the batch exceeds one wave of 128-row tiles; the one-SM engine below that), 1 = one-SM
+ * engine, 2 = CTA-pair engine whenever its tile fits rows_per_scene.  Both compute the same function with the same
+ * noise stream; the reference has one code path (nusc_train.py:557-645), this only picks the kernel. */
+int pstl_denoiser_set_engine(pstl_denoiser_t d, int engine);
+
 /* Philox offset word in DEVICE memory (or NULL to clear): the sampler adds *device_counter to the
  * `offset` argument of pstl_denoiser_sample when it draws noise.  A CUDA graph that captured the
  * sampler bumps this word in-graph so every replay draws fresh normals (upstream: randn_like per

@@ -62,6 +62,8 @@ constexpr uint32_t kColD = 0, kColH1 = 256, kColH2 = 384, kColD3 = 256, kColX = 
 struct TcState {
   uint8_t* image;    // device: swizzled bf16 weight image of policy_net (kWeightBytes)
   uint8_t* image_r;  // same for rect_net (RefineNet head), or null
+  uint8_t* image2;   // pair-engine layout of policy_net (two per-rank halves, denoiser_tc2.cuh)
+  uint8_t* image2_r; // same for rect_net, or null
   float* zeros;      // 256 zeros: the "time" bias row of the RefineNet pass
   int sm_count;
 };
@@ -683,14 +685,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 
 }  // namespace
 
+#include "denoiser_tc2.cuh"
+
 // (re)build the bf16 weight images from the handle's current fp32 weights: no allocation, no synchronisation
 int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st) {
   TcState* s = (TcState*)d->tc;
   PSTL_CHECK_ARG(s, "engine not created");
   k_build_image<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image);
   PSTL_LAUNCH_CHECK();
+  k_build_image2<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image2);
+  PSTL_LAUNCH_CHECK();
   if (s->image_r) {
     k_build_image<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_r);
+    PSTL_LAUNCH_CHECK();
+    k_build_image2<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image2_r);
     PSTL_LAUNCH_CHECK();
   }
   return PSTL_OK;
@@ -711,21 +719,26 @@ int pstl_tc_create(pstl_denoiser* d) {
   }
   TcState* s = new TcState();
   s->sm_count = sms;
-  s->image = s->image_r = nullptr;
+  s->image = s->image_r = s->image2 = s->image2_r = nullptr;
   s->zeros = nullptr;
   PSTL_CUDA(cudaMalloc(&s->image, kWeightBytes));
   PSTL_CUDA(cudaMemset(s->image, 0, kWeightBytes));
+  PSTL_CUDA(cudaMalloc(&s->image2, 2 * k2WeightBytes));
+  PSTL_CUDA(cudaMemset(s->image2, 0, 2 * k2WeightBytes));
   PSTL_CUDA(cudaMalloc(&s->zeros, kH * sizeof(float)));
   PSTL_CUDA(cudaMemset(s->zeros, 0, kH * sizeof(float)));
   if (d->r1p && d->w.rect_hidden == kH) {
     PSTL_CUDA(cudaMalloc(&s->image_r, kWeightBytes));
     PSTL_CUDA(cudaMemset(s->image_r, 0, kWeightBytes));
+    PSTL_CUDA(cudaMalloc(&s->image2_r, 2 * k2WeightBytes));
+    PSTL_CUDA(cudaMemset(s->image2_r, 0, 2 * k2WeightBytes));
   }
   d->tc = s;
   int rc = pstl_tc_refresh(d, nullptr);
   if (rc) return rc;
   PSTL_CUDA(cudaDeviceSynchronize());
   PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+  PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes + 1024));
   d->tc = s;
   return PSTL_OK;
 }
@@ -735,9 +748,41 @@ void pstl_tc_destroy(pstl_denoiser* d) {
   if (!s) return;
   cudaFree(s->image);
   cudaFree(s->image_r);
+  cudaFree(s->image2);
+  cudaFree(s->image2_r);
   cudaFree(s->zeros);
   delete s;
   d->tc = nullptr;
+}
+
+// Engine choice.  The pair engine (denoiser_tc2.cuh) wins once there is more than one wave of 128-row tiles; below
+// that the one-SM engine spreads a small batch over more SMs.  PSTL_TC_ENGINE=1|2 (read once) pins one for tests.
+static int tc_engine_for(const TcState* s, int engine, int N, int rows_per_scene) {
+  static const int forced = [] {
+    const char* e = getenv("PSTL_TC_ENGINE");
+    return e ? atoi(e) : 0;
+  }();
+  const bool pair_ok = (k2TileM + rows_per_scene - 1) / rows_per_scene + 1 <= kMaxClasses && s->sm_count >= 2;
+  if (engine == 0) engine = forced;
+  if (engine == 1 || !pair_ok) return 1;
+  if (engine == 2) return 2;
+  return 1;
+}
+
+static int tc_launch(const TcState* s, int engine, TcArgs& a, int rows_per_scene, const uint8_t* image1, const uint8_t* image2, cudaStream_t st) {
+  if (tc_engine_for(s, engine, a.N, rows_per_scene) == 2) {
+    a.image = image2;
+    const int n_tiles = (a.N + k2TileM - 1) / k2TileM;
+    const int pairs = n_tiles < s->sm_count / 2 ? n_tiles : s->sm_count / 2;
+    k_denoiser_tc2<<<2 * pairs, kThreads, k2SmemBytes + 1024, st>>>(a);
+  } else {
+    a.image = image1;
+    const int n_tiles = (a.N + kTileM - 1) / kTileM;
+    const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
+    k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
+  }
+  PSTL_LAUNCH_CHECK();
+  return PSTL_OK;
 }
 
 // runs reverse steps first_step .. last_step (inclusive, descending) on xin in place
@@ -751,7 +796,7 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   PSTL_CHECK_ARG((kTileM + rows_per_scene - 1) / rows_per_scene + 1 <= kMaxClasses, "rows_per_scene too small for the tcgen05 tile");
   TcArgs a;
   memset(&a, 0, sizeof(a));
-  a.image = s->image; a.cscene = cscene; a.ct = ct; a.b2 = d->w.p2_b; a.b3 = d->w.p4_b; a.xin = xin;
+  a.cscene = cscene; a.ct = ct; a.b2 = d->w.p2_b; a.b3 = d->w.p4_b; a.xin = xin;
   a.noise = noise; a.iterates = keep_last_k > 0 ? iterates_out : nullptr;
   a.mu_out = mu_out;
   const float *beta = sched, *alpha = sched + steps, *abar = sched + 2 * steps;
@@ -762,26 +807,36 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   }
   a.N = N; a.rows_per_scene = rows_per_scene; a.steps = steps; a.first_step = first_step; a.last_step = last_step;
   a.keep = keep_last_k; a.clip = clip; a.w_max = w_max; a.a_max = a_max; a.seed = seed; a.offset = offset; a.offset_dev = d->offset_dev;
-  const int n_tiles = (N + kTileM - 1) / kTileM;
-  const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
-  long long* dbg = nullptr;
 #ifdef PSTL_TC_DEBUG
-  if (getenv("PSTL_TC_DEBUG")) { cudaMalloc(&dbg, 32 * sizeof(long long)); cudaMemset(dbg, 0, 32 * sizeof(long long)); }
-#endif
+  long long* dbg = nullptr;
+  if (getenv("PSTL_TC_DEBUG")) { cudaMalloc(&dbg, 48 * sizeof(long long)); cudaMemset(dbg, 0, 48 * sizeof(long long)); }
   a.dbg = dbg;
-  k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
+#endif
+  int rc = tc_launch(s, d->tc_engine, a, rows_per_scene, s->image, s->image2, st);
+#ifdef PSTL_TC_DEBUG
   if (dbg) {
     cudaStreamSynchronize(st);
-    long long h[32];
+    long long h[48];
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    if (tc_engine_for(s, d->tc_engine, N, rows_per_scene) == 2) {
+      const long long t0 = h[0];
+      auto R = [&](int i) { return h[i] ? h[i] - t0 : -1LL; };
+      fprintf(stderr, "[pstl pair-engine timeline, pair 0, 3rd step, cycles rel. to the MMA warp reaching L1(A)]\n"
+                      "  MMA : L1A ready %lld issued %lld | L3B h2a %lld h2b %lld issued %lld | L2A h1 %lld issued %lld | L1B at %lld ready %lld issued %lld |"
+                      " L3A h2a %lld h2b %lld issued %lld | L2B h1 %lld issued %lld\n"
+                      "  EPI : E1A d1 %lld done %lld | E3B d3 %lld done %lld | prepA %lld | E2A d2 %lld part0 %lld done %lld | E1B d1 %lld done %lld |"
+                      " E3A d3 %lld done %lld | prepB %lld | E2B d2 %lld part0 %lld done %lld\n",
+              R(1), R(2), R(3), R(4), R(15), R(5), R(6), R(7), R(8), R(9), R(10), R(11), R(12), R(13), R(14),
+              R(20), R(21), R(36), R(37), R(28), R(23), R(25), R(24), R(30), R(31), R(26), R(27), R(38), R(33), R(35), R(34));
+    } else
     fprintf(stderr, "[pstl tc timeline, CTA 0, 3rd tile-step, cycles rel. to bar_x ready]\n  MMA : x %lld | mma1 issued %lld | h1[0] %lld | mma2 issued %lld | h2[0] %lld | mma3 issued %lld\n"
                     "  EPI0: d1 %lld | epi1 done %lld | noise done %lld | d2 %lld | epi2 done %lld | d3 %lld | epi3 done %lld\n",
             0LL, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0],
             h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
     cudaFree(dbg);
   }
-  PSTL_LAUNCH_CHECK();
-  return PSTL_OK;
+#endif
+  return rc;
 }
 
 // RefineNet head on the same engine: xin rows = [fused(40) | hl | stlp], one pass, tanh-interval epilogue
@@ -792,16 +847,12 @@ int pstl_tc_refine(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   PSTL_CHECK_ARG((kTileM + rows_per_scene - 1) / rows_per_scene + 1 <= kMaxClasses, "rows_per_scene too small for the tcgen05 tile");
   TcArgs a;
   memset(&a, 0, sizeof(a));
-  a.image = s->image_r; a.cscene = cscene; a.ct = s->zeros; a.b2 = d->w.r2_b; a.b3 = d->w.r4_b;
+  a.cscene = cscene; a.ct = s->zeros; a.b2 = d->w.r2_b; a.b3 = d->w.r4_b;
   a.xin = const_cast<float*>(xin);
   a.N = N; a.rows_per_scene = rows_per_scene; a.steps = 2; a.first_step = 0; a.last_step = 0;  // one pass, ct row 0
   a.clip = clip_rect; a.w_max = w_max; a.a_max = a_max;
   a.refine = 1; a.u0 = u0; a.scores = scores; a.out = out;
-  const int n_tiles = (N + kTileM - 1) / kTileM;
-  const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
-  k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
-  PSTL_LAUNCH_CHECK();
-  return PSTL_OK;
+  return tc_launch(s, d->tc_engine, a, rows_per_scene, s->image_r, s->image2_r, st);
 }
 
 bool pstl_tc_has_refine(pstl_denoiser* d) { return d->tc && ((TcState*)d->tc)->image_r; }

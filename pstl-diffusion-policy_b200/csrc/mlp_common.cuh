@@ -12,6 +12,7 @@ struct pstl_denoiser {
   float* w1p;          // (hidden, kin)   policy_net.0 columns [x | hl | stlp]
   float* r1p;          // (rect_hidden, kin) rect_net.0 columns [fused | hl | stlp]
   void* tc;            // tcgen05 engine state (bf16 images), owned by denoiser_tc.cu
+  int tc_engine;       // 0 = automatic, 1 = one-SM engine, 2 = CTA-pair engine (pstl_denoiser_set_engine)
   const unsigned long long* offset_dev;  // optional device word added to the Philox offset (CUDA-graph replays)
 };
 

@@ -646,6 +646,13 @@ extern "C" int pstl_denoiser_destroy(pstl_denoiser_t d) {
   return PSTL_OK;
 }
 
+extern "C" int pstl_denoiser_set_engine(pstl_denoiser_t d, int engine) {
+  PSTL_CHECK_ARG(d, "null handle");
+  PSTL_CHECK_ARG(engine >= 0 && engine <= 2, "engine must be 0 (automatic), 1 (one-SM) or 2 (CTA pair)");
+  d->tc_engine = engine;
+  return PSTL_OK;
+}
+
 extern "C" int pstl_denoiser_set_noise_counter(pstl_denoiser_t d, const uint64_t* device_counter) {
   PSTL_CHECK_ARG(d, "null handle");
   d->offset_dev = reinterpret_cast<const unsigned long long*>(device_counter);

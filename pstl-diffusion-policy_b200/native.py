@@ -26,7 +26,7 @@ EXPORTS = [
     "pstl_encoder_pool", "pstl_mlp3", "pstl_mlp3_batch", "pstl_trajopt_step", "pstl_diversity", "pstl_accuracy",
     "pstl_refine_losses_workspace_bytes", "pstl_refine_losses", "pstl_refine_backward_workspace_bytes",
     "pstl_refine_backward", "pstl_denoiser_eps_rows", "pstl_denoiser_eps_backward", "pstl_car_distances",
-    "pstl_denoiser_refresh",
+    "pstl_denoiser_refresh", "pstl_denoiser_set_engine",
 ]
 
 

@@ -161,6 +161,13 @@ class Net(nn.Module):
             self._handles[prec] = ((c[0][0], None), c[1], c[2], c[3])
 
     def native_handle(self, precision="fp32"):
+        """The handle of ``_native_handle`` with ``args.tc_engine`` applied (0 automatic, 1 one-SM tcgen05 engine, 2 CTA-pair
+        engine; ``pstl_denoiser_set_engine``)."""
+        h = self._native_handle(precision)
+        _nv.check(_nv.lib().pstl_denoiser_set_engine(h, int(getattr(self.args, "tc_engine", 0) or 0)), "pstl_denoiser_set_engine")
+        return h
+
+    def _native_handle(self, precision="fp32"):
         """pstl_denoiser_t over this module's parameters.  The handle points at the parameter storage; an in-place update
         (optimiser step: same storage, new version) only refreshes the library's own copies — the hoisted first-layer
         blocks and the bf16 operand images — on the current stream (``pstl_denoiser_refresh``: no allocation, no

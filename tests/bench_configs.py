@@ -5,6 +5,7 @@
    python tests/bench_configs.py losses [scenes]       # RefineNet training losses, value + gradient (§8(f) item 4)
    python tests/bench_configs.py train [scenes] [steps]  # full --rect_head training iterations (sampler .. Adam step)
    python tests/bench_configs.py train_ddpm [scenes] [steps]  # denoiser training iterations (README step 1)
+   python tests/bench_configs.py sampler [scenes] [engine]    # the bf16 sampler alone (99 reverse steps), tcgen05 engine 1 | 2
 """
 import os
 import sys
@@ -44,6 +45,25 @@ def guidance(scenes):
     out = NT.sample_and_score(net, b, stls, co, args)
     print("config3 (Ours+guidance, K=10, n_rolls=3): scenes=%d chains=%d  %.2f ms/batch  %.3g chains/s  acc=%.3f"
           % (scenes, n, ms, n / ms * 1e3, out["acc"].item()))
+
+
+def sampler(scenes, engine):
+    args = NT.default_args(precision="bf16", tc_engine=engine)
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007))
+    net = net.cuda()
+    b = NT.LazyBatch({k: v.cuda() for k, v in synthetic.make_scene_batch(scenes, seed=3).items()})
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    S_ = args.n_randoms
+    b = NT.augment_batch_data(b, None, args, n_randoms=S_)
+    n = scenes * S_ * 3
+    noise = torch.empty((n, 40), device="cuda")
+    co = NT.get_diffusion_coeffs(args)
+    with torch.no_grad():
+        feat = net.encode_feat(b)
+    ms = timeit(lambda: NT.diffusion_rollout(noise, net, b, b["highlevel_dense"], feat, args, co, n_randoms=S_), reps=5, warm=2)
+    fl = 99 * 2 * (47 * 256 + 256 * 256 + 256 * 40) * n
+    print("sampler (engine %d): scenes=%d chains=%d  %.3f ms  %.1f TFLOP/s (minimal count)" % (engine, scenes, n, ms, fl / ms / 1e9))
 
 
 def dense(n, T, K):
@@ -219,6 +239,8 @@ if __name__ == "__main__":
         sweep(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 512)
     elif sys.argv[1] == "trajopt":
         trajopt(int(sys.argv[2]) if len(sys.argv) > 2 else 256, int(sys.argv[3]) if len(sys.argv) > 3 else 100)
+    elif sys.argv[1] == "sampler":
+        sampler(int(sys.argv[2]) if len(sys.argv) > 2 else 1024, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     elif sys.argv[1] == "guidance":
         guidance(int(sys.argv[2]) if len(sys.argv) > 2 else 256)
     else:

@@ -1,0 +1,104 @@
+"""The CTA-pair tcgen05 engine (csrc/denoiser_tc2.cuh: cta_group::2, two 256-row tiles in flight per SM pair) against
+the one-SM engine and the fp32 path.  Both engines compute reference nusc_model.py:118-162 + nusc_train.py:580-629 with
+bf16 operands and fp32 accumulation; they differ in tile shape, in where b2 is added (fp32 epilogue vs a bf16 (hi, lo)
+K-step) and in nothing else, so they agree far inside the north-star's 2e-2 bf16 bound; the Philox stream is a function
+of (row, column, step) only, so both draw the same noise."""
+import numpy as np
+import pytest
+import torch
+
+import pstl_b200  # noqa: F401
+from pstl_b200 import nusc_train as NT
+from pstl_b200 import synthetic
+from pstl_b200.nusc_model import Net
+
+pytestmark = pytest.mark.gpu
+SCALE = [0.5, 5.0]  # normalised control units (w_max, a_max)
+
+
+def cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def _sample(bs, S_, steps, seed, engine, precision="bf16", inject=True, keep=0):
+    nt = 20
+    W = synthetic.make_weights(1007, nt=nt)
+    batch = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=seed))
+    N = bs * S_ * 3
+    args = NT.default_args(n_randoms=S_, sampling_size=S_, diffusion_steps=steps, precision=precision, multi_cands=max(keep, 1),
+                           tc_engine=engine)
+    net = Net(args)
+    net.load_state_dict(W)
+    net = net.cuda()
+    if inject:
+        args.inject_noise = [t.cuda() for t in synthetic.noise_stream(seed + 1, N, nt * 2, steps - 1)]
+    else:
+        args.seed = 1234
+        NT._call_counter[0] = 41  # the Philox offset of the call is (_call_counter + 1) * 1000: same stream in every run
+    b = NT.LazyBatch(dict(batch))
+    b["neighbor_trajs_aug"] = b["neighbors_traj"][..., :7]
+    b = NT.augment_batch_data(b, None, args, n_randoms=S_)
+    noise = torch.empty((N, nt * 2), device="cuda")
+    torch.manual_seed(seed)
+    res = NT.diffusion_rollout(noise, net, b, b["highlevel_dense"], None, args, NT.get_diffusion_coeffs(args), n_randoms=S_)
+    torch.cuda.synchronize()
+    return res
+
+
+def _err(a, b):
+    return ((a - b).reshape(-1, 2) / torch.tensor(SCALE, device=a.device)).abs().max().item()
+
+
+@pytest.mark.parametrize("bs,S_,steps", [(2, 16, 2), (3, 16, 100), (24, 64, 100), (160, 64, 12)])
+def test_pair_engine_vs_one_sm_engine_injected_noise(bs, S_, steps):
+    """same injected z: final iterate of the pair engine vs the one-SM engine (both bf16) and vs fp32.
+    (160, 64, 12): 30,720 rows = 120 pair tiles over 74 pairs: both slots busy, a partial second round."""
+    a = _sample(bs, S_, steps, 4242, engine=2)[0]
+    b = _sample(bs, S_, steps, 4242, engine=1)[0]
+    assert torch.isfinite(a).all()
+    assert _err(a, b) < 5e-3, _err(a, b)
+    if bs <= 24:
+        c = _sample(bs, S_, steps, 4242, engine=0, precision="fp32")[0]
+        assert _err(a, c) < 2e-2, _err(a, c)
+
+
+def test_pair_engine_philox_stream_and_kept_iterates():
+    """in-kernel Philox: same (row, column, step) -> same z in both engines; the five kept iterates (multi_cands 5)
+    leave through the staged bulk store of each engine and must agree too.  N = 10,560 rows is not a multiple of 256."""
+    ra = _sample(55, 64, 100, 7, engine=2, inject=False, keep=5)
+    rb = _sample(55, 64, 100, 7, engine=1, inject=False, keep=5)
+    assert _err(ra[0], rb[0]) < 5e-3, _err(ra[0], rb[0])
+    ka, kb = ra[-1].stacked_last(5), rb[-1].stacked_last(5)
+    assert ka.shape == (5, 55 * 64 * 3, 20, 2) and torch.isfinite(ka).all()
+    assert torch.equal(ka[-1], ra[0])
+    for j in range(5):
+        assert _err(ka[j], kb[j]) < 5e-3, (j, _err(ka[j], kb[j]))
+    # x_0 is no copy of an earlier iterate and the chain moved: the stream really was drawn
+    assert (ka[0] - ka[-1]).abs().max().item() > 1e-3
+
+
+def test_pair_engine_refinenet_head():
+    """Net.rect_forward (reference nusc_model.py:209-233) through the pair engine vs the one-SM engine"""
+    bs, S_, nt = 12, 64, 20
+    W = synthetic.make_weights(1007, nt=nt)
+    g = torch.Generator().manual_seed(77)
+    N = bs * S_ * 3
+    u0 = ((torch.rand(N, nt, 2, generator=g) * 2 - 1) * torch.tensor([0.45, 4.5])).cuda()
+    scores = (torch.rand(N, generator=g) - 0.7).cuda()
+    batch = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=5))
+    stlp = batch["pre_stlp"].reshape(bs, S_, 3, 6)[:, 0:1].repeat(1, S_, 1, 1).reshape(N, 6)
+    hl = torch.tensor([0.0, 1.0, 2.0], device="cuda").repeat(bs * S_)[:, None]
+    outs = {}
+    for eng in (1, 2):
+        args = NT.default_args(n_randoms=S_, sampling_size=S_, precision="bf16", tc_engine=eng)
+        net = Net(args)
+        net.load_state_dict(W)
+        net = net.cuda()
+        with torch.no_grad():
+            feat = net.encode_feat(batch)
+        dense = feat.reshape(bs, 1, -1).expand(bs, S_ * 3, feat.shape[-1]).reshape(N, -1)
+        dense._pstl_scene_feat = feat
+        outs[eng] = net.rect_forward(dense, hl, stlp, u0, scores)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[2][scores >= 0], u0[scores >= 0])
+    assert _err(outs[2], outs[1]) < 5e-3, _err(outs[2], outs[1])
