@@ -605,8 +605,11 @@ __device__ __forceinline__ int stream_sort_rows_by_mode(const float* __restrict_
 
 #define PSTL_STREAM_BLOCK_MAX 192
 
-template <bool SMEM_SCENE, int MINB>
-__global__ void __launch_bounds__(PSTL_STREAM_BLOCK_MAX, MINB)
+// CHUNKED (horizon walked in tiles of a.tc steps) is a template parameter: compiled into the same kernel, the two walks
+// made it 11,200 instructions (180 KB, more than the instruction cache: 11 % of the pipeline launch's stall samples were
+// "no instruction"); the whole-horizon instance the pipeline launches carries only its own walk.
+template <bool SMEM_SCENE, bool CHUNKED>
+__global__ void __launch_bounds__(PSTL_STREAM_BLOCK_MAX, 4)
 k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ StreamPlans sp) {
   extern __shared__ float4 sm4[];
   const PstlEvalCfg c = a.cfg;
@@ -626,7 +629,7 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
   // the scene tile holds a.tc steps: the whole horizon when it fits (staged once), else the horizon is walked in
   // chunks and the tile re-staged per chunk (long horizons / many neighbours, BASELINE config 5)
   const int TC = SMEM_SCENE ? a.tc : T;
-  const bool chunked = SMEM_SCENE && TC < T;
+  constexpr bool chunked = SMEM_SCENE && CHUNKED;
   float4* tile = sm4;
   float* tape = reinterpret_cast<float*>(sm4);
   int tstride = B;
@@ -724,7 +727,7 @@ k_score_stream(const __grid_constant__ ScoreArgs a, const __grid_constant__ Stre
 
 // Reverse mode (guidance, autograd of compute_stl_dense): forward with the per-step record in a global tape
 // (element-major, stride N: coalesced), then pstl_stream_bwd.  C == 1.
-template <bool SMEM_SCENE>
+template <bool SMEM_SCENE, bool CHUNKED>
 __global__ void __launch_bounds__(PSTL_STREAM_BLOCK_MAX, 3)
 k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ StreamPlans sp) {
   extern __shared__ float4 sm4[];
@@ -741,7 +744,7 @@ k_score_stream_bwd(const __grid_constant__ ScoreArgs a, const __grid_constant__ 
   }
   const int n = n0 + li;
   const int TC = SMEM_SCENE ? a.tc : T;
-  const bool chunked = SMEM_SCENE && TC < T;
+  constexpr bool chunked = SMEM_SCENE && CHUNKED;
   float4* tile = sm4;
   if (SMEM_SCENE && !chunked) {
     stream_stage_scene(a, n0 / a.rows_per_scene, n0, tile, 0, T);

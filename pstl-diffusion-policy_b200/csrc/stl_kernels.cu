@@ -496,11 +496,9 @@ static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaSt
   if (a.rows_per_scene % 32 == 0 && tile_bytes <= tile_budget && (tc == c.T || tc >= 4)) {
     // one scene per block, staged in shared memory (whole horizon, or chunk by chunk)
     static const int cands[] = {192, 96, 128, 64, 32};
-    int first = 0;  // largest block that divides the scene's rows (PSTL_STREAM_BLOCK: upper bound, for experiments)
-    const char* fb = getenv("PSTL_STREAM_BLOCK");
-    const int cap = fb ? atoi(fb) : 1024;
+    int first = 0;  // largest block that divides the scene's rows
     for (int b : cands)
-      if (!first && b <= cap && a.rows_per_scene % b == 0) first = b;
+      if (!first && a.rows_per_scene % b == 0) first = b;
     if (!first) first = 32;
     if (tile_bytes + (size_t)first * tape_row <= budget) {
       block = first;
@@ -528,16 +526,15 @@ static int launch_score_stream(ScoreArgs& a, pstl_program_t const* progs, cudaSt
   a.tape_global = tape_global ? 1 : 0;
   const size_t smem = (smem_scene ? tile_bytes : 0) + (tape_global ? 0 : (size_t)block * tape_row);
   const int grid = pstl_ceil_div(a.N, block);
-  const char* mb = getenv("PSTL_STREAM_MINB");
-  if (smem_scene && !(mb && atoi(mb) == 5)) {
-    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    k_score_stream<true, 4><<<grid, block, smem, st>>>(a, sp);
+  if (smem_scene && tc < c.T) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<true, true><<<grid, block, smem, st>>>(a, sp);
   } else if (smem_scene) {
-    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    k_score_stream<true, 5><<<grid, block, smem, st>>>(a, sp);
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<true, false><<<grid, block, smem, st>>>(a, sp);
   } else {
-    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    k_score_stream<false, 4><<<grid, block, smem, st>>>(a, sp);
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream<false, false><<<grid, block, smem, st>>>(a, sp);
   }
   PSTL_LAUNCH_CHECK();
   *took = 1;
@@ -574,11 +571,14 @@ static int launch_score_stream_bwd(ScoreArgs& a, pstl_program_t const* progs, cu
   }
   a.tc = smem_scene ? tc : c.T;
   const int grid = pstl_ceil_div(a.N, block);
-  if (smem_scene) {
-    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    k_score_stream_bwd<true><<<grid, block, tile_bytes, st>>>(a, sp);
+  if (smem_scene && tc < c.T) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream_bwd<true, true><<<grid, block, tile_bytes, st>>>(a, sp);
+  } else if (smem_scene) {
+    PSTL_CUDA(cudaFuncSetAttribute(k_score_stream_bwd<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    k_score_stream_bwd<true, false><<<grid, block, tile_bytes, st>>>(a, sp);
   } else {
-    k_score_stream_bwd<false><<<grid, block, 0, st>>>(a, sp);
+    k_score_stream_bwd<false, false><<<grid, block, 0, st>>>(a, sp);
   }
   PSTL_LAUNCH_CHECK();
   *took = 1;
