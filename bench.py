@@ -49,10 +49,11 @@ def parse():
 
 
 def measured_traffic(chains):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json);
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r2_traffic.json);
     None when the workload differs from the captured one."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        name = "r2_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_traffic.json")) else "r1_traffic.json"
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             t = json.load(f)["k_denoiser_tc"]
         return t["dram_read_bytes"] + t["dram_write_bytes"] if t["chains"] == chains else None
     except Exception:
@@ -569,7 +570,7 @@ def main():
                                     "the graph-replay region", src)}}
     if extra:
         line["extra"] = extra
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:  # the CPU port is timed at N=1 only (the scaling runs do not repeat it)
         n, times = oracle_batch_time(a.cpu_scenes, 3)
         best = min(times[1:]) if len(times) > 1 else times[0]
         line["cpu_baseline"] = {"value": n / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
