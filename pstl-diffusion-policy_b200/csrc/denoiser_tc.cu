@@ -64,6 +64,8 @@ struct TcState {
   uint8_t* image_r;  // same for rect_net (RefineNet head), or null
   uint8_t* image2;   // pair-engine layout of policy_net (two per-rank halves, denoiser_tc2.cuh)
   uint8_t* image2_r; // same for rect_net, or null
+  uint8_t* image3;   // split-operand (hi | lo) pair images of policy_net (denoiser_tc3.cuh), PSTL_PRECISION_BF16X3 handles only
+  uint8_t* image3_r;
   float* zeros;      // 256 zeros: the "time" bias row of the RefineNet pass
   int sm_count;
 };
@@ -686,6 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 }  // namespace
 
 #include "denoiser_tc2.cuh"
+#include "denoiser_tc3.cuh"
 
 // (re)build the bf16 weight images from the handle's current fp32 weights: no allocation, no synchronisation
 int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st) {
@@ -695,11 +698,19 @@ int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st) {
   PSTL_LAUNCH_CHECK();
   k_build_image2<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image2);
   PSTL_LAUNCH_CHECK();
+  if (s->image3) {
+    k_build_image3<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image3);
+    PSTL_LAUNCH_CHECK();
+  }
   if (s->image_r) {
     k_build_image<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_r);
     PSTL_LAUNCH_CHECK();
     k_build_image2<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image2_r);
     PSTL_LAUNCH_CHECK();
+    if (s->image3_r) {
+      k_build_image3<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image3_r);
+      PSTL_LAUNCH_CHECK();
+    }
   }
   return PSTL_OK;
 }
@@ -719,12 +730,16 @@ int pstl_tc_create(pstl_denoiser* d) {
   }
   TcState* s = new TcState();
   s->sm_count = sms;
-  s->image = s->image_r = s->image2 = s->image2_r = nullptr;
+  s->image = s->image_r = s->image2 = s->image2_r = s->image3 = s->image3_r = nullptr;
   s->zeros = nullptr;
   PSTL_CUDA(cudaMalloc(&s->image, kWeightBytes));
   PSTL_CUDA(cudaMemset(s->image, 0, kWeightBytes));
   PSTL_CUDA(cudaMalloc(&s->image2, 2 * k2WeightBytes));
   PSTL_CUDA(cudaMemset(s->image2, 0, 2 * k2WeightBytes));
+  if (d->precision == PSTL_PRECISION_BF16X3) {
+    PSTL_CUDA(cudaMalloc(&s->image3, 4 * k2WeightBytes));
+    PSTL_CUDA(cudaMemset(s->image3, 0, 4 * k2WeightBytes));
+  }
   PSTL_CUDA(cudaMalloc(&s->zeros, kH * sizeof(float)));
   PSTL_CUDA(cudaMemset(s->zeros, 0, kH * sizeof(float)));
   if (d->r1p && d->w.rect_hidden == kH) {
@@ -732,6 +747,10 @@ int pstl_tc_create(pstl_denoiser* d) {
     PSTL_CUDA(cudaMemset(s->image_r, 0, kWeightBytes));
     PSTL_CUDA(cudaMalloc(&s->image2_r, 2 * k2WeightBytes));
     PSTL_CUDA(cudaMemset(s->image2_r, 0, 2 * k2WeightBytes));
+    if (d->precision == PSTL_PRECISION_BF16X3) {
+      PSTL_CUDA(cudaMalloc(&s->image3_r, 4 * k2WeightBytes));
+      PSTL_CUDA(cudaMemset(s->image3_r, 0, 4 * k2WeightBytes));
+    }
   }
   d->tc = s;
   int rc = pstl_tc_refresh(d, nullptr);
@@ -739,6 +758,7 @@ int pstl_tc_create(pstl_denoiser* d) {
   PSTL_CUDA(cudaDeviceSynchronize());
   PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
   PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes + 1024));
+  PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemBytes + 1024));
   d->tc = s;
   return PSTL_OK;
 }
@@ -750,6 +770,8 @@ void pstl_tc_destroy(pstl_denoiser* d) {
   cudaFree(s->image_r);
   cudaFree(s->image2);
   cudaFree(s->image2_r);
+  cudaFree(s->image3);
+  cudaFree(s->image3_r);
   cudaFree(s->zeros);
   delete s;
   d->tc = nullptr;
@@ -769,7 +791,21 @@ static int tc_engine_for(const TcState* s, int engine, int N, int rows_per_scene
   return 1;
 }
 
-static int tc_launch(const TcState* s, int engine, TcArgs& a, int rows_per_scene, const uint8_t* image1, const uint8_t* image2, cudaStream_t st) {
+static bool tc_pair_fits(const TcState* s, int rows_per_scene) {
+  return (k2TileM + rows_per_scene - 1) / rows_per_scene + 1 <= kMaxClasses && s->sm_count >= 2;
+}
+
+static int tc_launch(const TcState* s, int engine, TcArgs& a, int rows_per_scene, const uint8_t* image1, const uint8_t* image2,
+                     const uint8_t* image3, cudaStream_t st) {
+  if (image3) {  // PSTL_PRECISION_BF16X3: the split-operand pair engine
+    PSTL_CHECK_ARG(tc_pair_fits(s, rows_per_scene), "rows_per_scene too small for the split-operand tcgen05 tile");
+    a.image = image3;
+    const int n_tiles = (a.N + k2TileM - 1) / k2TileM;
+    const int pairs = n_tiles < s->sm_count / 2 ? n_tiles : s->sm_count / 2;
+    k_denoiser_tc3<<<2 * pairs, kThreads, k3SmemBytes + 1024, st>>>(a);
+    PSTL_LAUNCH_CHECK();
+    return PSTL_OK;
+  }
   if (tc_engine_for(s, engine, a.N, rows_per_scene) == 2) {
     a.image = image2;
     const int n_tiles = (a.N + k2TileM - 1) / k2TileM;
@@ -812,7 +848,7 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   if (getenv("PSTL_TC_DEBUG")) { cudaMalloc(&dbg, 48 * sizeof(long long)); cudaMemset(dbg, 0, 48 * sizeof(long long)); }
   a.dbg = dbg;
 #endif
-  int rc = tc_launch(s, d->tc_engine, a, rows_per_scene, s->image, s->image2, st);
+  int rc = tc_launch(s, d->tc_engine, a, rows_per_scene, s->image, s->image2, s->image3, st);
 #ifdef PSTL_TC_DEBUG
   if (dbg) {
     cudaStreamSynchronize(st);
@@ -852,7 +888,9 @@ int pstl_tc_refine(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   a.N = N; a.rows_per_scene = rows_per_scene; a.steps = 2; a.first_step = 0; a.last_step = 0;  // one pass, ct row 0
   a.clip = clip_rect; a.w_max = w_max; a.a_max = a_max;
   a.refine = 1; a.u0 = u0; a.scores = scores; a.out = out;
-  return tc_launch(s, d->tc_engine, a, rows_per_scene, s->image_r, s->image2_r, st);
+  return tc_launch(s, d->tc_engine, a, rows_per_scene, s->image_r, s->image2_r, s->image3_r, st);
 }
+
+bool pstl_tc_fits(pstl_denoiser* d, int rows_per_scene) { return d->tc && tc_pair_fits((TcState*)d->tc, rows_per_scene); }
 
 bool pstl_tc_has_refine(pstl_denoiser* d) { return d->tc && ((TcState*)d->tc)->image_r; }

@@ -102,3 +102,55 @@ def test_pair_engine_refinenet_head():
     torch.cuda.synchronize()
     assert torch.equal(outs[2][scores >= 0], u0[scores >= 0])
     assert _err(outs[2], outs[1]) < 5e-3, _err(outs[2], outs[1])
+
+
+# ------------------------------------------------------------------------------------------
+# PSTL_PRECISION_BF16X3: split-operand pair engine (csrc/denoiser_tc3.cuh) — the fp32 bound of the north star (1e-5)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bs,S_,steps", [(2, 16, 2), (3, 16, 100), (24, 64, 100), (55, 64, 30)])
+def test_bf16x3_sampler_meets_the_fp32_bound(bs, S_, steps):
+    """same injected z: the final iterate of the split-operand tcgen05 engine vs the fp32 SIMT chain, 1e-5 of the control
+    range on every element ((55, 64, 30): 10,560 rows, a ragged last tile)."""
+    a = _sample(bs, S_, steps, 4242, engine=0, precision="bf16x3")[0]
+    c = _sample(bs, S_, steps, 4242, engine=0, precision="fp32")[0]
+    assert torch.isfinite(a).all()
+    assert _err(a, c) < 1e-5, _err(a, c)
+
+
+def test_bf16x3_philox_stream_and_kept_iterates():
+    """in-kernel Philox: the split-operand engine draws the stream of the bf16 engines; its five kept iterates agree with
+    the one-SM bf16 engine's inside the bf16 bound (and are not bit-identical: the arithmetic differs)"""
+    ra = _sample(55, 64, 100, 7, engine=0, precision="bf16x3", inject=False, keep=5)
+    rb = _sample(55, 64, 100, 7, engine=1, precision="bf16", inject=False, keep=5)
+    ka, kb = ra[-1].stacked_last(5), rb[-1].stacked_last(5)
+    assert torch.isfinite(ka).all() and torch.equal(ka[-1], ra[0])
+    for j in range(5):
+        assert _err(ka[j], kb[j]) < 2e-2, (j, _err(ka[j], kb[j]))
+    assert not torch.equal(ka, kb)
+
+
+def test_bf16x3_refinenet_head_meets_the_fp32_bound():
+    """Net.rect_forward (reference nusc_model.py:209-233): split-operand engine vs the fp32 SIMT kernels, 1e-5"""
+    bs, S_, nt = 12, 64, 20
+    W = synthetic.make_weights(1007, nt=nt)
+    g = torch.Generator().manual_seed(77)
+    N = bs * S_ * 3
+    u0 = ((torch.rand(N, nt, 2, generator=g) * 2 - 1) * torch.tensor([0.45, 4.5])).cuda()
+    scores = (torch.rand(N, generator=g) - 0.7).cuda()
+    batch = cuda(synthetic.make_scene_batch(bs, nt=nt, n_randoms=S_, seed=5))
+    stlp = batch["pre_stlp"].reshape(bs, S_, 3, 6)[:, 0:1].repeat(1, S_, 1, 1).reshape(N, 6)
+    hl = torch.tensor([0.0, 1.0, 2.0], device="cuda").repeat(bs * S_)[:, None]
+    outs = {}
+    for prec in ("fp32", "bf16x3"):
+        args = NT.default_args(n_randoms=S_, sampling_size=S_, precision=prec)
+        net = Net(args)
+        net.load_state_dict(W)
+        net = net.cuda()
+        with torch.no_grad():
+            feat = net.encode_feat(batch)
+        dense = feat.reshape(bs, 1, -1).expand(bs, S_ * 3, feat.shape[-1]).reshape(N, -1)
+        dense._pstl_scene_feat = feat
+        outs[prec] = net.rect_forward(dense, hl, stlp, u0, scores)
+    torch.cuda.synchronize()
+    assert torch.equal(outs["bf16x3"][scores >= 0], u0[scores >= 0])
+    assert _err(outs["bf16x3"], outs["fp32"]) < 1e-5, _err(outs["bf16x3"], outs["fp32"])

@@ -249,9 +249,12 @@ def _run_pipeline(flags, seed, **over):
     return out, net, batch, args
 
 
-def test_pipeline_ours_golden(golden_dir):
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_pipeline_ours_golden(golden_dir, precision):
+    """fp32: the SIMT chain.  bf16x3: the split-operand tcgen05 engine (csrc/denoiser_tc3.cuh) — the same 1e-5 bound against
+    the unmodified reference's run."""
     G = np.load(os.path.join(golden_dir, "pipeline.npz"))
-    out, net, batch, args = _run_pipeline(NT.OURS_FLAGS, 2001)
+    out, net, batch, args = _run_pipeline(NT.OURS_FLAGS, 2001, precision=precision)
     close(net.encode_feat(cuda(batch)), G["ours|feature"], what="feature")
     close(out["final_iterate"], G["ours|final_iterate"], what="final_iterate")
     close(out["cand_scores"], G["ours|cand_scores"], what="cand_scores")
