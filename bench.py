@@ -249,14 +249,14 @@ def extra_scene_indexed(T, K, dev, seed, scenes=5209, base=256):
     return out
 
 
-def extra_pipeline(flags, scenes, dev, W, what, cpu_scenes, cpu_kw, reps=3):
+def extra_pipeline(flags, scenes, dev, W, what, cpu_scenes, cpu_kw, reps=3, precision="bf16"):
     """a pipeline config under one captured CUDA graph: ms per batch, chains/s, CPU port on a bounded sample"""
     from pstl_b200 import synthetic
     from pstl_b200 import nusc_train as NT
     from pstl_b200.nusc_model import Net
     from oracle import pstl_oracle as O
     S, nt = 64, 20
-    args = NT.default_args(flags, precision="bf16")
+    args = NT.default_args(flags, precision=precision)
     net = Net(args)
     net.load_state_dict(W)
     net = net.to(dev)
@@ -267,7 +267,7 @@ def extra_pipeline(flags, scenes, dev, W, what, cpu_scenes, cpu_kw, reps=3):
     n = scenes * S * 3
     acc = float(runner(b)["acc"])
     out = {"workload": what, "scenes": scenes, "chains": n, "multi_cands": args.multi_cands, "n_rolls": args.n_rolls,
-           "guidance": bool(args.guidance), "ms": ms, "chains_per_s": n / ms * 1e3, "acc": acc,
+           "guidance": bool(args.guidance), "ms": ms, "chains_per_s": n / ms * 1e3, "acc": acc, "precision": precision,
            "launch": "CUDA graph replay (NT.CapturedPipeline)", "l2": "inputs + state > L2"}
     if cpu_scenes:
         torch.set_num_threads(os.cpu_count() or 1)
@@ -294,6 +294,14 @@ def run_extras(a, world, rank, dev, net, W):
         ex["config1"] = extra_dense(4096, 20, 8, dev, hbm_peak, 1008, cpu_rows=4096, flush=flush)
         ex["config1_at_262144_rows"] = extra_dense(262144, 20, 8, dev, hbm_peak, 1008, cpu_rows=0)
         del flush
+        # the headline workload at the reference's own precision: split-operand tcgen05 denoiser (PSTL_PRECISION_F16X3,
+        # inside the 1e-5 fp32 bound: tests/test_gpu_parity.py::test_pipeline_ours_golden[f16x3]), fp32 everything else
+        c2 = extra_pipeline(list(NT.OURS_FLAGS), a.scenes, dev, W,
+                            "config2 at fp32-grade precision: the headline workload with the split-operand (f16x3) tcgen05 "
+                            "denoiser, 1e-5 parity with the reference's fp32 run", cpu_scenes=0, cpu_kw={}, reps=5,
+                            precision="f16x3")
+        c2["flops_per_chain_minimal"] = FLOP_PER_CHAIN
+        ex["config2_fp32_grade"] = c2
         ex["config3"] = extra_pipeline(NT.GUIDANCE_FLAGS, 4096, dev, W,
                                        "config3: Ours+guidance (last 10 reverse steps, 1 iteration, lr 0.01), K=10, n_rolls 3",
                                        cpu_scenes=8, cpu_kw=dict(K=10, n_rolls=3, guidance=dict(before=10, lr=0.01, thres=0.0005, niters=1)))

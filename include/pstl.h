@@ -169,10 +169,11 @@ int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_view* scene
 #define PSTL_MAX_STEPS 1024   /* most diffusion steps a sampler call takes (workspace's per-step table) */
 #define PSTL_PRECISION_FP32 0 /* SIMT fp32, 1e-5 parity mode                       */
 #define PSTL_PRECISION_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate (2e-2)     */
-#define PSTL_PRECISION_BF16X3 2 /* tcgen05, every operand as two bf16 pieces and every product as three MMAs (hi.hi +
-                                 * lo.hi + hi.lo), fp32 accumulate: fp32-grade results (inside the 1e-5 bound of
-                                 * PSTL_PRECISION_FP32) at tensor-core speed.  The sampler and the RefineNet head use it;
-                                 * the training entry points of such a handle run the fp32 SIMT kernels.            */
+#define PSTL_PRECISION_F16X3 2 /* tcgen05, every operand as two fp16 pieces (22 mantissa bits) and every product as three
+                                * MMAs (hi.hi + lo.hi + hi.lo), fp32 accumulate: the accuracy of fp32 arithmetic (inside the
+                                * 1e-5 bound of PSTL_PRECISION_FP32) at tensor-core speed; |weights|, |activations| < 65,504.
+                                * The sampler and the RefineNet head use it; the training entry points of such a handle
+                                * run the fp32 SIMT kernels.                                                      */
 
 typedef struct {
   /* device pointers to state_dict tensors (row-major (out,in) like nn.Linear) */

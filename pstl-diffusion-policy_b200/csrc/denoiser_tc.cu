@@ -64,7 +64,7 @@ struct TcState {
   uint8_t* image_r;  // same for rect_net (RefineNet head), or null
   uint8_t* image2;   // pair-engine layout of policy_net (two per-rank halves, denoiser_tc2.cuh)
   uint8_t* image2_r; // same for rect_net, or null
-  uint8_t* image3;   // split-operand (hi | lo) pair images of policy_net (denoiser_tc3.cuh), PSTL_PRECISION_BF16X3 handles only
+  uint8_t* image3;   // split-operand (hi | lo) pair images of policy_net (denoiser_tc3.cuh), PSTL_PRECISION_F16X3 handles only
   uint8_t* image3_r;
   float* zeros;      // 256 zeros: the "time" bias row of the RefineNet pass
   int sm_count;
@@ -736,7 +736,7 @@ int pstl_tc_create(pstl_denoiser* d) {
   PSTL_CUDA(cudaMemset(s->image, 0, kWeightBytes));
   PSTL_CUDA(cudaMalloc(&s->image2, 2 * k2WeightBytes));
   PSTL_CUDA(cudaMemset(s->image2, 0, 2 * k2WeightBytes));
-  if (d->precision == PSTL_PRECISION_BF16X3) {
+  if (d->precision == PSTL_PRECISION_F16X3) {
     PSTL_CUDA(cudaMalloc(&s->image3, 4 * k2WeightBytes));
     PSTL_CUDA(cudaMemset(s->image3, 0, 4 * k2WeightBytes));
   }
@@ -747,7 +747,7 @@ int pstl_tc_create(pstl_denoiser* d) {
     PSTL_CUDA(cudaMemset(s->image_r, 0, kWeightBytes));
     PSTL_CUDA(cudaMalloc(&s->image2_r, 2 * k2WeightBytes));
     PSTL_CUDA(cudaMemset(s->image2_r, 0, 2 * k2WeightBytes));
-    if (d->precision == PSTL_PRECISION_BF16X3) {
+    if (d->precision == PSTL_PRECISION_F16X3) {
       PSTL_CUDA(cudaMalloc(&s->image3_r, 4 * k2WeightBytes));
       PSTL_CUDA(cudaMemset(s->image3_r, 0, 4 * k2WeightBytes));
     }
@@ -797,7 +797,7 @@ static bool tc_pair_fits(const TcState* s, int rows_per_scene) {
 
 static int tc_launch(const TcState* s, int engine, TcArgs& a, int rows_per_scene, const uint8_t* image1, const uint8_t* image2,
                      const uint8_t* image3, cudaStream_t st) {
-  if (image3) {  // PSTL_PRECISION_BF16X3: the split-operand pair engine
+  if (image3) {  // PSTL_PRECISION_F16X3: the split-operand pair engine
     PSTL_CHECK_ARG(tc_pair_fits(s, rows_per_scene), "rows_per_scene too small for the split-operand tcgen05 tile");
     a.image = image3;
     const int n_tiles = (a.N + k2TileM - 1) / k2TileM;

@@ -1,15 +1,17 @@
-// denoiser_tc3.cuh — the fp32-GRADE tcgen05 engine of the DDPM reverse loop (PSTL_PRECISION_BF16X3): every operand is
-// carried as TWO bf16 pieces (x = x_hi + x_lo, 16 mantissa bits) and every product as three tensor-core MMAs
-// (hi.hi + lo.hi + hi.lo, the lo.lo term is below 2^-17 of the product) with fp32 accumulation in TMEM.  Emulated on the
-// CPU over the whole 99-step chain the final controls deviate from an fp64 run by 2.4e-6 of the
-// control range — inside the north-star's 1e-5 fp32 bound, where plain bf16 operands sit at 1e-3 — so this engine
-// replaces the fp32 CUDA-core sampler (156 ms per 196,608 chains) at tensor-core speed.
+// denoiser_tc3.cuh — the fp32-GRADE tcgen05 engine of the DDPM reverse loop (PSTL_PRECISION_F16X3): every operand is
+// carried as TWO fp16 pieces (x = x_hi + x_lo: 2 x 11 = 22 mantissa bits) and every product as three tensor-core MMAs
+// (hi.hi + lo.hi + hi.lo; the lo.lo term is below 2^-22 of the product) with fp32 accumulation in TMEM.  Emulated on
+// the CPU over the whole 99-step chain the final controls deviate from an fp64 run by 5.4e-7 of
+// the control range — exactly what fp32 arithmetic deviates by (bf16 pieces: 2.4e-6; plain bf16 operands: 1e-3) — so
+// this engine replaces the fp32 CUDA-core sampler (156 ms per 196,608 chains) at tensor-core speed.
+// Range: a piece is an fp16 number, so |activation|, |weight| must stay below 65,504 (conversions saturate instead of
+// producing inf); pieces below 6e-5 are fp16 subnormals (absolute error <= 3e-8, irrelevant next to O(1) sums).
 // Included by denoiser_tc.cu after denoiser_tc2.cuh (cluster / pair helpers).
 //
 // Layout: the CTA pair of denoiser_tc2.cuh (tcgen05.mma.cta_group::2, each CTA holds half of N of every weight matrix,
 // now as a hi image and a lo image: 2 x 92 KB of shared memory) with the TS operand form of k_denoiser_tc (activations
 // never leave TMEM).  One 256-row tile per pair; per CTA
-//   TMEM  D [0,256) fp32 | H_hi [256,384) | H_lo [384,512)   (bf16 pairs; H2 overwrites H1 in place once layer 2 has
+//   TMEM  D [0,256) fp32 | H_hi [256,384) | H_lo [384,512)   (fp16 pairs; H2 overwrites H1 in place once layer 2 has
 //         retired); the layer-1 operand X = [x 40 | hl stlp 0 | one-hot class pairs] aliases H_hi/H_lo[0,32) (dead once
 //         layer 1 has retired), layer 3's 48 columns alias D[0,48).
 //   Biases: layer 1 through the one-hot K-step against the per-step bias columns (W1'_hi columns 48..63, (hi, lo) pairs
@@ -18,12 +20,13 @@
 // With H, D and X all in TMEM there is no room for N-half pipelining: the layers run back to back (L1 -> E1 -> L2 ->
 // E2 -> L3 -> E3), layer 3 starting on the first half of H2; the noise of the step is drawn under layer 2.
 #pragma once
+#include <cuda_fp16.h>
 
 namespace {
 
 constexpr int k3OffWhi = 0;
 constexpr int k3OffWlo = k2WeightBytes;
-constexpr int k3OffB2 = 2 * k2WeightBytes;            // [128 n x 16 k] bf16, K-major no-swizzle: k 0..2 = (hi, mid, lo) of b2
+constexpr int k3OffB2 = 2 * k2WeightBytes;            // [128 n x 16 k] fp16, K-major no-swizzle: k 0..2 = (hi, mid, lo) of b2
 constexpr int k3OffOnes = k3OffB2 + 128 * 16 * 2;      // [128 m x 16 k]: k 0..2 = 1
 constexpr int k3OffB3 = k3OffOnes + 128 * 16 * 2;
 constexpr int k3OffBar = k3OffB3 + 64 * 4;
@@ -41,11 +44,23 @@ __device__ __forceinline__ void mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 
-// (hi, lo) bf16 images of a pair of fp32 values: hi = rn(v), lo = rn(v - hi); packed {second:16 | first:16}
+// kind::f16 instruction descriptor with fp16 A and B (format code 0), D = f32, both K-major
+__device__ __forceinline__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// (hi, lo) fp16 images of a pair of fp32 values: hi = rn(v) (saturating), lo = rn(v - hi); packed {second:16 | first:16}
 __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  hi = pack_bf16(v0, v1);
-  const float r0 = v0 - __uint_as_float(hi << 16), r1 = v1 - __uint_as_float(hi & 0xffff0000u);
-  lo = pack_bf16(r0, r1);
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float r0 = v0 - f.x, r1 = v1 - f.y;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ __half half_sat(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+// (hi, lo) of one value packed {lo:16 | hi:16}: hi at the lower address
+__device__ __forceinline__ uint32_t split_f16(float v) {
+  const __half h = half_sat(v);
+  const __half l = half_sat(v - __half2float(h));
+  return (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
 }
 
 // pair images: rank r at r * 2 * k2WeightBytes: [hi image | lo image], each in the layout of k_build_image2
@@ -53,11 +68,11 @@ __global__ void k_build_image3(const float* __restrict__ w1p, int kin, const flo
                                const float* __restrict__ w3, int n3, uint8_t* __restrict__ img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   auto put = [&](int rank, int off, float v) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const __half h = half_sat(v);
+    const __half l = half_sat(v - __half2float(h));
     uint8_t* base = img + (size_t)rank * 2 * k2WeightBytes + off;
-    *reinterpret_cast<__nv_bfloat16*>(base) = h;
-    *reinterpret_cast<__nv_bfloat16*>(base + k2WeightBytes) = l;
+    *reinterpret_cast<__half*>(base) = h;
+    *reinterpret_cast<__half*>(base + k2WeightBytes) = l;
   };
   if (i < 256 * 64) {
     const int n = i / 64, k = i % 64;
@@ -109,15 +124,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_denoi
   // b2 image of this CTA's half of N ((hi, mid, lo) in k = 0..2) and the ones tile it is multiplied with
   for (int n = threadIdx.x; n < 128; n += kThreads) {
     const float v = a.b2[rank * 128 + n];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const float r1 = v - __bfloat162float(h);
-    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
-    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    const __half h = half_sat(v);
+    const float r1 = v - __half2float(h);
+    const __half m = half_sat(r1);
+    const __half l = half_sat(r1 - __half2float(m));
+    const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      *reinterpret_cast<__nv_bfloat16*>(smem + k3OffB2 + flat16_off(n, k)) = k == 0 ? h : (k == 1 ? m : (k == 2 ? l : zero));
-      *reinterpret_cast<__nv_bfloat16*>(smem + k3OffOnes + flat16_off(n, k)) = k < 3 ? one : zero;
+      *reinterpret_cast<__half*>(smem + k3OffB2 + flat16_off(n, k)) = k == 0 ? h : (k == 1 ? m : (k == 2 ? l : zero));
+      *reinterpret_cast<__half*>(smem + k3OffOnes + flat16_off(n, k)) = k < 3 ? one : zero;
     }
   }
   for (int i = threadIdx.x; i < 64; i += kThreads) b3s[i] = i < 40 ? a.b3[i] : 0.f;
@@ -155,7 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_denoi
           const float* src = a.cscene + (size_t)(scene0 + c) * kH + rank * 128;
 #pragma unroll
           for (int n = lane; n < 128; n += 32)
-            *reinterpret_cast<uint32_t*>(smem + k3OffWhi + k2OffW1 + sw128_off(n, 48 + 2 * c)) = split_bf16(__ldg(src + n) + __ldg(ctr + n));
+            *reinterpret_cast<uint32_t*>(smem + k3OffWhi + k2OffW1 + sw128_off(n, 48 + 2 * c)) = split_f16(__ldg(src + n) + __ldg(ctr + n));
         }
         fence_proxy_async();
         __syncwarp();
@@ -166,7 +181,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_denoi
     if (rank == 0) {
       // ================= MMA issuer (leader CTA) =================
       mbar_wait(bar(k3BW), 0);
-      constexpr uint32_t idN = make_idesc(k2TileM, kH), id3 = make_idesc(k2TileM, kN3);
+      constexpr uint32_t idN = make_idesc_f16(k2TileM, kH), id3 = make_idesc_f16(k2TileM, kN3);
       const uint64_t dW1h = make_desc(sbase + k3OffWhi + k2OffW1), dW1l = make_desc(sbase + k3OffWlo + k2OffW1);
       const uint64_t dB2 = make_desc_flat(sbase + k3OffB2, 128, 256), dOnes = make_desc_flat(sbase + k3OffOnes, 128, 256);
       uint32_t it = 0;
@@ -190,7 +205,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_denoi
           mbar_spin_cluster(bar(k3BH1), ph);
           tc_fence_after();
           if (elect_one()) {
-            mma2_ss(tmem + k3ColD, dOnes, dB2, idN, 0);  // D = b2 (three bf16 pieces): the only shared-memory A operand
+            mma2_ss(tmem + k3ColD, dOnes, dB2, idN, 0);  // D = b2 (three fp16 pieces): the only shared-memory A operand
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               const uint64_t o = (uint64_t)((k & 3) * 2);
@@ -271,7 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_denoi
         if (ch == 1) {
           uint32_t oh[8], zz[8];
 #pragma unroll
-          for (int c = 0; c < kMaxClasses; ++c) { oh[c] = (c == cls) ? 0x3F803F80u : 0u; zz[c] = 0u; }
+          for (int c = 0; c < kMaxClasses; ++c) { oh[c] = (c == cls) ? 0x3C003C00u : 0u; zz[c] = 0u; }
           TMEM_ST_X4(tmem + lane_addr + k3ColHhi + 20, pch);
           TMEM_ST_X8(tmem + lane_addr + k3ColHhi + 24, oh);
           TMEM_ST_X4(tmem + lane_addr + k3ColHlo + 20, pcl);
@@ -284,12 +299,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_denoi
       for (int s = 0; s < S; ++s, ++it) {
         const uint32_t ph = it & 1u;
         const int i = a.first_step - s;
-        // ---- layers 1 and 2: D -> relu -> (hi, lo) bf16 images -> H_hi / H_lo ----
+        // ---- layers 1 and 2: D -> relu -> (hi, lo) fp16 images -> H_hi / H_lo ----
 #pragma unroll 1
         for (int layer = 0; layer < 2; ++layer) {
           mbar_spin(bar(layer == 0 ? k3BD1 : k3BD2), ph);
           tc_fence_after();
-          // this thread: columns [128 p + 64 ch, +64) in part p (bf16 pairs: TMEM columns [64 p + 32 ch, +32) of H_hi / H_lo)
+          // this thread: columns [128 p + 64 ch, +64) in part p (fp16 pairs: TMEM columns [64 p + 32 ch, +32) of H_hi / H_lo)
           uint32_t ra[16], rb[16];
           const uint32_t dsrc = tmem + lane_addr + k3ColD + ch * 64;
           const uint32_t hdst = tmem + lane_addr + ch * 32;

@@ -105,22 +105,22 @@ def test_pair_engine_refinenet_head():
 
 
 # ------------------------------------------------------------------------------------------
-# PSTL_PRECISION_BF16X3: split-operand pair engine (csrc/denoiser_tc3.cuh) — the fp32 bound of the north star (1e-5)
+# PSTL_PRECISION_F16X3: split-operand pair engine (csrc/denoiser_tc3.cuh) — the fp32 bound of the north star (1e-5)
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("bs,S_,steps", [(2, 16, 2), (3, 16, 100), (24, 64, 100), (55, 64, 30)])
-def test_bf16x3_sampler_meets_the_fp32_bound(bs, S_, steps):
+def test_f16x3_sampler_meets_the_fp32_bound(bs, S_, steps):
     """same injected z: the final iterate of the split-operand tcgen05 engine vs the fp32 SIMT chain, 1e-5 of the control
     range on every element ((55, 64, 30): 10,560 rows, a ragged last tile)."""
-    a = _sample(bs, S_, steps, 4242, engine=0, precision="bf16x3")[0]
+    a = _sample(bs, S_, steps, 4242, engine=0, precision="f16x3")[0]
     c = _sample(bs, S_, steps, 4242, engine=0, precision="fp32")[0]
     assert torch.isfinite(a).all()
     assert _err(a, c) < 1e-5, _err(a, c)
 
 
-def test_bf16x3_philox_stream_and_kept_iterates():
+def test_f16x3_philox_stream_and_kept_iterates():
     """in-kernel Philox: the split-operand engine draws the stream of the bf16 engines; its five kept iterates agree with
     the one-SM bf16 engine's inside the bf16 bound (and are not bit-identical: the arithmetic differs)"""
-    ra = _sample(55, 64, 100, 7, engine=0, precision="bf16x3", inject=False, keep=5)
+    ra = _sample(55, 64, 100, 7, engine=0, precision="f16x3", inject=False, keep=5)
     rb = _sample(55, 64, 100, 7, engine=1, precision="bf16", inject=False, keep=5)
     ka, kb = ra[-1].stacked_last(5), rb[-1].stacked_last(5)
     assert torch.isfinite(ka).all() and torch.equal(ka[-1], ra[0])
@@ -129,7 +129,7 @@ def test_bf16x3_philox_stream_and_kept_iterates():
     assert not torch.equal(ka, kb)
 
 
-def test_bf16x3_refinenet_head_meets_the_fp32_bound():
+def test_f16x3_refinenet_head_meets_the_fp32_bound():
     """Net.rect_forward (reference nusc_model.py:209-233): split-operand engine vs the fp32 SIMT kernels, 1e-5"""
     bs, S_, nt = 12, 64, 20
     W = synthetic.make_weights(1007, nt=nt)
@@ -141,7 +141,7 @@ def test_bf16x3_refinenet_head_meets_the_fp32_bound():
     stlp = batch["pre_stlp"].reshape(bs, S_, 3, 6)[:, 0:1].repeat(1, S_, 1, 1).reshape(N, 6)
     hl = torch.tensor([0.0, 1.0, 2.0], device="cuda").repeat(bs * S_)[:, None]
     outs = {}
-    for prec in ("fp32", "bf16x3"):
+    for prec in ("fp32", "f16x3"):
         args = NT.default_args(n_randoms=S_, sampling_size=S_, precision=prec)
         net = Net(args)
         net.load_state_dict(W)
@@ -152,5 +152,5 @@ def test_bf16x3_refinenet_head_meets_the_fp32_bound():
         dense._pstl_scene_feat = feat
         outs[prec] = net.rect_forward(dense, hl, stlp, u0, scores)
     torch.cuda.synchronize()
-    assert torch.equal(outs["bf16x3"][scores >= 0], u0[scores >= 0])
-    assert _err(outs["bf16x3"], outs["fp32"]) < 1e-5, _err(outs["bf16x3"], outs["fp32"])
+    assert torch.equal(outs["f16x3"][scores >= 0], u0[scores >= 0])
+    assert _err(outs["f16x3"], outs["fp32"]) < 1e-5, _err(outs["f16x3"], outs["fp32"])

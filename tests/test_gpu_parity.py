@@ -249,9 +249,9 @@ def _run_pipeline(flags, seed, **over):
     return out, net, batch, args
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
 def test_pipeline_ours_golden(golden_dir, precision):
-    """fp32: the SIMT chain.  bf16x3: the split-operand tcgen05 engine (csrc/denoiser_tc3.cuh) — the same 1e-5 bound against
+    """fp32: the SIMT chain.  f16x3: the split-operand tcgen05 engine (csrc/denoiser_tc3.cuh) — the same 1e-5 bound against
     the unmodified reference's run."""
     G = np.load(os.path.join(golden_dir, "pipeline.npz"))
     out, net, batch, args = _run_pipeline(NT.OURS_FLAGS, 2001, precision=precision)
