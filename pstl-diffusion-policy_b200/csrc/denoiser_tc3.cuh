@@ -1,8 +1,8 @@
 // denoiser_tc3.cuh — the fp32-GRADE tcgen05 engine of the DDPM reverse loop (PSTL_PRECISION_F16X3): every operand is
 // carried as TWO fp16 pieces (x = x_hi + x_lo: 2 x 11 = 22 mantissa bits) and every product as three tensor-core MMAs
 // (hi.hi + lo.hi + hi.lo; the lo.lo term is below 2^-22 of the product) with fp32 accumulation in TMEM.  Emulated on
-// the CPU over the whole 99-step chain the final controls deviate from an fp64 run by 5.4e-7 of
-// the control range — exactly what fp32 arithmetic deviates by (bf16 pieces: 2.4e-6; plain bf16 operands: 1e-3) — so
+// the CPU over the whole 99-step chain the final controls deviate from an fp64 run by 6e-7 of
+// the control range — what fp32 arithmetic itself deviates by (5.4e-7; bf16 pieces: 2.4e-6; plain bf16 operands: 1e-3) — so
 // this engine replaces the fp32 CUDA-core sampler (156 ms per 196,608 chains) at tensor-core speed.
 // Range: a piece is an fp16 number, so |activation|, |weight| must stay below 65,504 (conversions saturate instead of
 // producing inf); pieces below 6e-5 are fp16 subnormals (absolute error <= 3e-8, irrelevant next to O(1) sums).
