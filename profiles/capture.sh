@@ -24,6 +24,13 @@ for K in k_denoiser_tc k_score_stream; do
     $PY bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --eager > $OUT/${TAG}_ncu_${K}.log 2>&1
   ncu -i $OUT/${TAG}_${K}.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/rawpick.py "$METRICS" > $OUT/${TAG}_${K}_metrics.txt
 done
+# the split-operand (f16x3) engine and the CTA-pair bf16 engine: one sampler launch each
+for E in 3 2; do
+  KN=k_denoiser_tc$E
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${KN}\$" -s 2 -c 1 -f -o $OUT/${TAG}_${KN} \
+    $PY tests/bench_configs.py sampler 1024 $E > $OUT/${TAG}_ncu_${KN}.log 2>&1
+  ncu -i $OUT/${TAG}_${KN}.ncu-rep --page raw --csv 2>/dev/null | $PY profiles/rawpick.py "$METRICS" > $OUT/${TAG}_${KN}_metrics.txt
+done
 for CELL in "20 8" "200 64"; do
   set -- $CELL
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_score_dense -s 3 -c 1 -f -o $OUT/${TAG}_dense_T$1_K$2 \

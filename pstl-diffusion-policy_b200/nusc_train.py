@@ -215,17 +215,14 @@ def build_stl_cache(args):
 
 
 def _fused_programs(stls_cac, T):
-    """Compile the three formulas for the fused kernel; None if a leaf is an untyped lambda."""
-    key = "_pstl_fused_%d_%d" % (T, torch.cuda.current_device())
-    cache = getattr(stls_cac[0], "__dict__", {})
-    if key in cache:
-        return cache[key]
+    """Compile the three formulas for the fused kernel; None if a leaf is an untyped lambda.  Nothing is cached on the
+    formula objects: ``get_program`` keys the device programs on WHAT a formula compiles to (18 us for the driving spec),
+    so a list that shares its first formula with an earlier one, or a ListAnd edited after its first use, never sees
+    another list's programs."""
     try:
-        progs = [get_program(compile_formula(f, fused=True)[0], 0, T, 1) for f in stls_cac]
+        return [get_program(compile_formula(f, fused=True)[0], 0, T, 1) for f in stls_cac]
     except ValueError:
-        progs = None
-    cache[key] = progs
-    return progs
+        return None
 
 
 def _spec(args, w_scale=1.0, a_scale=1.0, clip_controls=0):

@@ -387,3 +387,20 @@ def test_captured_pipeline_with_guidance():
     acc0 = float(NT.sample_and_score(net, b1, stls, co, a0)["acc"])
     acc1 = float(runner(b1)["acc"])
     assert acc1 >= acc0 - 0.02, (acc0, acc1)
+
+
+def test_fused_programs_follow_the_formulas_not_the_first_object():
+    """the compiled programs used to be cached on stls_cac[0] keyed by (T, device) only, so a second list that
+    shared its first formula — or a ListAnd edited in place — silently reused the first list's programs."""
+    args = NT.default_args()
+    a = NT.build_stl_cache(args)
+    pa = NT._fused_programs(a, 20)
+    b = [a[0], a[2], a[1]]  # same first formula, the other two swapped
+    pb = NT._fused_programs(b, 20)
+    assert pb[0] is pa[0] and pb[1] is pa[2] and pb[2] is pa[1]
+    assert NT._fused_programs(a, 20)[1] is pa[1]
+    if hasattr(a[1], "lists") and len(a[1].lists) > 1:
+        import copy
+        c = [a[0], copy.copy(a[1]), a[2]]
+        c[1].lists = list(a[1].lists[:-1])  # an edited ListAnd compiles to another program
+        assert NT._fused_programs(c, 20)[1] is not pa[1]
