@@ -170,6 +170,16 @@ def test_guided_steps_golden(golden_dir):
     assert np.median(err) < 1e-5 and err.max() < args.guidance_lr * 10, (np.median(err), err.max())
 
 
+def test_guided_run_on_the_split_operand_engine(golden_dir):
+    """README "Ours+guidance" with --precision f16x3: the unguided runs and the posterior means of the guided steps come from
+    k_denoiser_tc3; the whole run is held to the bounds the fp32 path is held to above"""
+    G = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    out, net, batch, args = _pipeline(NT.GUIDANCE_FLAGS, 2002, 2, precision="f16x3")
+    a, b = npy(out["final_iterate"]), G["guide|final_iterate"]
+    err = (np.abs(a - b) / np.array([0.5, 5.0])).reshape(a.shape[0], -1).max(axis=1)
+    assert np.median(err) < 1e-5 and err.max() < args.guidance_lr * 10, (np.median(err), err.max())
+
+
 @pytest.mark.parametrize("tag,seed,extra", [("freq", 2011, ["--guidance_freq", "7"]),
                                             ("sets", 2012, ["--guidance_sets", "3", "40", "41", "--guidance_reverse"])])
 def test_guidance_triggers_golden(golden_dir, tag, seed, extra):
