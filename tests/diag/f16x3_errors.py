@@ -1,5 +1,5 @@
 """Where the split-operand (f16x3) path's error sits: per-stage worst deviation from the CPU oracle on the smoke() batch and
-a larger one, next to the fp32 SIMT path.   python tests/diag/x3_errors.py"""
+a larger one, next to the fp32 SIMT path.   python tests/diag/f16x3_errors.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
