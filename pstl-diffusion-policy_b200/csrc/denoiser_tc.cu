@@ -717,7 +717,7 @@ int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st) {
 
 int pstl_tc_create(pstl_denoiser* d) {
   if (d->w.hidden != kH || d->T2 != 40 || d->kin != 47) {
-    pstl_set_error("PSTL_PRECISION_BF16 engine is built for hidden=256, nt=20 (got hidden=%d, nt=%d)", d->w.hidden, d->w.T);
+    pstl_set_error("the tcgen05 engines (PSTL_PRECISION_BF16 / _F16X3) are built for hidden=256, nt=20 (got hidden=%d, nt=%d)", d->w.hidden, d->w.T);
     return PSTL_ERR_UNSUPPORTED;
   }
   int dev = 0, cc_major = 0, sms = 0;
