@@ -169,6 +169,8 @@ int pstl_guidance_step(pstl_program_t const* progs, const pstl_scene_view* scene
 #define PSTL_MAX_STEPS 1024   /* most diffusion steps a sampler call takes (workspace's per-step table) */
 #define PSTL_PRECISION_FP32 0 /* SIMT fp32, 1e-5 parity mode                       */
 #define PSTL_PRECISION_BF16 1 /* tcgen05 bf16 operands, fp32 accumulate (2e-2)     */
+#define PSTL_PRECISION_F16 3 /* the bf16 engine on fp16 operands: 11 mantissa bits instead of 8 at the same tensor-core rate
+                              * (measured 8x closer to the fp32 chain); |weights|, |activations| < 65,504 (saturating)  */
 #define PSTL_PRECISION_F16X3 2 /* tcgen05, every operand as two fp16 pieces (22 mantissa bits) and every product as three
                                 * MMAs (hi.hi + lo.hi + hi.lo), fp32 accumulate: the accuracy of fp32 arithmetic (inside the
                                 * 1e-5 bound of PSTL_PRECISION_FP32) at tensor-core speed; |weights|, |activations| < 65,504.

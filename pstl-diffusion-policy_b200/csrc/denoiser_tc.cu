@@ -22,6 +22,7 @@
 // layer-1 operand X aliases H2[0,32) (dead once layer 3 retired).  Warp 8: barrier init, TMEM alloc, weight load
 // and the MMA-issuing lane.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "mlp_common.cuh"
 
@@ -64,6 +65,8 @@ struct TcState {
   uint8_t* image_r;  // same for rect_net (RefineNet head), or null
   uint8_t* image2;   // pair-engine layout of policy_net (two per-rank halves, denoiser_tc2.cuh)
   uint8_t* image2_r; // same for rect_net, or null
+  uint8_t* image_h;  // fp16 operand images of the one-SM engine (PSTL_PRECISION_F16 handles only)
+  uint8_t* image_h_r;
   uint8_t* image3;   // split-operand (hi | lo) pair images of policy_net (denoiser_tc3.cuh), PSTL_PRECISION_F16X3 handles only
   uint8_t* image3_r;
   float* zeros;      // 256 zeros: the "time" bias row of the RefineNet pass
@@ -229,6 +232,36 @@ __device__ __forceinline__ uint32_t split_bf16(float v) {
   return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
 }
 
+// The one-SM engine carries its operands either as bf16 (PSTL_PRECISION_BF16: 8 mantissa bits, fp32's exponent range) or as
+// fp16 (PSTL_PRECISION_F16: 11 mantissa bits, saturating at 65,504); kind::f16 runs both at the same rate.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  uint32_t d;
+  if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_relu16(float lo, float hi) {
+  uint32_t d;
+  if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t split16(float v) {  // (hi, lo) pieces packed {lo:16 | hi:16}
+  if (F16) {
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    const __half l = __float2half_rn(v - __half2float(h));
+    return (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+  }
+  return split_bf16(v);
+}
+template <bool F16>
+__device__ __forceinline__ constexpr uint32_t make_idesc_t(int M, int N) {  // A/B format: 1 = bf16, 0 = fp16
+  return (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // byte offset of element (row, k) inside a [rows x 64] bf16 K-major SW128 block
 __host__ __device__ __forceinline__ int sw128_off(int row, int k) {
   return (row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) & 7) ^ (row & 7)) << 4) + (k & 7) * 2;
@@ -237,10 +270,14 @@ __host__ __device__ __forceinline__ int sw128_off(int row, int k) {
 // ---------------------------------------------------------------------------------------
 // weight image (run once per handle)
 // ---------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void k_build_image(const float* __restrict__ w1p, int kin, const float* __restrict__ w2,
                               const float* __restrict__ w3, int n3, uint8_t* __restrict__ img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  auto put = [&](int off, float v) { *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v); };
+  auto put = [&](int off, float v) {
+    if (F16) *reinterpret_cast<__half*>(img + off) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    else *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v);
+  };
   if (i < 256 * 64) {  // W1'
     const int n = i / 64, k = i % 64;
     put(kOffW1 + sw128_off(n, k), k < kin ? w1p[n * kin + k] : 0.f);
@@ -281,6 +318,7 @@ struct TcArgs {
   long long* dbg;       // optional clock64 timeline of one tile-step (PSTL_TC_DEBUG)
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the shared-window address of the dynamic segment is uniform: keep the 1 KB alignment arithmetic on
@@ -317,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int n = threadIdx.x; n < kH; n += kThreads) {  // layer-2 bias tile: every class pair carries (hi, lo) of b2[n]
-    const uint32_t v = split_bf16(a.b2[n]);
+    const uint32_t v = split16<F16>(a.b2[n]);
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c) *reinterpret_cast<uint32_t*>(smem + kOffB2 + flat16_off(n, 2 * c)) = v;
   }
@@ -358,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
         const float* src = a.cscene + (size_t)(scene0 + c) * kH;
 #pragma unroll
         for (int n = lane; n < kH; n += 32)
-          *reinterpret_cast<uint32_t*>(smem + kOffW1 + sw128_off(n, 48 + 2 * c)) = split_bf16(__ldg(src + n) + __ldg(ctr + n));
+          *reinterpret_cast<uint32_t*>(smem + kOffW1 + sw128_off(n, 48 + 2 * c)) = split16<F16>(__ldg(src + n) + __ldg(ctr + n));
       }
       fence_proxy_async();
       __syncwarp();
@@ -374,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
   } else if (warp == kEpiWarps) {
     // ================= MMA issuer: the whole warp walks the protocol, one elected lane issues =================
     mbar_wait(bar_w, 0);
-    const uint32_t idh = make_idesc(kTileM, kH / 2), id256 = make_idesc(kTileM, kH), id3 = make_idesc(kTileM, kN3);
+    const uint32_t idh = make_idesc_t<F16>(kTileM, kH / 2), id256 = make_idesc_t<F16>(kTileM, kH), id3 = make_idesc_t<F16>(kTileM, kN3);
     const uint64_t dW1 = make_desc(sbase + kOffW1);
     // Biases ride on the tensor pipe.  The X tile carries, in columns 48..63, a pair of ones at the row's
     // scene class; W1' columns 48..63 carry (hi, lo) bf16 halves of c_scene[scene0+class] + c_t[step], rewritten
@@ -488,15 +526,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 #pragma unroll
       for (int j = 0; j < 8; j += 4) {
         const float4 q = *reinterpret_cast<const float4*>(xr + 40 + j);
-        pc[j / 2] = pack_bf16(q.x, q.y);
-        pc[j / 2 + 1] = pack_bf16(q.z, q.w);
+        pc[j / 2] = pack16<F16>(q.x, q.y);
+        pc[j / 2 + 1] = pack16<F16>(q.z, q.w);
       }
 #pragma unroll
-      for (int c = 0; c < kMaxClasses; ++c) pc[4 + c] = (c == cls) ? 0x3F803F80u : 0u;
+      for (int c = 0; c < kMaxClasses; ++c) pc[4 + c] = (c == cls) ? (F16 ? 0x3C003C00u : 0x3F803F80u) : 0u;
       auto store_x = [&]() {
         uint32_t px[10];
 #pragma unroll
-        for (int j = 0; j < 20; j += 2) px[j / 2] = pack_bf16(x[j], x[j + 1]);
+        for (int j = 0; j < 20; j += 2) px[j / 2] = pack16<F16>(x[j], x[j + 1]);
         TMEM_ST_X8(tmem + lane_addr + kColX + c0 / 2, px);
         TMEM_ST_X2(tmem + lane_addr + kColX + c0 / 2 + 8, (px + 8));
         if (half == 1) {
@@ -565,12 +603,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
             tmem_wait_ld();
             TMEM_LD_X16(dsrc + (ch + 1) * 16, rb);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
+            for (int j = 0; j < 16; j += 2) p[j / 2] = pack_relu16<F16>(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]));
             TMEM_ST_X8(hdst + ch * 8, p);
             tmem_wait_ld();
             if (ch + 2 < 8) TMEM_LD_X16(dsrc + (ch + 2) * 16, ra);
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) p[j / 2] = pack_relu_bf16(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
+            for (int j = 0; j < 16; j += 2) p[j / 2] = pack_relu16<F16>(__uint_as_float(rb[j]), __uint_as_float(rb[j + 1]));
             TMEM_ST_X8(hdst + (ch + 1) * 8, p);
           }
           tmem_wait_st();
@@ -694,8 +732,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_denoiser_tc(const __grid_consta
 int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st) {
   TcState* s = (TcState*)d->tc;
   PSTL_CHECK_ARG(s, "engine not created");
-  k_build_image<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image);
+  k_build_image<false><<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image);
   PSTL_LAUNCH_CHECK();
+  if (s->image_h) {
+    k_build_image<true><<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image_h);
+    PSTL_LAUNCH_CHECK();
+  }
   k_build_image2<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->w1p, d->kin, d->w.p2_w, d->w.p4_w, d->T2, s->image2);
   PSTL_LAUNCH_CHECK();
   if (s->image3) {
@@ -703,8 +745,12 @@ int pstl_tc_refresh(pstl_denoiser* d, cudaStream_t st) {
     PSTL_LAUNCH_CHECK();
   }
   if (s->image_r) {
-    k_build_image<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_r);
+    k_build_image<false><<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_r);
     PSTL_LAUNCH_CHECK();
+    if (s->image_h_r) {
+      k_build_image<true><<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image_h_r);
+      PSTL_LAUNCH_CHECK();
+    }
     k_build_image2<<<(256 * 256 + 255) / 256, 256, 0, st>>>(d->r1p, d->kin, d->w.r2_w, d->w.r4_w, d->T2, s->image2_r);
     PSTL_LAUNCH_CHECK();
     if (s->image3_r) {
@@ -730,7 +776,7 @@ int pstl_tc_create(pstl_denoiser* d) {
   }
   TcState* s = new TcState();
   s->sm_count = sms;
-  s->image = s->image_r = s->image2 = s->image2_r = s->image3 = s->image3_r = nullptr;
+  s->image = s->image_r = s->image2 = s->image2_r = s->image3 = s->image3_r = s->image_h = s->image_h_r = nullptr;
   s->zeros = nullptr;
   PSTL_CUDA(cudaMalloc(&s->image, kWeightBytes));
   PSTL_CUDA(cudaMemset(s->image, 0, kWeightBytes));
@@ -739,6 +785,10 @@ int pstl_tc_create(pstl_denoiser* d) {
   if (d->precision == PSTL_PRECISION_F16X3) {
     PSTL_CUDA(cudaMalloc(&s->image3, 4 * k2WeightBytes));
     PSTL_CUDA(cudaMemset(s->image3, 0, 4 * k2WeightBytes));
+  }
+  if (d->precision == PSTL_PRECISION_F16) {
+    PSTL_CUDA(cudaMalloc(&s->image_h, kWeightBytes));
+    PSTL_CUDA(cudaMemset(s->image_h, 0, kWeightBytes));
   }
   PSTL_CUDA(cudaMalloc(&s->zeros, kH * sizeof(float)));
   PSTL_CUDA(cudaMemset(s->zeros, 0, kH * sizeof(float)));
@@ -751,12 +801,17 @@ int pstl_tc_create(pstl_denoiser* d) {
       PSTL_CUDA(cudaMalloc(&s->image3_r, 4 * k2WeightBytes));
       PSTL_CUDA(cudaMemset(s->image3_r, 0, 4 * k2WeightBytes));
     }
+    if (d->precision == PSTL_PRECISION_F16) {
+      PSTL_CUDA(cudaMalloc(&s->image_h_r, kWeightBytes));
+      PSTL_CUDA(cudaMemset(s->image_h_r, 0, kWeightBytes));
+    }
   }
   d->tc = s;
   int rc = pstl_tc_refresh(d, nullptr);
   if (rc) return rc;
   PSTL_CUDA(cudaDeviceSynchronize());
-  PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+  PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+  PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
   PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes + 1024));
   PSTL_CUDA(cudaFuncSetAttribute(k_denoiser_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemBytes + 1024));
   d->tc = s;
@@ -771,6 +826,8 @@ void pstl_tc_destroy(pstl_denoiser* d) {
   cudaFree(s->image2);
   cudaFree(s->image2_r);
   cudaFree(s->image3);
+  cudaFree(s->image_h);
+  cudaFree(s->image_h_r);
   cudaFree(s->image3_r);
   cudaFree(s->zeros);
   delete s;
@@ -796,13 +853,21 @@ static bool tc_pair_fits(const TcState* s, int rows_per_scene) {
 }
 
 static int tc_launch(const TcState* s, int engine, TcArgs& a, int rows_per_scene, const uint8_t* image1, const uint8_t* image2,
-                     const uint8_t* image3, cudaStream_t st) {
+                     const uint8_t* image3, const uint8_t* image_h, cudaStream_t st) {
   if (image3) {  // PSTL_PRECISION_F16X3: the split-operand pair engine
     PSTL_CHECK_ARG(tc_pair_fits(s, rows_per_scene), "rows_per_scene too small for the split-operand tcgen05 tile");
     a.image = image3;
     const int n_tiles = (a.N + k2TileM - 1) / k2TileM;
     const int pairs = n_tiles < s->sm_count / 2 ? n_tiles : s->sm_count / 2;
     k_denoiser_tc3<<<2 * pairs, kThreads, k3SmemBytes + 1024, st>>>(a);
+    PSTL_LAUNCH_CHECK();
+    return PSTL_OK;
+  }
+  if (image_h) {  // PSTL_PRECISION_F16: the one-SM engine on fp16 operands
+    a.image = image_h;
+    const int n_tiles = (a.N + kTileM - 1) / kTileM;
+    const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
+    k_denoiser_tc<true><<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
     PSTL_LAUNCH_CHECK();
     return PSTL_OK;
   }
@@ -815,7 +880,7 @@ static int tc_launch(const TcState* s, int engine, TcArgs& a, int rows_per_scene
     a.image = image1;
     const int n_tiles = (a.N + kTileM - 1) / kTileM;
     const int grid = n_tiles < s->sm_count ? n_tiles : s->sm_count;
-    k_denoiser_tc<<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
+    k_denoiser_tc<false><<<grid, kThreads, kSmemBytes + 1024, st>>>(a);
   }
   PSTL_LAUNCH_CHECK();
   return PSTL_OK;
@@ -848,7 +913,7 @@ int pstl_tc_sample(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   if (getenv("PSTL_TC_DEBUG")) { cudaMalloc(&dbg, 48 * sizeof(long long)); cudaMemset(dbg, 0, 48 * sizeof(long long)); }
   a.dbg = dbg;
 #endif
-  int rc = tc_launch(s, d->tc_engine, a, rows_per_scene, s->image, s->image2, s->image3, st);
+  int rc = tc_launch(s, d->tc_engine, a, rows_per_scene, s->image, s->image2, s->image3, s->image_h, st);
 #ifdef PSTL_TC_DEBUG
   if (dbg) {
     cudaStreamSynchronize(st);
@@ -888,7 +953,7 @@ int pstl_tc_refine(pstl_denoiser* d, const float* cscene, int rows_per_scene, co
   a.N = N; a.rows_per_scene = rows_per_scene; a.steps = 2; a.first_step = 0; a.last_step = 0;  // one pass, ct row 0
   a.clip = clip_rect; a.w_max = w_max; a.a_max = a_max;
   a.refine = 1; a.u0 = u0; a.scores = scores; a.out = out;
-  return tc_launch(s, d->tc_engine, a, rows_per_scene, s->image_r, s->image2_r, s->image3_r, st);
+  return tc_launch(s, d->tc_engine, a, rows_per_scene, s->image_r, s->image2_r, s->image3_r, s->image_h_r, st);
 }
 
 bool pstl_tc_fits(pstl_denoiser* d, int rows_per_scene) { return d->tc && tc_pair_fits((TcState*)d->tc, rows_per_scene); }

@@ -605,7 +605,8 @@ extern "C" int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_d
   PSTL_CHECK_ARG(w && out, "null argument");
   PSTL_CHECK_ARG(w->p0_w && w->p0_b && w->p2_w && w->p2_b && w->p4_w && w->p4_b, "policy_net weights required");
   PSTL_CHECK_ARG(w->T > 0 && w->hidden > 0 && w->feat_dim > 0 && w->time_dim > 0, "bad dims");
-  PSTL_CHECK_ARG(precision == PSTL_PRECISION_FP32 || precision == PSTL_PRECISION_BF16 || precision == PSTL_PRECISION_F16X3, "bad precision");
+  PSTL_CHECK_ARG(precision == PSTL_PRECISION_FP32 || precision == PSTL_PRECISION_BF16 || precision == PSTL_PRECISION_F16X3 ||
+                 precision == PSTL_PRECISION_F16, "bad precision");
   if (2 * w->T + 7 > PSTL_XIN_LD) {  // the packed input row [x | hl | stlp] has a fixed leading dimension
     pstl_set_error("pstl_denoiser_create: T = %d needs 2T+7 <= %d packed input columns", w->T, PSTL_XIN_LD);
     return PSTL_ERR_UNSUPPORTED;
@@ -627,7 +628,7 @@ extern "C" int pstl_denoiser_create(const pstl_weights* w, int precision, pstl_d
     pstl_denoiser_destroy(d);
     return PSTL_ERR_CUDA;
   }
-  if (precision == PSTL_PRECISION_BF16 || precision == PSTL_PRECISION_F16X3) {
+  if (precision != PSTL_PRECISION_FP32) {
     int rc = pstl_tc_create(d);
     if (rc) {
       pstl_denoiser_destroy(d);
@@ -780,7 +781,8 @@ extern "C" int pstl_denoiser_sample(pstl_denoiser_t d, const float* scene_feat, 
   };
   // the tcgen05 engines run the unguided steps (and the posterior mean of guided ones); a split-operand handle whose
   // 256-row tile does not fit rows_per_scene falls back to the fp32 SIMT chain
-  const bool tc_guided = d->precision == PSTL_PRECISION_BF16 || (d->precision == PSTL_PRECISION_F16X3 && pstl_tc_fits(d, rows_per_scene));
+  const bool tc_guided = d->precision == PSTL_PRECISION_BF16 || d->precision == PSTL_PRECISION_F16 ||
+                         (d->precision == PSTL_PRECISION_F16X3 && pstl_tc_fits(d, rows_per_scene));
   for (int i = steps - 1; i >= 1; --i) {
     const bool guided = guided_at(i);
     if (tc_guided && !guided) {
@@ -900,7 +902,7 @@ extern "C" int pstl_refine(pstl_denoiser_t d, const float* scene_feat, int n_sce
   int rc = refine_inputs(d, w, scene_feat, n_scenes, hl, stlp, u0, N, n_randoms, n_shards, st);
   if (rc) return rc;
   LinArgs a;
-  if (((d->precision == PSTL_PRECISION_BF16 && (128 + rows_per_scene - 1) / rows_per_scene + 1 <= 8) ||
+  if ((((d->precision == PSTL_PRECISION_BF16 || d->precision == PSTL_PRECISION_F16) && (128 + rows_per_scene - 1) / rows_per_scene + 1 <= 8) ||
        (d->precision == PSTL_PRECISION_F16X3 && pstl_tc_fits(d, rows_per_scene))) && pstl_tc_has_refine(d))
     return pstl_tc_refine(d, w.cscene, rows_per_scene, w.xin, N, u0, scores, w_max, a_max, clip_rect, out, st);
   rc = mlp_hidden(d, w, N, rows_per_scene, d->r1p, H, nullptr, d->w.r2_w, d->w.r2_b, st);

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libpstl_b200.so")
 OP_SIGNAL, OP_PRED, OP_NEG, OP_SMIN2, OP_SMAX2, OP_SMIN_K, OP_WIN_SMIN, OP_WIN_SMAX, OP_PREFIX_SMIN, OP_SUFFIX_SMAX = range(10)
 SIG_V, SIG_D_CURR, SIG_TH_CURR, SIG_D_LEFT, SIG_TH_LEFT, SIG_D_RIGHT, SIG_TH_RIGHT, SIG_NEI = range(8)
 DEN_ONE, DEN_THMAX, DEN_VFACTOR, DEN_DFACTOR, DEN_SFACTOR = range(5)
-PRECISION_FP32, PRECISION_BF16, PRECISION_F16X3 = 0, 1, 2
+PRECISION_FP32, PRECISION_BF16, PRECISION_F16X3, PRECISION_F16 = 0, 1, 2, 3
 
 EXPORTS = [
     "pstl_last_error", "pstl_device_info", "pstl_version", "pstl_program_create", "pstl_program_destroy",

@@ -172,7 +172,7 @@ class Net(nn.Module):
         (optimiser step: same storage, new version) only refreshes the library's own copies — the hoisted first-layer
         blocks and the bf16 operand images — on the current stream (``pstl_denoiser_refresh``: no allocation, no
         synchronisation); parameters that moved to other storage rebuild the handle."""
-        prec = {"fp32": _nv.PRECISION_FP32, "bf16": _nv.PRECISION_BF16, "f16x3": _nv.PRECISION_F16X3}[precision]
+        prec = {"fp32": _nv.PRECISION_FP32, "bf16": _nv.PRECISION_BF16, "f16x3": _nv.PRECISION_F16X3, "f16": _nv.PRECISION_F16}[precision]
         ps = list(self.parameters())
         ptrs, vers = tuple(p.data_ptr() for p in ps), tuple(p._version for p in ps)
         cached = self._handles.get(prec)

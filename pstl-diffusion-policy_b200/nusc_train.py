@@ -1557,8 +1557,8 @@ def generate_parser(argv=None):
     add("--suffix", type=str, default=None)
     # additive flags (not in the reference)
     add("--synthetic", type=int, default=None, help="run on this many synthetic scenes per batch")
-    add("--precision", type=str, default="fp32", choices=["fp32", "bf16", "f16x3"],
-        help="denoiser arithmetic: fp32 SIMT, bf16 tensor cores (2e-2), or split-bf16 tensor cores (fp32-grade, 1e-5)")
+    add("--precision", type=str, default="fp32", choices=["fp32", "bf16", "f16", "f16x3"],
+        help="denoiser arithmetic: fp32 SIMT, bf16 / fp16 tensor-core operands (2e-2 bound; fp16 8x closer), or split fp16 operands (fp32-grade, 1e-5)")
     args = parser.parse_args(argv)
     # post-parse overrides, reference :1780-1812
     args.gt_nei = True

@@ -48,8 +48,8 @@ def guidance(scenes):
 
 
 def sampler(scenes, engine):
-    # engine 1 | 2: the bf16 engines; 3: the split-operand (f16x3, fp32-grade) engine; 0: the fp32 SIMT chain
-    args = NT.default_args(precision={0: "fp32", 3: "f16x3"}.get(engine, "bf16"), tc_engine=engine if engine in (1, 2) else 0)
+    # engine 1 | 2: the bf16 engines; 3: the split-operand (f16x3, fp32-grade) engine; 4: the one-SM engine on fp16 operands; 0: fp32 SIMT
+    args = NT.default_args(precision={0: "fp32", 3: "f16x3", 4: "f16"}.get(engine, "bf16"), tc_engine=engine if engine in (1, 2) else 0)
     net = Net(args)
     net.load_state_dict(synthetic.make_weights(1007))
     net = net.cuda()

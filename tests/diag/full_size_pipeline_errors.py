@@ -12,7 +12,7 @@ bs, S, nt = 1024, 64, 20
 W = synthetic.make_weights(1007, nt=nt)
 batch = {k: v.cuda() for k, v in synthetic.make_scene_batch(bs, nt=nt, n_randoms=S, seed=3).items()}
 outs = {}
-for prec in ("fp32", "f16x3", "bf16"):
+for prec in ("fp32", "f16x3", "f16", "bf16"):
     args = NT.default_args(precision=prec)
     args.seed = 99
     net = Net(args); net.load_state_dict(W); net = net.cuda()
@@ -24,7 +24,7 @@ for prec in ("fp32", "f16x3", "bf16"):
 ref = outs["fp32"]
 cs = np.sort(ref["cand_scores"], axis=0)
 margin = cs[-1] - cs[-2]
-for prec in ("f16x3", "bf16"):
+for prec in ("f16x3", "f16", "bf16"):
     o = outs[prec]
     e_it = (np.abs(o["final_iterate"] - ref["final_iterate"]) / np.array([0.5, 5.0])).max()
     e_u = (np.abs(o["controls"] - ref["controls"]) / np.array([0.5, 5.0])).reshape(len(margin), -1).max(1)
