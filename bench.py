@@ -262,13 +262,30 @@ def extra_pipeline(flags, scenes, dev, W, what, cpu_scenes, cpu_kw, reps=3, prec
     net = net.to(dev)
     stls, co = NT.build_stl_cache(args), NT.get_diffusion_coeffs(args)
     b = {k: v.to(dev) for k, v in synthetic.make_scene_batch(scenes, nt=nt, n_randoms=S, seed=3003).items()}
-    runner = NT.CapturedPipeline(net, stls, co, args, b)
-    ms = _timeit(lambda: runner(b), reps=reps, warm=1)
+    runner = NT.BatchPipeliner(net, stls, co, args, b, depth=2)  # as the headline: two batches in flight
+
+    def burst(k):
+        for _ in range(k):
+            runner.submit(b)
+        runner.drain()
+
+    burst(2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2 * max(2, reps)
+    e0.record()
+    burst(reps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
     n = scenes * S * 3
-    acc = float(runner(b)["acc"])
+    out, _, _ = runner.submit(b)
+    runner.drain()
+    torch.cuda.synchronize()
+    acc = float(out["acc"])
     out = {"workload": what, "scenes": scenes, "chains": n, "multi_cands": args.multi_cands, "n_rolls": args.n_rolls,
            "guidance": bool(args.guidance), "ms": ms, "chains_per_s": n / ms * 1e3, "acc": acc, "precision": precision,
-           "launch": "CUDA graph replay (NT.CapturedPipeline)", "l2": "inputs + state > L2"}
+           "launch": "CUDA graph replay, two batches in flight (NT.BatchPipeliner)", "l2": "inputs + state > L2"}
     if cpu_scenes:
         torch.set_num_threads(os.cpu_count() or 1)
         bc = synthetic.make_scene_batch(cpu_scenes, nt=nt, n_randoms=S, seed=3004)
@@ -411,10 +428,11 @@ def main():
             "left_id", "right_id", "gt_high_level", "pre_stlp")
     h2d_bytes = sum(host[0][k].numel() * 4 for k in need)
     resident = [{k: hb[k].to(dev) for k in need} for hb in host]
-    host_scores = torch.empty(N, dtype=torch.float32).pin_memory()
-    host_idx = torch.empty(N, dtype=torch.int32).pin_memory()
-    host_plan = torch.empty((a.scenes, nt, 2), dtype=torch.float32).pin_memory()
-    host_pick = torch.empty(a.scenes, dtype=torch.int64).pin_memory()
+    DEPTH = 2  # batches in flight (NT.BatchPipeliner); every slot has its own pinned result buffers
+    host_res = [dict(scores=torch.empty(N, dtype=torch.float32).pin_memory(), idx=torch.empty(N, dtype=torch.int32).pin_memory(),
+                     plan=torch.empty((a.scenes, nt, 2), dtype=torch.float32).pin_memory(),
+                     pick=torch.empty(a.scenes, dtype=torch.int64).pin_memory()) for _ in range(DEPTH)]
+    res_ready = [None] * DEPTH
     d2h_bytes = N * 8 + a.scenes * (nt * 2 * 4 + 8)
     gather = sharding.AsyncScoreGather(N, dev)
     flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -422,33 +440,47 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
     samp_ms = []
 
-    # the public call: NT.CapturedPipeline replays sample_and_score as one CUDA graph (static shapes);
-    # --eager launches the same kernels one by one from Python
-    runner = None if a.eager else NT.CapturedPipeline(net, stls, coeffs, args, resident[0])
+    # the public call: NT.BatchPipeliner — sample_and_score captured as CUDA graphs (NT.CapturedPipeline, static shapes),
+    # two runners replayed alternately on two streams so consecutive batches overlap; --eager launches the same kernels
+    # one by one from Python on one stream
+    runner = None if a.eager else NT.BatchPipeliner(net, stls, coeffs, args, resident[0], depth=DEPTH)
     L = native.lib()
+
+    def d2h(out, slot):
+        """the step's result on the host: per-chain scores and selected-iterate index, per-scene chosen chain and its
+        control sequence (the plan a caller executes) — asynchronous copies on the current stream into the slot's pinned
+        buffers; the host waits for them when the slot comes round again (and at the end of the timed region)"""
+        h = host_res[slot]
+        h["scores"].copy_(out["scores"], non_blocking=True)
+        h["idx"].copy_(out["best_idx"], non_blocking=True)
+        h["plan"].copy_(out["scene_plan"], non_blocking=True)
+        h["pick"].copy_(out["scene_pick"], non_blocking=True)
+        e = torch.cuda.Event()
+        e.record()
+        res_ready[slot] = e
 
     def step(i, e2e):
         b = host[i % n_host] if e2e else resident[i % n_host]
         if runner is not None:
-            out = runner(b)  # copies the batch (pinned host or device) into the graph's static inputs, replays
-        else:
-            if e2e:
-                b = {k: b[k].to(dev, non_blocking=True) for k in need}
-            out = NT.sample_and_score(net, b, stls, coeffs, args)
-        if world > 1:
-            gather.submit(out["scores"], out["best_idx"])  # side stream: runs under the next step's kernels
+            slot = i % DEPTH
+            if e2e and res_ready[slot] is not None:
+                res_ready[slot].synchronize()  # the host has this slot's previous result before the buffers are reused
+            out, _, slot = runner.submit(b)  # copies the batch (pinned host: the H2D; or device) into the runner's inputs, replays
+            with torch.cuda.stream(runner.streams[slot]):
+                if world > 1:
+                    gather.submit(out["scores"], out["best_idx"])  # side stream: runs under the next steps' kernels
+                if e2e:
+                    d2h(out, slot)
+            return out
         if e2e:
-            d2h(out)
+            b = {k: b[k].to(dev, non_blocking=True) for k in need}
+        out = NT.sample_and_score(net, b, stls, coeffs, args)
+        if world > 1:
+            gather.submit(out["scores"], out["best_idx"])
+        if e2e:
+            d2h(out, 0)
+            torch.cuda.current_stream().synchronize()
         return out
-
-    def d2h(out):
-        """the step's result on the host: per-chain scores and selected-iterate index, per-scene chosen chain and its
-        control sequence (the plan a caller executes)"""
-        host_scores.copy_(out["scores"], non_blocking=True)
-        host_idx.copy_(out["best_idx"], non_blocking=True)
-        host_plan.copy_(out["scene_plan"], non_blocking=True)
-        host_pick.copy_(out["scene_pick"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
 
     # roofline numerator's time: CUDA events immediately around the native sampler call
     # (pstl_denoiser_sample = hoist GEMMs + input pack + the persistent tcgen05 kernel)
@@ -472,6 +504,8 @@ def main():
     launches = int(L.pstl_launch_count() - c0)
 
     def barrier():
+        if runner is not None:
+            runner.drain()
         if world > 1:
             gather.result()  # the last step's gather belongs to the step
         torch.cuda.synchronize()
@@ -490,8 +524,10 @@ def main():
     w0 = time.time()
     e0.record()
     for i in range(a.steps):
-        flush.zero_()  # L2 flush between timed iterations (inputs < L2)
+        flush.zero_()  # L2 flush between timed iterations (inputs < L2); the step's stream waits for it
         step(i, False)
+    if runner is not None:
+        runner.drain()  # current stream waits for both pipelines
     if world > 1:
         gather.result()  # current stream waits for the last gather: it is inside the timed region
     e1.record()
@@ -510,29 +546,19 @@ def main():
         barrier()
         NT.KERNEL_TIMER = None
     sampler_ms = sum(x.elapsed_time(y) for x, y in samp_ms) / max(1, len(samp_ms))
-    # end to end: pinned host inputs -> H2D -> pipeline -> D2H of scores + selected indices, every step.
-    # With the graph runner the H2D copy of step i+1 is issued on a copy stream while step i replays
-    # (CapturedPipeline.prefetch); step 0's copy is inside the timed region like all the others.
-    def step_e2e(i, last):
-        if runner is None:
-            return step(i, True)
-        out = runner()  # consumes the prefetched batch
-        if not last:
-            runner.prefetch(host[(i + 1) % n_host])
-        if world > 1:
-            gather.submit(out["scores"], out["best_idx"])
-        d2h(out)
-        return out
-
+    # end to end: pinned host inputs -> H2D -> pipeline -> D2H of scores + selected indices + per-scene plan, every step, two
+    # batches in flight: step i's H2D, replay and D2H are enqueued on its runner's stream (they overlap the other runner's
+    # kernels); the host takes a slot's result before it reuses the slot and everything is on the host when the clock stops
     step(0, True)
     barrier()
     t0 = time.perf_counter()
-    if runner is not None:
-        runner.prefetch(host[0])
     for i in range(a.steps):
         flush.zero_()
-        step_e2e(i, i == a.steps - 1)
+        step(i, True)
     barrier()
+    for e in res_ready:
+        if e is not None:
+            e.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clk.mark(time.time() - e2e_ms / 1e3, time.time())
     tm = torch.tensor([dev_ms, e2e_ms, gather_us or 0.0], device=dev, dtype=torch.float64)
@@ -565,7 +591,8 @@ def main():
                                    "%d scenes x 64 samples x 3 modes = %d chains per GPU per step" % (a.scenes, N),
                        "scenes_per_gpu": a.scenes, "chains_per_gpu": N, "multi_cands": K, "precision": precision,
                        "noise": "in-kernel Philox", "l2": "flushed between timed steps (160 MB write)",
-                       "launch": "eager" if a.eager else "CUDA graph replay of sample_and_score (NT.CapturedPipeline)",
+                       "launch": "eager" if a.eager else "CUDA graph replay of sample_and_score; two runners alternate on two streams "
+                                 "(NT.BatchPipeliner: consecutive batches overlap; each step = one full batch)",
                        "parallelism": "scene-sharded x%d, NCCL all-gather of scores + selected indices on a side stream "
                                       "(overlaps the next step; the last one is inside the timed region)" % world},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
