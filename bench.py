@@ -40,7 +40,8 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--scenes", type=int, default=1024, help="scenes per GPU per step")
-    p.add_argument("--precision", default=os.environ.get("PSTL_PRECISION", "auto"), choices=["auto", "fp32", "bf16"])
+    p.add_argument("--precision", default=os.environ.get("PSTL_PRECISION", "auto"), choices=["auto", "fp32", "bf16", "f16", "f16x3"],
+                   help="denoiser arithmetic (auto = bf16 tensor-core operands, the headline; f16 / f16x3: fp16 / split-fp16 operands)")
     p.add_argument("--cpu-scenes", type=int, default=32, help="scenes per CPU-baseline batch")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
@@ -409,6 +410,8 @@ def main():
         except native.PstlNativeError:
             if precision == "bf16":
                 raise
+    if precision in ("f16", "f16x3"):
+        args.precision = precision
     precision = args.precision
     W = synthetic.make_weights(1007, nt=nt)
     net = Net(args)
@@ -585,7 +588,10 @@ def main():
     achieved = FLOP_PER_CHAIN * N / (sampler_ms / 1e3) / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if precision == "fp32" else "bf16 (denoiser operands; fp32 accumulate, fp32 STL/rollout)",
+            "dtype": {"fp32": "f32", "bf16": "bf16 (denoiser operands; fp32 accumulate, fp32 STL/rollout)",
+                      "f16": "f16 (denoiser operands; fp32 accumulate, fp32 STL/rollout)",
+                      "f16x3": "f16x3 (denoiser operands as two fp16 pieces, three MMAs per product: fp32-grade; fp32 accumulate, "
+                               "fp32 STL/rollout)"}[precision],
             "data": "synthetic",
             "config": {"workload": "config2: DDPM(99 reverse steps)+best-of-5+RefineNet+final STL, README 'Ours' flags, "
                                    "%d scenes x 64 samples x 3 modes = %d chains per GPU per step" % (a.scenes, N),
@@ -603,7 +609,7 @@ def main():
             "gpu_launches": launches * a.steps,
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": measured_traffic(N) if precision == "bf16" else None,
+                         "frac": achieved / tf_peak, "traffic": measured_traffic(N) if precision in ("bf16", "f16") else None,
                          "kernel": "denoiser reverse loop (%s)" % precision,
                          "note": "minimal hoisted FLOP count 17.39 MFLOP/chain / sampler time %.3f ms (CUDA events around "
                                  "pstl_denoiser_sample, %s); peak = %s"
