@@ -46,6 +46,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     p.add_argument("--no-extras", action="store_true", help="skip the short runs of BASELINE configs 1/3/4/5")
+    p.add_argument("--depth", type=int, default=2, help="batches in flight (NT.BatchPipeliner); 1 = one CUDA-graph runner on one stream")
     return p.parse_args()
 
 
@@ -431,7 +432,7 @@ def main():
             "left_id", "right_id", "gt_high_level", "pre_stlp")
     h2d_bytes = sum(host[0][k].numel() * 4 for k in need)
     resident = [{k: hb[k].to(dev) for k in need} for hb in host]
-    DEPTH = 2  # batches in flight (NT.BatchPipeliner); every slot has its own pinned result buffers
+    DEPTH = max(1, a.depth)  # batches in flight (NT.BatchPipeliner); every slot has its own pinned result buffers
     host_res = [dict(scores=torch.empty(N, dtype=torch.float32).pin_memory(), idx=torch.empty(N, dtype=torch.int32).pin_memory(),
                      plan=torch.empty((a.scenes, nt, 2), dtype=torch.float32).pin_memory(),
                      pick=torch.empty(a.scenes, dtype=torch.int64).pin_memory()) for _ in range(DEPTH)]
@@ -597,8 +598,9 @@ def main():
                                    "%d scenes x 64 samples x 3 modes = %d chains per GPU per step" % (a.scenes, N),
                        "scenes_per_gpu": a.scenes, "chains_per_gpu": N, "multi_cands": K, "precision": precision,
                        "noise": "in-kernel Philox", "l2": "flushed between timed steps (160 MB write)",
-                       "launch": "eager" if a.eager else "CUDA graph replay of sample_and_score; two runners alternate on two streams "
-                                 "(NT.BatchPipeliner: consecutive batches overlap; each step = one full batch)",
+                       "launch": "eager" if a.eager else "CUDA graph replay of sample_and_score; %d runner(s) alternate on their own "
+                                 "streams (NT.BatchPipeliner: consecutive batches overlap; each step = one full batch)" % DEPTH,
+                       "batches_in_flight": 1 if a.eager else DEPTH,
                        "parallelism": "scene-sharded x%d, NCCL all-gather of scores + selected indices on a side stream "
                                       "(overlaps the next step; the last one is inside the timed region)" % world},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
