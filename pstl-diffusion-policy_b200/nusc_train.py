@@ -1451,7 +1451,8 @@ class BatchPipeliner:
     the runner's stream, which first waits for the caller's current stream; ``out`` holds that runner's static outputs,
     valid from ``done`` (a CUDA event on ``pipe.streams[slot]``) until the runner is used again ``depth`` submits later —
     enqueue whatever reads them on ``pipe.streams[slot]`` or after ``done``.  ``drain()`` makes the current stream wait for
-    everything submitted."""
+    everything submitted.  The runners share the model's weight images read-only: ``drain()`` and synchronise before an
+    optimiser step or ``load_state_dict`` (an in-place refresh would race the other runner's replay)."""
 
     def __init__(self, net, stls_cac, coeffs, args, example_batch, depth=2):
         dev = next(net.parameters()).device
