@@ -340,6 +340,23 @@ def run_extras(a, world, rank, dev, net, W):
             s["cpu_port_traj_per_s"] = d["cpu_port_traj_per_s"]
             cells.append({"T": T, "Knei": K, "dense": d, "scene_indexed": s})
         ex["config5"] = cells
+    if world > 1:
+        # config 5 at N GPUs: the two corner cells of the robustness sweep, 1,000,128 trajectories PER GPU (weak scaling, no
+        # exchange: trajectories shard), max over ranks of the per-rank device time
+        cells = []
+        for T, K in ((20, 8), (200, 64)):
+            by = dense_bytes(T, K)
+            n = int(min(1000128, 6e9 // by))
+            d = extra_dense(n, T, K, dev, hbm_peak, 1100 + T + rank, cpu_rows=0)
+            si = extra_scene_indexed(T, K, dev, 1200 + T + rank)
+            t = torch.tensor([d["ms"], si["ms"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cells.append({"T": T, "Knei": K, "n_gpus": world,
+                          "dense": {"rows_per_gpu": n, "ms": float(t[0]), "traj_per_s_all_gpus": world * n / float(t[0]) * 1e3,
+                                    "GBps_per_gpu": n * by / float(t[0]) / 1e6, "frac_hbm": n * by / float(t[0]) / 1e6 / hbm_peak},
+                          "scene_indexed": {"rows_per_gpu": si["rows"], "ms": float(t[1]),
+                                            "traj_per_s_all_gpus": world * si["rows"] / float(t[1]) * 1e3}})
+        ex["config5"] = cells
     if world == 8 or (world > 1 and os.environ.get("PSTL_BENCH_CONFIG4")):
         flags = [f for f in NT.OURS_FLAGS]
         flags[flags.index("--multi_cands") + 1] = "10"
