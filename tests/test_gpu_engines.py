@@ -287,3 +287,21 @@ def test_batch_pipeliner_concurrent_replays_do_not_interact():
     # interleaved Philox ranges: consecutive submits never reuse a step word
     c = [int(r.counter.item()) for r in pipe.runners]
     assert c[0] != c[1] and pipe.runners[0]._counter_stride == 2 * 4096
+
+
+def test_engine_and_precision_arguments_are_checked():
+    """bad engine ids / precisions fail loudly with a message instead of picking something"""
+    from pstl_b200 import native as nv
+    args = NT.default_args(precision="bf16")
+    net = Net(args)
+    net.load_state_dict(synthetic.make_weights(1007))
+    net = net.cuda()
+    h = net.native_handle("bf16")
+    L = nv.lib()
+    assert L.pstl_denoiser_set_engine(h, 3) != 0 and b"engine" in L.pstl_last_error()
+    assert L.pstl_denoiser_set_engine(h, 2) == 0 and L.pstl_denoiser_set_engine(h, 0) == 0
+    with pytest.raises(KeyError):
+        net.native_handle("fp8")
+    out = nv.C.c_void_p()
+    w = nv.Weights()
+    assert L.pstl_denoiser_create(nv.C.byref(w), 7, nv.C.byref(out)) != 0  # null weights / unknown precision
