@@ -623,7 +623,11 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "h2d": "scene batch (ego, neighbours + tracks, 3 lanes, ids, pSTL parameters) from pinned host memory",
                     "d2h": "per chain: final score + selected-iterate index; per scene: chosen chain and its 20x2 control "
-                           "sequence (the refined controls of all chains, 31 MB, stay on the device)"},
+                           "sequence (the refined controls of all chains, 31 MB, stay on the device)",
+                    "how": "wall clock over the K steps through NT.BatchPipeliner.submit with PINNED HOST batches: every step's "
+                           "H2D, graph replay and D2H are enqueued on its runner's stream (so they overlap the other runner's "
+                           "kernels); the host takes a slot's result before reusing the slot and holds every result when the "
+                           "clock stops" if not a.eager else "wall clock over the K steps, eager launches, synchronous D2H"},
             "gather_us": gather_us if world > 1 else None,
             "gpu_launches": launches * a.steps,
             "clocks": clk.summary(),
